@@ -1,0 +1,665 @@
+// api.cu -- context management and the C ABI of libchalkydri_b200.so (include/chalkydri_b200.h).
+//
+// Host-side orchestration only: every stage of the hot path is a CUDA kernel from the headers below; there is
+// no CPU implementation behind any entry point (a missing / non-sm_100 device makes cb_create fail).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "threshold.cuh"
+#include "ccl.cuh"
+#include "clusters.cuh"
+#include "quads.cuh"
+#include "decode.cuh"
+#include "sqpnp.cuh"
+#include "cat.cuh"
+
+using namespace cb;
+
+static const unsigned long long kHostCodes[kNumCodes] = {
+#include "tag36h11_codes.inc"
+};
+static const int kHostBitX[36] = {1,2,3,4,5,2,3,4,3, 6,6,6,6,6,5,5,5,4, 6,5,4,3,2,5,4,3,4, 1,1,1,1,1,2,2,2,3};
+static const int kHostBitY[36] = {1,1,1,1,1,2,2,2,3, 1,2,3,4,5,2,3,4,3, 6,6,6,6,6,5,5,5,4, 6,5,4,3,2,5,4,3,4};
+
+static thread_local std::string g_create_error;
+
+enum Stage { ST_THRESH = 1, ST_LABELS = 2, ST_QUADS = 3, ST_FULL = 4 };
+
+struct cb_ctx {
+    int device = 0;
+    int max_w = 0, max_h = 0, max_batch = 0, max_dets = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool family_set = false;
+    DetParams prm{};
+    DecodeConst dc{};
+    int sq_max_iter = 15;
+    double sq_tol_sq = 1e-16;
+    int num_sms = 148;
+
+    // device buffers (sized for max_batch frames of max_w x max_h at decimation >= 1)
+    uint8_t *d_in = nullptr;      size_t in_bytes = 0;
+    uint8_t *d_gray = nullptr;    size_t gray_bytes = 0;
+    uint8_t *d_thresh = nullptr, *d_mark = nullptr;  size_t map_bytes = 0;
+    uint8_t *d_tmin = nullptr, *d_tmax = nullptr;    size_t tile_bytes = 0;
+    uint32_t *d_labels = nullptr, *d_sizes = nullptr; size_t label_bytes = 0;
+    ClusterSlot *d_table = nullptr;
+    ClusterRec *d_clusters = nullptr;
+    uint32_t *d_worklist = nullptr;
+    unsigned long long *d_pts = nullptr;
+    uint32_t *d_scankey = nullptr;
+    double *d_lfps = nullptr;
+    unsigned long long *d_scratch = nullptr;
+    QuadRec *d_quads = nullptr;
+    RawDet *d_raw = nullptr;
+    cb_detection *d_dets = nullptr;
+    int32_t *d_counts = nullptr;
+    uint32_t *d_small = nullptr;   // [nclusters B][npoints B][nquads B][nraw B][misc 16]
+    Caps caps{};
+    size_t max_npix = 0;           // per frame, at decimation 1 (worst case)
+    // pinned staging for outputs
+    cb_detection *h_dets = nullptr;
+    int32_t *h_counts = nullptr;
+    uint32_t *h_small = nullptr;
+
+    cudaEvent_t ev[10]{};
+    cb_timing timing{};
+};
+
+static int fail(cb_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(ctx, CB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+__global__ void table_init_kernel(ClusterSlot *t, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { t[i].key = EMPTY_KEY; t[i].count = 0; t[i].cluster = 0xffffffffu; }
+}
+
+static void set_default_params(cb_ctx *ctx)
+{
+    DetParams &p = ctx->prm;
+    p.quad_decimate = 2.0f; p.refine_edges = 1; p.decode_sharpening = 0.25; p.min_cluster_pixels = 5; p.max_nmaxima = 10;
+    p.critical_rad = (float)(10 * M_PI / 180); p.max_line_fit_mse = 10.0f; p.min_white_black_diff = 5; p.bits_corrected = 3;
+    p.cos_critical_rad = cos(p.critical_rad);
+    for (int i = 0; i < 7; i++) { int j = i - 3; p.smooth_f[i] = (float)exp(-j * j / (2 * 1.0 * 1.0)); }
+    int mtw = (int)(8 / p.quad_decimate); if (mtw < 3) mtw = 3;
+    p.min_tag_width = mtw;
+    for (int k = 0; k < 4; k++) { double th = k * M_PI / 2.0; ctx->dc.rot_c[k] = cos(th); ctx->dc.rot_s[k] = sin(th); }
+}
+
+extern "C" {
+
+const char *cb_version(void) { return "chalkydri_b200 0.1 (sm_100a)"; }
+
+int cb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *cb_last_error(const cb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void cb_destroy(cb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
+                    ctx->d_table, ctx->d_clusters, ctx->d_worklist, ctx->d_pts, ctx->d_scankey, ctx->d_lfps, ctx->d_scratch,
+                    ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int max_dets_per_frame)
+{
+    cb_ctx *ctx = nullptr;
+    if (max_width < 8 || max_height < 8 || max_batch < 1 || max_dets_per_frame < 1 || max_width >= 65536 || max_height >= 65536) {
+        fail(nullptr, CB_ERR_ARG, "cb_create: bad sizes %dx%d batch %d dets %d", max_width, max_height, max_batch, max_dets_per_frame);
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fail(nullptr, CB_ERR_CUDA, "cb_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { fail(nullptr, CB_ERR_ARG, "cb_create: device %d out of range (0..%d)", device, ndev - 1); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        fail(nullptr, CB_ERR_CUDA, "cb_create: device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(nullptr, CB_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    ctx = new cb_ctx();
+    ctx->device = device; ctx->max_w = max_width; ctx->max_h = max_height; ctx->max_batch = max_batch; ctx->max_dets = max_dets_per_frame;
+    ctx->num_sms = prop.multiProcessorCount;
+    set_default_params(ctx);
+    const size_t B = (size_t)max_batch;
+    const size_t npix = (size_t)max_width * max_height;   // worst case: decimation 1
+    ctx->max_npix = npix;
+    if (B * npix >= 0xffffffffull) { fail(nullptr, CB_ERR_ARG, "cb_create: batch*pixels must stay below 2^32 (labels are 32-bit)"); delete ctx; return nullptr; }
+    // capacities are per frame and scale with the decimated frame (default decimation 2 => npix/4), computed for the
+    // worst case decimation 1 only when the caller asks for it through cb_set_params; allocate for decimation >= 2 by
+    // default and grow lazily in ensure_capacity().
+    auto alloc = [&](void **p, size_t bytes) -> bool {
+        cudaError_t er = cudaMalloc(p, bytes);
+        if (er != cudaSuccess) { fail(nullptr, CB_ERR_CUDA, "cb_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(er)); return false; }
+        return true;
+    };
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    // decimated worst case handled by this allocation: ceil(W/2) x ceil(H/2); decimation 1 re-allocates on demand
+    const size_t dw = (max_width + 1) / 2, dh = (max_height + 1) / 2;
+    const size_t dpix = dw * dh;
+    const size_t tp = (dw + 15) / 16 * 16;
+    ctx->in_bytes = B * (npix + 16);
+    ctx->map_bytes = B * dh * tp;
+    ctx->tile_bytes = B * ((dw / 4) + 1) * ((dh / 4) + 1);
+    ctx->label_bytes = B * dpix * sizeof(uint32_t);
+    Caps &c = ctx->caps;
+    c.slots_per_frame = next_pow2((uint32_t)std::max<size_t>(1024, dpix / 8));
+    c.clusters_per_frame = (uint32_t)std::max<size_t>(2048, dpix / 128);
+    c.points_per_frame = (uint32_t)std::max<size_t>(65536, dpix + dpix / 2);   // noisy frames emit ~0.85 points / pixel
+    c.quads_per_frame = (uint32_t)std::max<size_t>(512, dpix / 1024);
+    c.dets_per_frame = (uint32_t)max_dets_per_frame;
+    ok = ok && alloc((void **)&ctx->d_in, ctx->in_bytes + 64);
+    ok = ok && alloc((void **)&ctx->d_thresh, ctx->map_bytes) && alloc((void **)&ctx->d_mark, ctx->map_bytes);
+    ok = ok && alloc((void **)&ctx->d_tmin, ctx->tile_bytes) && alloc((void **)&ctx->d_tmax, ctx->tile_bytes);
+    ok = ok && alloc((void **)&ctx->d_labels, ctx->label_bytes) && alloc((void **)&ctx->d_sizes, ctx->label_bytes);
+    ok = ok && alloc((void **)&ctx->d_table, B * c.slots_per_frame * sizeof(ClusterSlot));
+    ok = ok && alloc((void **)&ctx->d_clusters, B * c.clusters_per_frame * sizeof(ClusterRec));
+    ok = ok && alloc((void **)&ctx->d_worklist, B * c.clusters_per_frame * sizeof(uint32_t));
+    ok = ok && alloc((void **)&ctx->d_pts, B * c.points_per_frame * sizeof(unsigned long long));
+    ok = ok && alloc((void **)&ctx->d_scankey, B * c.points_per_frame * sizeof(uint32_t));
+    ok = ok && alloc((void **)&ctx->d_lfps, B * c.points_per_frame * 6 * sizeof(double));
+    ok = ok && alloc((void **)&ctx->d_scratch, B * c.points_per_frame * 3 * sizeof(unsigned long long));
+    ok = ok && alloc((void **)&ctx->d_quads, B * c.quads_per_frame * sizeof(QuadRec));
+    ok = ok && alloc((void **)&ctx->d_raw, B * c.quads_per_frame * sizeof(RawDet));
+    ok = ok && alloc((void **)&ctx->d_dets, B * c.dets_per_frame * sizeof(cb_detection));
+    ok = ok && alloc((void **)&ctx->d_counts, B * sizeof(int32_t));
+    ok = ok && alloc((void **)&ctx->d_small, (4 * B + 16) * sizeof(uint32_t));
+    ok = ok && cudaMallocHost((void **)&ctx->h_dets, B * c.dets_per_frame * sizeof(cb_detection)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&ctx->h_counts, B * sizeof(int32_t)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&ctx->h_small, (4 * B + 16) * sizeof(uint32_t)) == cudaSuccess;
+    if (ok) {
+        ok = ok && cudaMemcpyToSymbol(c_codes, kHostCodes, sizeof(kHostCodes)) == cudaSuccess;
+        ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
+        ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(fit_quads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QfShared)) == cudaSuccess;
+        if (!ok && g_create_error.empty()) fail(nullptr, CB_ERR_CUDA, "cb_create: device setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!ok) {
+        if (g_create_error.empty()) fail(nullptr, CB_ERR_CUDA, "cb_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cb_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+int cb_set_family_tag36h11(cb_ctx *ctx, int bits_corrected)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (bits_corrected < 0 || bits_corrected > 3) return fail(ctx, CB_ERR_UNSUPPORTED, "bits_corrected %d: upstream's quick-decode table supports 0..3", bits_corrected);
+    ctx->prm.bits_corrected = bits_corrected;
+    ctx->family_set = true;
+    return CB_OK;
+}
+
+int cb_set_params(cb_ctx *ctx, float quad_decimate, float quad_sigma, int refine_edges, double decode_sharpening,
+                  int min_cluster_pixels, int max_nmaxima, float critical_rad, float max_line_fit_mse, int min_white_black_diff)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (quad_sigma != 0.0f) return fail(ctx, CB_ERR_UNSUPPORTED, "quad_sigma %g: blur is not implemented (the reference leaves it at 0)", quad_sigma);
+    if (quad_decimate != 2.0f) return fail(ctx, CB_ERR_UNSUPPORTED, "quad_decimate %g: only 2 (the reference's setting) is implemented in this build", quad_decimate);
+    if (max_nmaxima < 4 || max_nmaxima > 10) return fail(ctx, CB_ERR_UNSUPPORTED, "max_nmaxima %d outside 4..10", max_nmaxima);
+    DetParams &p = ctx->prm;
+    p.quad_decimate = quad_decimate; p.refine_edges = refine_edges; p.decode_sharpening = decode_sharpening;
+    p.min_cluster_pixels = min_cluster_pixels; p.max_nmaxima = max_nmaxima; p.critical_rad = critical_rad;
+    p.max_line_fit_mse = max_line_fit_mse; p.min_white_black_diff = min_white_black_diff;
+    p.cos_critical_rad = cos(p.critical_rad);
+    int mtw = (int)(8 / p.quad_decimate); if (mtw < 3) mtw = 3;
+    p.min_tag_width = mtw;
+    return CB_OK;
+}
+
+int cb_decimated_size(const cb_ctx *ctx, int width, int height, int *w, int *h)
+{
+    if (!ctx || !w || !h) return CB_ERR_ARG;
+    const int f = (int)ctx->prm.quad_decimate;
+    *w = 1 + (width - 1) / f; *h = 1 + (height - 1) / f;
+    return CB_OK;
+}
+
+int cb_get_timing(const cb_ctx *ctx, cb_timing *t)
+{
+    if (!ctx || !t) return CB_ERR_ARG;
+    *t = ctx->timing;
+    return CB_OK;
+}
+
+}  // extern "C"
+
+static int make_geom(cb_ctx *ctx, int width, int height, int stride, size_t frame_stride, int batch, Geom &g)
+{
+    if (width < 8 || height < 8 || width > ctx->max_w || height > ctx->max_h)
+        return fail(ctx, CB_ERR_ARG, "frame %dx%d outside the context's capacity %dx%d", width, height, ctx->max_w, ctx->max_h);
+    if (stride < width || frame_stride < (size_t)stride * (height - 1) + width) return fail(ctx, CB_ERR_ARG, "bad stride");
+    if (batch < 1 || batch > ctx->max_batch) return fail(ctx, CB_ERR_ARG, "batch %d outside 1..%d", batch, ctx->max_batch);
+    g.W = width; g.H = height; g.stride = stride; g.frame_stride = frame_stride;
+    g.f = (int)ctx->prm.quad_decimate;
+    g.w = 1 + (width - 1) / g.f; g.h = 1 + (height - 1) / g.f;
+    g.tp = (g.w + 15) / 16 * 16;
+    g.tw = g.w / 4; g.th = g.h / 4;
+    g.batch = batch;
+    g.npix = (uint32_t)g.w * g.h;
+    return CB_OK;
+}
+
+// Runs the device pipeline on `d_frames` (device memory) up to `stage`.  Events: ev[1] start, ev[2] after threshold,
+// ev[3] after ccl, ev[4] after clusters, ev[5] after quads, ev[6] after decode+reconcile.
+static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int stage)
+{
+    cudaStream_t st = ctx->stream;
+    const Caps &caps = ctx->caps;
+    const DetParams &prm = ctx->prm;
+    const int B = g.batch;
+    int launches = 0, thr_launches = 0;
+    uint32_t *d_ncl = ctx->d_small, *d_npt = ctx->d_small + ctx->max_batch, *d_nq = ctx->d_small + 2 * ctx->max_batch,
+             *d_nraw = ctx->d_small + 3 * ctx->max_batch, *d_misc = ctx->d_small + 4 * ctx->max_batch;
+    // misc: [0] errflag, [1] nwork, [2] work_counter, [3] nquads_total, [4] decode counter
+    CK(cudaMemsetAsync(ctx->d_small, 0, (4 * (size_t)ctx->max_batch + 16) * sizeof(uint32_t), st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    // ---- A1+A2 threshold ----
+    const bool fast = g.f == 2 && (g.stride % 16 == 0) && (g.frame_stride % 16 == 0) && ((uintptr_t)d_frames % 16 == 0) && g.tw > 0 && g.th > 0;
+    if (fast) {
+        dim3 grid((g.tw + THR_IW - 1) / THR_IW, (g.th + THR_IH - 1) / THR_IH, B), block(THR_TX, THR_TY);
+        threshold_f2_kernel<<<grid, block, 0, st>>>(d_frames, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g, prm.min_white_black_diff);
+        launches++; thr_launches++;
+        if (g.w % 4 || g.h % 4) {
+            dim3 gr((g.w + 127) / 128, g.h, B);
+            threshold_generic_kernel<<<gr, 128, 0, st>>>(d_frames, ctx->d_tmin, ctx->d_tmax, ctx->d_thresh, g, prm.min_white_black_diff, 1);
+            launches++;
+        }
+    } else {
+        if (g.tw > 0 && g.th > 0) {
+            dim3 gr((g.tw * g.th + 127) / 128, B);
+            tile_minmax_generic_kernel<<<gr, 128, 0, st>>>(d_frames, ctx->d_tmin, ctx->d_tmax, g);
+            launches++;
+        }
+        dim3 gr((g.w + 127) / 128, g.h, B);
+        threshold_generic_kernel<<<gr, 128, 0, st>>>(d_frames, ctx->d_tmin, ctx->d_tmax, ctx->d_thresh, g, prm.min_white_black_diff, 0);
+        launches++; thr_launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+    if (stage >= ST_LABELS) {
+        // ---- A3 connected components ----
+        dim3 grid((g.w + CCL_TW - 1) / CCL_TW, (g.h + CCL_TH - 1) / CCL_TH, B);
+        ccl_local_kernel<0><<<grid, CCL_THREADS, 0, st>>>(ctx->d_thresh, ctx->d_labels, g);
+        launches++;
+        const int nrows = (g.h - 1) / CCL_TH, ncols = (g.w - 1) / CCL_TW + 1;   // borders: rows k*TH (k>=1); columns k*TW and k*TW-1
+        if (nrows > 0) {
+            dim3 gm((g.w + 127) / 128, nrows, B);
+            ccl_merge_kernel<0><<<gm, 128, 0, st>>>(ctx->d_thresh, ctx->d_labels, g, 0);
+            launches++;
+        }
+        {
+            dim3 gm((g.h + 127) / 128, ncols, B);
+            ccl_merge_kernel<0><<<gm, 128, 0, st>>>(ctx->d_thresh, ctx->d_labels, g, 1);
+            launches++;
+        }
+        const uint32_t total = (uint32_t)B * g.npix;
+        CK(cudaMemsetAsync(ctx->d_sizes, 0, (size_t)total * sizeof(uint32_t), st));
+        ccl_flatten_kernel<<<(total + 255) / 256, 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, total);
+        launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[3], st));
+    if (stage >= ST_QUADS) {
+        // ---- A4 gradient clusters ----
+        dim3 gmark((g.w + 255) / 256, g.h, B);
+        ccl_mark_kernel<<<gmark, 256, 0, st>>>(ctx->d_thresh, ctx->d_labels, ctx->d_sizes, ctx->d_mark, g);
+        const size_t nslots = (size_t)B * caps.slots_per_frame;
+        table_init_kernel<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(ctx->d_table, nslots);
+        launches += 2;
+        if (g.h > 2 && g.w > 2) {
+            dim3 gc((g.w + 255) / 256, g.h - 2, B);
+            cluster_pass_kernel<false><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_pts, ctx->d_scankey, d_misc, g, caps);
+            cluster_select_kernel<<<B, 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, d_misc + 1, d_misc, g, caps, prm.min_cluster_pixels);
+            cluster_pass_kernel<true><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_pts, ctx->d_scankey, d_misc, g, caps);
+            launches += 3;
+        }
+        CK(cudaEventRecord(ctx->ev[4], st));
+        // ---- A5 quad fitting ----
+        const int qf_blocks = ctx->num_sms * 4;
+        fit_quads_kernel<<<qf_blocks, QF_THREADS, sizeof(QfShared), st>>>(d_frames, ctx->d_pts, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist,
+                                                                        d_misc + 1, d_misc + 2, ctx->d_lfps, ctx->d_scratch, ctx->d_quads, d_nq,
+                                                                        d_misc + 3, d_misc, g, caps, prm);
+        launches++;
+        CK(cudaEventRecord(ctx->ev[5], st));
+    } else {
+        CK(cudaEventRecord(ctx->ev[4], st));
+        CK(cudaEventRecord(ctx->ev[5], st));
+    }
+    if (stage >= ST_FULL) {
+        // ---- A6-A9 refine, homography, decode, reconcile ----
+        decode_quads_kernel<<<ctx->num_sms * 4, DEC_WARPS * 32, 0, st>>>(d_frames, ctx->d_quads, d_misc + 3, d_misc + 4, ctx->d_raw, d_nraw, g, caps, prm, ctx->dc);
+        reconcile_kernel<<<(B + 63) / 64, 64, 0, st>>>(ctx->d_raw, d_nraw, ctx->d_dets, ctx->d_counts, caps, B);
+        launches += 2;
+    }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaGetLastError());
+    ctx->timing.kernel_launches = launches;
+    ctx->timing.threshold_launches = thr_launches;
+    return CB_OK;
+}
+
+static int finish_timing(cb_ctx *ctx, bool h2d, bool d2h)
+{
+    cb_timing &t = ctx->timing;
+    auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return ms; };
+    t.h2d_ms = h2d ? el(0, 1) : 0.f;
+    t.preprocess_ms = 0.f;
+    t.threshold_ms = el(1, 2); t.ccl_ms = el(2, 3); t.cluster_ms = el(3, 4); t.quad_ms = el(4, 5); t.decode_ms = el(5, 6);
+    t.d2h_ms = d2h ? el(6, 7) : 0.f;
+    t.total_ms = el(h2d ? 0 : 1, d2h ? 7 : 6);
+    return CB_OK;
+}
+
+static int check_errflag(cb_ctx *ctx)
+{
+    const uint32_t flag = ctx->h_small[4 * (size_t)ctx->max_batch];
+    if (flag) {
+        return fail(ctx, CB_ERR_OVERFLOW, "device table overflow (flags 0x%x:%s%s%s%s); create the context with a larger frame size / batch capacity",
+                    flag, (flag & ERR_HASH_FULL) ? " cluster-hash" : "", (flag & ERR_CLUSTERS_FULL) ? " clusters" : "",
+                    (flag & ERR_POINTS_FULL) ? " points" : "", (flag & ERR_QUADS_FULL) ? " quads" : "");
+    }
+    return CB_OK;
+}
+
+// full detector on device frames; copies detections back to the caller's arrays
+static int detect_device_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, cb_detection *out, int32_t *out_counts, bool timed_h2d)
+{
+    if (!ctx->family_set) return fail(ctx, CB_ERR_STATE, "no tag family set: call cb_set_family_tag36h11 first");
+    int rc = run_pipeline(ctx, d_frames, g, ST_FULL);
+    if (rc) return rc;
+    const size_t B = g.batch;
+    CK(cudaMemcpyAsync(ctx->h_dets, ctx->d_dets, B * ctx->caps.dets_per_frame * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (4 * (size_t)ctx->max_batch + 16) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx, timed_h2d, true);
+    rc = check_errflag(ctx);
+    if (rc) return rc;
+    memcpy(out_counts, ctx->h_counts, B * sizeof(int32_t));
+    for (size_t b = 0; b < B; b++)
+        memcpy(out + b * ctx->caps.dets_per_frame, ctx->h_dets + b * ctx->caps.dets_per_frame, (size_t)ctx->h_counts[b] * sizeof(cb_detection));
+    return CB_OK;
+}
+
+static void accumulate_timing(cb_timing &acc, const cb_timing &t)
+{
+    acc.h2d_ms += t.h2d_ms; acc.preprocess_ms += t.preprocess_ms; acc.threshold_ms += t.threshold_ms; acc.ccl_ms += t.ccl_ms;
+    acc.cluster_ms += t.cluster_ms; acc.quad_ms += t.quad_ms; acc.decode_ms += t.decode_ms; acc.d2h_ms += t.d2h_ms; acc.total_ms += t.total_ms;
+    acc.threshold_launches += t.threshold_launches; acc.kernel_launches += t.kernel_launches;
+}
+
+// upload a chunk of host frames into d_in with pitch == stride
+static int upload_chunk(cb_ctx *ctx, const uint8_t *frames, size_t frame_stride, int height, int stride, int n, size_t &dev_frame_stride)
+{
+    const size_t bytes = (size_t)stride * height;
+    dev_frame_stride = (bytes + 15) / 16 * 16;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (frame_stride == dev_frame_stride) {
+        CK(cudaMemcpyAsync(ctx->d_in, frames, (size_t)n * frame_stride, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CK(cudaMemcpy2DAsync(ctx->d_in, dev_frame_stride, frames, frame_stride, bytes, n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return CB_OK;
+}
+
+extern "C" {
+
+int cb_detect_gray_device(cb_ctx *ctx, const uint8_t *frames_dev, int width, int height, int stride, size_t frame_stride,
+                          int batch, cb_detection *out, int32_t *out_counts)
+{
+    if (!ctx || !frames_dev || !out || !out_counts) return CB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cb_timing acc{};
+    for (int b0 = 0; b0 < batch; b0 += ctx->max_batch) {
+        const int n = std::min(ctx->max_batch, batch - b0);
+        Geom g;
+        int rc = make_geom(ctx, width, height, stride, frame_stride, n, g);
+        if (rc) return rc;
+        rc = detect_device_chunk(ctx, frames_dev + (size_t)b0 * frame_stride, g, out + (size_t)b0 * ctx->caps.dets_per_frame, out_counts + b0, false);
+        if (rc) return rc;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < out_counts[b0 + i]; k++) out[(size_t)(b0 + i) * ctx->caps.dets_per_frame + k].frame = b0 + i;
+        accumulate_timing(acc, ctx->timing);
+    }
+    ctx->timing = acc;
+    return CB_OK;
+}
+
+int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
+                   cb_detection *out, int32_t *out_counts)
+{
+    if (!ctx || !frames || !out || !out_counts) return CB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if ((size_t)stride * height > ctx->max_npix) return fail(ctx, CB_ERR_ARG, "stride*height exceeds the context's frame capacity");
+    cb_timing acc{};
+    for (int b0 = 0; b0 < batch; b0 += ctx->max_batch) {
+        const int n = std::min(ctx->max_batch, batch - b0);
+        size_t dfs;
+        int rc = upload_chunk(ctx, frames + (size_t)b0 * frame_stride, frame_stride, height, stride, n, dfs);
+        if (rc) return rc;
+        Geom g;
+        rc = make_geom(ctx, width, height, stride, dfs, n, g);
+        if (rc) return rc;
+        rc = detect_device_chunk(ctx, ctx->d_in, g, out + (size_t)b0 * ctx->caps.dets_per_frame, out_counts + b0, true);
+        if (rc) return rc;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < out_counts[b0 + i]; k++) out[(size_t)(b0 + i) * ctx->caps.dets_per_frame + k].frame = b0 + i;
+        accumulate_timing(acc, ctx->timing);
+    }
+    ctx->timing = acc;
+    return CB_OK;
+}
+
+// pre-processing front ends: convert into a gray buffer on the device, then the gray pipeline
+static int detect_converted(cb_ctx *ctx, const uint8_t *frames, int width, int height, int bytes_per_px, int batch, cb_detection *out,
+                            int32_t *out_counts)
+{
+    if (!ctx || !frames || !out || !out_counts) return CB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (width > ctx->max_w || height > ctx->max_h) return fail(ctx, CB_ERR_ARG, "frame larger than the context's capacity");
+    const size_t npix = (size_t)width * height;
+    const size_t gfs = (npix + 15) / 16 * 16;
+    const size_t need_gray = (size_t)ctx->max_batch * gfs, need_raw = (size_t)ctx->max_batch * npix * bytes_per_px;
+    if (ctx->gray_bytes < need_gray + need_raw + 64) {
+        if (ctx->d_gray) cudaFree(ctx->d_gray);
+        ctx->d_gray = nullptr;
+        CK(cudaMalloc((void **)&ctx->d_gray, need_gray + need_raw + 64));
+        ctx->gray_bytes = need_gray + need_raw + 64;
+    }
+    uint8_t *d_rawin = ctx->d_gray + (need_gray + 15) / 16 * 16;
+    cb_timing acc{};
+    for (int b0 = 0; b0 < batch; b0 += ctx->max_batch) {
+        const int n = std::min(ctx->max_batch, batch - b0);
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        CK(cudaMemcpyAsync(d_rawin, frames + (size_t)b0 * npix * bytes_per_px, (size_t)n * npix * bytes_per_px, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev[8], ctx->stream));
+        for (int i = 0; i < n; i++) {   // one launch per frame keeps every frame's gray plane 16-byte aligned
+            const unsigned blocks = (unsigned)((npix + 16 * 256 - 1) / (16 * 256));
+            if (bytes_per_px == 3) rgb_to_gray_kernel<<<blocks, 256, 0, ctx->stream>>>(d_rawin + (size_t)i * npix * 3, ctx->d_gray + (size_t)i * gfs, npix);
+            else yuyv_to_gray_kernel<<<blocks, 256, 0, ctx->stream>>>(d_rawin + (size_t)i * npix * 2, ctx->d_gray + (size_t)i * gfs, npix);
+        }
+        CK(cudaEventRecord(ctx->ev[9], ctx->stream));
+        Geom g;
+        int rc = make_geom(ctx, width, height, width, gfs, n, g);
+        if (rc) return rc;
+        rc = detect_device_chunk(ctx, ctx->d_gray, g, out + (size_t)b0 * ctx->caps.dets_per_frame, out_counts + b0, true);
+        if (rc) return rc;
+        float pre = 0, h2d = 0;
+        cudaEventElapsedTime(&pre, ctx->ev[8], ctx->ev[9]);
+        cudaEventElapsedTime(&h2d, ctx->ev[0], ctx->ev[8]);
+        ctx->timing.preprocess_ms = pre; ctx->timing.h2d_ms = h2d; ctx->timing.kernel_launches += n;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < out_counts[b0 + i]; k++) out[(size_t)(b0 + i) * ctx->caps.dets_per_frame + k].frame = b0 + i;
+        accumulate_timing(acc, ctx->timing);
+    }
+    ctx->timing = acc;
+    return CB_OK;
+}
+
+int cb_detect_rgb(cb_ctx *ctx, const uint8_t *frames_rgb, int width, int height, int batch, cb_detection *out, int32_t *out_counts)
+{
+    return detect_converted(ctx, frames_rgb, width, height, 3, batch, out, out_counts);
+}
+
+int cb_detect_yuyv(cb_ctx *ctx, const uint8_t *frames_yuyv, int width, int height, int batch, cb_detection *out, int32_t *out_counts)
+{
+    if (width % 2) return fail(ctx, CB_ERR_ARG, "YUYV needs an even width");
+    return detect_converted(ctx, frames_yuyv, width, height, 2, batch, out, out_counts);
+}
+
+// ---- stage taps ----
+static int tap_common(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, int stage, Geom &g)
+{
+    if (!ctx || !frames) return CB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (batch > ctx->max_batch) return fail(ctx, CB_ERR_ARG, "tap batch %d exceeds max_batch %d", batch, ctx->max_batch);
+    if ((size_t)stride * height > ctx->max_npix) return fail(ctx, CB_ERR_ARG, "stride*height exceeds the context's frame capacity");
+    size_t dfs;
+    int rc = upload_chunk(ctx, frames, frame_stride, height, stride, batch, dfs);
+    if (rc) return rc;
+    rc = make_geom(ctx, width, height, stride, dfs, batch, g);
+    if (rc) return rc;
+    rc = run_pipeline(ctx, ctx->d_in, g, stage);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (4 * (size_t)ctx->max_batch + 16) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx, true, true);
+    return check_errflag(ctx);
+}
+
+int cb_threshold(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, uint8_t *out)
+{
+    Geom g;
+    if (!out) return CB_ERR_ARG;
+    int rc = tap_common(ctx, frames, width, height, stride, frame_stride, batch, ST_THRESH, g);
+    if (rc) return rc;
+    CK(cudaMemcpy2D(out, g.w, ctx->d_thresh, g.tp, g.w, (size_t)g.h * batch, cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+int cb_labels(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, uint32_t *labels, uint32_t *sizes)
+{
+    Geom g;
+    if (!labels) return CB_ERR_ARG;
+    int rc = tap_common(ctx, frames, width, height, stride, frame_stride, batch, ST_LABELS, g);
+    if (rc) return rc;
+    const size_t n = (size_t)batch * g.npix;
+    CK(cudaMemcpy(labels, ctx->d_labels, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    // labels are batch-global indices; report them frame-local, sizes per pixel (size of its component)
+    std::vector<uint32_t> sz;
+    if (sizes) { sz.resize(n); CK(cudaMemcpy(sz.data(), ctx->d_sizes, n * sizeof(uint32_t), cudaMemcpyDeviceToHost)); }
+    for (size_t i = 0; i < n; i++) {
+        if (sizes) sizes[i] = sz[labels[i]];
+        labels[i] -= (uint32_t)(i / g.npix) * g.npix;
+    }
+    return CB_OK;
+}
+
+int cb_quads(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, float *quads, int cap,
+             int32_t *counts, int64_t *npoints_total)
+{
+    Geom g;
+    if (!quads || !counts) return CB_ERR_ARG;
+    int rc = tap_common(ctx, frames, width, height, stride, frame_stride, batch, ST_QUADS, g);
+    if (rc) return rc;
+    const uint32_t total = ctx->h_small[4 * (size_t)ctx->max_batch + 3];
+    std::vector<QuadRec> q(total);
+    if (total) CK(cudaMemcpy(q.data(), ctx->d_quads, total * sizeof(QuadRec), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < batch; b++) counts[b] = 0;
+    for (uint32_t i = 0; i < total; i++) {
+        const int b = q[i].frame;
+        if (counts[b] < cap) memcpy(quads + ((size_t)b * cap + counts[b]) * 8, q[i].p, 8 * sizeof(float));
+        counts[b]++;
+    }
+    if (npoints_total) {
+        int64_t t = 0;
+        for (int b = 0; b < batch; b++) t += ctx->h_small[ctx->max_batch + b];
+        *npoints_total = t;
+    }
+    return CB_OK;
+}
+
+// ---- plumbing ----
+void *cb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void cb_host_free(void *p) { if (p) cudaFreeHost(p); }
+void *cb_device_alloc(cb_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { fail(ctx, CB_ERR_CUDA, "cudaMalloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void cb_device_free(cb_ctx *ctx, void *p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFree(p); } }
+int cb_memcpy_h2d(cb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (!ctx) return CB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+    return CB_OK;
+}
+int cb_memcpy_d2h(cb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+    if (!ctx) return CB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+}  // extern "C"
+
+#include "api_solver.inc"
+#include "api_cat.inc"

@@ -1,0 +1,193 @@
+// ccl.cuh -- row A3 of SURVEY.md 8a: connected_components() as a parallel union-find.
+//
+// Upstream (apriltag_quad_thresh.c do_unionfind_first_line / do_unionfind_line2): for every pixel with
+// 1 <= x <= w-2 and v != 127, connect to the left, up, and for white pixels up-left / up-right neighbour of
+// equal value, with redundancy guards.  The guards are evaluated here exactly as upstream writes them, so the
+// edge set -- and therefore the partition -- is identical; only the tree shape differs (roots are the smallest
+// pixel index of each component, which is also the canonical form the oracle reports).
+//
+// B200 mapping: latency / atomic bound.  Pass 1 resolves 64x16-pixel tiles in shared memory (atomicMin
+// union-find on 32-bit smem words), pass 2 stitches tile borders with global atomicMin, pass 3 flattens every
+// pixel to its root and histograms component sizes with warp-aggregated atomics (match.any on the label).
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+constexpr int CCL_TW = 64, CCL_TH = 16, CCL_THREADS = 256;
+
+enum : uint32_t { LINK_LEFT = 1, LINK_UP = 2, LINK_UPLEFT = 4, LINK_UPRIGHT = 8 };
+
+// link mask of pixel (x,y) from the ternary map t (pitch tp).
+// MODE 0: upstream AprilTag-3 (skip 127, white 255), exact transcription of its redundancy guards.
+// MODE 1: CAT connected_components (crates/chalkydri-apriltags/src/lib.rs:501-549): Color map (skip Other = 2,
+//         White = 1), same neighbourhood (left, up; white also up-left / up-right), no guards.
+template <int MODE>
+__device__ __forceinline__ uint32_t link_mask(const uint8_t *__restrict__ t, int tp, int w, int x, int y)
+{
+    if (x < 1 || x > w - 2) return 0;
+    const uint8_t *row = t + (size_t)y * tp;
+    const uint32_t v = row[x];
+    const uint32_t SKIP = MODE == 0 ? 127u : 2u, WHITE = MODE == 0 ? 255u : 1u;
+    if (v == SKIP) return 0;
+    uint32_t m = 0;
+    const uint32_t v_m1_0 = row[x - 1];
+    if (v_m1_0 == v) m |= LINK_LEFT;
+    if (y > 0) {
+        const uint8_t *up = row - tp;
+        const uint32_t v_m1_m1 = up[x - 1], v_0_m1 = up[x], v_1_m1 = up[x + 1];
+        if (MODE == 0) {
+            if (v_0_m1 == v && (x == 1 || !((v_m1_0 == v_m1_m1) && (v_m1_m1 == v_0_m1)))) m |= LINK_UP;
+            if (v == WHITE) {
+                if (v_m1_m1 == v && (x == 1 || !(v_m1_0 == v_m1_m1 || v_0_m1 == v_m1_m1))) m |= LINK_UPLEFT;
+                if (v_1_m1 == v && !(v_0_m1 == v_1_m1)) m |= LINK_UPRIGHT;
+            }
+        } else {
+            if (v_0_m1 == v) m |= LINK_UP;
+            if (v == WHITE) {
+                if (v_m1_m1 == v) m |= LINK_UPLEFT;
+                if (v_1_m1 == v) m |= LINK_UPRIGHT;
+            }
+        }
+    }
+    return m;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t uf_find(const T *L, uint32_t i)
+{
+    const volatile T *V = L;
+    uint32_t p = V[i];
+    while (p != i) { i = p; p = V[i]; }
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(uint32_t *L, uint32_t a, uint32_t b)
+{
+    for (;;) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a > b) { uint32_t t = a; a = b; b = t; }   // a < b: hang b under a
+        uint32_t old = atomicMin(&L[b], a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+// pass 1: tile-local union-find in shared memory, then write global labels (index of the local root)
+template <int MODE>
+__global__ void __launch_bounds__(CCL_THREADS)
+ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labels, Geom g)
+{
+    __shared__ uint32_t L[CCL_TW * CCL_TH];
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * CCL_TW, y0 = blockIdx.y * CCL_TH;
+    const uint8_t *t = thresh + (size_t)b * g.h * g.tp;
+    for (int i = threadIdx.x; i < CCL_TW * CCL_TH; i += CCL_THREADS) L[i] = i;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CCL_TW * CCL_TH / CCL_THREADS; k++) {
+        const int i = threadIdx.x + k * CCL_THREADS;
+        const int lx = i % CCL_TW, ly = i / CCL_TW;
+        const int x = x0 + lx, y = y0 + ly;
+        uint32_t m = 0;
+        if (x < g.w && y < g.h) m = link_mask<MODE>(t, g.tp, g.w, x, y);
+        if ((m & LINK_LEFT) && lx > 0) uf_union(L, i, i - 1);
+        if ((m & LINK_UP) && ly > 0) uf_union(L, i, i - CCL_TW);
+        if ((m & LINK_UPLEFT) && ly > 0 && lx > 0) uf_union(L, i, i - CCL_TW - 1);
+        if ((m & LINK_UPRIGHT) && ly > 0 && lx < CCL_TW - 1) uf_union(L, i, i - CCL_TW + 1);
+    }
+    __syncthreads();
+    uint32_t *lab = labels + (size_t)b * g.npix;
+    const uint32_t base = (uint32_t)b * g.npix;
+#pragma unroll
+    for (int k = 0; k < CCL_TW * CCL_TH / CCL_THREADS; k++) {
+        const int i = threadIdx.x + k * CCL_THREADS;
+        const int lx = i % CCL_TW, ly = i / CCL_TW;
+        const int x = x0 + lx, y = y0 + ly;
+        if (x < g.w && y < g.h) {
+            uint32_t r = uf_find(L, (uint32_t)i);
+            const int rx = x0 + (int)(r % CCL_TW), ry = y0 + (int)(r / CCL_TW);
+            lab[(size_t)y * g.w + x] = base + (uint32_t)(ry * g.w + rx);
+        }
+    }
+}
+
+// pass 2: links that cross a tile border.  One thread per pixel of a border row / column.
+// mode 0: rows y = k*CCL_TH (k >= 1), all x: up / up-left / up-right links.
+// mode 1: columns x = k*CCL_TW (k >= 1): left link always, up-left unless y is a tile-row border (done by mode 0);
+//         columns x = k*CCL_TW - 1: up-right unless y is a tile-row border.
+template <int MODE>
+__global__ void ccl_merge_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labels, Geom g, int mode)
+{
+    const int b = blockIdx.z;
+    const uint8_t *t = thresh + (size_t)b * g.h * g.tp;
+    const uint32_t base = (uint32_t)b * g.npix;
+    uint32_t *L = labels;   // global label space of the whole batch
+    int x, y;
+    if (mode == 0) {
+        x = blockIdx.x * blockDim.x + threadIdx.x;
+        y = (blockIdx.y + 1) * CCL_TH;
+        if (x >= g.w || y >= g.h) return;
+        const uint32_t m = link_mask<MODE>(t, g.tp, g.w, x, y);
+        const uint32_t i = base + (uint32_t)(y * g.w + x);
+        if (m & LINK_UP) uf_union(L, i, i - g.w);
+        if (m & LINK_UPLEFT) uf_union(L, i, i - g.w - 1);
+        if (m & LINK_UPRIGHT) uf_union(L, i, i - g.w + 1);
+    } else {
+        y = blockIdx.x * blockDim.x + threadIdx.x;
+        const int k = blockIdx.y + 1;
+        if (y >= g.h) return;
+        const bool yborder = (y % CCL_TH) == 0;
+        x = k * CCL_TW;
+        if (x < g.w) {
+            const uint32_t m = link_mask<MODE>(t, g.tp, g.w, x, y);
+            const uint32_t i = base + (uint32_t)(y * g.w + x);
+            if (m & LINK_LEFT) uf_union(L, i, i - 1);
+            if ((m & LINK_UPLEFT) && !yborder) uf_union(L, i, i - g.w - 1);
+        }
+        x = k * CCL_TW - 1;
+        if (x < g.w && !yborder) {
+            const uint32_t m = link_mask<MODE>(t, g.tp, g.w, x, y);
+            const uint32_t i = base + (uint32_t)(y * g.w + x);
+            if (m & LINK_UPRIGHT) uf_union(L, i, i - g.w + 1);
+        }
+    }
+}
+
+// pass 3: flatten + component sizes (sizes must be zeroed before the launch)
+__global__ void ccl_flatten_kernel(uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, uint32_t total)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t root = 0xffffffffu;
+    if (i < total) {
+        root = uf_find(labels, i);
+        labels[i] = root;
+    }
+    // warp-aggregated histogram: lanes with the same root elect one leader
+    const uint32_t act = __activemask();
+    const uint32_t peers = __match_any_sync(act, root);
+    if (i < total) {
+        const int leader = __ffs(peers) - 1;
+        if ((int)(threadIdx.x & 31) == leader) atomicAdd(&sizes[root], (uint32_t)__popc(peers));
+    }
+}
+
+// component-size gate of gradient_clusters(): pixels of components smaller than 25 become 127 ("ignore")
+__global__ void ccl_mark_kernel(const uint8_t *__restrict__ thresh, const uint32_t *__restrict__ labels,
+                                const uint32_t *__restrict__ sizes, uint8_t *__restrict__ mark, Geom g)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    if (x >= g.w) return;
+    const size_t ti = (size_t)b * g.h * g.tp + (size_t)y * g.tp + x;
+    uint8_t v = thresh[ti];
+    if (v != 127) {
+        const uint32_t root = labels[(size_t)b * g.npix + (size_t)y * g.w + x];
+        if (sizes[root] < 25) v = 127;
+    }
+    mark[ti] = v;
+}
+
+}  // namespace cb

@@ -1,0 +1,203 @@
+// clusters.cuh -- row A4 of SURVEY.md 8a: gradient_clusters().
+//
+// Upstream (apriltag_quad_thresh.c do_gradient_clusters): every pixel (1..w-2, 1..h-2) whose component has
+// >= 25 pixels looks at the neighbours (1,0) (0,1) (-1,1) (1,1); where the two pixels are black/white opposites
+// and the neighbour's component is also >= 25 pixels, the half-way point {2x+dx, 2y+dy, gx, gy} is appended to
+// the cluster keyed by the ordered pair of component representatives.  The (-1,1) probe is skipped when the
+// previous pixel's (1,1) probe fired (`connected_last`), a purely local rule that is re-evaluated here.
+//
+// B200 mapping (atomic / latency bound): the size gate is folded into the `mark` map, so one pass over the
+// pixels only reads that map plus two labels per emitted point.  Pass "count" inserts the 64-bit pair key into
+// a per-frame open-addressing table and counts points per cluster (warp-aggregated with match.any); a per-frame
+// CTA then selects the clusters fit_quad() would accept (24 <= n <= 3(2w+2h)) and prefix-sums their offsets;
+// pass "scatter" re-walks the pixels and writes only the points of selected clusters.  The huge clusters that
+// dominate the point count on noisy frames (and that upstream discards after building them) are never stored.
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+// find-or-insert; returns slot index inside the frame's sub-table or 0xffffffff when the table is full
+__device__ __forceinline__ uint32_t slot_insert(ClusterSlot *tab, uint32_t nslots, unsigned long long key)
+{
+    uint32_t s = hash_key(key) & (nslots - 1);
+    for (uint32_t probe = 0; probe < nslots; probe++) {
+        unsigned long long cur = *((volatile unsigned long long *)&tab[s].key);
+        if (cur == key) return s;
+        if (cur == EMPTY_KEY) {
+            unsigned long long old = atomicCAS(&tab[s].key, EMPTY_KEY, key);
+            if (old == EMPTY_KEY || old == key) return s;
+        }
+        s = (s + 1) & (nslots - 1);
+    }
+    return 0xffffffffu;
+}
+
+__device__ __forceinline__ uint32_t slot_find(const ClusterSlot *tab, uint32_t nslots, unsigned long long key)
+{
+    uint32_t s = hash_key(key) & (nslots - 1);
+    for (uint32_t probe = 0; probe < nslots; probe++) {
+        unsigned long long cur = tab[s].key;
+        if (cur == key) return s;
+        if (cur == EMPTY_KEY) return 0xffffffffu;
+        s = (s + 1) & (nslots - 1);
+    }
+    return 0xffffffffu;
+}
+
+// One thread per pixel.  SCATTER = false: count; true: write points of selected clusters.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, ClusterSlot *__restrict__ table,
+                    ClusterRec *__restrict__ clusters, unsigned long long *__restrict__ pts, uint32_t *__restrict__ scankey,
+                    uint32_t *__restrict__ errflag, Geom g, Caps caps)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y + 1, b = blockIdx.z;
+    const uint8_t *m = mark + (size_t)b * g.h * g.tp;
+    const bool inside = x >= 1 && x <= g.w - 2 && y <= g.h - 2;
+    uint32_t v0 = 127;
+    if (inside) v0 = m[(size_t)y * g.tp + x];
+    const uint32_t full = 0xffffffffu;
+    // all lanes stay in the loop so that the warp-aggregation below sees a full mask
+    uint32_t vn[4] = {127, 127, 127, 127};
+    bool emit[4] = {false, false, false, false};
+    if (v0 != 127) {
+        const uint8_t *r0 = m + (size_t)y * g.tp, *r1 = r0 + g.tp;
+        vn[0] = r0[x + 1]; vn[1] = r1[x]; vn[2] = r1[x - 1]; vn[3] = r1[x + 1];
+        const uint32_t vprev = r0[x - 1];
+        const bool connected_last = (x - 1 >= 1) && vprev != 127 && (vprev + vn[1] == 255);
+        emit[0] = v0 + vn[0] == 255;
+        emit[1] = v0 + vn[1] == 255;
+        emit[2] = (v0 + vn[2] == 255) && !connected_last;
+        emit[3] = v0 + vn[3] == 255;
+    }
+    const uint32_t *lab = labels + (size_t)b * g.npix;
+    ClusterSlot *tab = table + (size_t)b * caps.slots_per_frame;
+    uint32_t rep0 = 0;
+    if (emit[0] | emit[1] | emit[2] | emit[3]) rep0 = lab[(size_t)y * g.w + x];
+    const int dxs[4] = {1, 0, -1, 1}, dys[4] = {0, 1, 1, 1};
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        unsigned long long key = EMPTY_KEY;
+        if (emit[d]) {
+            const uint32_t rep1 = lab[(size_t)(y + dys[d]) * g.w + x + dxs[d]];
+            key = rep0 < rep1 ? ((unsigned long long)rep1 << 32) | rep0 : ((unsigned long long)rep0 << 32) | rep1;
+        }
+        const uint32_t peers = __match_any_sync(full, key);
+        if (!emit[d]) continue;
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+        if (!SCATTER) {
+            if (lane == leader) {
+                uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
+                if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
+                else atomicAdd(&tab[s].count, (uint32_t)__popc(peers));
+            }
+        } else {
+            uint32_t pos = 0xffffffffu;
+            if (lane == leader) {
+                uint32_t s = slot_find(tab, caps.slots_per_frame, key);
+                if (s != 0xffffffffu) {
+                    uint32_t c = tab[s].cluster;
+                    if (c != 0xffffffffu) {
+                        ClusterRec *cr = clusters + (size_t)b * caps.clusters_per_frame + c;
+                        pos = cr->offset + atomicAdd(&cr->cursor, (uint32_t)__popc(peers));
+                    }
+                }
+            }
+            pos = __shfl_sync(peers, pos, leader);
+            if (pos != 0xffffffffu) {
+                pos += rank;
+                const int dv = (int)vn[d] - (int)v0;
+                const uint32_t px = (uint32_t)(2 * x + dxs[d]), py = (uint32_t)(2 * y + dys[d]);
+                const uint32_t gx = (uint32_t)(uint16_t)(int16_t)(dxs[d] * dv), gy = (uint32_t)(uint16_t)(int16_t)(dys[d] * dv);
+                const size_t o = (size_t)b * caps.points_per_frame + pos;
+                pts[o] = (unsigned long long)px | ((unsigned long long)py << 16) | ((unsigned long long)gx << 32) | ((unsigned long long)gy << 48);
+                scankey[o] = ((uint32_t)(y * g.w + x) << 2) | (uint32_t)d;
+            }
+        }
+    }
+}
+
+// One CTA per frame: pick the clusters fit_quad() can accept and lay their points out contiguously.
+// Order of the selected list is the slot order (deterministic for a given table size).
+__global__ void __launch_bounds__(256)
+cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ clusters, uint32_t *__restrict__ nclusters,
+                      uint32_t *__restrict__ npoints, uint32_t *__restrict__ worklist, uint32_t *__restrict__ nwork,
+                      uint32_t *__restrict__ errflag, Geom g, Caps caps, int min_cluster_pixels)
+{
+    const int b = blockIdx.x;
+    ClusterSlot *tab = table + (size_t)b * caps.slots_per_frame;
+    ClusterRec *out = clusters + (size_t)b * caps.clusters_per_frame;
+    __shared__ uint32_t s_ncl, s_npt;
+    __shared__ uint32_t w_cnt[8], w_pts[8];
+    if (threadIdx.x == 0) { s_ncl = 0; s_npt = 0; }
+    __syncthreads();
+    const uint32_t maxsz = 3u * (2u * g.w + 2u * g.h);
+    const uint32_t minsz = (uint32_t)max(24, min_cluster_pixels);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t s0 = 0; s0 < caps.slots_per_frame; s0 += blockDim.x) {
+        const uint32_t s = s0 + threadIdx.x;
+        uint32_t cnt = 0;
+        bool sel = false;
+        if (s < caps.slots_per_frame && tab[s].key != EMPTY_KEY) {
+            cnt = tab[s].count;
+            sel = cnt >= minsz && cnt <= maxsz;
+        }
+        // block-wide exclusive scan of (sel, cnt)
+        const uint32_t bal = __ballot_sync(0xffffffffu, sel);
+        uint32_t c = sel ? cnt : 0, incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        if (lane == 31) { w_cnt[wid] = __popc(bal); w_pts[wid] = incl; }
+        __syncthreads();
+        uint32_t base_c = s_ncl, base_p = s_npt;
+        for (int k = 0; k < wid; k++) { base_c += w_cnt[k]; base_p += w_pts[k]; }
+        const uint32_t my_c = base_c + __popc(bal & ((1u << lane) - 1));
+        const uint32_t my_p = base_p + incl - c;
+        if (s < caps.slots_per_frame) {
+            uint32_t ci = 0xffffffffu;
+            if (sel) {
+                if (my_c >= caps.clusters_per_frame) atomicOr(errflag, ERR_CLUSTERS_FULL);
+                else {
+                    ClusterRec r;
+                    r.key = tab[s].key; r.offset = my_p; r.count = cnt; r.cursor = 0; r.pad = 0;
+                    if (my_p + cnt > caps.points_per_frame) {   // keep the list dense, but make the record inert
+                        atomicOr(errflag, ERR_POINTS_FULL);
+                        r.offset = 0; r.count = 0;
+                    } else ci = my_c;
+                    out[my_c] = r;
+                }
+            }
+            tab[s].cluster = ci;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tc = 0, tp = 0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { tc += w_cnt[k]; tp += w_pts[k]; }
+            s_ncl += tc; s_npt += tp;
+        }
+        __syncthreads();
+    }
+    __shared__ uint32_t s_wbase;
+    const uint32_t ncl = min(s_ncl, caps.clusters_per_frame);
+    if (threadIdx.x == 0) {
+        nclusters[b] = ncl;
+        npoints[b] = s_npt;
+        s_wbase = atomicAdd(nwork, ncl);   // batch-wide work list for the quad-fitting kernel
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ncl; i += blockDim.x) worklist[s_wbase + i] = (uint32_t)b * caps.clusters_per_frame + i;
+}
+
+}  // namespace cb

@@ -1,0 +1,495 @@
+// decode.cuh -- rows A6-A9 of SURVEY.md 8a: refine_edges, homography, tag36h11 decode, reconcile.
+//
+// Upstream (apriltag.c refine_edges / quad_update_homographies / quad_decode / quick_decode_codeword and the
+// reconcile loop of apriltag_detector_detect; homography.c homography_compute2).  One warp per candidate quad:
+// lanes sample edge / border / bit positions in parallel (sparse, L2-resident gathers from the full-resolution
+// frame), while every accumulation whose result depends on summation order is replayed in upstream's order
+// through warp shuffles, so the double arithmetic matches the CPU restatement operation by operation.
+#pragma once
+#include "common.cuh"
+
+namespace cb {
+
+__constant__ unsigned long long c_codes[kNumCodes];
+__constant__ int c_bit_x[36];
+__constant__ int c_bit_y[36];
+
+struct DecodeConst {
+    double rot_c[4], rot_s[4];    // host libm cos/sin of k*pi/2, like upstream's cos(theta)/sin(theta)
+};
+
+struct RawDet {
+    cb_detection d;
+    int32_t valid;
+    int32_t pad;
+};
+
+constexpr int DEC_WARPS = 4;
+
+__device__ __forceinline__ void homography_project(const double *H, double x, double y, double *ox, double *oy)
+{
+    const double xx = H[0] * x + H[1] * y + H[2];
+    const double yy = H[3] * x + H[4] * y + H[5];
+    const double zz = H[6] * x + H[7] * y + H[8];
+    *ox = xx / zz;
+    *oy = yy / zz;
+}
+
+__device__ bool homography_compute2(const double c[4][4], double *H)
+{
+    double A[72];
+    for (int i = 0; i < 4; i++) {
+        double *r0 = &A[(2 * i) * 9], *r1 = &A[(2 * i + 1) * 9];
+        r0[0] = c[i][0]; r0[1] = c[i][1]; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0;
+        r0[6] = -c[i][0] * c[i][2]; r0[7] = -c[i][1] * c[i][2]; r0[8] = c[i][2];
+        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = c[i][0]; r1[4] = c[i][1]; r1[5] = 1;
+        r1[6] = -c[i][0] * c[i][3]; r1[7] = -c[i][1] * c[i][3]; r1[8] = c[i][3];
+    }
+    const double epsilon = 1e-10;
+    for (int col = 0; col < 8; col++) {
+        double max_val = 0;
+        int max_val_idx = -1;
+        for (int row = col; row < 8; row++) {
+            const double val = fabs(A[row * 9 + col]);
+            if (val > max_val) { max_val = val; max_val_idx = row; }
+        }
+        if (max_val_idx < 0) return false;
+        if (max_val < epsilon) return false;
+        if (max_val_idx != col)
+            for (int i = col; i < 9; i++) { const double t = A[col * 9 + i]; A[col * 9 + i] = A[max_val_idx * 9 + i]; A[max_val_idx * 9 + i] = t; }
+        for (int i = col + 1; i < 8; i++) {
+            const double f = A[i * 9 + col] / A[col * 9 + col];
+            A[i * 9 + col] = 0;
+            for (int j = col + 1; j < 9; j++) A[i * 9 + j] -= f * A[col * 9 + j];
+        }
+    }
+    for (int col = 7; col >= 0; col--) {
+        double sum = 0;
+        for (int i = col + 1; i < 8; i++) sum += A[col * 9 + i] * A[i * 9 + 8];
+        A[col * 9 + 8] = (A[col * 9 + 8] - sum) / A[col * 9 + col];
+    }
+    for (int i = 0; i < 8; i++) H[i] = A[i * 9 + 8];
+    H[8] = 1;
+    return true;
+}
+
+// matd_plu() singular flag of the 3x3 H (matd_inverse inside quad_update_homographies)
+__device__ bool mat33_plu_nonsingular(const double *H)
+{
+    double lu[9];
+    for (int i = 0; i < 9; i++) lu[i] = H[i];
+    for (int j = 0; j < 3; j++) {
+        for (int i = 0; i < 3; i++) {
+            const int kmax = i < j ? i : j;
+            double acc = 0;
+            for (int k = 0; k < kmax; k++) acc += lu[i * 3 + k] * lu[k * 3 + j];
+            lu[i * 3 + j] -= acc;
+        }
+        int p = j;
+        for (int i = j + 1; i < 3; i++)
+            if (fabs(lu[i * 3 + j]) > fabs(lu[p * 3 + j])) p = i;
+        if (p != j)
+            for (int k = 0; k < 3; k++) { const double t = lu[p * 3 + k]; lu[p * 3 + k] = lu[j * 3 + k]; lu[j * 3 + k] = t; }
+        const double LUjj = lu[j * 3 + j];
+        if (fabs(LUjj) < 1e-8) return false;
+        for (int i = j + 1; i < 3; i++) lu[i * 3 + j] /= LUjj;
+    }
+    return true;
+}
+
+struct GrayModel { double A00, A01, A02, A11, A12, A22, B0, B1, B2, C0, C1, C2; };
+
+__device__ __forceinline__ void gm_solve(GrayModel &gm)
+{
+    // mat33_sym_solve: Cholesky, lower-triangular inverse, two triangular products
+    double L0 = sqrt(gm.A00), L3 = gm.A01 / L0, L6 = gm.A02 / L0;
+    double L4 = sqrt(gm.A11 - L3 * L3), L7 = (gm.A12 - L3 * L6) / L4;
+    double L8 = sqrt(gm.A22 - L6 * L6 - L7 * L7);
+    double M0 = 1 / L0, M3 = -L3 * M0 / L4, M4 = 1 / L4;
+    double M6 = (-L6 * M0 - L7 * M3) / L8, M7 = -L7 * M4 / L8, M8 = 1 / L8;
+    double t0 = M0 * gm.B0;
+    double t1 = M3 * gm.B0 + M4 * gm.B1;
+    double t2 = M6 * gm.B0 + M7 * gm.B1 + M8 * gm.B2;
+    gm.C0 = M0 * t0 + M3 * t1 + M6 * t2;
+    gm.C1 = M4 * t1 + M7 * t2;
+    gm.C2 = M8 * t2;
+}
+__device__ __forceinline__ double gm_interp(const GrayModel &gm, double x, double y) { return gm.C0 * x + gm.C1 * y + gm.C2; }
+
+__device__ __forceinline__ double value_for_pixel(const uint8_t *img, int W, int H, int stride, double px, double py)
+{
+    const int x1 = (int)floor(px - 0.5), x2 = (int)ceil(px - 0.5);
+    const double x = px - 0.5 - x1;
+    const int y1 = (int)floor(py - 0.5), y2 = (int)ceil(py - 0.5);
+    const double y = py - 0.5 - y1;
+    if (x1 < 0 || x2 >= W || y1 < 0 || y2 >= H) return -1;
+    return img[(size_t)y1 * stride + x1] * (1 - x) * (1 - y) + img[(size_t)y1 * stride + x2] * x * (1 - y) +
+           img[(size_t)y2 * stride + x1] * (1 - x) * y + img[(size_t)y2 * stride + x2] * x * y;
+}
+
+__device__ __forceinline__ unsigned long long rotate90_36(unsigned long long w)
+{
+    return ((w << 9) | (w >> 27)) & ((1ull << 36) - 1);
+}
+
+// one candidate quad, executed by a full warp
+__device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q, RawDet *__restrict__ raw, uint32_t *__restrict__ nraw,
+                                const Geom &g, const Caps &caps, const DetParams &prm, const DecodeConst &dc, double *values)
+{
+    const int lane = threadIdx.x & 31;
+    const int b = q.frame;
+    const uint32_t full = 0xffffffffu;
+    const uint8_t *img = in + (size_t)b * g.frame_stride;
+    const int W = g.W, H = g.H, stride = g.stride;
+
+    float p[4][2];
+    for (int j = 0; j < 4; j++) {
+        if (prm.quad_decimate > 1) {
+            p[j][0] = (float)(((double)q.p[j][0] - 0.5) * (double)prm.quad_decimate + 0.5);
+            p[j][1] = (float)(((double)q.p[j][1] - 0.5) * (double)prm.quad_decimate + 0.5);
+        } else { p[j][0] = q.p[j][0]; p[j][1] = q.p[j][1]; }
+    }
+
+    // ---- refine_edges ----------------------------------------------------------------------------------
+    if (prm.refine_edges) {
+        double lines[4][4];
+        for (int edge = 0; edge < 4; edge++) {
+            const int a = edge, bb = (edge + 1) & 3;
+            double nx = (double)p[bb][1] - (double)p[a][1];
+            double ny = -(double)p[bb][0] + (double)p[a][0];
+            const double mag = sqrt(nx * nx + ny * ny);
+            nx /= mag; ny /= mag;
+            if (q.reversed_border) { nx = -nx; ny = -ny; }
+            const int nsamples = max(16, (int)(mag / 8));
+            double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
+            const double range = (double)prm.quad_decimate + 1;
+            for (int s0 = 0; s0 < nsamples; s0 += 32) {
+                const int s = s0 + lane;
+                double bestx = 0, besty = 0;
+                int have = 0;
+                if (s < nsamples) {
+                    const double alpha = (1.0 + s) / (nsamples + 1);
+                    const double x0 = alpha * (double)p[a][0] + (1 - alpha) * (double)p[bb][0];
+                    const double y0 = alpha * (double)p[a][1] + (1 - alpha) * (double)p[bb][1];
+                    double Mn = 0, Mcount = 0;
+                    for (double n = -range; n <= range; n += 0.25) {
+                        const double grange = 1;
+                        const int x1 = (int)(x0 + (n + grange) * nx), y1 = (int)(y0 + (n + grange) * ny);
+                        if (x1 < 0 || x1 >= W || y1 < 0 || y1 >= H) continue;
+                        const int x2 = (int)(x0 + (n - grange) * nx), y2 = (int)(y0 + (n - grange) * ny);
+                        if (x2 < 0 || x2 >= W || y2 < 0 || y2 >= H) continue;
+                        const int g1 = img[(size_t)y1 * stride + x1], g2 = img[(size_t)y2 * stride + x2];
+                        if (g1 < g2) continue;
+                        const double weight = (double)((g2 - g1) * (g2 - g1));
+                        Mn += weight * n;
+                        Mcount += weight;
+                    }
+                    if (Mcount != 0) {
+                        const double n0 = Mn / Mcount;
+                        bestx = x0 + n0 * nx; besty = y0 + n0 * ny;
+                        have = 1;
+                    }
+                }
+                // replay the accumulation in sample order (uniform across lanes)
+                const int cnt = min(32, nsamples - s0);
+                for (int k = 0; k < cnt; k++) {
+                    const int hv = __shfl_sync(full, have, k);
+                    const double bx = __shfl_sync(full, bestx, k), by = __shfl_sync(full, besty, k);
+                    if (hv) { Mx += bx; My += by; Mxx += bx * bx; Mxy += bx * by; Myy += by * by; N++; }
+                }
+            }
+            const double Ex = Mx / N, Ey = My / N;
+            const double Cxx = Mxx / N - Ex * Ex, Cxy = Mxy / N - Ex * Ey, Cyy = Myy / N - Ey * Ey;
+            const double normal_theta = .5 * atan2f((float)(-2 * Cxy), (float)(Cyy - Cxx));
+            nx = cosf((float)normal_theta);
+            ny = sinf((float)normal_theta);
+            lines[edge][0] = Ex; lines[edge][1] = Ey; lines[edge][2] = nx; lines[edge][3] = ny;
+        }
+        for (int i = 0; i < 4; i++) {
+            const double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
+            const double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
+            const double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
+            const double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
+            const double det = A00 * A11 - A10 * A01;
+            if (fabs(det) > 0.001) {
+                const double W00 = A11 / det, W01 = -A01 / det;
+                const double L0 = W00 * B0 + W01 * B1;
+                p[i][0] = (float)(lines[i][0] + L0 * A00);
+                p[i][1] = (float)(lines[i][1] + L0 * A10);
+            }
+        }
+    }
+
+    // ---- quad_update_homographies ------------------------------------------------------------------------
+    double Hq[9];
+    {
+        double corr[4][4];
+        for (int i = 0; i < 4; i++) {
+            corr[i][0] = (i == 0 || i == 3) ? -1 : 1;
+            corr[i][1] = (i == 0 || i == 1) ? -1 : 1;
+            corr[i][2] = p[i][0];
+            corr[i][3] = p[i][1];
+        }
+        if (!homography_compute2(corr, Hq)) return;
+        if (!mat33_plu_nonsingular(Hq)) return;
+    }
+
+    // ---- quad_decode: gray models from the border samples ------------------------------------------------
+    GrayModel wm = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, bm = wm;
+    {
+        const float wab = 8.f;
+        double s_tagx[2], s_tagy[2];
+        int s_v[2], s_flag[2];   // flag: 0 skip, 1 white, 2 black
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int k = lane + 32 * h, pi = k >> 3, i = k & 7;
+            float p0, p1, p2, p3; int is_white;
+            switch (pi) {
+                case 0: p0 = -0.5f; p1 = 0.5f; p2 = 0; p3 = 1; is_white = 1; break;
+                case 1: p0 = 0.5f; p1 = 0.5f; p2 = 0; p3 = 1; is_white = 0; break;
+                case 2: p0 = wab + 0.5f; p1 = .5f; p2 = 0; p3 = 1; is_white = 1; break;
+                case 3: p0 = wab - 0.5f; p1 = .5f; p2 = 0; p3 = 1; is_white = 0; break;
+                case 4: p0 = 0.5f; p1 = -0.5f; p2 = 1; p3 = 0; is_white = 1; break;
+                case 5: p0 = 0.5f; p1 = 0.5f; p2 = 1; p3 = 0; is_white = 0; break;
+                case 6: p0 = 0.5f; p1 = wab + 0.5f; p2 = 1; p3 = 0; is_white = 1; break;
+                default: p0 = 0.5f; p1 = wab - 0.5f; p2 = 1; p3 = 0; is_white = 0; break;
+            }
+            const double tagx01 = (double)(p0 + (float)i * p2) / 8.0;
+            const double tagy01 = (double)(p1 + (float)i * p3) / 8.0;
+            const double tagx = 2 * (tagx01 - 0.5), tagy = 2 * (tagy01 - 0.5);
+            double px, py;
+            homography_project(Hq, tagx, tagy, &px, &py);
+            const int ix = (int)px, iy = (int)py;
+            s_tagx[h] = tagx; s_tagy[h] = tagy; s_v[h] = 0; s_flag[h] = 0;
+            if (!(ix < 0 || iy < 0 || ix >= W || iy >= H)) {
+                s_v[h] = img[(size_t)iy * stride + ix];
+                s_flag[h] = is_white ? 1 : 2;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            for (int k = 0; k < 32; k++) {
+                const int fl = __shfl_sync(full, s_flag[h], k);
+                const double x = __shfl_sync(full, s_tagx[h], k), y = __shfl_sync(full, s_tagy[h], k);
+                const double gray = (double)__shfl_sync(full, s_v[h], k);
+                if (fl == 0) continue;
+                GrayModel &gm = fl == 1 ? wm : bm;
+                gm.A00 += x * x; gm.A01 += x * y; gm.A02 += x; gm.A11 += y * y; gm.A12 += y; gm.A22 += 1;
+                gm.B0 += x * gray; gm.B1 += y * gray; gm.B2 += gray;
+            }
+    }
+    gm_solve(wm);
+    gm_solve(bm);
+    if ((gm_interp(wm, 0, 0) - gm_interp(bm, 0, 0) < 0) != false) return;
+
+    // ---- bit samples, sharpening, code word ---------------------------------------------------------------
+    for (int k = lane; k < 100; k += 32) values[k] = 0;
+    __syncwarp();
+    for (int i = lane; i < 36; i += 32) {
+        const int bity = c_bit_y[i], bitx = c_bit_x[i];
+        const double tagx01 = (bitx + 0.5) / 8.0, tagy01 = (bity + 0.5) / 8.0;
+        const double tagx = 2 * (tagx01 - 0.5), tagy = 2 * (tagy01 - 0.5);
+        double px, py;
+        homography_project(Hq, tagx, tagy, &px, &py);
+        const double v = value_for_pixel(img, W, H, stride, px, py);
+        if (v == -1) continue;
+        const double thresh = (gm_interp(bm, tagx, tagy) + gm_interp(wm, tagx, tagy)) / 2.0;
+        values[10 * (bity + 1) + bitx + 1] = v - thresh;
+    }
+    __syncwarp();
+    {
+        double sh[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int k = lane + 32 * r;
+            sh[r] = 0;
+            if (k < 100) {
+                const int y = k / 10, x = k % 10;
+                double acc = 0;
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) {
+                        if ((y + i - 1) < 0 || (y + i - 1) > 9 || (x + j - 1) < 0 || (x + j - 1) > 9) continue;
+                        const double kern = (i == 1 && j == 1) ? 4.0 : ((i == 1 || j == 1) ? -1.0 : 0.0);
+                        acc += values[(y + i - 1) * 10 + (x + j - 1)] * kern;
+                    }
+                sh[r] = acc;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int k = lane + 32 * r;
+            if (k < 100) values[k] = values[k] + prm.decode_sharpening * sh[r];
+        }
+        __syncwarp();
+    }
+    unsigned long long rcode = 0;
+    float black_score = 0, white_score = 0, black_score_count = 1, white_score_count = 1;
+    for (int i = 0; i < 36; i++) {
+        rcode <<= 1;
+        const double v = values[(c_bit_y[i] + 1) * 10 + c_bit_x[i] + 1];
+        if (v > 0) { white_score += (float)v; white_score_count++; rcode |= 1; }
+        else { black_score -= (float)v; black_score_count++; }
+    }
+    // ---- quick_decode_codeword: first rotation with a code within bits_corrected ----------------------------
+    int id = 65535, hamming = 255, rotation = 0;
+    {
+        unsigned long long rc = rcode;
+        for (int ridx = 0; ridx < 4; ridx++) {
+            int best = 1 << 30;   // (id << 8) | hamming, smallest id first
+            for (int c = lane; c < kNumCodes; c += 32) {
+                const int d = __popcll(rc ^ c_codes[c]);
+                if (d <= prm.bits_corrected) { best = min(best, (c << 8) | d); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(full, best, o));
+            if (best != (1 << 30)) { id = best >> 8; hamming = best & 255; rotation = ridx; break; }
+            rc = rotate90_36(rc);
+        }
+    }
+    const float decision_margin = fminf(white_score / white_score_count, black_score / black_score_count);
+    if (!(decision_margin >= 0 && hamming < 255)) return;
+    if (lane != 0) return;
+
+    RawDet out;
+    out.valid = 1; out.pad = 0;
+    out.d.frame = b; out.d.id = id; out.d.hamming = hamming; out.d.decision_margin = decision_margin;
+    {
+        const double c = dc.rot_c[rotation], s = dc.rot_s[rotation];
+        const double R[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                double acc = 0;
+                for (int k = 0; k < 3; k++) acc += Hq[i * 3 + k] * R[k * 3 + j];
+                out.d.H[i * 3 + j] = acc;
+            }
+        homography_project(out.d.H, 0, 0, &out.d.c[0], &out.d.c[1]);
+        for (int i = 0; i < 4; i++) {
+            const int tcx = (i == 1 || i == 2) ? 1 : -1;
+            const int tcy = (i < 2) ? 1 : -1;
+            homography_project(out.d.H, tcx, tcy, &out.d.p[i][0], &out.d.p[i][1]);
+        }
+    }
+    const uint32_t slot = atomicAdd(&nraw[b], 1u);
+    if (slot < caps.quads_per_frame) raw[(size_t)b * caps.quads_per_frame + slot] = out;
+}
+
+// persistent warps pull candidate quads from the batch-wide list
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+decode_quads_kernel(const uint8_t *__restrict__ in, const QuadRec *__restrict__ quads, const uint32_t *__restrict__ nquads_total,
+                    uint32_t *__restrict__ counter, RawDet *__restrict__ raw, uint32_t *__restrict__ nraw, Geom g, Caps caps,
+                    DetParams prm, DecodeConst dc)
+{
+    __shared__ double s_values[DEC_WARPS][100];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t total = *nquads_total;
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(counter, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= total) return;
+        const QuadRec q = quads[qi];
+        decode_one_quad(in, q, raw, nraw, g, caps, prm, dc, s_values[wid]);
+        __syncwarp();
+    }
+}
+
+// ---- reconcile + sort: one thread per frame (a handful of detections) ------------------------------------
+__device__ __forceinline__ double cross2(const double *a, const double *b, const double *c)
+{
+    return (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]);
+}
+__device__ bool on_seg(const double *a, const double *b, const double *c)
+{
+    return fmin(a[0], b[0]) <= c[0] && c[0] <= fmax(a[0], b[0]) && fmin(a[1], b[1]) <= c[1] && c[1] <= fmax(a[1], b[1]);
+}
+__device__ bool seg_intersect(const double *p0, const double *p1, const double *q0, const double *q1)
+{
+    const double d1 = cross2(q0, q1, p0), d2 = cross2(q0, q1, p1), d3 = cross2(p0, p1, q0), d4 = cross2(p0, p1, q1);
+    if (((d1 > 0 && d2 < 0) || (d1 < 0 && d2 > 0)) && ((d3 > 0 && d4 < 0) || (d3 < 0 && d4 > 0))) return true;
+    if (d1 == 0 && on_seg(q0, q1, p0)) return true;
+    if (d2 == 0 && on_seg(q0, q1, p1)) return true;
+    if (d3 == 0 && on_seg(p0, p1, q0)) return true;
+    if (d4 == 0 && on_seg(p0, p1, q1)) return true;
+    return false;
+}
+__device__ bool poly_contains(const double (*poly)[2], const double *q)
+{
+    bool in = false;
+    for (int i = 0, j = 3; i < 4; j = i++) {
+        if (((poly[i][1] > q[1]) != (poly[j][1] > q[1])) &&
+            (q[0] < (poly[j][0] - poly[i][0]) * (q[1] - poly[i][1]) / (poly[j][1] - poly[i][1]) + poly[i][0]))
+            in = !in;
+    }
+    return in;
+}
+__device__ bool polygons_overlap(const double (*a)[2], const double (*b)[2])
+{
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            if (seg_intersect(a[i], a[(i + 1) & 3], b[j], b[(j + 1) & 3])) return true;
+    double ca[2] = {0, 0}, cb2[2] = {0, 0};
+    for (int i = 0; i < 4; i++) { ca[0] += a[i][0] / 4; ca[1] += a[i][1] / 4; cb2[0] += b[i][0] / 4; cb2[1] += b[i][1] / 4; }
+    if (poly_contains(a, cb2)) return true;
+    if (poly_contains(b, ca)) return true;
+    return false;
+}
+__device__ __forceinline__ int prefer_smaller(int pref, double q0, double q1)
+{
+    if (pref) return pref;
+    if (q0 < q1) return -1;
+    if (q1 < q0) return 1;
+    return 0;
+}
+__device__ __forceinline__ bool det_less(const cb_detection &a, const cb_detection &b)
+{
+    if (a.id != b.id) return a.id < b.id;
+    if (a.hamming != b.hamming) return a.hamming < b.hamming;
+    if (a.c[0] != b.c[0]) return a.c[0] < b.c[0];
+    return a.c[1] < b.c[1];
+}
+
+__global__ void reconcile_kernel(RawDet *__restrict__ raw, const uint32_t *__restrict__ nraw, cb_detection *__restrict__ out,
+                                 int32_t *__restrict__ counts, Caps caps, int batch)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    RawDet *r = raw + (size_t)b * caps.quads_per_frame;
+    int n = (int)min(nraw[b], caps.quads_per_frame);
+    // The decode kernel appends in arbitrary order; upstream's outcome depends on list order only through the
+    // swap-remove bookkeeping, not through which detection of an overlapping pair survives.  Put the list into a
+    // canonical order first so the result is deterministic.
+    for (int i = 1; i < n; i++) {
+        RawDet t = r[i];
+        int j = i;
+        while (j > 0 && det_less(t.d, r[j - 1].d)) { r[j] = r[j - 1]; j--; }
+        r[j] = t;
+    }
+    for (int i0 = 0; i0 < n; i0++) {
+        for (int i1 = i0 + 1; i1 < n; i1++) {
+            const cb_detection &d0 = r[i0].d, &d1 = r[i1].d;
+            if (d0.id != d1.id) continue;
+            if (!polygons_overlap(d0.p, d1.p)) continue;
+            int pref = 0;
+            pref = prefer_smaller(pref, d0.hamming, d1.hamming);
+            pref = prefer_smaller(pref, -d0.decision_margin, -d1.decision_margin);
+            for (int i = 0; i < 4; i++) {
+                pref = prefer_smaller(pref, d0.p[i][0], d1.p[i][0]);
+                pref = prefer_smaller(pref, d0.p[i][1], d1.p[i][1]);
+            }
+            if (pref < 0) { r[i1] = r[n - 1]; n--; i1--; }
+            else { r[i0] = r[n - 1]; n--; i0--; break; }
+        }
+    }
+    for (int i = 1; i < n; i++) {
+        RawDet t = r[i];
+        int j = i;
+        while (j > 0 && det_less(t.d, r[j - 1].d)) { r[j] = r[j - 1]; j--; }
+        r[j] = t;
+    }
+    const int m = min(n, (int)caps.dets_per_frame);
+    for (int i = 0; i < m; i++) out[(size_t)b * caps.dets_per_frame + i] = r[i].d;
+    counts[b] = m;
+}
+
+}  // namespace cb

@@ -1,0 +1,155 @@
+/*
+ * chalkydri_b200.h -- C ABI of libchalkydri_b200.so, the B200 (sm_100a) drop-in for Chalkydri's
+ * AprilTag detection + SQPnP hot path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to /root/reference).
+ * Conventions: int return, 0 = ok, <0 = error (cb_last_error gives the text); nothing
+ * unwinds across the boundary; the caller owns every buffer it passes in; outputs are caller-allocated
+ * fixed-capacity arrays.  A context is single-threaded (like one `AprilTags` task instance,
+ * crates/apriltags/src/lib.rs:166-182); several contexts (one per GPU / stream) may run concurrently.
+ * There is no CPU fallback: every call fails with CB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef CHALKYDRI_B200_H
+#define CHALKYDRI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_OK 0
+#define CB_ERR_ARG (-1)        /* bad argument (null pointer, size beyond the context's capacity, ...) */
+#define CB_ERR_CUDA (-2)       /* CUDA runtime error; text in cb_last_error */
+#define CB_ERR_UNSUPPORTED (-3)/* parameter value the kernels do not implement (quad_sigma != 0, decimate 1.5, ...) */
+#define CB_ERR_OVERFLOW (-4)   /* a per-frame device table overflowed (clusters / points / quads); raise capacities */
+#define CB_ERR_STATE (-5)      /* family not set etc. */
+
+typedef struct cb_ctx cb_ctx;
+
+/* mirrors apriltag_detection_t as exposed by `apriltag::Detection` (id(), hamming(), decision_margin(),
+ * corners(), center(), homography(); used at crates/apriltags/src/lib.rs:306,310-314) plus the frame index */
+typedef struct {
+    int32_t frame;            /* index inside the batch */
+    int32_t id;
+    int32_t hamming;
+    float   decision_margin;
+    double  H[9];             /* row-major 3x3 */
+    double  c[2];             /* centre */
+    double  p[4][2];          /* corners, counter-clockwise starting at tag (-1, 1) like apriltag.c */
+} cb_detection;
+
+/* nalgebra Isometry3<f64> (chalkydri_sqpnp Iso3, crates/chalkydri_sqpnp/src/lib.rs:24) */
+typedef struct {
+    double t[3];
+    double q[4];              /* unit quaternion w, x, y, z */
+} cb_iso3;
+
+/* Some((Rot3, Vec3 position, Vec3 std_devs)) of SqPnP::solve_robot_pose (lib.rs:297-304,376) */
+typedef struct {
+    double rot[9];            /* column-major 3x3 like nalgebra */
+    double pos[3];
+    double std_devs[3];
+} cb_pose;
+
+/* per-stage device time of the last detect call, CUDA events on the context's stream */
+typedef struct {
+    float h2d_ms, preprocess_ms, threshold_ms, ccl_ms, cluster_ms, quad_ms, decode_ms, d2h_ms, total_ms;
+    int32_t threshold_launches;   /* launches of the fused decimate+threshold kernel inside the call */
+    int32_t kernel_launches;      /* all kernel launches inside the call */
+} cb_timing;
+
+/* ---- lifetime: replaces apriltag_detector_create/destroy behind DetectorBuilder::build()
+ *      (crates/apriltags/src/lib.rs:258-261) ---- */
+cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int max_dets_per_frame);
+void cb_destroy(cb_ctx *ctx);
+/* last error text of this context; ctx == NULL returns the text of the last failed cb_create on this thread */
+const char *cb_last_error(const cb_ctx *ctx);
+
+/* tag36h11_create + apriltag_detector_add_family_bits (DetectorBuilder::add_family_bits, lib.rs:259,280).
+ * bits_corrected in [0,3]. */
+int cb_set_family_tag36h11(cb_ctx *ctx, int bits_corrected);
+
+/* apriltag_detector_t fields the reference leaves at their defaults.  quad_decimate must be an
+ * integer >= 1 (2 takes the fused fast path); quad_sigma must be 0; deglitch is not offered. */
+int cb_set_params(cb_ctx *ctx, float quad_decimate, float quad_sigma, int refine_edges, double decode_sharpening,
+                  int min_cluster_pixels, int max_nmaxima, float critical_rad, float max_line_fit_mse,
+                  int min_white_black_diff);
+
+/* Detector::detect (crates/apriltags/src/lib.rs:301) on a batch of 8-bit gray frames in HOST memory
+ * (image_u8_t{buf,width,height,stride}, lib.rs:197-213; frame b starts at frames + b*frame_stride bytes).
+ * out holds batch*max_dets_per_frame records, frame b's detections start at out[b*max_dets_per_frame],
+ * sorted by id; out_counts[b] is their number.  Includes H2D of the frames and D2H of the lists. */
+int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride,
+                   int batch, cb_detection *out, int32_t *out_counts);
+/* same with the frames already resident in device memory (frames_dev is a device pointer) */
+int cb_detect_gray_device(cb_ctx *ctx, const uint8_t *frames_dev, int width, int height, int stride,
+                          size_t frame_stride, int batch, cb_detection *out, int32_t *out_counts);
+/* packed-RGB input (CAT contract, crates/chalkydri-apriltags/src/lib.rs:265-267): gray = utils.rs:43 */
+int cb_detect_rgb(cb_ctx *ctx, const uint8_t *frames_rgb, int width, int height, int batch, cb_detection *out,
+                  int32_t *out_counts);
+/* YUYV (YUY2) camera buffers (crates/chalkydri/src/cameras/gst_to_cu.rs:152-188 lists the formats): gray = Y */
+int cb_detect_yuyv(cb_ctx *ctx, const uint8_t *frames_yuyv, int width, int height, int batch, cb_detection *out,
+                   int32_t *out_counts);
+
+/* ---- stage taps (parity tests; run the pipeline up to that stage on HOST input) ---- */
+/* decimated size the detector works on */
+int cb_decimated_size(const cb_ctx *ctx, int width, int height, int *w, int *h);
+/* threshold(): out[batch][h][w] in {0,127,255} */
+int cb_threshold(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
+                 uint8_t *out);
+/* connected_components(): labels[batch][h][w] = smallest pixel index (y*w+x) of the component; sizes = its size */
+int cb_labels(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
+              uint32_t *labels, uint32_t *sizes);
+/* fit_quads(): quads[batch][cap] corners in decimated coordinates (float[4][2]) + counts */
+int cb_quads(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
+             float *quads, int cap, int32_t *counts, int64_t *npoints_total);
+
+int cb_get_timing(const cb_ctx *ctx, cb_timing *t);
+
+/* ---- solver: SqPnP::solve_robot_pose (crates/chalkydri_sqpnp/src/lib.rs:297-377), batched.
+ * Problem i uses tags[i*max_tags .. +n_tags[i]) and bearings[(i*max_tags*4) .. ) (3 doubles each, 4 per tag in the
+ * detector's corner order).  ok[i] = 1 for Some, 0 for None.  max_iter / tol mirror the builder (lib.rs:214-222). */
+int cb_sqpnp_set(cb_ctx *ctx, int max_iter, double tolerance);
+int cb_sqpnp_batch(cb_ctx *ctx, const cb_iso3 *tags, const double *bearings, const int32_t *n_tags, int max_tags,
+                   const cb_iso3 *robot_to_cam, const double *gyro, double sign_change_error, int64_t n,
+                   cb_pose *out, uint8_t *ok);
+/* same with every array already in device memory */
+int cb_sqpnp_batch_device(cb_ctx *ctx, const cb_iso3 *tags, const double *bearings, const int32_t *n_tags, int max_tags,
+                          const cb_iso3 *robot_to_cam, const double *gyro, double sign_change_error, int64_t n,
+                          cb_pose *out, uint8_t *ok);
+/* SqPnP::create_solver_camera_transform (lib.rs:430-461); host-side scalar helper */
+int cb_create_solver_camera_transform(double fwd_m, double left_m, double up_m, double roll_deg, double pitch_deg,
+                                      double yaw_deg, cb_iso3 *out);
+/* GenericModel::unproject for OpenCVModel5 (crates/apriltags/src/lib.rs:316-321), batched on the device:
+ * params = fx,fy,cx,cy,k1,k2,p1,p2,k3; px[n][2] -> bearings[n][3], ok[n] */
+int cb_unproject_opencv5(cb_ctx *ctx, const double *params9, const double *px, int64_t n, double *bearings, uint8_t *ok);
+
+/* ---- CAT stages (crates/chalkydri-apriltags/src/lib.rs), HOST buffers ---- */
+/* Detector::calc_otsu (lib.rs:191-259): packed RGB -> Color map (0 Black, 1 White, 2 Other) */
+int cb_cat_calc_otsu(cb_ctx *ctx, const uint8_t *rgb, int width, int height, uint8_t *color);
+/* Detector::thresh (lib.rs:319-334) */
+int cb_cat_thresh(cb_ctx *ctx, const uint8_t *rgb, int width, int height, uint8_t *color);
+/* Detector::detect_corners (lib.rs:291-309,345-400): (x,y) pairs in the reference's scan order (x-major) */
+int cb_cat_detect_corners(cb_ctx *ctx, const uint8_t *color, int width, int height, int32_t *xy, int64_t cap, int64_t *n);
+/* Detector::check_edges (lib.rs:409-499): (x1,y1,x2,y2) in the reference's order */
+int cb_cat_check_edges(cb_ctx *ctx, const uint8_t *color, int width, int height, const int32_t *xy, int64_t npts,
+                       int32_t *lines, int64_t cap, int64_t *n);
+/* Detector::connected_components (lib.rs:501-549): min-index labels and component sizes */
+int cb_cat_connected_components(cb_ctx *ctx, const uint8_t *color, int width, int height, uint32_t *labels, uint32_t *sizes);
+
+/* ---- plumbing ---- */
+void *cb_host_alloc(size_t bytes);        /* pinned host memory for frames / outputs */
+void cb_host_free(void *p);
+void *cb_device_alloc(cb_ctx *ctx, size_t bytes);
+void cb_device_free(cb_ctx *ctx, void *p);
+int cb_memcpy_h2d(cb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int cb_memcpy_d2h(cb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int cb_device_count(void);
+const char *cb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

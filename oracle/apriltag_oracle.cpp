@@ -259,13 +259,18 @@ struct LineFitPt { double Mx, My, Mxx, Mxy, Myy, W; };
 
 void ptsort(Pt *pts, int sz, Pt *tmp)
 {
-    /* upstream: small sorting networks for sz<=5, then a merge sort that takes from the SECOND half on ties */
+    /* upstream: sorting networks for sz<=5, then a merge sort that takes from the SECOND half on ties */
     if (sz <= 1) return;
-    if (sz <= 5) { /* same comparison (a.slope - b.slope > 0 swaps), insertion form gives the same order for distinct keys */
-        for (int i = 1; i < sz; i++)
-            for (int j = i; j > 0 && pts[j - 1].slope - pts[j].slope > 0; j--) std::swap(pts[j - 1], pts[j]);
+#define MAYBE_SWAP(a, b) if (pts[a].slope - pts[b].slope > 0) std::swap(pts[a], pts[b])
+    if (sz == 2) { MAYBE_SWAP(0, 1); return; }
+    if (sz == 3) { MAYBE_SWAP(0, 1); MAYBE_SWAP(1, 2); MAYBE_SWAP(0, 1); return; }
+    if (sz == 4) { MAYBE_SWAP(0, 1); MAYBE_SWAP(2, 3); MAYBE_SWAP(0, 2); MAYBE_SWAP(1, 3); MAYBE_SWAP(1, 2); return; }
+    if (sz == 5) {
+        MAYBE_SWAP(0, 1); MAYBE_SWAP(3, 4); MAYBE_SWAP(2, 4); MAYBE_SWAP(2, 3); MAYBE_SWAP(0, 3);
+        MAYBE_SWAP(0, 2); MAYBE_SWAP(1, 4); MAYBE_SWAP(1, 3); MAYBE_SWAP(1, 2);
         return;
     }
+#undef MAYBE_SWAP
     memcpy(tmp, pts, sizeof(Pt) * sz);
     int asz = sz / 2, bsz = sz - asz;
     Pt *as = tmp, *bs = tmp + asz;
@@ -969,7 +974,15 @@ int detect_impl(const uint8_t *buf, int W, int H, int stride, const orc_params &
             dets.push_back(d);
         }
     }
-    /* reconcile */
+    /* reconcile.  Upstream walks the detections in quad order, which follows its hash-bucket order; the list is put
+       into a canonical order first (frozen choice) so that the outcome does not depend on that order. */
+    auto det_less = [](const orc_detection &a, const orc_detection &b) {
+        if (a.id != b.id) return a.id < b.id;
+        if (a.hamming != b.hamming) return a.hamming < b.hamming;
+        if (a.c[0] != b.c[0]) return a.c[0] < b.c[0];
+        return a.c[1] < b.c[1];
+    };
+    std::sort(dets.begin(), dets.end(), det_less);
     for (int i0 = 0; i0 < (int)dets.size(); i0++) {
         bool removed0 = false;
         for (int i1 = i0 + 1; i1 < (int)dets.size(); i1++) {
