@@ -55,7 +55,6 @@ struct cb_ctx {
     ClusterSlot *d_table = nullptr;
     ClusterRec *d_clusters = nullptr;
     uint32_t *d_worklist = nullptr;
-    unsigned long long *d_pts = nullptr;
     uint32_t *d_scankey = nullptr;
     double *d_lfps = nullptr;
     unsigned long long *d_scratch = nullptr;
@@ -130,7 +129,7 @@ void cb_destroy(cb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
-                    ctx->d_table, ctx->d_clusters, ctx->d_worklist, ctx->d_pts, ctx->d_scankey, ctx->d_lfps, ctx->d_scratch,
+                    ctx->d_table, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_lfps, ctx->d_scratch,
                     ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
@@ -192,7 +191,7 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     c.slots_per_frame = next_pow2((uint32_t)std::max<size_t>(1024, dpix / 8));
     c.clusters_per_frame = (uint32_t)std::max<size_t>(2048, dpix / 128);
     c.points_per_frame = (uint32_t)std::max<size_t>(65536, dpix + dpix / 2);   // noisy frames emit ~0.85 points / pixel
-    c.quads_per_frame = (uint32_t)std::max<size_t>(512, dpix / 1024);
+    c.quads_per_frame = (uint32_t)std::max<size_t>(2048, dpix / 32);   // pure-noise frames produce thousands of candidate quads
     c.dets_per_frame = (uint32_t)max_dets_per_frame;
     ok = ok && alloc((void **)&ctx->d_in, ctx->in_bytes + 64);
     ok = ok && alloc((void **)&ctx->d_thresh, ctx->map_bytes) && alloc((void **)&ctx->d_mark, ctx->map_bytes);
@@ -200,11 +199,10 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     ok = ok && alloc((void **)&ctx->d_labels, ctx->label_bytes) && alloc((void **)&ctx->d_sizes, ctx->label_bytes);
     ok = ok && alloc((void **)&ctx->d_table, B * c.slots_per_frame * sizeof(ClusterSlot));
     ok = ok && alloc((void **)&ctx->d_clusters, B * c.clusters_per_frame * sizeof(ClusterRec));
-    ok = ok && alloc((void **)&ctx->d_worklist, B * c.clusters_per_frame * sizeof(uint32_t));
-    ok = ok && alloc((void **)&ctx->d_pts, B * c.points_per_frame * sizeof(unsigned long long));
+    ok = ok && alloc((void **)&ctx->d_worklist, 2 * B * c.clusters_per_frame * sizeof(uint32_t));
     ok = ok && alloc((void **)&ctx->d_scankey, B * c.points_per_frame * sizeof(uint32_t));
     ok = ok && alloc((void **)&ctx->d_lfps, B * c.points_per_frame * 6 * sizeof(double));
-    ok = ok && alloc((void **)&ctx->d_scratch, B * c.points_per_frame * 3 * sizeof(unsigned long long));
+    ok = ok && alloc((void **)&ctx->d_scratch, B * c.points_per_frame * 2 * sizeof(unsigned long long));
     ok = ok && alloc((void **)&ctx->d_quads, B * c.quads_per_frame * sizeof(QuadRec));
     ok = ok && alloc((void **)&ctx->d_raw, B * c.quads_per_frame * sizeof(RawDet));
     ok = ok && alloc((void **)&ctx->d_dets, B * c.dets_per_frame * sizeof(cb_detection));
@@ -217,7 +215,17 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaMemcpyToSymbol(c_codes, kHostCodes, sizeof(kHostCodes)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QfShared)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(fit_quads_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared)) == cudaSuccess;
+        {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
+            uint16_t combos[210];
+            int nc = 0;
+            for (int m3 = 3; m3 < 10; m3++)
+                for (int m2 = 2; m2 < m3; m2++)
+                    for (int m1 = 1; m1 < m2; m1++)
+                        for (int m0 = 0; m0 < m1; m0++) combos[nc++] = (uint16_t)((m0 << 12) | (m1 << 8) | (m2 << 4) | m3);
+            ok = ok && nc == 210 && cudaMemcpyToSymbol(c_combos, combos, sizeof(combos)) == cudaSuccess;
+        }
         if (!ok && g_create_error.empty()) fail(nullptr, CB_ERR_CUDA, "cb_create: device setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (!ok) {
@@ -296,6 +304,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     const DetParams &prm = ctx->prm;
     const int B = g.batch;
     int launches = 0, thr_launches = 0;
+    uint32_t *d_wl_large = ctx->d_worklist + (size_t)ctx->max_batch * caps.clusters_per_frame;
     uint32_t *d_ncl = ctx->d_small, *d_npt = ctx->d_small + ctx->max_batch, *d_nq = ctx->d_small + 2 * ctx->max_batch,
              *d_nraw = ctx->d_small + 3 * ctx->max_batch, *d_misc = ctx->d_small + 4 * ctx->max_batch;
     // misc: [0] errflag, [1] nwork, [2] work_counter, [3] nquads_total, [4] decode counter
@@ -354,17 +363,22 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         launches += 2;
         if (g.h > 2 && g.w > 2) {
             dim3 gc((g.w + 255) / 256, g.h - 2, B);
-            cluster_pass_kernel<false><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_pts, ctx->d_scankey, d_misc, g, caps);
-            cluster_select_kernel<<<B, 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, d_misc + 1, d_misc, g, caps, prm.min_cluster_pixels);
-            cluster_pass_kernel<true><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_pts, ctx->d_scankey, d_misc, g, caps);
+            cluster_pass_kernel<false><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
+            cluster_select_kernel<<<B, 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, d_misc + 1, d_wl_large, d_misc + 5,
+                                                     (uint32_t)QS_MAXN, d_misc, g, caps, prm.min_cluster_pixels);
+            cluster_pass_kernel<true><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
             launches += 3;
         }
         CK(cudaEventRecord(ctx->ev[4], st));
         // ---- A5 quad fitting ----
-        const int qf_blocks = ctx->num_sms * 4;
-        fit_quads_kernel<<<qf_blocks, QF_THREADS, sizeof(QfShared), st>>>(d_frames, ctx->d_pts, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist,
-                                                                        d_misc + 1, d_misc + 2, ctx->d_lfps, ctx->d_scratch, ctx->d_quads, d_nq,
-                                                                        d_misc + 3, d_misc, g, caps, prm);
+        // tier L first (long jobs), then tier S; misc: [1] n small, [2] small counter, [5] n large, [6] large counter
+        fit_quads_large_kernel<<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared), st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, d_wl_large, d_misc + 5,
+                                                                                   d_misc + 6, ctx->d_lfps, ctx->d_scratch, ctx->d_quads, d_nq,
+                                                                                   d_misc + 3, d_misc, g, caps, prm);
+        fit_quads_small_kernel<<<ctx->num_sms * 4, QS_WARPS * 32, sizeof(QsShared), st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist,
+                                                                                      d_misc + 1, d_misc + 2, ctx->d_lfps, ctx->d_quads, d_nq,
+                                                                                      d_misc + 3, d_misc, g, caps, prm);
+        launches += 2;
         launches++;
         CK(cudaEventRecord(ctx->ev[5], st));
     } else {

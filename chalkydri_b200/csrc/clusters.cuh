@@ -57,8 +57,7 @@ __device__ __forceinline__ uint32_t slot_find(const ClusterSlot *tab, uint32_t n
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, ClusterSlot *__restrict__ table,
-                    ClusterRec *__restrict__ clusters, unsigned long long *__restrict__ pts, uint32_t *__restrict__ scankey,
-                    uint32_t *__restrict__ errflag, Geom g, Caps caps)
+                    ClusterRec *__restrict__ clusters, uint32_t *__restrict__ scankey, uint32_t *__restrict__ errflag, Geom g, Caps caps)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y + 1, b = blockIdx.z;
@@ -118,12 +117,9 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
             pos = __shfl_sync(peers, pos, leader);
             if (pos != 0xffffffffu) {
                 pos += rank;
-                const int dv = (int)vn[d] - (int)v0;
-                const uint32_t px = (uint32_t)(2 * x + dxs[d]), py = (uint32_t)(2 * y + dys[d]);
-                const uint32_t gx = (uint32_t)(uint16_t)(int16_t)(dxs[d] * dv), gy = (uint32_t)(uint16_t)(int16_t)(dys[d] * dv);
+                // a boundary point is fully described by (pixel, probe, gradient sign): 2x+dx, 2y+dy, g = d*(v1-v0)
                 const size_t o = (size_t)b * caps.points_per_frame + pos;
-                pts[o] = (unsigned long long)px | ((unsigned long long)py << 16) | ((unsigned long long)gx << 32) | ((unsigned long long)gy << 48);
-                scankey[o] = ((uint32_t)(y * g.w + x) << 2) | (uint32_t)d;
+                scankey[o] = ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | (vn[d] > v0 ? 1u : 0u);
             }
         }
     }
@@ -133,7 +129,8 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
 // Order of the selected list is the slot order (deterministic for a given table size).
 __global__ void __launch_bounds__(256)
 cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ clusters, uint32_t *__restrict__ nclusters,
-                      uint32_t *__restrict__ npoints, uint32_t *__restrict__ worklist, uint32_t *__restrict__ nwork,
+                      uint32_t *__restrict__ npoints, uint32_t *__restrict__ worklist_small, uint32_t *__restrict__ nwork_small,
+                      uint32_t *__restrict__ worklist_large, uint32_t *__restrict__ nwork_large, uint32_t small_max,
                       uint32_t *__restrict__ errflag, Geom g, Caps caps, int min_cluster_pixels)
 {
     const int b = blockIdx.x;
@@ -189,15 +186,24 @@ cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ 
         }
         __syncthreads();
     }
-    __shared__ uint32_t s_wbase;
+    // batch-wide work lists for the two quad-fitting tiers (one warp per small cluster, one CTA per large one)
+    __shared__ uint32_t s_cnt[2], s_base[2];
     const uint32_t ncl = min(s_ncl, caps.clusters_per_frame);
+    if (threadIdx.x == 0) { nclusters[b] = ncl; npoints[b] = s_npt; s_cnt[0] = 0; s_cnt[1] = 0; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ncl; i += blockDim.x) atomicAdd(&s_cnt[out[i].count > small_max ? 1 : 0], 1u);
+    __syncthreads();
     if (threadIdx.x == 0) {
-        nclusters[b] = ncl;
-        npoints[b] = s_npt;
-        s_wbase = atomicAdd(nwork, ncl);   // batch-wide work list for the quad-fitting kernel
+        s_base[0] = atomicAdd(nwork_small, s_cnt[0]);
+        s_base[1] = atomicAdd(nwork_large, s_cnt[1]);
+        s_cnt[0] = 0; s_cnt[1] = 0;
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < ncl; i += blockDim.x) worklist[s_wbase + i] = (uint32_t)b * caps.clusters_per_frame + i;
+    for (uint32_t i = threadIdx.x; i < ncl; i += blockDim.x) {
+        const int t = out[i].count > small_max ? 1 : 0;
+        const uint32_t pos = s_base[t] + atomicAdd(&s_cnt[t], 1u);
+        (t ? worklist_large : worklist_small)[pos] = (uint32_t)b * caps.clusters_per_frame + i;
+    }
 }
 
 }  // namespace cb

@@ -1,4 +1,4 @@
-// quads.cuh -- row A5 of SURVEY.md 8a: fit_quads() / fit_quad(), one CTA per gradient cluster.
+// quads.cuh -- row A5 of SURVEY.md 8a: fit_quads() / fit_quad().
 //
 // Upstream (apriltag_quad_thresh.c fit_quad, ptsort, compute_lfps, fit_line, quad_segment_maxima).  The float /
 // double arithmetic below follows upstream operation by operation (the library is built with --fmad=false), and
@@ -6,18 +6,27 @@
 //   * points are first put back into scan order (y, x, probe) -- the order upstream's hash map appends them in;
 //   * ptsort()'s merge sort is emulated exactly: same recursive split (sz/2), same 2..5 element sorting networks
 //     at the leaves, merges that take from the SECOND half on ties -- done as parallel rank merges;
-//   * the line-fit prefix moments are accumulated sequentially by six lanes (one lane per moment);
+//   * the line-fit prefix moments are accumulated sequentially (six lanes, one per moment), fed 32 points at a time
+//     through a small shared-memory staging tile so that the dependent chain is one DADD per point;
 //   * the 4-corner search evaluates all <=210 subsets in parallel and keeps the first minimum in loop order.
-// Work distribution: a persistent grid pulls (frame, cluster) items from a device-side work list, so cluster size
-// imbalance is absorbed by the scheduler.  Clusters up to QF_NSM points are processed out of shared memory; larger
-// ones use a global scratch area with the same code (generic pointers).
+//
+// B200 mapping: the work is thousands of small, irregular, partly sequential jobs per frame (a c2 frame has ~700
+// clusters of 24..7000 points), so the design maximises the number of clusters in flight instead of the threads per
+// cluster.  Two persistent kernels pull (frame, cluster) items from device-side work lists:
+//   tier S: clusters of <= 512 points, ONE WARP per cluster (8 KB smem per warp, 24 warps per SM);
+//   tier L: larger clusters, one 256-thread CTA per cluster (96 KB smem, 2 CTAs per SM; clusters above 6144 points
+//           run the same code out of a global scratch area).
+// A boundary point is fully described by its 32-bit scan key (pixel index, probe, gradient sign), so the only
+// per-point input is 4 bytes; sorting happens on packed (slope, scan key) 64-bit words in shared memory.
 #pragma once
 #include "common.cuh"
 
 namespace cb {
 
-constexpr int QF_THREADS = 256;
-constexpr int QF_NSM = 2048;   // points handled in shared memory
+constexpr int QS_MAXN = 512;      // tier S: points per warp
+constexpr int QS_WARPS = 4;
+constexpr int QL_THREADS = 256;
+constexpr int QL_MAXN = 6144;     // tier L: points per CTA in shared memory
 
 struct LineFit { double Ex, Ey, nx, ny, err, mse; };
 
@@ -25,6 +34,17 @@ __device__ __forceinline__ uint32_t float_orderable(float f)
 {
     uint32_t b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// scan key layout (clusters.cuh): (pixel index << 3) | (probe << 1) | (v1 > v0)
+__device__ __forceinline__ void decode_point(uint32_t key, int w, int &px, int &py, int &gx, int &gy)
+{
+    const uint32_t pix = key >> 3;
+    const int d = (key >> 1) & 3, s = key & 1;
+    const int x = pix % w, y = pix / w;
+    const int dx = d == 2 ? -1 : (d == 1 ? 0 : 1), dy = d == 0 ? 0 : 1;
+    const int dv = s ? 255 : -255;
+    px = 2 * x + dx; py = 2 * y + dy; gx = dx * dv; gy = dy * dv;
 }
 
 // fit_line() on prefix moments lfps[j*6 + {Mx,My,Mxx,Mxy,Myy,W}]
@@ -65,8 +85,7 @@ __device__ __forceinline__ void fit_line(const double *__restrict__ lfps, int sz
     o.mse = eig_small;
 }
 
-// node of ptsort()'s recursion tree that contains position i at depth d; returns false when the branch ended
-// in a leaf (size <= 5) before reaching depth d.  leaf_here = node at depth d is itself a leaf.
+// node of ptsort()'s recursion tree that contains position i at depth d; false when the branch ended in a leaf earlier
 __device__ __forceinline__ bool ptsort_node(int n, int i, int d, int &lo, int &hi)
 {
     lo = 0; hi = n;
@@ -80,100 +99,84 @@ __device__ __forceinline__ bool ptsort_node(int n, int i, int d, int &lo, int &h
 
 __device__ __forceinline__ uint32_t hi32(unsigned long long v) { return (uint32_t)(v >> 32); }
 
-// block-wide helpers ---------------------------------------------------------------------------------------
-template <typename T, typename Op>
-__device__ __forceinline__ T block_reduce(T v, Op op, T *scratch /* >= 8 entries */)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) scratch[wid] = v;
-    __syncthreads();
-    T r = scratch[0];
-    for (int k = 1; k < (int)(blockDim.x >> 5); k++) r = op(r, scratch[k]);
-    return r;
-}
+// 4-subsets of {0..9} packed (m0<<12|m1<<8|m2<<4|m3), in colex order so that the subsets of {0..k-1} are the first
+// C(k,4) entries; filled by the host (api.cu)
+__constant__ uint16_t c_combos[210];
 
-struct QfShared {
-    unsigned long long bufA[QF_NSM];
-    unsigned long long bufB[QF_NSM];
-    double bufD[QF_NSM];
+struct QfScratch {       // per group (warp or CTA)
     double red_d[8];
     int red_i[8];
     float red_f[8];
-    unsigned long long red_u[8];
-    int work;
+    uint32_t w_cnt[8];
     int nmax;
     int kept[16];
     int nkept;
+    int taken[16];
     double thresh;
-    int has_thresh;
-    // pair tables for the 4-corner search
-    double p_err[10][10], p_mse[10][10], p_nx[10][10], p_ny[10][10];
-    uint32_t w_cnt[8];
-    int ok;
+    double stage[2][32][6];   // staging tiles of the sequential prefix pass
 };
 
-__global__ void __launch_bounds__(QF_THREADS)
-fit_quads_kernel(const uint8_t *__restrict__ in, const unsigned long long *__restrict__ pts, const uint32_t *__restrict__ scankey,
-                 const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork,
-                 uint32_t *__restrict__ work_counter, double *__restrict__ lfps_all, unsigned long long *__restrict__ scratch,
-                 QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
-                 uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm)
+// group abstraction: NT = 32 (one warp) or 256 (one CTA) working on one cluster
+template <int NT>
+struct Grp {
+    static __device__ __forceinline__ int tid() { return NT == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+    static __device__ __forceinline__ void sync() { if (NT == 32) __syncwarp(); else __syncthreads(); }
+    template <typename T, typename Op>
+    static __device__ __forceinline__ T reduce(T v, Op op, T *scratch)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (NT == 32) return v;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        __syncthreads();
+        if (lane == 0) scratch[wid] = v;
+        __syncthreads();
+        T r = scratch[0];
+#pragma unroll
+        for (int k = 1; k < NT / 32; k++) r = op(r, scratch[k]);
+        return r;
+    }
+};
+
+// Processes one cluster.  A and B are 8-byte-per-point work arrays (shared or global), lfps the 48-byte-per-point
+// prefix-moment array (global).  Every thread of the group must call it; control flow is group-uniform.
+template <int NT>
+__device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t *__restrict__ K, int n, unsigned long long *A,
+                                 unsigned long long *B, double *__restrict__ lfps, QfScratch &S, const ClusterRec &rec, int b,
+                                 QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
+                                 uint32_t *__restrict__ errflag, const Geom &g, const Caps &caps, const DetParams &prm)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    QfShared &S = *reinterpret_cast<QfShared *>(smem_raw);
-    const int tid = threadIdx.x;
-    const uint32_t total = *nwork;
+    typedef Grp<NT> G;
+    const int tid = G::tid();
+    const int lane = threadIdx.x & 31;
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) S.work = (int)atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const uint32_t wi = (uint32_t)S.work;
-        if (wi >= total) return;
-        const uint32_t item = worklist[wi];
-        const int b = item / caps.clusters_per_frame;
-        const ClusterRec rec = clusters[item];
-        const int n = (int)rec.count;
-        if (n < 24) continue;   // inert record (capacity overflow was flagged)
-        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
-        const unsigned long long *P = pts + pbase;
-        const uint32_t *K = scankey + pbase;
-        double *lfps = lfps_all + pbase * 6;
-        unsigned long long *A, *B;
-        double *D;
-        if (n <= QF_NSM) { A = S.bufA; B = S.bufB; D = S.bufD; }
-        else {
-            A = scratch + pbase * 3; B = A + n; D = reinterpret_cast<double *>(B + n);
-        }
-        const uint8_t *img = in + (size_t)b * g.frame_stride;
+    // ---- scan keys -> work array; bounding box ----------------------------------------------------------------
+    uint32_t *k0 = reinterpret_cast<uint32_t *>(A), *k1 = k0 + n;      // two u32 halves of A for the scan-order sort
+    int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
+    for (int i = tid; i < n; i += NT) {
+        const uint32_t key = K[i];
+        k0[i] = key;
+        int px, py, gx, gy;
+        decode_point(key, g.w, px, py, gx, gy);
+        xmin = min(xmin, px); xmax = max(xmax, px); ymin = min(ymin, py); ymax = max(ymax, py);
+    }
+    xmin = G::reduce(xmin, [](int a, int c) { return min(a, c); }, S.red_i);
+    xmax = G::reduce(xmax, [](int a, int c) { return max(a, c); }, S.red_i);
+    ymin = G::reduce(ymin, [](int a, int c) { return min(a, c); }, S.red_i);
+    ymax = G::reduce(ymax, [](int a, int c) { return max(a, c); }, S.red_i);
+    if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) return;
+    const float cx = (float)((xmin + xmax) * 0.5 + 0.05118);
+    const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
+    G::sync();
 
-        // ---- bounding box -----------------------------------------------------------------------------
-        int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
-        for (int i = tid; i < n; i += QF_THREADS) {
-            const unsigned long long p = P[i];
-            const int x = (int)(p & 0xffff), y = (int)((p >> 16) & 0xffff);
-            xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
-        }
-        xmin = block_reduce(xmin, [](int a, int c) { return min(a, c); }, S.red_i);
-        xmax = block_reduce(xmax, [](int a, int c) { return max(a, c); }, S.red_i);
-        ymin = block_reduce(ymin, [](int a, int c) { return min(a, c); }, S.red_i);
-        ymax = block_reduce(ymax, [](int a, int c) { return max(a, c); }, S.red_i);
-        if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) continue;
-        const float cx = (float)((xmin + xmax) * 0.5 + 0.05118);
-        const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
-
-        // ---- restore scan order: merge sort on (scankey, index), keys are unique ------------------------
-        for (int i = tid; i < n; i += QF_THREADS) A[i] = ((unsigned long long)K[i] << 32) | (uint32_t)i;
-        __syncthreads();
-        unsigned long long *src = A, *dst = B;
+    // ---- restore scan order: rank-merge sort of the (unique) scan keys -----------------------------------------
+    {
+        uint32_t *src = k0, *dst = k1;
         for (int run = 1; run < n; run <<= 1) {
-            for (int i = tid; i < n; i += QF_THREADS) {
+            for (int i = tid; i < n; i += NT) {
                 const int pair0 = (i / (2 * run)) * (2 * run);
                 const int mid = min(pair0 + run, n), end = min(pair0 + 2 * run, n);
-                const unsigned long long v = src[i];
+                const uint32_t v = src[i];
                 int lo, hi;
                 if (i < mid) { lo = mid; hi = end; } else { lo = pair0; hi = mid; }
                 const int sbase = lo;
@@ -181,292 +184,412 @@ fit_quads_kernel(const uint8_t *__restrict__ in, const unsigned long long *__res
                 const int pos = (i < mid) ? (i + (lo - sbase)) : (pair0 + (i - mid) + (lo - sbase));
                 dst[pos] = v;
             }
-            __syncthreads();
-            unsigned long long *t = src; src = dst; dst = t;
+            G::sync();
+            uint32_t *t = src; src = dst; dst = t;
         }
-        // ---- slopes in scan order (upstream fit_quad step 1) --------------------------------------------
-        float dot = 0.f;
-        for (int j = tid; j < n; j += QF_THREADS) {
-            const uint32_t idx = (uint32_t)src[j];
-            const unsigned long long p = P[idx];
-            const int x = (int)(p & 0xffff), y = (int)((p >> 16) & 0xffff);
-            const int gx = (int)(int16_t)((p >> 32) & 0xffff), gy = (int)(int16_t)((p >> 48) & 0xffff);
-            float dx = (float)x - cx, dy = (float)y - cy;
-            dot += dx * (float)gx + dy * (float)gy;
-            float quadrant;
-            if (dy > 0) quadrant = dx > 0 ? 65536.f : 131072.f; else quadrant = dx > 0 ? 0.f : -65536.f;
-            if (dy < 0) { dy = -dy; dx = -dx; }
-            if (dx < 0) { const float t = dx; dx = dy; dy = -t; }
-            const float slope = quadrant + dy / dx;
-            dst[j] = ((unsigned long long)float_orderable(slope) << 32) | idx;
-        }
-        dot = block_reduce(dot, [](float a, float c) { return a + c; }, S.red_f);
-        const int reversed_border = dot < 0.f;
-        if (reversed_border) continue;              // tag36h11 has a normal border only
-        { unsigned long long *t = src; src = dst; dst = t; }
-        __syncthreads();
+        k0 = src;   // sorted keys
+    }
+    // ---- slopes in scan order (upstream fit_quad step 1) ---------------------------------------------------------
+    float dot = 0.f;
+    for (int j = tid; j < n; j += NT) {
+        const uint32_t key = k0[j];
+        int px, py, gx, gy;
+        decode_point(key, g.w, px, py, gx, gy);
+        float dx = (float)px - cx, dy = (float)py - cy;
+        dot += dx * (float)gx + dy * (float)gy;
+        float quadrant;
+        if (dy > 0) quadrant = dx > 0 ? 65536.f : 131072.f; else quadrant = dx > 0 ? 0.f : -65536.f;
+        if (dy < 0) { dy = -dy; dx = -dx; }
+        if (dx < 0) { const float t = dx; dx = dy; dy = -t; }
+        const float slope = quadrant + dy / dx;
+        B[j] = ((unsigned long long)float_orderable(slope) << 32) | key;
+    }
+    dot = G::reduce(dot, [](float a, float c) { return a + c; }, S.red_f);
+    const int reversed_border = dot < 0.f;
+    if (reversed_border) return;                   // tag36h11 has a normal border only
+    G::sync();
 
-        // ---- ptsort(): leaves (sorting networks), then merges bottom-up with "second half first on ties" --
-        int maxd = 0;
-        { int sz = n; while (sz > 5) { sz = sz - sz / 2; maxd++; } }
-        for (int i = tid; i < n; i += QF_THREADS) {
-            int lo = 0, hi = n;
-            while (hi - lo > 5) { const int mid = lo + (hi - lo) / 2; if (i < mid) hi = mid; else lo = mid; }
-            if (i != lo) continue;
-            const int sz = hi - lo;
-            unsigned long long *a = src + lo;
+    // ---- ptsort(): leaves (sorting networks), then merges bottom-up with "second half first on ties" -------------
+    unsigned long long *src = B, *dst = A;
+    int maxd = 0;
+    { int sz = n; while (sz > 5) { sz = sz - sz / 2; maxd++; } }
+    for (int i = tid; i < n; i += NT) {
+        int lo = 0, hi = n;
+        while (hi - lo > 5) { const int mid = lo + (hi - lo) / 2; if (i < mid) hi = mid; else lo = mid; }
+        if (i != lo) continue;
+        const int sz = hi - lo;
+        unsigned long long *a = src + lo;
 #define QF_SWAP(x, y) if (hi32(a[x]) > hi32(a[y])) { const unsigned long long t = a[x]; a[x] = a[y]; a[y] = t; }
-            if (sz == 2) { QF_SWAP(0, 1); }
-            else if (sz == 3) { QF_SWAP(0, 1); QF_SWAP(1, 2); QF_SWAP(0, 1); }
-            else if (sz == 4) { QF_SWAP(0, 1); QF_SWAP(2, 3); QF_SWAP(0, 2); QF_SWAP(1, 3); QF_SWAP(1, 2); }
-            else if (sz == 5) { QF_SWAP(0, 1); QF_SWAP(3, 4); QF_SWAP(2, 4); QF_SWAP(2, 3); QF_SWAP(0, 3); QF_SWAP(0, 2); QF_SWAP(1, 4); QF_SWAP(1, 3); QF_SWAP(1, 2); }
+        if (sz == 2) { QF_SWAP(0, 1); }
+        else if (sz == 3) { QF_SWAP(0, 1); QF_SWAP(1, 2); QF_SWAP(0, 1); }
+        else if (sz == 4) { QF_SWAP(0, 1); QF_SWAP(2, 3); QF_SWAP(0, 2); QF_SWAP(1, 3); QF_SWAP(1, 2); }
+        else if (sz == 5) { QF_SWAP(0, 1); QF_SWAP(3, 4); QF_SWAP(2, 4); QF_SWAP(2, 3); QF_SWAP(0, 3); QF_SWAP(0, 2); QF_SWAP(1, 4); QF_SWAP(1, 3); QF_SWAP(1, 2); }
 #undef QF_SWAP
+    }
+    G::sync();
+    for (int d = maxd - 1; d >= 0; d--) {
+        for (int i = tid; i < n; i += NT) {
+            int lo, hi;
+            const unsigned long long v = src[i];
+            if (!ptsort_node(n, i, d, lo, hi) || hi - lo <= 5) { dst[i] = v; continue; }
+            const int mid = lo + (hi - lo) / 2;
+            const uint32_t key = hi32(v);
+            int pos;
+            if (i < mid) {   // from the first half: all second-half keys <= key go before it
+                int l = mid, h = hi;
+                while (l < h) { const int m = (l + h) >> 1; if (hi32(src[m]) <= key) l = m + 1; else h = m; }
+                pos = i + (l - mid);
+            } else {         // from the second half: only strictly smaller first-half keys go before it
+                int l = lo, h = mid;
+                while (l < h) { const int m = (l + h) >> 1; if (hi32(src[m]) < key) l = m + 1; else h = m; }
+                pos = lo + (i - mid) + (l - lo);
+            }
+            dst[pos] = v;
         }
-        __syncthreads();
-        for (int d = maxd - 1; d >= 0; d--) {
-            for (int i = tid; i < n; i += QF_THREADS) {
-                int lo, hi;
-                const unsigned long long v = src[i];
-                if (!ptsort_node(n, i, d, lo, hi) || hi - lo <= 5) { dst[i] = v; continue; }
-                const int mid = lo + (hi - lo) / 2;
-                const uint32_t key = hi32(v);
-                int pos;
-                if (i < mid) {   // from the first half: all second-half keys <= key go before it
-                    int l = mid, h = hi;
-                    while (l < h) { const int m = (l + h) >> 1; if (hi32(src[m]) <= key) l = m + 1; else h = m; }
-                    pos = i + (l - mid);
-                } else {         // from the second half: only strictly smaller first-half keys go before it
-                    int l = lo, h = mid;
-                    while (l < h) { const int m = (l + h) >> 1; if (hi32(src[m]) < key) l = m + 1; else h = m; }
-                    pos = lo + (i - mid) + (l - lo);
+        G::sync();
+        unsigned long long *t = src; src = dst; dst = t;
+    }
+    // src: sorted (slope key, scan key).  ---- compute_lfps -----------------------------------------------------------
+    // per-point weight (parallel), then the sequential prefix: each block of 32 points is expanded into its six
+    // terms by 32 lanes, staged in shared memory, and accumulated in order by lanes 0..5 of the first warp.
+    double *Wd = reinterpret_cast<double *>(dst);
+    for (int j = tid; j < n; j += NT) {
+        int px, py, gx, gy;
+        decode_point((uint32_t)src[j], g.w, px, py, gx, gy);
+        const double x = px * .5 + 0.5, y = py * .5 + 0.5;
+        const int ix = (int)x, iy = (int)y;
+        double W = 1;
+        if (ix > 0 && ix + 1 < g.w && iy > 0 && iy + 1 < g.h) {
+            const int grad_x = (int)img[(size_t)(iy * g.f) * g.stride + (ix + 1) * g.f] - (int)img[(size_t)(iy * g.f) * g.stride + (ix - 1) * g.f];
+            const int grad_y = (int)img[(size_t)((iy + 1) * g.f) * g.stride + ix * g.f] - (int)img[(size_t)((iy - 1) * g.f) * g.stride + ix * g.f];
+            W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
+        }
+        Wd[j] = W;
+    }
+    G::sync();
+    if (tid < 32) {
+        double acc = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            const int buf = (j0 >> 5) & 1;
+            if (j < n) {
+                int px, py, gx, gy;
+                decode_point((uint32_t)src[j], g.w, px, py, gx, gy);
+                const double W = Wd[j];
+                const double fx = px * .5 + 0.5, fy = py * .5 + 0.5;
+                double *t = S.stage[buf][lane];
+                t[0] = W * fx; t[1] = W * fy; t[2] = W * fx * fx; t[3] = W * fx * fy; t[4] = W * fy * fy; t[5] = W;
+            }
+            __syncwarp();
+            if (lane < 6) {
+                const int cnt = min(32, n - j0);
+                double *o = lfps + (size_t)j0 * 6 + lane;
+#pragma unroll 8
+                for (int k = 0; k < cnt; k++) {
+                    acc += S.stage[buf][k][lane];
+                    o[(size_t)k * 6] = acc;
                 }
-                dst[pos] = v;
             }
-            __syncthreads();
-            unsigned long long *t = src; src = dst; dst = t;
+            // tile `buf` is rewritten two rounds later, after another __syncwarp(): lanes 0..5 are done with it by then
         }
-        // src: sorted (key, idx).  ---- compute_lfps: per-point weight, then sequential prefix moments ------
-        uint32_t *XY = reinterpret_cast<uint32_t *>(dst);
-        for (int j = tid; j < n; j += QF_THREADS) {
-            const uint32_t idx = (uint32_t)src[j];
-            const unsigned long long p = P[idx];
-            const int px = (int)(p & 0xffff), py = (int)((p >> 16) & 0xffff);
-            const double x = px * .5 + 0.5, y = py * .5 + 0.5;
-            const int ix = (int)x, iy = (int)y;
-            double W = 1;
-            if (ix > 0 && ix + 1 < g.w && iy > 0 && iy + 1 < g.h) {
-                const int grad_x = (int)img[(size_t)(iy * g.f) * g.stride + (ix + 1) * g.f] - (int)img[(size_t)(iy * g.f) * g.stride + (ix - 1) * g.f];
-                const int grad_y = (int)img[(size_t)((iy + 1) * g.f) * g.stride + ix * g.f] - (int)img[(size_t)((iy - 1) * g.f) * g.stride + ix * g.f];
-                W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
-            }
-            D[j] = W;
-            XY[j] = (uint32_t)px | ((uint32_t)py << 16);
-        }
-        __syncthreads();
-        if (tid < 6) {
-            double acc = 0;
-            for (int j = 0; j < n; j++) {
-                const double W = D[j];
-                const uint32_t xy = XY[j];
-                const double fx = (double)(xy & 0xffff) * .5 + 0.5, fy = (double)(xy >> 16) * .5 + 0.5;
-                double term;
-                switch (tid) {
-                    case 0: term = W * fx; break;
-                    case 1: term = W * fy; break;
-                    case 2: term = W * fx * fx; break;
-                    case 3: term = W * fx * fy; break;
-                    case 4: term = W * fy * fy; break;
-                    default: term = W; break;
-                }
-                acc += term;
-                lfps[(size_t)j * 6 + tid] = acc;
-            }
-        }
-        __syncthreads();
+    }
+    G::sync();
 
-        // ---- quad_segment_maxima ---------------------------------------------------------------------------
-        const int ksz = min(20, n / 12);
-        if (ksz < 2) continue;
-        double *errs = reinterpret_cast<double *>(src);   // sorted keys are no longer needed
-        double *ysm = reinterpret_cast<double *>(dst);
-        for (int i = tid; i < n; i += QF_THREADS) {
-            LineFit lf;
-            fit_line(lfps, n, (i + n - ksz) % n, (i + ksz) % n, false, lf);
-            errs[i] = lf.err;
-        }
-        __syncthreads();
-        for (int iy = tid; iy < n; iy += QF_THREADS) {
-            double acc = 0;
+    // ---- quad_segment_maxima -------------------------------------------------------------------------------------
+    const int ksz = min(20, n / 12);
+    if (ksz < 2) return;
+    double *errs = reinterpret_cast<double *>(src);   // sorted keys are no longer needed
+    double *ysm = reinterpret_cast<double *>(dst);    // neither are the weights
+    for (int i = tid; i < n; i += NT) {
+        LineFit lf;
+        int i0 = i - ksz; if (i0 < 0) i0 += n;
+        int i1 = i + ksz; if (i1 >= n) i1 -= n;
+        fit_line(lfps, n, i0, i1, false, lf);
+        errs[i] = lf.err;
+    }
+    G::sync();
+    for (int iy = tid; iy < n; iy += NT) {
+        double acc = 0;
 #pragma unroll
-            for (int i = 0; i < 7; i++) acc += errs[(iy + i - 3 + n) % n] * prm.smooth_f[i];
-            ysm[iy] = acc;
+        for (int i = 0; i < 7; i++) {
+            int q = iy + i - 3;
+            if (q < 0) q += n; else if (q >= n) q -= n;
+            acc += errs[q] * prm.smooth_f[i];
         }
-        __syncthreads();
-        // local maxima, collected in index order into (int) maxima[] / D-backed maxima_errs
-        int *maxima = reinterpret_cast<int *>(errs);      // errs is dead after smoothing
-        double *maxima_errs = D;
-        if (tid == 0) S.nmax = 0;
-        __syncthreads();
-        for (int i0 = 0; i0 < n; i0 += QF_THREADS) {
-            const int i = i0 + tid;
-            bool is_max = false;
-            double e = 0;
-            if (i < n) { e = ysm[i]; is_max = e > ysm[(i + 1) % n] && e > ysm[(i + n - 1) % n]; }
-            const uint32_t bal = __ballot_sync(0xffffffffu, is_max);
-            const int lane = tid & 31, wid = tid >> 5;
+        ysm[iy] = acc;
+    }
+    G::sync();
+    // local maxima, collected in index order (two maxima are never adjacent, so there are at most n/2)
+    int *maxima = reinterpret_cast<int *>(errs);
+    double *maxima_errs = reinterpret_cast<double *>(errs) + (n + 3) / 4;
+    if (tid == 0) S.nmax = 0;
+    G::sync();
+    for (int i0 = 0; i0 < n; i0 += NT) {
+        const int i = i0 + tid;
+        bool is_max = false;
+        double e = 0;
+        if (i < n) {
+            e = ysm[i];
+            const int nx = i + 1 == n ? 0 : i + 1, pv = i == 0 ? n - 1 : i - 1;
+            is_max = e > ysm[nx] && e > ysm[pv];
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, is_max);
+        int base;
+        if (NT == 32) {
+            base = S.nmax;
+        } else {
+            const int wid = threadIdx.x >> 5;
             if (lane == 0) S.w_cnt[wid] = __popc(bal);
             __syncthreads();
-            int base = S.nmax;
+            base = S.nmax;
             for (int k = 0; k < wid; k++) base += S.w_cnt[k];
-            if (is_max) {
-                const int pos = base + __popc(bal & ((1u << lane) - 1));
-                maxima[pos] = i;
-                maxima_errs[pos] = e;
-            }
-            __syncthreads();
-            if (tid == 0) { int t = 0; for (int k = 0; k < QF_THREADS / 32; k++) t += S.w_cnt[k]; S.nmax += t; }
-            __syncthreads();
         }
-        const int nmaxima = S.nmax;
-        if (nmaxima < 4) continue;
-        // keep only the best max_nmaxima
-        if (tid == 0) { S.nkept = 0; S.has_thresh = 0; }
-        __syncthreads();
-        const int max_nmaxima = min(prm.max_nmaxima, 10);
-        if (nmaxima > max_nmaxima) {
-            // maxima_thresh = element [max_nmaxima] of the descending sort = value v with #(>v) <= max_nmaxima < #(>=v)
-            for (int m = tid; m < nmaxima; m += QF_THREADS) {
-                const double e = maxima_errs[m];
-                int gt = 0, ge = 0;
-                for (int k = 0; k < nmaxima; k++) { const double o = maxima_errs[k]; gt += o > e; ge += o >= e; }
-                if (gt <= max_nmaxima && ge > max_nmaxima) { S.thresh = e; S.has_thresh = 1; }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int out = 0;
-                const double th = S.thresh;
-                for (int m = 0; m < nmaxima; m++) {
-                    if (maxima_errs[m] <= th) continue;
-                    if (out < 16) S.kept[out] = maxima[m];
-                    out++;
-                }
-                S.nkept = min(out, 16);
-            }
-        } else if (tid == 0) {
-            for (int m = 0; m < nmaxima; m++) S.kept[m] = maxima[m];
-            S.nkept = nmaxima;
+        if (is_max) {
+            const int pos = base + __popc(bal & ((1u << lane) - 1));
+            maxima[pos] = i;
+            maxima_errs[pos] = e;
         }
-        __syncthreads();
-        const int nk = S.nkept;
-        if (nk < 4) continue;   // (upstream's loops would simply find nothing)
-        // pair table: fit_line(kept[a], kept[b]) for a != b
-        for (int t = tid; t < nk * nk; t += QF_THREADS) {
-            const int a = t / nk, c = t % nk;
-            if (a == c) continue;
-            LineFit lf;
-            fit_line(lfps, n, S.kept[a], S.kept[c], true, lf);
-            S.p_err[a][c] = lf.err; S.p_mse[a][c] = lf.mse; S.p_nx[a][c] = lf.nx; S.p_ny[a][c] = lf.ny;
-        }
-        __syncthreads();
-        // 4-corner search: combination index in upstream's loop order; keep the first minimum
-        double best_err = __longlong_as_double(0x7ff0000000000000ll);
-        int best_combo = 1 << 30;
-        {
-            const double max_mse = (double)prm.max_line_fit_mse;
-            int ci = 0;
-            for (int m0 = 0; m0 < nk - 3; m0++)
-                for (int m1 = m0 + 1; m1 < nk - 2; m1++)
-                    for (int m2 = m1 + 1; m2 < nk - 1; m2++)
-                        for (int m3 = m2 + 1; m3 < nk; m3++, ci++) {
-                            if ((ci % QF_THREADS) != tid) continue;
-                            if (S.p_mse[m0][m1] > max_mse) continue;
-                            if (S.p_mse[m1][m2] > max_mse) continue;
-                            const double dt = S.p_nx[m0][m1] * S.p_nx[m1][m2] + S.p_ny[m0][m1] * S.p_ny[m1][m2];
-                            if (fabs(dt) > prm.cos_critical_rad) continue;
-                            if (S.p_mse[m2][m3] > max_mse) continue;
-                            if (S.p_mse[m3][m0] > max_mse) continue;
-                            const double err = S.p_err[m0][m1] + S.p_err[m1][m2] + S.p_err[m2][m3] + S.p_err[m3][m0];
-                            if (err < best_err) { best_err = err; best_combo = (m0 << 12) | (m1 << 8) | (m2 << 4) | m3; }
-                        }
-        }
-        // (m0,m1,m2,m3) packed big-endian orders exactly like the loop nest, so min over (err, packed) = first minimum
-        {
-            // reduce on err first, then on combo among equal err
-            const double bmin = block_reduce(best_err, [](double a, double c) { return a < c ? a : c; }, S.red_d);
-            int cand = (best_err == bmin && best_combo != (1 << 30)) ? best_combo : (1 << 30);
-            cand = block_reduce(cand, [](int a, int c) { return min(a, c); }, S.red_i);
-            best_err = bmin; best_combo = cand;
-        }
-        if (best_combo == (1 << 30)) continue;
-        if (!(best_err / n < (double)prm.max_line_fit_mse)) continue;
-
-        // ---- corners, area and convexity tests (thread 0) --------------------------------------------------
+        G::sync();
         if (tid == 0) {
-            S.ok = 0;
-            const int mi[4] = {(best_combo >> 12) & 15, (best_combo >> 8) & 15, (best_combo >> 4) & 15, best_combo & 15};
-            int indices[4];
-            for (int i = 0; i < 4; i++) indices[i] = S.kept[mi[i]];
-            double lines[4][4];
-            bool good = true;
-            for (int i = 0; i < 4 && good; i++) {
-                LineFit lf;
-                fit_line(lfps, n, indices[i], indices[(i + 1) & 3], true, lf);
-                lines[i][0] = lf.Ex; lines[i][1] = lf.Ey; lines[i][2] = lf.nx; lines[i][3] = lf.ny;
-                if (lf.mse > (double)prm.max_line_fit_mse) good = false;
+            if (NT == 32) S.nmax += __popc(bal);
+            else { int t = 0; for (int k = 0; k < NT / 32; k++) t += S.w_cnt[k]; S.nmax += t; }
+        }
+        G::sync();
+    }
+    const int nmaxima = S.nmax;
+    if (nmaxima < 4) return;
+    // keep only the best max_nmaxima: maxima_thresh = element [max_nmaxima] of the descending sort, found by
+    // max_nmaxima + 1 rounds of "largest not yet taken" (ties -> lowest position, one element per round)
+    const int max_nmaxima = min(prm.max_nmaxima, 10);
+    if (nmaxima > max_nmaxima) {
+        for (int r = 0; r <= max_nmaxima; r++) {
+            double best = 0;
+            int bpos = 1 << 30;       // 1<<30 = nothing found yet
+            for (int m = tid; m < nmaxima; m += NT) {
+                bool tk = false;
+                for (int q = 0; q < r; q++) tk |= (S.taken[q] == m);
+                if (tk) continue;
+                const double e = maxima_errs[m];
+                if (bpos == (1 << 30) || e > best) { best = e; bpos = m; }
             }
-            float qp[4][2];
-            for (int i = 0; i < 4 && good; i++) {
-                const double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
-                const double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
-                const double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
-                const double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
-                const double det = A00 * A11 - A10 * A01;
-                const double W00 = A11 / det, W01 = -A01 / det;
-                if (fabs(det) < 0.001) { good = false; break; }
-                const double L0 = W00 * B0 + W01 * B1;
-                qp[i][0] = (float)(lines[i][0] + L0 * A00);
-                qp[i][1] = (float)(lines[i][1] + L0 * A10);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+                if (op != (1 << 30) && (bpos == (1 << 30) || ob > best || (ob == best && op < bpos))) { best = ob; bpos = op; }
             }
-            if (good) {
-                double area = 0, length[3], p;
-                for (int i = 0; i < 3; i++) {
-                    const int a = i, c = (i + 1) % 3;
-                    const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
-                    length[i] = sqrt(ddx * ddx + ddy * ddy);
-                }
-                p = (length[0] + length[1] + length[2]) / 2;
-                area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
-                const int idxs[4] = {2, 3, 0, 2};
-                for (int i = 0; i < 3; i++) {
-                    const int a = idxs[i], c = idxs[i + 1];
-                    const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
-                    length[i] = sqrt(ddx * ddx + ddy * ddy);
-                }
-                p = (length[0] + length[1] + length[2]) / 2;
-                area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
-                if (area < 0.95 * prm.min_tag_width * prm.min_tag_width) good = false;
-            }
-            if (good) {
-                for (int i = 0; i < 4; i++) {
-                    const int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
-                    const double dx1 = (double)qp[i1][0] - (double)qp[i0][0], dy1 = (double)qp[i1][1] - (double)qp[i0][1];
-                    const double dx2 = (double)qp[i2][0] - (double)qp[i1][0], dy2 = (double)qp[i2][1] - (double)qp[i1][1];
-                    const double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
-                    if ((cos_dtheta > prm.cos_critical_rad || cos_dtheta < -prm.cos_critical_rad) || dx1 * dy2 < dy1 * dx2) { good = false; break; }
+            if (NT != 32) {
+                const int wid = threadIdx.x >> 5;
+                __syncthreads();
+                if (lane == 0) { S.red_d[wid] = best; S.red_i[wid] = bpos; }
+                __syncthreads();
+                best = S.red_d[0]; bpos = S.red_i[0];
+                for (int k = 1; k < NT / 32; k++) {
+                    const double ob = S.red_d[k]; const int op = S.red_i[k];
+                    if (op != (1 << 30) && (bpos == (1 << 30) || ob > best || (ob == best && op < bpos))) { best = ob; bpos = op; }
                 }
             }
-            if (good) {
-                const uint32_t qf = atomicAdd(&nquads[b], 1u);
-                if (qf >= caps.quads_per_frame) atomicOr(errflag, ERR_QUADS_FULL);
-                else {
-                    const uint32_t qi = atomicAdd(nquads_total, 1u);   // < batch * quads_per_frame by construction
-                    QuadRec q;
-                    for (int i = 0; i < 4; i++) { q.p[i][0] = qp[i][0]; q.p[i][1] = qp[i][1]; }
-                    q.reversed_border = reversed_border; q.npoints = n; q.key = rec.key; q.frame = b; q.pad = 0;
-                    quads[qi] = q;
-                }
+            G::sync();
+            if (tid == 0) { S.taken[r] = bpos; S.thresh = best; }
+            G::sync();
+        }
+        if (tid == 0) {
+            int out = 0;
+            const double th = S.thresh;
+            // the kept maxima are among the positions taken in the first max_nmaxima rounds; emit them in index order
+            int pos[10];
+            for (int q = 0; q < max_nmaxima; q++) pos[q] = S.taken[q];
+            for (int a = 1; a < max_nmaxima; a++) { const int t = pos[a]; int c = a; while (c > 0 && pos[c - 1] > t) { pos[c] = pos[c - 1]; c--; } pos[c] = t; }
+            for (int q = 0; q < max_nmaxima; q++) {
+                if (maxima_errs[pos[q]] <= th) continue;
+                S.kept[out++] = maxima[pos[q]];
+            }
+            S.nkept = out;
+        }
+    } else if (tid == 0) {
+        for (int m = 0; m < nmaxima; m++) S.kept[m] = maxima[m];
+        S.nkept = nmaxima;
+    }
+    G::sync();
+    const int nk = S.nkept;
+    if (nk < 4) return;   // (upstream's loops would simply find nothing)
+    // pair table: fit_line(kept[a], kept[c]) for a != c; lives in the (now dead) second work array, whose capacity is
+    // at least 24 points x 8 B x ... = QS_MAXN x 8 B = 4 KB in tier S and larger elsewhere (3200 B needed)
+    double (*p_err)[10] = reinterpret_cast<double (*)[10]>(dst);
+    double (*p_mse)[10] = p_err + 10, (*p_nx)[10] = p_err + 20, (*p_ny)[10] = p_err + 30;
+    for (int t = tid; t < nk * nk; t += NT) {
+        const int a = t / nk, c = t % nk;
+        if (a == c) continue;
+        LineFit lf;
+        fit_line(lfps, n, S.kept[a], S.kept[c], true, lf);
+        p_err[a][c] = lf.err; p_mse[a][c] = lf.mse; p_nx[a][c] = lf.nx; p_ny[a][c] = lf.ny;
+    }
+    G::sync();
+    // 4-corner search; (m0,m1,m2,m3) packed big-endian orders like upstream's loop nest, so the minimum over
+    // (err, packed) is upstream's "first minimum"
+    double best_err = __longlong_as_double(0x7ff0000000000000ll);
+    int best_combo = 1 << 30;
+    {
+        const double max_mse = (double)prm.max_line_fit_mse;
+        const int ncomb = nk * (nk - 1) * (nk - 2) * (nk - 3) / 24;
+        for (int ci = tid; ci < ncomb; ci += NT) {
+            const int pk = c_combos[ci];
+            const int m0 = pk >> 12, m1 = (pk >> 8) & 15, m2 = (pk >> 4) & 15, m3 = pk & 15;
+            if (p_mse[m0][m1] > max_mse) continue;
+            if (p_mse[m1][m2] > max_mse) continue;
+            const double dt = p_nx[m0][m1] * p_nx[m1][m2] + p_ny[m0][m1] * p_ny[m1][m2];
+            if (fabs(dt) > prm.cos_critical_rad) continue;
+            if (p_mse[m2][m3] > max_mse) continue;
+            if (p_mse[m3][m0] > max_mse) continue;
+            const double err = p_err[m0][m1] + p_err[m1][m2] + p_err[m2][m3] + p_err[m3][m0];
+            if (err < best_err || (err == best_err && pk < best_combo)) { best_err = err; best_combo = pk; }
+        }
+    }
+    {
+        const double bmin = G::reduce(best_err, [](double a, double c) { return a < c ? a : c; }, S.red_d);
+        int cand = (best_err == bmin && best_combo != (1 << 30)) ? best_combo : (1 << 30);
+        cand = G::reduce(cand, [](int a, int c) { return min(a, c); }, S.red_i);
+        best_err = bmin; best_combo = cand;
+    }
+    if (best_combo == (1 << 30)) return;
+    if (!(best_err / n < (double)prm.max_line_fit_mse)) return;
+
+    // ---- corners, area and convexity tests (one thread) -------------------------------------------------------------
+    if (tid == 0) {
+        const int mi[4] = {(best_combo >> 12) & 15, (best_combo >> 8) & 15, (best_combo >> 4) & 15, best_combo & 15};
+        int indices[4];
+        for (int i = 0; i < 4; i++) indices[i] = S.kept[mi[i]];
+        double lines[4][4];
+        bool good = true;
+        for (int i = 0; i < 4 && good; i++) {
+            LineFit lf;
+            fit_line(lfps, n, indices[i], indices[(i + 1) & 3], true, lf);
+            lines[i][0] = lf.Ex; lines[i][1] = lf.Ey; lines[i][2] = lf.nx; lines[i][3] = lf.ny;
+            if (lf.mse > (double)prm.max_line_fit_mse) good = false;
+        }
+        float qp[4][2];
+        for (int i = 0; i < 4 && good; i++) {
+            const double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
+            const double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
+            const double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
+            const double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
+            const double det = A00 * A11 - A10 * A01;
+            const double W00 = A11 / det, W01 = -A01 / det;
+            if (fabs(det) < 0.001) { good = false; break; }
+            const double L0 = W00 * B0 + W01 * B1;
+            qp[i][0] = (float)(lines[i][0] + L0 * A00);
+            qp[i][1] = (float)(lines[i][1] + L0 * A10);
+        }
+        if (good) {
+            double area = 0, length[3], p;
+            for (int i = 0; i < 3; i++) {
+                const int a = i, c = (i + 1) % 3;
+                const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
+                length[i] = sqrt(ddx * ddx + ddy * ddy);
+            }
+            p = (length[0] + length[1] + length[2]) / 2;
+            area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
+            const int idxs[4] = {2, 3, 0, 2};
+            for (int i = 0; i < 3; i++) {
+                const int a = idxs[i], c = idxs[i + 1];
+                const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
+                length[i] = sqrt(ddx * ddx + ddy * ddy);
+            }
+            p = (length[0] + length[1] + length[2]) / 2;
+            area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
+            if (area < 0.95 * prm.min_tag_width * prm.min_tag_width) good = false;
+        }
+        if (good) {
+            for (int i = 0; i < 4; i++) {
+                const int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
+                const double dx1 = (double)qp[i1][0] - (double)qp[i0][0], dy1 = (double)qp[i1][1] - (double)qp[i0][1];
+                const double dx2 = (double)qp[i2][0] - (double)qp[i1][0], dy2 = (double)qp[i2][1] - (double)qp[i1][1];
+                const double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
+                if ((cos_dtheta > prm.cos_critical_rad || cos_dtheta < -prm.cos_critical_rad) || dx1 * dy2 < dy1 * dx2) { good = false; break; }
             }
         }
+        if (good) {
+            const uint32_t qf = atomicAdd(&nquads[b], 1u);
+            if (qf >= caps.quads_per_frame) atomicOr(errflag, ERR_QUADS_FULL);
+            else {
+                const uint32_t qi = atomicAdd(nquads_total, 1u);   // < batch * quads_per_frame by construction
+                QuadRec q;
+                for (int i = 0; i < 4; i++) { q.p[i][0] = qp[i][0]; q.p[i][1] = qp[i][1]; }
+                q.reversed_border = reversed_border; q.npoints = n; q.key = rec.key; q.frame = b; q.pad = 0;
+                quads[qi] = q;
+            }
+        }
+    }
+}
+
+struct QsShared {
+    unsigned long long A[QS_WARPS][QS_MAXN];
+    unsigned long long B[QS_WARPS][QS_MAXN];
+    QfScratch S[QS_WARPS];
+};
+
+// tier S: persistent warps, one cluster (<= QS_MAXN points) per warp at a time
+__global__ void __launch_bounds__(QS_WARPS * 32)
+fit_quads_small_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ scankey, const ClusterRec *__restrict__ clusters,
+                       const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
+                       double *__restrict__ lfps_all, QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads,
+                       uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QsShared &SH = *reinterpret_cast<QsShared *>(smem_raw);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t total = *nwork;
+    for (;;) {
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(work_counter, 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= total) return;
+        const uint32_t item = worklist[wi];
+        const int b = item / caps.clusters_per_frame;
+        const ClusterRec rec = clusters[item];
+        const int n = (int)rec.count;
+        if (n < 24 || n > QS_MAXN) continue;
+        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
+        fit_quad_cluster<32>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.A[wid], SH.B[wid], lfps_all + pbase * 6, SH.S[wid], rec, b,
+                             quads, nquads, nquads_total, errflag, g, caps, prm);
+        __syncwarp();
+    }
+}
+
+struct QlShared {
+    unsigned long long A[QL_MAXN];
+    unsigned long long B[QL_MAXN];
+    QfScratch S;
+    int work;
+};
+
+// tier L: persistent CTAs, one cluster (> QS_MAXN points) per CTA at a time
+__global__ void __launch_bounds__(QL_THREADS)
+fit_quads_large_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ scankey, const ClusterRec *__restrict__ clusters,
+                       const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
+                       double *__restrict__ lfps_all, unsigned long long *__restrict__ scratch, QuadRec *__restrict__ quads,
+                       uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps,
+                       DetParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    QlShared &SH = *reinterpret_cast<QlShared *>(smem_raw);
+    const uint32_t total = *nwork;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) SH.work = (int)atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t wi = (uint32_t)SH.work;
+        if (wi >= total) return;
+        const uint32_t item = worklist[wi];
+        const int b = item / caps.clusters_per_frame;
+        const ClusterRec rec = clusters[item];
+        const int n = (int)rec.count;
+        if (n <= QS_MAXN) continue;
+        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
+        unsigned long long *A = SH.A, *B = SH.B;
+        if (n > QL_MAXN) { A = scratch + pbase * 2; B = A + n; }
+        fit_quad_cluster<QL_THREADS>(in + (size_t)b * g.frame_stride, scankey + pbase, n, A, B, lfps_all + pbase * 6, SH.S, rec, b, quads, nquads,
+                                     nquads_total, errflag, g, caps, prm);
     }
 }
 

@@ -1,0 +1,99 @@
+"""Mirror of the Copper sink task `AprilTags` (/root/reference/crates/apriltags/src/lib.rs:166-379), row B0.
+
+`AprilTags.new(config, comm)` reads the same config keys (`family`, `bits_corrected`, `cam_id`, `robot_to_cam`, `calib`;
+lib.rs:227-233) and `process(now_us, frame_time_us, gray)` runs detect -> field lookup -> un-project -> one multi-tag
+SQPnP -> publish, with the reference's skip rules (tags missing from field.json, lib.rs:306-308; corners that fail to
+un-project, lib.rs:324-327) and the >5 ms empty heartbeat (lib.rs:365-376).  `comm` is any object with
+`gyro_angle() -> float | None` and `publish(cam_id, tag_count, ts_us, pose, uncertainty)` (whacknet::Comm, whacknet/src/lib.rs:152-178).
+The batched variant `process_batch` keeps detections on one device context and solves every frame's pose in one launch.
+"""
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import field
+from .capi import ISO_DTYPE
+from .detector import DetectorBuilder, FAMILY
+from .solver import SIGN_FLIP_CONST, SqPnP, euler_angles
+
+
+@dataclass
+class RobotPose:             # whacknet/src/lib.rs:17-26
+    x: float = 0.0
+    y: float = 0.0
+    rot: float = 0.0
+
+
+@dataclass
+class VisionUncertainty:     # whacknet/src/lib.rs (x, y, rot std-devs)
+    x: float = 0.0
+    y: float = 0.0
+    rot: float = 0.0
+
+
+def calib_params(calib_json: str):
+    m = json.loads(calib_json)["OpenCVModel5"]
+    return np.array([m[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3")], np.float64)
+
+
+class AprilTags:
+    def __init__(self, config: dict | None, comm, max_width=1600, max_height=1304, max_batch=1, device=0, field_path=None):
+        self.comm = comm
+        self.last_time = None
+        self.tags = field.load(field_path)
+        if config is not None:
+            family = config.get("family", FAMILY)
+            bits = int(config.get("bits_corrected", 3))
+            self.cam_id = int(config["cam_id"])
+            off = json.loads(config["robot_to_cam"])
+            self.robot_to_cam = SqPnP.create_solver_camera_transform(off["x"], off["y"], off["z"], off["roll"], off["pitch"], off["yaw"])
+            self.cam_params = calib_params(config["calib"])
+            self.yaw = off["yaw"]
+        else:                      # lib.rs:277-290
+            family, bits, self.cam_id = FAMILY, 1, 255
+            self.robot_to_cam = None
+            self.cam_params = np.zeros(9)
+            self.yaw = 0.0
+        self.detector = (DetectorBuilder.default().add_family_bits(family, bits).device(device)
+                         .capacity(max_width, max_height, max_batch, 64).build())
+        self.solver = SqPnP(ctx=self.detector.ctx)
+
+    @staticmethod
+    def new(config, comm, **kw):
+        return AprilTags(config, comm, **kw)
+
+    def _correspondences(self, dets):
+        world, cam = [], []
+        for d in dets:
+            tag = self.tags.get(int(d["id"]))
+            if tag is None:
+                continue
+            bearings, ok = self.solver.unproject(self.cam_params, d["p"])
+            if ok.all():
+                world.append(tag)
+                cam.append(bearings)
+        return world, cam
+
+    def process(self, now_us: int, frame_time_us: int, gray: np.ndarray):
+        out, counts = self.detector.detect_batch(np.ascontiguousarray(gray)[None])
+        dets = out[0, :counts[0]]
+        if len(dets) > 0:
+            world, cam = self._correspondences(dets)
+            gyro = self.comm.gyro_angle()
+            if gyro is not None and world:
+                r2c = self.robot_to_cam if self.robot_to_cam is not None else np.array(((0, 0, 0), (1, 0, 0, 0)), ISO_DTYPE)
+                res = self.solver.solve_robot_pose(np.array(world, ISO_DTYPE), np.concatenate(cam), r2c, gyro, SIGN_FLIP_CONST)
+                if res is not None:
+                    rot, pos, std = res
+                    pose = RobotPose(pos[0], pos[1], euler_angles(rot)[2])
+                    unc = VisionUncertainty(std[0], std[1], std[2])
+                    self.comm.publish(self.cam_id, min(len(dets), 255), now_us - frame_time_us, pose, unc)
+                    return pose, unc
+        now_ms = now_us // 1000
+        if self.last_time is None or (now_ms - self.last_time) > 5:
+            self.comm.publish(self.cam_id, 0, now_us - frame_time_us, RobotPose(), VisionUncertainty())
+            self.last_time = now_ms
+        return None

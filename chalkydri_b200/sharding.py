@@ -1,0 +1,63 @@
+"""Multi-GPU sharding of the frame batch: independent frames, contiguous chunks per rank, no collective on the
+data path.  The only exchange is the gather of the fixed-size detection records to rank 0 (`gather_detections`).
+
+One process per GPU; `torch.distributed` (NCCL on the GPU box, gloo in the CPU tests) is plumbing for the gather only.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous chunk [lo, hi) of rank `rank`: frames[g*B/N : (g+1)*B/N] with the remainder spread over the first ranks."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def camera_to_rank(camera: int, world: int) -> int:
+    """Multi-camera stream (BASELINE configs[3]): camera c -> GPU c mod N."""
+    return camera % world
+
+
+def gather_detections(local_out: np.ndarray, local_counts: np.ndarray, lo: int, n_total: int, dist=None, device=None):
+    """Gather every rank's [n_local, cap] detection records + counts into rank 0's [n_total, cap] array, ordered by frame index.
+
+    Returns (out, counts) on rank 0 and (None, None) elsewhere.  With dist=None (single process) it is the identity."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        out = local_out.copy()
+        out["frame"] += 0
+        return out, local_counts.copy()
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    cap = local_out.shape[1]
+    rec = local_out.dtype.itemsize
+    max_local = -(-n_total // world)
+    pad_out = np.zeros((max_local, cap), local_out.dtype)
+    pad_out[:len(local_out)] = local_out
+    pad_cnt = np.full(max_local, -1, np.int32)
+    pad_cnt[:len(local_counts)] = local_counts
+    dev = device if device is not None else "cpu"
+    t_out = torch.from_numpy(pad_out.view(np.uint8).reshape(max_local, cap * rec)).to(dev)
+    t_cnt = torch.from_numpy(pad_cnt).to(dev)
+    t_lo = torch.tensor([lo, len(local_out)], dtype=torch.int64, device=dev)
+    if rank == 0:
+        g_out = [torch.empty_like(t_out) for _ in range(world)]
+        g_cnt = [torch.empty_like(t_cnt) for _ in range(world)]
+        g_lo = [torch.empty_like(t_lo) for _ in range(world)]
+    else:
+        g_out = g_cnt = g_lo = None
+    dist.gather(t_out, g_out, dst=0)
+    dist.gather(t_cnt, g_cnt, dst=0)
+    dist.gather(t_lo, g_lo, dst=0)
+    if rank != 0:
+        return None, None
+    out = np.zeros((n_total, cap), local_out.dtype)
+    counts = np.zeros(n_total, np.int32)
+    for r in range(world):
+        l, n = (int(v) for v in g_lo[r].cpu())
+        o = g_out[r].cpu().numpy().reshape(max_local, cap * rec).view(local_out.dtype).reshape(max_local, cap)[:n].copy()
+        o["frame"] += l                   # frame index inside the whole job
+        out[l:l + n] = o
+        counts[l:l + n] = g_cnt[r].cpu().numpy()[:n]
+    return out, counts

@@ -1,0 +1,63 @@
+"""GPU parity tests of the CAT stages vs the oracle restatement of crates/chalkydri-apriltags (all bit-exact)."""
+import numpy as np
+import pytest
+
+from chalkydri_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rgb_frame(w, h, seed, tags=2):
+    gray, _ = synth.render_frame(w, h, tags, seed=seed, edge_px=(40, 90))
+    return synth.gray_to_rgb(gray, seed=seed)
+
+
+@pytest.mark.parametrize("w,h,seed", [(320, 240, 1), (703, 905, 2), (101, 67, 3)])
+def test_cat_stages(oracle, w, h, seed):
+    from chalkydri_b200.cat import CatDetector
+    rgb = rgb_frame(w, h, seed)
+    d = CatDetector(w, h, ())
+    d.calc_otsu(rgb)
+    ref = oracle.cat_calc_otsu(rgb)
+    assert (d.buf == ref).all(), "calc_otsu colour map differs"
+    d.detect_corners()
+    rxy, rn = oracle.cat_detect_corners(ref)
+    assert len(d.points) == rn and (d.points == rxy).all()
+    if rn > 3000:                       # keep the O(P^2) edge test bounded
+        d.points = d.points[:3000]; rxy = rxy[:3000]
+    d.check_edges()
+    rl, rln = oracle.cat_check_edges(ref, rxy)
+    assert len(d.lines) == rln and (d.lines == rl).all()
+    uf = d.connected_components()
+    lab, sz = oracle.cat_connected_components(ref)
+    assert (uf.parent == lab).all() and (uf.cluster_sizes == sz).all()
+    d.thresh(rgb)
+    assert (d.buf == oracle.cat_thresh(rgb)).all()
+    d.close()
+
+
+def test_process_frame_and_assert(oracle):
+    from chalkydri_b200.cat import CatDetector
+    rgb = rgb_frame(320, 240, 7)
+    d = CatDetector(320, 240, ())
+    d.process_frame(rgb.reshape(-1))
+    ref = oracle.cat_calc_otsu(rgb)
+    rxy, _ = oracle.cat_detect_corners(ref)
+    rl, _ = oracle.cat_check_edges(ref, rxy)
+    assert (d.points == rxy).all() and (d.lines == rl).all()
+    with pytest.raises(AssertionError):
+        d.process_frame(rgb.reshape(-1)[:-3])       # wrong length panics in the reference (lib.rs:267)
+    d.close()
+
+
+def test_grayscale_exhaustive_sample(oracle):
+    """utils.rs:43 on a dense RGB sample: the fused-multiply-add form is reproduced bit for bit."""
+    from chalkydri_b200.cat import CatDetector
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    d = CatDetector(64, 64, ())
+    d.thresh(rgb)
+    g = np.array([oracle.cat_grayscale(int(r), int(gg), int(b)) for r, gg, b in rgb.reshape(-1, 3)]).reshape(64, 64)
+    want = np.where(g < 60, 0, np.where(g > 160, 1, 2))
+    assert (d.buf == want).all()
+    d.close()

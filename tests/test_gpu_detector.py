@@ -1,0 +1,194 @@
+"""GPU parity tests of the detector: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): threshold bitmap, component partition, tag ids and hamming BIT-EXACT; corners within
+1e-3 px; decision margin within 1e-3 relative.  Full-size cases are checked through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+from chalkydri_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CORNER_TOL = 1e-3       # px (north_star)
+MARGIN_RTOL = 1e-3
+
+
+def make_detector(W, H, B=1, dets=128):
+    from chalkydri_b200.detector import DetectorBuilder
+    return DetectorBuilder.default().add_family_bits("tag36h11", 3).capacity(W, H, B, dets).build()
+
+
+def canon_quads(q):
+    out = []
+    for c in q:
+        c = np.asarray(c, np.float64).reshape(4, 2)
+        k = min(range(4), key=lambda i: (c[i, 0], c[i, 1]))
+        out.append(tuple(np.roll(c, -k, 0).reshape(-1)))
+    return sorted(out)
+
+
+def assert_same_detections(got, ref):
+    assert got["id"].tolist() == ref["id"].tolist()
+    assert got["hamming"].tolist() == ref["hamming"].tolist()
+    if len(got):
+        assert np.abs(got["p"] - ref["p"]).max() < CORNER_TOL
+        assert np.abs(got["c"] - ref["c"]).max() < CORNER_TOL
+        assert np.allclose(got["decision_margin"], ref["decision_margin"], rtol=MARGIN_RTOL, atol=1e-3)
+        assert np.allclose(got["H"], ref["H"], rtol=1e-4, atol=2e-3)
+
+
+CASES = [  # W, H, tags, seed, edge range
+    (1280, 720, 4, 1, (60, 150)),      # c1
+    (1456, 1088, 8, 2, (40, 200)),     # c2 frame
+    (1280, 800, 6, 3, (40, 160)),      # c4 frame
+    (642, 486, 3, 4, (40, 100)),       # decimates to 321x243: partial tiles, unaligned rows -> generic kernels
+    (1000, 750, 5, 5, (40, 120)),      # w = 500 (multiple of 4) but stride not a multiple of 16
+]
+
+
+@pytest.mark.parametrize("W,H,tags,seed,edge", CASES)
+def test_stages_bit_exact(oracle, W, H, tags, seed, edge):
+    frames, _ = synth.render_batch(W, H, 2, tags, seed=seed, edge_px=edge)
+    det = make_detector(W, H, 2)
+    thr = det.threshold(frames)
+    lab, sz = det.labels(frames)
+    q, qc, _ = det.quads(frames)
+    out, counts = det.detect_batch(frames)
+    for b in range(2):
+        ref, taps = oracle.detect(frames[b], taps=True)
+        assert (thr[b] == taps["thresh"]).all(), "threshold bitmap differs"
+        assert (lab[b] == taps["labels"]).all(), "component partition differs"
+        assert (sz[b] == taps["comp_size"]).all()
+        assert qc[b] == taps["nquads"]
+        gq, oq = canon_quads(q[b, :qc[b]]), canon_quads(taps["quads"]["p"])
+        assert np.abs(np.array(gq) - np.array(oq)).max() < 1e-4 if gq else True
+        assert_same_detections(out[b, :counts[b]], ref)
+    det.close()
+
+
+def test_c3_full_resolution_small_tags(oracle):
+    frame, truth = synth.render_frame(4608, 2592, 40, seed=4, edge_px=(40, 300), small_tags=10)
+    det = make_detector(4608, 2592, 1, 256)
+    out, counts = det.detect_batch(frame[None])
+    ref = oracle.detect(frame)
+    assert_same_detections(out[0, :counts[0]], ref)
+    assert counts[0] >= 28
+    det.close()
+
+
+def test_golden_fixture(oracle):
+    g = np.load(os.path.join(GOLD, "detector_c1.npz"))
+    det = make_detector(1280, 720, 1)
+    out, counts = det.detect_batch(g["frame"][None])
+    d = out[0, :counts[0]]
+    assert d["id"].tolist() == g["ids"].tolist() and d["hamming"].tolist() == g["hamming"].tolist()
+    assert np.abs(d["p"] - g["corners"]).max() < CORNER_TOL
+    thr = det.threshold(g["frame"][None])[0]
+    assert (np.packbits(thr == 255) == g["thresh_white_bits"]).all() and (np.packbits(thr == 0) == g["thresh_black_bits"]).all()
+    det.close()
+
+
+def test_edge_cases(oracle):
+    det = make_detector(640, 480, 3)
+    flat = np.full((480, 640), 128, np.uint8)
+    rng = np.random.default_rng(0)
+    noise = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    checker = ((np.add.outer(np.arange(480) // 16, np.arange(640) // 16) % 2) * 200 + 20).astype(np.uint8)
+    frames = np.stack([flat, noise, checker])
+    thr = det.threshold(frames)
+    lab, sz = det.labels(frames)
+    out, counts = det.detect_batch(frames)
+    for b in range(3):
+        ref, taps = oracle.detect(frames[b], taps=True)
+        assert (thr[b] == taps["thresh"]).all() and (lab[b] == taps["labels"]).all() and (sz[b] == taps["comp_size"]).all()
+        assert_same_detections(out[b, :counts[b]], ref)
+    assert counts[0] == 0 and (thr[0] == 127).all()
+    det.close()
+
+
+def test_batch_64_c2_matches_oracle(oracle):
+    frames, truths = synth.render_batch(1456, 1088, 64, 8, seed=11, unique=8, edge_px=(40, 200))
+    det = make_detector(1456, 1088, 64, 64)
+    out, counts = det.detect_batch(frames)
+    ref, rc = oracle.detect_batch(frames, cap=64, nthreads=os.cpu_count() or 1)
+    assert counts.tolist() == rc.tolist()
+    for b in range(64):
+        assert_same_detections(out[b, :counts[b]], ref[b, :rc[b]])
+    # every rendered tag of 40+ px edge is found
+    found = sum(int(np.isin(t["ids"], out[b, :counts[b]]["id"]).sum()) for b, t in enumerate(truths))
+    assert found >= 0.97 * sum(len(t["ids"]) for t in truths)
+    det.close()
+
+
+def test_full_size_properties_c2():
+    """256 x 1456x1088 (BASELINE configs[1]): chunking, determinism, frame-order independence."""
+    frames, truths = synth.render_batch(1456, 1088, 256, 8, seed=21, unique=4, edge_px=(40, 200))
+    det = make_detector(1456, 1088, 96, 64)          # max_batch 96 < 256 exercises the internal chunking
+    out, counts = det.detect_batch(frames)
+    out2, counts2 = det.detect_batch(frames)
+    assert counts.tolist() == counts2.tolist() and out.tobytes() == out2.tobytes(), "not deterministic"
+    perm = np.random.default_rng(0).permutation(256)
+    outp, countsp = det.detect_batch(np.ascontiguousarray(frames[perm]))
+    for i, b in enumerate(perm):
+        assert countsp[i] == counts[b]
+        a, c = outp[i, :countsp[i]].copy(), out[b, :counts[b]].copy()
+        a["frame"] = 0; c["frame"] = 0
+        assert a.tobytes() == c.tobytes(), "result depends on the position inside the batch"
+    assert (out["frame"][np.arange(256)[:, None].repeat(64, 1) < 0].size == 0)
+    for b in range(256):
+        assert (out[b, :counts[b]]["frame"] == b).all()
+        ids = out[b, :counts[b]]["id"]
+        assert (np.diff(ids) >= 0).all(), "detections must be sorted by id"
+        assert np.isin(truths[b]["ids"], ids).mean() >= 0.75
+    det.close()
+
+
+def test_rgb_and_yuyv_inputs(oracle):
+    gray, _ = synth.render_frame(1280, 720, 4, seed=8, edge_px=(60, 150))
+    det = make_detector(1280, 720, 2)
+    rgb = synth.gray_to_rgb(gray, seed=1)
+    g_ref = np.array([oracle.cat_grayscale(int(r), int(g), int(b)) for r, g, b in rgb.reshape(-1, 3)[:4096]], np.uint8)
+    out, counts = det.detect_rgb_batch(rgb[None])
+    # oracle on the oracle's own gray conversion of the same RGB frame
+    lut = {}
+    flat = rgb.reshape(-1, 3)
+    keys = flat[:, 0].astype(np.uint32) << 16 | flat[:, 1].astype(np.uint32) << 8 | flat[:, 2]
+    uk, inv = np.unique(keys, return_inverse=True)
+    gv = np.array([oracle.cat_grayscale(int(k >> 16), int((k >> 8) & 255), int(k & 255)) for k in uk], np.uint8)
+    gray2 = gv[inv].reshape(gray.shape)
+    assert (gray2.reshape(-1)[:4096] == g_ref).all()
+    assert_same_detections(out[0, :counts[0]], oracle.detect(gray2))
+    yuyv = np.empty((720, 1280 * 2), np.uint8)
+    yuyv[:, 0::2] = gray
+    yuyv[:, 1::2] = 128
+    out, counts = det.detect_yuyv_batch(yuyv[None])
+    assert_same_detections(out[0, :counts[0]], oracle.detect(gray))
+    det.close()
+
+
+def test_reference_call_shape(oracle):
+    """The reference's own call: one frame in, Vec<Detection> out (crates/apriltags/src/lib.rs:301-314)."""
+    from chalkydri_b200.detector import Image
+    gray, truth = synth.render_frame(1280, 720, 4, seed=9, edge_px=(60, 150))
+    det = make_detector(1280, 720, 1)
+    dets = det.detect(Image(gray))
+    assert sorted(d.id() for d in dets) == sorted(truth["ids"].tolist())
+    for d in dets:
+        k = truth["ids"].tolist().index(d.id())
+        assert np.abs(np.array(d.corners()) - truth["corners"][k]).max() < 0.5
+        assert d.hamming() == 0 and d.decision_margin() > 20 and d.homography().shape == (3, 3)
+    det.close()
+
+
+def test_error_behaviour():
+    from chalkydri_b200.capi import ChalkydriError
+    det = make_detector(640, 480, 1)
+    with pytest.raises(ChalkydriError):
+        det.detect_batch(np.zeros((1, 600, 800), np.uint8))          # larger than the context
+    with pytest.raises(ChalkydriError):
+        det.set_params(quad_sigma=0.8)                                 # not implemented: loud, not silent
+    with pytest.raises(ChalkydriError):
+        det._check(det._L.cb_set_family_tag36h11(det.ctx, 4))
+    det.close()
