@@ -335,7 +335,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     if (stage >= ST_LABELS) {
         // ---- A3 connected components ----
         dim3 grid((g.w + CCL_TW - 1) / CCL_TW, (g.h + CCL_TH - 1) / CCL_TH, B);
-        ccl_local_kernel<0><<<grid, CCL_THREADS, 0, st>>>(ctx->d_thresh, ctx->d_labels, g);
+        ccl_local_kernel<0><<<grid, CCL_THREADS, 0, st>>>(ctx->d_thresh, ctx->d_labels, ctx->d_sizes, g);
         launches++;
         const int nrows = (g.h - 1) / CCL_TH, ncols = (g.w - 1) / CCL_TW + 1;   // borders: rows k*TH (k>=1); columns k*TW and k*TW-1
         if (nrows > 0) {
@@ -349,7 +349,6 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             launches++;
         }
         const uint32_t total = (uint32_t)B * g.npix;
-        CK(cudaMemsetAsync(ctx->d_sizes, 0, (size_t)total * sizeof(uint32_t), st));
         ccl_flatten_kernel<<<(total + 255) / 256, 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, total);
         launches++;
     }
@@ -364,7 +363,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         if (g.h > 2 && g.w > 2) {
             dim3 gc((g.w + 255) / 256, g.h - 2, B);
             cluster_pass_kernel<false><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
-            cluster_select_kernel<<<B, 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, d_misc + 1, d_wl_large, d_misc + 5,
+            cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, d_misc + 1, d_wl_large, d_misc + 5,
                                                      (uint32_t)QS_MAXN, d_misc, g, caps, prm.min_cluster_pixels);
             cluster_pass_kernel<true><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
             launches += 3;

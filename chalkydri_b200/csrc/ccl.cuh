@@ -75,41 +75,76 @@ __device__ __forceinline__ void uf_union(uint32_t *L, uint32_t a, uint32_t b)
     }
 }
 
-// pass 1: tile-local union-find in shared memory, then write global labels (index of the local root)
+// pass 1: tile-local union-find in shared memory, then write global labels (index of the local root) and the local
+// component sizes.  Horizontal runs are labelled without atomics (ballot of run starts inside each 32-pixel row
+// segment); vertical links that are implied by the neighbouring column of the same two runs are skipped, so the
+// number of smem atomics is about one per run overlap instead of one per pixel.
 template <int MODE>
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labels, Geom g)
+ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, Geom g)
 {
     __shared__ uint32_t L[CCL_TW * CCL_TH];
+    __shared__ uint32_t Cnt[CCL_TW * CCL_TH];
+    __shared__ uint8_t Ms[CCL_TW * CCL_TH];
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * CCL_TW, y0 = blockIdx.y * CCL_TH;
     const uint8_t *t = thresh + (size_t)b * g.h * g.tp;
-    for (int i = threadIdx.x; i < CCL_TW * CCL_TH; i += CCL_THREADS) L[i] = i;
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    constexpr int PER = CCL_TW * CCL_TH / CCL_THREADS;
+    uint32_t masks[PER];
 #pragma unroll
-    for (int k = 0; k < CCL_TW * CCL_TH / CCL_THREADS; k++) {
+    for (int k = 0; k < PER; k++) {
         const int i = threadIdx.x + k * CCL_THREADS;
         const int lx = i % CCL_TW, ly = i / CCL_TW;
         const int x = x0 + lx, y = y0 + ly;
         uint32_t m = 0;
         if (x < g.w && y < g.h) m = link_mask<MODE>(t, g.tp, g.w, x, y);
-        if ((m & LINK_LEFT) && lx > 0) uf_union(L, i, i - 1);
-        if ((m & LINK_UP) && ly > 0) uf_union(L, i, i - CCL_TW);
+        masks[k] = m;
+        const uint32_t starts = __ballot_sync(0xffffffffu, !(m & LINK_LEFT) || lane == 0);
+        const int start_lane = 31 - __clz(starts & ((2u << lane) - 1u));
+        L[i] = (uint32_t)(i - lane + start_lane);
+        Ms[i] = (uint8_t)m;
+        Cnt[i] = 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int i = threadIdx.x + k * CCL_THREADS;
+        const int lx = i % CCL_TW, ly = i / CCL_TW;
+        const uint32_t m = masks[k];
+        if (lane == 0 && (m & LINK_LEFT) && lx > 0) uf_union(L, i, i - 1);      // run continues across the 32-pixel segment
+        if ((m & LINK_UP) && ly > 0) {
+            const bool implied = (m & LINK_LEFT) && lx > 0 && (Ms[i - 1] & LINK_UP) && (Ms[i - CCL_TW] & LINK_LEFT);
+            if (!implied) uf_union(L, i, i - CCL_TW);
+        }
         if ((m & LINK_UPLEFT) && ly > 0 && lx > 0) uf_union(L, i, i - CCL_TW - 1);
         if ((m & LINK_UPRIGHT) && ly > 0 && lx < CCL_TW - 1) uf_union(L, i, i - CCL_TW + 1);
     }
     __syncthreads();
-    uint32_t *lab = labels + (size_t)b * g.npix;
+    uint32_t roots[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int i = threadIdx.x + k * CCL_THREADS;
+        const int lx = i % CCL_TW, ly = i / CCL_TW;
+        const bool in = (x0 + lx < g.w) && (y0 + ly < g.h);
+        const uint32_t r = in ? uf_find(L, (uint32_t)i) : 0xffffffffu;
+        roots[k] = r;
+        const uint32_t peers = __match_any_sync(0xffffffffu, r);
+        if (in && lane == __ffs(peers) - 1) atomicAdd(&Cnt[r], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
     const uint32_t base = (uint32_t)b * g.npix;
 #pragma unroll
-    for (int k = 0; k < CCL_TW * CCL_TH / CCL_THREADS; k++) {
+    for (int k = 0; k < PER; k++) {
         const int i = threadIdx.x + k * CCL_THREADS;
         const int lx = i % CCL_TW, ly = i / CCL_TW;
         const int x = x0 + lx, y = y0 + ly;
         if (x < g.w && y < g.h) {
-            uint32_t r = uf_find(L, (uint32_t)i);
+            const uint32_t r = roots[k];
             const int rx = x0 + (int)(r % CCL_TW), ry = y0 + (int)(r / CCL_TW);
-            lab[(size_t)y * g.w + x] = base + (uint32_t)(ry * g.w + rx);
+            const size_t gi = (size_t)base + (size_t)y * g.w + x;
+            labels[gi] = base + (uint32_t)(ry * g.w + rx);
+            sizes[gi] = (r == (uint32_t)i) ? Cnt[i] : 0u;     // local component size at the local root, 0 elsewhere
         }
     }
 }
@@ -156,21 +191,17 @@ __global__ void ccl_merge_kernel(const uint8_t *__restrict__ thresh, uint32_t *_
     }
 }
 
-// pass 3: flatten + component sizes (sizes must be zeroed before the launch)
+// pass 3: flatten every pixel to its root; local roots that were merged into another root add their local
+// component size to it (a few atomics per component instead of one per pixel).  sizes[root] ends up as the full size.
 __global__ void ccl_flatten_kernel(uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, uint32_t total)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t root = 0xffffffffu;
-    if (i < total) {
-        root = uf_find(labels, i);
-        labels[i] = root;
-    }
-    // warp-aggregated histogram: lanes with the same root elect one leader
-    const uint32_t act = __activemask();
-    const uint32_t peers = __match_any_sync(act, root);
-    if (i < total) {
-        const int leader = __ffs(peers) - 1;
-        if ((int)(threadIdx.x & 31) == leader) atomicAdd(&sizes[root], (uint32_t)__popc(peers));
+    if (i >= total) return;
+    const uint32_t root = uf_find(labels, i);
+    labels[i] = root;
+    if (root != i) {
+        const uint32_t c = sizes[i];
+        if (c) atomicAdd(&sizes[root], c);
     }
 }
 

@@ -125,85 +125,36 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
     }
 }
 
-// One CTA per frame: pick the clusters fit_quad() can accept and lay their points out contiguously.
-// Order of the selected list is the slot order (deterministic for a given table size).
+// One thread per hash slot: pick the clusters fit_quad() can accept (24 <= n <= 3(2w+2h)), give each a slot in the
+// frame's cluster list and a contiguous range of the frame's point buffer (atomic bump allocation: the layout is
+// arbitrary, which is fine because every later stage is order independent), and append it to the batch-wide work list
+// of its tier (one warp per small cluster, one CTA per large one).
 __global__ void __launch_bounds__(256)
 cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ clusters, uint32_t *__restrict__ nclusters,
                       uint32_t *__restrict__ npoints, uint32_t *__restrict__ worklist_small, uint32_t *__restrict__ nwork_small,
                       uint32_t *__restrict__ worklist_large, uint32_t *__restrict__ nwork_large, uint32_t small_max,
                       uint32_t *__restrict__ errflag, Geom g, Caps caps, int min_cluster_pixels)
 {
-    const int b = blockIdx.x;
-    ClusterSlot *tab = table + (size_t)b * caps.slots_per_frame;
-    ClusterRec *out = clusters + (size_t)b * caps.clusters_per_frame;
-    __shared__ uint32_t s_ncl, s_npt;
-    __shared__ uint32_t w_cnt[8], w_pts[8];
-    if (threadIdx.x == 0) { s_ncl = 0; s_npt = 0; }
-    __syncthreads();
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (s >= caps.slots_per_frame) return;
+    ClusterSlot *slot = table + (size_t)b * caps.slots_per_frame + s;
+    if (slot->key == EMPTY_KEY) return;
+    const uint32_t cnt = slot->count;
     const uint32_t maxsz = 3u * (2u * g.w + 2u * g.h);
     const uint32_t minsz = (uint32_t)max(24, min_cluster_pixels);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint32_t s0 = 0; s0 < caps.slots_per_frame; s0 += blockDim.x) {
-        const uint32_t s = s0 + threadIdx.x;
-        uint32_t cnt = 0;
-        bool sel = false;
-        if (s < caps.slots_per_frame && tab[s].key != EMPTY_KEY) {
-            cnt = tab[s].count;
-            sel = cnt >= minsz && cnt <= maxsz;
-        }
-        // block-wide exclusive scan of (sel, cnt)
-        const uint32_t bal = __ballot_sync(0xffffffffu, sel);
-        uint32_t c = sel ? cnt : 0, incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
-        if (lane == 31) { w_cnt[wid] = __popc(bal); w_pts[wid] = incl; }
-        __syncthreads();
-        uint32_t base_c = s_ncl, base_p = s_npt;
-        for (int k = 0; k < wid; k++) { base_c += w_cnt[k]; base_p += w_pts[k]; }
-        const uint32_t my_c = base_c + __popc(bal & ((1u << lane) - 1));
-        const uint32_t my_p = base_p + incl - c;
-        if (s < caps.slots_per_frame) {
-            uint32_t ci = 0xffffffffu;
-            if (sel) {
-                if (my_c >= caps.clusters_per_frame) atomicOr(errflag, ERR_CLUSTERS_FULL);
-                else {
-                    ClusterRec r;
-                    r.key = tab[s].key; r.offset = my_p; r.count = cnt; r.cursor = 0; r.pad = 0;
-                    if (my_p + cnt > caps.points_per_frame) {   // keep the list dense, but make the record inert
-                        atomicOr(errflag, ERR_POINTS_FULL);
-                        r.offset = 0; r.count = 0;
-                    } else ci = my_c;
-                    out[my_c] = r;
-                }
-            }
-            tab[s].cluster = ci;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tc = 0, tp = 0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); k++) { tc += w_cnt[k]; tp += w_pts[k]; }
-            s_ncl += tc; s_npt += tp;
-        }
-        __syncthreads();
-    }
-    // batch-wide work lists for the two quad-fitting tiers (one warp per small cluster, one CTA per large one)
-    __shared__ uint32_t s_cnt[2], s_base[2];
-    const uint32_t ncl = min(s_ncl, caps.clusters_per_frame);
-    if (threadIdx.x == 0) { nclusters[b] = ncl; npoints[b] = s_npt; s_cnt[0] = 0; s_cnt[1] = 0; }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < ncl; i += blockDim.x) atomicAdd(&s_cnt[out[i].count > small_max ? 1 : 0], 1u);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s_base[0] = atomicAdd(nwork_small, s_cnt[0]);
-        s_base[1] = atomicAdd(nwork_large, s_cnt[1]);
-        s_cnt[0] = 0; s_cnt[1] = 0;
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < ncl; i += blockDim.x) {
-        const int t = out[i].count > small_max ? 1 : 0;
-        const uint32_t pos = s_base[t] + atomicAdd(&s_cnt[t], 1u);
-        (t ? worklist_large : worklist_small)[pos] = (uint32_t)b * caps.clusters_per_frame + i;
-    }
+    if (cnt < minsz || cnt > maxsz) return;          // slot->cluster stays 0xffffffff
+    const uint32_t ci = atomicAdd(&nclusters[b], 1u);
+    if (ci >= caps.clusters_per_frame) { atomicOr(errflag, ERR_CLUSTERS_FULL); return; }
+    const uint32_t off = atomicAdd(&npoints[b], cnt);
+    if (off + cnt > caps.points_per_frame) { atomicOr(errflag, ERR_POINTS_FULL); return; }
+    ClusterRec r;
+    r.key = slot->key; r.offset = off; r.count = cnt; r.cursor = 0; r.pad = 0;
+    clusters[(size_t)b * caps.clusters_per_frame + ci] = r;
+    slot->cluster = ci;
+    const uint32_t item = (uint32_t)b * caps.clusters_per_frame + ci;
+    if (cnt > small_max) worklist_large[atomicAdd(nwork_large, 1u)] = item;
+    else worklist_small[atomicAdd(nwork_small, 1u)] = item;
 }
 
 }  // namespace cb

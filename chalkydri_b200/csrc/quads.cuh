@@ -103,19 +103,6 @@ __device__ __forceinline__ uint32_t hi32(unsigned long long v) { return (uint32_
 // C(k,4) entries; filled by the host (api.cu)
 __constant__ uint16_t c_combos[210];
 
-struct QfScratch {       // per group (warp or CTA)
-    double red_d[8];
-    int red_i[8];
-    float red_f[8];
-    uint32_t w_cnt[8];
-    int nmax;
-    int kept[16];
-    int nkept;
-    int taken[16];
-    double thresh;
-    double stage[2][32][6];   // staging tiles of the sequential prefix pass
-};
-
 // group abstraction: NT = 32 (one warp) or 256 (one CTA) working on one cluster
 template <int NT>
 struct Grp {
@@ -136,6 +123,71 @@ struct Grp {
         for (int k = 1; k < NT / 32; k++) r = op(r, scratch[k]);
         return r;
     }
+};
+
+
+// Emulation of upstream ptsort() on an array of packed words whose sort key is key_of(word):
+//   recursion tree split at sz/2, leaves of <= 5 elements sorted by upstream's networks (swap only when strictly
+//   greater), every internal node merged with "take from the first half only when strictly smaller".
+// Parallelisation: leaves one thread each; every level is a merge-path pass -- each thread owns a contiguous chunk of
+// the output, finds its split of the two input runs with one binary search and then merges sequentially, so the work is
+// O(n log n) compare-moves instead of a binary search per element per level.  Used for both sorts (the scan-key sort has
+// unique keys, so any merge tree gives the same result).
+template <int NT, typename T, typename KeyOf>
+__device__ __forceinline__ void ptsort_emulate(T *&src, T *&dst, int n, int tid, KeyOf key_of)
+{
+    for (int i = tid; i < n; i += NT) {
+        int lo = 0, hi = n;
+        while (hi - lo > 5) { const int mid = lo + (hi - lo) / 2; if (i < mid) hi = mid; else lo = mid; }
+        if (i != lo) continue;
+        const int sz = hi - lo;
+        T *a = src + lo;
+#define QF_SWAP(x, y) if (key_of(a[x]) > key_of(a[y])) { const T t = a[x]; a[x] = a[y]; a[y] = t; }
+        if (sz == 2) { QF_SWAP(0, 1); }
+        else if (sz == 3) { QF_SWAP(0, 1); QF_SWAP(1, 2); QF_SWAP(0, 1); }
+        else if (sz == 4) { QF_SWAP(0, 1); QF_SWAP(2, 3); QF_SWAP(0, 2); QF_SWAP(1, 3); QF_SWAP(1, 2); }
+        else if (sz == 5) { QF_SWAP(0, 1); QF_SWAP(3, 4); QF_SWAP(2, 4); QF_SWAP(2, 3); QF_SWAP(0, 3); QF_SWAP(0, 2); QF_SWAP(1, 4); QF_SWAP(1, 3); QF_SWAP(1, 2); }
+#undef QF_SWAP
+    }
+    Grp<NT>::sync();
+    int maxd = 0;
+    { int sz = n; while (sz > 5) { sz = sz - sz / 2; maxd++; } }
+    const int E = (n + NT - 1) / NT;
+    for (int d = maxd - 1; d >= 0; d--) {
+        int p = tid * E;
+        const int p1 = min(n, p + E);
+        while (p < p1) {
+            int lo, hi;
+            const bool internal = ptsort_node(n, p, d, lo, hi) && hi - lo > 5;
+            const int e = min(hi, p1);
+            if (!internal) { for (; p < e; p++) dst[p] = src[p]; continue; }
+            const int mid = lo + (hi - lo) / 2, an = mid - lo, bn = hi - mid, k = p - lo;
+            int l = max(0, k - bn), h = min(k, an);
+            while (l < h) { const int m = (l + h) >> 1; if (key_of(src[lo + m]) < key_of(src[mid + k - m - 1])) l = m + 1; else h = m; }
+            int ai = l, bi = k - l;
+            T av = src[lo + min(ai, an - 1)], bv = src[mid + min(bi, bn - 1)];
+            for (; p < e; p++) {
+                const bool take_a = (bi >= bn) || (ai < an && key_of(av) < key_of(bv));
+                if (take_a) { dst[p] = av; ai++; if (ai < an) av = src[lo + ai]; }
+                else { dst[p] = bv; bi++; if (bi < bn) bv = src[mid + bi]; }
+            }
+        }
+        Grp<NT>::sync();
+        T *t = src; src = dst; dst = t;
+    }
+}
+
+struct QfScratch {       // per group (warp or CTA)
+    double red_d[8];
+    int red_i[8];
+    float red_f[8];
+    uint32_t w_cnt[8];
+    int nmax;
+    int kept[16];
+    int nkept;
+    int taken[16];
+    double thresh;
+    double stage[2][32][6];   // staging tiles of the sequential prefix pass
 };
 
 // Processes one cluster.  A and B are 8-byte-per-point work arrays (shared or global), lfps the 48-byte-per-point
@@ -168,94 +220,52 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
     const float cx = (float)((xmin + xmax) * 0.5 + 0.05118);
     const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
     G::sync();
-
-    // ---- restore scan order: rank-merge sort of the (unique) scan keys -----------------------------------------
-    {
-        uint32_t *src = k0, *dst = k1;
-        for (int run = 1; run < n; run <<= 1) {
-            for (int i = tid; i < n; i += NT) {
-                const int pair0 = (i / (2 * run)) * (2 * run);
-                const int mid = min(pair0 + run, n), end = min(pair0 + 2 * run, n);
-                const uint32_t v = src[i];
-                int lo, hi;
-                if (i < mid) { lo = mid; hi = end; } else { lo = pair0; hi = mid; }
-                const int sbase = lo;
-                while (lo < hi) { const int m = (lo + hi) >> 1; if (src[m] < v) lo = m + 1; else hi = m; }
-                const int pos = (i < mid) ? (i + (lo - sbase)) : (pair0 + (i - mid) + (lo - sbase));
-                dst[pos] = v;
-            }
-            G::sync();
-            uint32_t *t = src; src = dst; dst = t;
-        }
-        k0 = src;   // sorted keys
-    }
-    // ---- slopes in scan order (upstream fit_quad step 1) ---------------------------------------------------------
+    // border polarity (upstream: dot = sum dx*gx + dy*gy, reversed_border = dot < 0).  Only the sign is used and the
+    // sum does not depend on the order of the points beyond float rounding, so it is evaluated before any sorting:
+    // about half of all clusters (white blobs inside black) are rejected here.
     float dot = 0.f;
-    for (int j = tid; j < n; j += NT) {
-        const uint32_t key = k0[j];
+    for (int i = tid; i < n; i += NT) {
         int px, py, gx, gy;
-        decode_point(key, g.w, px, py, gx, gy);
-        float dx = (float)px - cx, dy = (float)py - cy;
+        decode_point(k0[i], g.w, px, py, gx, gy);
+        const float dx = (float)px - cx, dy = (float)py - cy;
         dot += dx * (float)gx + dy * (float)gy;
-        float quadrant;
-        if (dy > 0) quadrant = dx > 0 ? 65536.f : 131072.f; else quadrant = dx > 0 ? 0.f : -65536.f;
-        if (dy < 0) { dy = -dy; dx = -dx; }
-        if (dx < 0) { const float t = dx; dx = dy; dy = -t; }
-        const float slope = quadrant + dy / dx;
-        B[j] = ((unsigned long long)float_orderable(slope) << 32) | key;
     }
     dot = G::reduce(dot, [](float a, float c) { return a + c; }, S.red_f);
     const int reversed_border = dot < 0.f;
     if (reversed_border) return;                   // tag36h11 has a normal border only
     G::sync();
 
-    // ---- ptsort(): leaves (sorting networks), then merges bottom-up with "second half first on ties" -------------
-    unsigned long long *src = B, *dst = A;
-    int maxd = 0;
-    { int sz = n; while (sz > 5) { sz = sz - sz / 2; maxd++; } }
-    for (int i = tid; i < n; i += NT) {
-        int lo = 0, hi = n;
-        while (hi - lo > 5) { const int mid = lo + (hi - lo) / 2; if (i < mid) hi = mid; else lo = mid; }
-        if (i != lo) continue;
-        const int sz = hi - lo;
-        unsigned long long *a = src + lo;
-#define QF_SWAP(x, y) if (hi32(a[x]) > hi32(a[y])) { const unsigned long long t = a[x]; a[x] = a[y]; a[y] = t; }
-        if (sz == 2) { QF_SWAP(0, 1); }
-        else if (sz == 3) { QF_SWAP(0, 1); QF_SWAP(1, 2); QF_SWAP(0, 1); }
-        else if (sz == 4) { QF_SWAP(0, 1); QF_SWAP(2, 3); QF_SWAP(0, 2); QF_SWAP(1, 3); QF_SWAP(1, 2); }
-        else if (sz == 5) { QF_SWAP(0, 1); QF_SWAP(3, 4); QF_SWAP(2, 4); QF_SWAP(2, 3); QF_SWAP(0, 3); QF_SWAP(0, 2); QF_SWAP(1, 4); QF_SWAP(1, 3); QF_SWAP(1, 2); }
-#undef QF_SWAP
+    // ---- restore scan order: merge sort of the (unique) scan keys -------------------------------------------------
+    {
+        uint32_t *ssrc = k0, *sdst = k1;
+        ptsort_emulate<NT>(ssrc, sdst, n, tid, [](uint32_t v) { return v; });
+        k0 = ssrc;   // sorted keys
+    }
+    // ---- slopes in scan order (upstream fit_quad step 1) ---------------------------------------------------------
+    for (int j = tid; j < n; j += NT) {
+        const uint32_t key = k0[j];
+        int px, py, gx, gy;
+        decode_point(key, g.w, px, py, gx, gy);
+        float dx = (float)px - cx, dy = (float)py - cy;
+        float quadrant;
+        if (dy > 0) quadrant = dx > 0 ? 65536.f : 131072.f; else quadrant = dx > 0 ? 0.f : -65536.f;
+        if (dy < 0) { dy = -dy; dx = -dx; }
+        if (dx < 0) { const float t = dx; dx = dy; dy = -t; }
+        const float slope = quadrant + dy / dx;
+        B[j] = ((unsigned long long)float_orderable(slope) << 32) | (uint32_t)px | ((uint32_t)py << 16);
     }
     G::sync();
-    for (int d = maxd - 1; d >= 0; d--) {
-        for (int i = tid; i < n; i += NT) {
-            int lo, hi;
-            const unsigned long long v = src[i];
-            if (!ptsort_node(n, i, d, lo, hi) || hi - lo <= 5) { dst[i] = v; continue; }
-            const int mid = lo + (hi - lo) / 2;
-            const uint32_t key = hi32(v);
-            int pos;
-            if (i < mid) {   // from the first half: all second-half keys <= key go before it
-                int l = mid, h = hi;
-                while (l < h) { const int m = (l + h) >> 1; if (hi32(src[m]) <= key) l = m + 1; else h = m; }
-                pos = i + (l - mid);
-            } else {         // from the second half: only strictly smaller first-half keys go before it
-                int l = lo, h = mid;
-                while (l < h) { const int m = (l + h) >> 1; if (hi32(src[m]) < key) l = m + 1; else h = m; }
-                pos = lo + (i - mid) + (l - lo);
-            }
-            dst[pos] = v;
-        }
-        G::sync();
-        unsigned long long *t = src; src = dst; dst = t;
-    }
-    // src: sorted (slope key, scan key).  ---- compute_lfps -----------------------------------------------------------
+
+    // ---- ptsort() on the slope keys -------------------------------------------------------------------------------
+    unsigned long long *src = B, *dst = A;
+    ptsort_emulate<NT>(src, dst, n, tid, [](unsigned long long v) { return (uint32_t)(v >> 32); });
+    // src: sorted (slope key, packed px | py << 16).  ---- compute_lfps -----------------------------------------------------------
     // per-point weight (parallel), then the sequential prefix: each block of 32 points is expanded into its six
     // terms by 32 lanes, staged in shared memory, and accumulated in order by lanes 0..5 of the first warp.
     double *Wd = reinterpret_cast<double *>(dst);
     for (int j = tid; j < n; j += NT) {
-        int px, py, gx, gy;
-        decode_point((uint32_t)src[j], g.w, px, py, gx, gy);
+        const uint32_t xy = (uint32_t)src[j];
+        const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
         const double x = px * .5 + 0.5, y = py * .5 + 0.5;
         const int ix = (int)x, iy = (int)y;
         double W = 1;
@@ -273,8 +283,8 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
             const int j = j0 + lane;
             const int buf = (j0 >> 5) & 1;
             if (j < n) {
-                int px, py, gx, gy;
-                decode_point((uint32_t)src[j], g.w, px, py, gx, gy);
+                const uint32_t xy = (uint32_t)src[j];
+                const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
                 const double W = Wd[j];
                 const double fx = px * .5 + 0.5, fy = py * .5 + 0.5;
                 double *t = S.stage[buf][lane];
