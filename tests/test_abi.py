@@ -82,3 +82,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inc", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("the oracle/", ""), f
+
+
+def test_cpp_mirror_compiles_and_fails_loudly(lib, tmp_path):
+    """include/chalkydri_b200.hpp builds against the .so; without a GPU the program reports the error instead of falling back."""
+    import subprocess
+    exe = str(tmp_path / "abi_smoke")
+    so_dir = os.path.join(ROOT, "chalkydri_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "abi_smoke.cpp"),
+           "-L", so_dir, "-lchalkydri_b200", "-Wl,-rpath," + so_dir, "-o", exe]
+    subprocess.check_call(cmd)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "version chalkydri_b200" in r.stdout
