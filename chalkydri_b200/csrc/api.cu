@@ -215,6 +215,7 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaMemcpyToSymbol(c_codes, kHostCodes, sizeof(kHostCodes)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ThrTmaWarp) * THR_TMA_WARPS)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(fit_quads_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared)) == cudaSuccess;
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
@@ -313,8 +314,26 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     // ---- A1+A2 threshold ----
     const bool fast = g.f == 2 && (g.stride % 16 == 0) && (g.frame_stride % 16 == 0) && ((uintptr_t)d_frames % 16 == 0) && g.tw > 0 && g.th > 0;
     if (fast) {
-        dim3 grid((g.tw + THR_IW - 1) / THR_IW, (g.th + THR_IH - 1) / THR_IH, B), block(THR_TX, THR_TY);
-        threshold_f2_kernel<<<grid, block, 0, st>>>(d_frames, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g, prm.min_white_black_diff);
+        // variant switch for A/B profiling: CB_THRESHOLD = tma (default) | tiled
+        static const char *variant_env = getenv("CB_THRESHOLD");
+        static const int variant = variant_env == nullptr ? 0 : (strcmp(variant_env, "tiled") == 0 ? 2 : 0);
+        if (variant == 2) {
+            dim3 grid((g.tw + THR_IW - 1) / THR_IW, (g.th + THR_IH - 1) / THR_IH, B), block(THR_TX, THR_TY);
+            threshold_f2_kernel<<<grid, block, 0, st>>>(d_frames, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g, prm.min_white_black_diff);
+        } else {
+            RollPlan plan;
+            plan.strips = (g.tw + THR_ROLL_MAXIW - 1) / THR_ROLL_MAXIW;
+            plan.iw = ((g.tw + plan.strips - 1) / plan.strips + 3) / 4 * 4;
+            const long long target_warps = (long long)ctx->num_sms * 24;
+            int ysegs = (int)((target_warps + (long long)plan.strips * B - 1) / ((long long)plan.strips * B));
+            ysegs = std::max(1, std::min(ysegs, std::max(1, g.th / 8)));
+            plan.seg_rows = (g.th + ysegs - 1) / ysegs;
+            plan.ysegs = (g.th + plan.seg_rows - 1) / plan.seg_rows;
+            const long long warps = (long long)plan.strips * plan.ysegs * B;
+            const int wt = (g.w % 4 || g.h % 4) ? 1 : 0;
+            threshold_f2_tma_kernel<<<(unsigned)((warps + THR_TMA_WARPS - 1) / THR_TMA_WARPS), THR_TMA_WARPS * 32, sizeof(ThrTmaWarp) * THR_TMA_WARPS, st>>>(
+                    d_frames, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g, prm.min_white_black_diff, plan, wt);
+        }
         launches++; thr_launches++;
         if (g.w % 4 || g.h % 4) {
             dim3 gr((g.w + 127) / 128, g.h, B);

@@ -142,6 +142,216 @@ threshold_f2_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, u
     }
 }
 
+constexpr int THR_ROLL_MAXIW = 124;      // inner tiles per strip (32 lanes x 4 tiles minus 2 + 2 halo tiles)
+struct RollPlan { int strips, iw, ysegs, seg_rows; };
+
+// ---- TMA-staged streaming variant (default) ----------------------------------------------------------------------
+// The CTA-tiled kernel above serialises load / exchange / dilate / store phases behind block barriers, so with 3 CTAs per
+// SM the memory system idles during the compute phases (ncu: 27 % of the HBM roofline, long-scoreboard bound).  Here one
+// WARP owns a strip of up to 124 tiles x a segment of tile rows and streams down it:
+//   * the 4 even input rows of each tile row are prefetched four tile rows ahead by the TMA engine (1-D bulk copies,
+//     cp.async.bulk ... mbarrier::complete_tx) into a per-warp shared-memory ring: 4 stages x 4 KB per warp, 12 warps per
+//     SM = 144 KB of loads in flight per SM, none of them holding registers.  One elected lane issues the copies; the
+//     warp waits on the stage's mbarrier phase;
+//   * lane l reads its 32 bytes per row (two LDS.128), reduces 4 tiles with the native 16-bit SIMD min/max
+//     (VIMNMX.U16x2 on the even bytes, which are exactly the decimated pixels) -- the byte-SIMD intrinsics are emulated
+//     on sm_100 and cost 5-7 instructions each, so they are kept off the per-pixel path except for the final compare;
+//   * the 3x3 tile dilation needs no shared memory: vertical neighbours are the lane's own packed min/max words of the
+//     last three tile rows, horizontal neighbours come from lane-1 / lane+1 through shuffles and a funnel shift;
+//   * no block barrier; the only redundancy is one halo tile row at each end of a segment.
+constexpr int THR_TMA_WARPS = 4, THR_TMA_STAGES = 4, THR_TMA_ROWB = 1024;
+
+struct __align__(128) ThrTmaWarp {
+    uint8_t buf[THR_TMA_STAGES][4][THR_TMA_ROWB];
+    unsigned long long bar[THR_TMA_STAGES];
+    unsigned long long pad[12];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// lane 0: start the copies of tile row rr (4 even input rows, `nbytes` bytes starting at byte x0s) into `stage`
+__device__ __forceinline__ void thr_tma_issue(ThrTmaWarp &W, int stage, const uint8_t *__restrict__ img, const Geom &g, int rr, int x0s, int nbytes)
+{
+    const int xs = max(x0s, 0), xe = min(x0s + nbytes, g.stride);
+    const int n = xe - xs;
+    uint32_t total = 0;
+    if (rr >= 0 && n > 0)
+        for (int dy = 0; dy < 4; dy++) if (rr * 4 + dy < g.h) total += (uint32_t)n;
+    if (total == 0) { mbar_arrive(&W.bar[stage]); return; }
+    mbar_expect_tx(&W.bar[stage], total);
+    for (int dy = 0; dy < 4; dy++) {
+        const int y = rr * 4 + dy;
+        if (y < g.h) tma_load_1d(&W.buf[stage][dy][xs - x0s], img + (size_t)(2 * y) * g.stride + xs, (uint32_t)n, &W.bar[stage]);
+    }
+}
+
+__global__ void __launch_bounds__(THR_TMA_WARPS * 32)
+threshold_f2_tma_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint8_t *__restrict__ tmin, uint8_t *__restrict__ tmax,
+                        Geom g, int min_diff, RollPlan plan, int write_tiles)
+{
+    extern __shared__ __align__(128) unsigned char thr_smem[];
+    ThrTmaWarp &W = reinterpret_cast<ThrTmaWarp *>(thr_smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const long long widx = (long long)blockIdx.x * THR_TMA_WARPS + (threadIdx.x >> 5);
+    const long long per_frame = (long long)plan.strips * plan.ysegs;
+    if (widx >= per_frame * g.batch) return;
+    const int b = (int)(widx / per_frame);
+    const int rem = (int)(widx % per_frame);
+    const int seg = rem / plan.strips, strip = rem % plan.strips;
+    const int s0 = strip * plan.iw;
+    const int s1 = min(s0 + plan.iw, g.tw);
+    const int y0 = seg * plan.seg_rows, y1 = min(y0 + plan.seg_rows, g.th);
+    if (y0 >= y1 || s0 >= s1) return;
+    const int gtx0 = s0 - 2 + 4 * lane;
+    const bool lane_on = gtx0 < s1 + 1;
+    const int x0s = (s0 - 2) * 8;                                   // byte offset of lane 0's data in an input row
+    const int nlanes = (s1 + 1 - (s0 - 2) + 3) / 4;                 // lanes with lane_on
+    const int nbytes = nlanes * 32;
+    const uint8_t *img = in + (size_t)b * g.frame_stride;
+    uint8_t *o = out + (size_t)b * g.h * g.tp;
+    const uint32_t full = 0xffffffffu;
+
+    if (lane == 0) {
+        for (int s = 0; s < THR_TMA_STAGES; s++) mbar_init(&W.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    const int rfirst = y0 - 1;
+    if (lane == 0)
+        for (int s = 0; s < THR_TMA_STAGES; s++)
+            if (rfirst + s <= y1) thr_tma_issue(W, s, img, g, rfirst + s, x0s, nbytes);
+
+    uint32_t px_prev[4][4], px_cur[4][4];
+    uint32_t mn_a = 0xffffffffu, mn_b = 0xffffffffu, mx_a = 0, mx_b = 0;
+#pragma unroll
+    for (int dy = 0; dy < 4; dy++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { px_prev[dy][k] = 0; px_cur[dy][k] = 0; }
+    // lane constants: which of the 4 tiles exist, which tile pairs are written, output column
+    uint32_t valid_mn = 0, valid_mx = 0;          // byte k = 0x00 (valid) / 0xff (force neutral min) resp. 0xff keep / 0x00 force neutral max
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool v = gtx0 + k >= 0 && gtx0 + k < g.tw;
+        if (!v) valid_mn |= 0xffu << (8 * k); else valid_mx |= 0xffu << (8 * k);
+    }
+    bool pair_in[2], pair_two[2];
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {
+        const int gtx = gtx0 + 2 * pr;
+        pair_in[pr] = lane_on && gtx >= s0 && gtx < s1;
+        pair_two[pr] = gtx + 1 < s1;
+    }
+    uint8_t *ocol = o + (ptrdiff_t)gtx0 * 4;
+    for (int r = rfirst; r <= y1; r++) {
+        const int it = r - rfirst, stage = it % THR_TMA_STAGES;
+        mbar_wait(&W.bar[stage], (uint32_t)((it / THR_TMA_STAGES) & 1));
+        // ---- read this lane's 4 x 32 bytes; tile min/max on 16-bit lanes (even bytes = decimated pixels) ----
+        uint32_t mnp[4], mxp[4];                  // per tile: running min / max as a U16x2 pair
+#pragma unroll
+        for (int dy = 0; dy < 4; dy++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) px_prev[dy][k] = px_cur[dy][k];
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+            if (lane_on) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(&W.buf[stage][dy][lane * 32]);
+                v0 = p[0]; v1 = p[1];
+            }
+            const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t e0 = w[2 * k] & 0x00ff00ffu, e1 = w[2 * k + 1] & 0x00ff00ffu;
+                const uint32_t lo = __vminu2(e0, e1), hi = __vmaxu2(e0, e1);
+                mnp[k] = dy == 0 ? lo : __vminu2(mnp[k], lo);
+                mxp[k] = dy == 0 ? hi : __vmaxu2(mxp[k], hi);
+                px_cur[dy][k] = __byte_perm(w[2 * k], w[2 * k + 1], 0x6420);
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && r + THR_TMA_STAGES <= y1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            thr_tma_issue(W, stage, img, g, r + THR_TMA_STAGES, x0s, nbytes);
+        }
+        uint32_t mn_c = 0xffffffffu, mx_c = 0;
+        if (r >= 0 && r < g.th) {
+            uint32_t mn = 0, mx = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t tmn = __vminu2(mnp[k], mnp[k] >> 16) & 0xffu, tmx = __vmaxu2(mxp[k], mxp[k] >> 16) & 0xffu;
+                mn |= tmn << (8 * k); mx |= tmx << (8 * k);
+            }
+            mn_c = mn | valid_mn; mx_c = mx & valid_mx;
+        }
+        const int ro = r - 1;
+        const uint32_t vmn = __vminu4(mn_a, __vminu4(mn_b, mn_c)), vmx = __vmaxu4(mx_a, __vmaxu4(mx_b, mx_c));
+        uint32_t lmn = __shfl_up_sync(full, vmn, 1), rmn = __shfl_down_sync(full, vmn, 1);
+        uint32_t lmx = __shfl_up_sync(full, vmx, 1), rmx = __shfl_down_sync(full, vmx, 1);
+        if (lane == 0) { lmn = 0xffffffffu; lmx = 0; }
+        if (lane == 31) { rmn = 0xffffffffu; rmx = 0; }
+        const uint32_t dmn = __vminu4(vmn, __vminu4(__funnelshift_r(lmn, vmn, 24), __funnelshift_r(vmn, rmn, 8)));
+        const uint32_t dmx = __vmaxu4(vmx, __vmaxu4(__funnelshift_r(lmx, vmx, 24), __funnelshift_r(vmx, rmx, 8)));
+        if (ro >= y0 && ro < y1 && (pair_in[0] || pair_in[1])) {
+            uint32_t wout[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t mn = (dmn >> (8 * k)) & 0xff, mx = (dmx >> (8 * k)) & 0xff;
+                const bool flat = (int)mx - (int)mn < min_diff;
+                const uint32_t th = (mn + (mx - mn) / 2) * 0x01010101u;
+#pragma unroll
+                for (int dy = 0; dy < 4; dy++) wout[dy][k] = flat ? 0x7f7f7f7fu : __vcmpgtu4(px_prev[dy][k], th);
+            }
+            uint8_t *orow = ocol + (size_t)(ro * 4) * g.tp;
+#pragma unroll
+            for (int pr = 0; pr < 2; pr++) {
+                if (!pair_in[pr]) continue;
+#pragma unroll
+                for (int dy = 0; dy < 4; dy++) {
+                    uint8_t *dst = orow + (size_t)dy * g.tp + 8 * pr;
+                    if (pair_two[pr]) *reinterpret_cast<uint2 *>(dst) = make_uint2(wout[dy][2 * pr], wout[dy][2 * pr + 1]);
+                    else *reinterpret_cast<uint32_t *>(dst) = wout[dy][2 * pr];
+                }
+                if (write_tiles) {
+                    const size_t ti = ((size_t)b * g.th + ro) * g.tw + gtx0 + 2 * pr;
+                    tmin[ti] = (uint8_t)(mn_b >> (8 * (2 * pr))); tmax[ti] = (uint8_t)(mx_b >> (8 * (2 * pr)));
+                    if (pair_two[pr]) { tmin[ti + 1] = (uint8_t)(mn_b >> (8 * (2 * pr + 1))); tmax[ti + 1] = (uint8_t)(mx_b >> (8 * (2 * pr + 1))); }
+                }
+            }
+        }
+        mn_a = mn_b; mn_b = mn_c; mx_a = mx_b; mx_b = mx_c;
+    }
+}
+
 // ---- generic path (any integer decimation factor, any alignment): three simple kernels ----
 __global__ void tile_minmax_generic_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ tmin, uint8_t *__restrict__ tmax, Geom g)
 {

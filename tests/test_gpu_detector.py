@@ -68,6 +68,30 @@ def test_stages_bit_exact(oracle, W, H, tags, seed, edge):
     det.close()
 
 
+def test_strided_frame_with_partial_tiles(oracle):
+    """stride != width and w, h not multiples of 4: vector loads + upstream's remainder rule (last full tile, never 127)."""
+    from chalkydri_b200.detector import Image
+    full, _ = synth.render_frame(1456, 1088, 8, seed=12, edge_px=(40, 200))
+    W, H = 1450, 1084                                     # decimates to 725 x 542
+    crop = np.ascontiguousarray(full[:H, :W])
+    det = make_detector(1456, 1088, 1)
+    got = det.detect(Image(full, W, H, 1456))
+    ref = oracle.detect(crop)
+    assert [d.id() for d in got] == ref["id"].tolist() and [d.hamming() for d in got] == ref["hamming"].tolist()
+    for d, r in zip(got, ref):
+        assert np.abs(np.array(d.corners()) - r["p"]).max() < CORNER_TOL
+    # threshold tap on a buffer whose stride is a multiple of 16 but whose decimated size leaves partial tiles
+    padded = np.zeros((H, 1456), np.uint8)
+    padded[:, :W] = crop
+    import ctypes as C
+    from chalkydri_b200 import capi
+    out = np.empty((542, 725), np.uint8)
+    rc = det._L.cb_threshold(det.ctx, capi.ptr(padded), W, H, 1456, 1456 * H, 1, capi.ptr(out))
+    assert rc == 0
+    assert (out == oracle.threshold(crop)).all()
+    det.close()
+
+
 def test_c3_full_resolution_small_tags(oracle):
     frame, truth = synth.render_frame(4608, 2592, 40, seed=4, edge_px=(40, 300), small_tags=10)
     det = make_detector(4608, 2592, 1, 256)
