@@ -38,6 +38,9 @@ struct cb_ctx {
     int device = 0;
     int max_w = 0, max_h = 0, max_batch = 0, max_dets = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;           // H2D of the next chunk overlaps the kernels of the current one
+    cudaEvent_t ev_copied[2]{}, ev_consumed[2]{};
+    uint32_t *h_chunk_err = nullptr;              // pinned: error flag of every chunk of a pipelined call
     std::string err;
     bool family_set = false;
     DetParams prm{};
@@ -135,6 +138,9 @@ void cb_destroy(cb_ctx *ctx)
     if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    if (ctx->h_chunk_err) cudaFreeHost(ctx->h_chunk_err);
+    for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -178,6 +184,9 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     };
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2; i++) ok = ok && cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&ctx->h_chunk_err, 4096 * sizeof(uint32_t)) == cudaSuccess;
     for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
     // decimated worst case handled by this allocation: ceil(W/2) x ceil(H/2); decimation 1 re-allocates on demand
     const size_t dw = (max_width + 1) / 2, dh = (max_height + 1) / 2;
@@ -504,12 +513,82 @@ int cb_detect_gray_device(cb_ctx *ctx, const uint8_t *frames_dev, int width, int
     return CB_OK;
 }
 
+// Host frames in, detection lists out.  Large batches are cut into chunks whose H2D copy (copy stream, second half of the
+// input buffer) overlaps the kernels of the previous chunk (compute stream): the PCIe transfer disappears behind the compute.
+static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
+                                 cb_detection *out, int32_t *out_counts)
+{
+    const size_t D = ctx->caps.dets_per_frame;
+    const size_t bytes = (size_t)stride * height;
+    const size_t dfs = (bytes + 15) / 16 * 16;
+    const int half = ctx->max_batch / 2;
+    int chunk = std::max(16, std::min(half, (batch + 3) / 4));
+    chunk = std::min(chunk, half);
+    const int nchunks = (batch + chunk - 1) / chunk;
+    if (nchunks > 4096) return fail(ctx, CB_ERR_ARG, "too many chunks");
+    uint8_t *bufs[2] = {ctx->d_in, ctx->d_in + (size_t)half * dfs};
+    cb_timing acc{};
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));   // make the first waits trivially satisfied
+    CK(cudaEventRecord(ctx->ev_consumed[1], ctx->stream));
+    int done_base = 0;    // first frame of the group currently staged in h_dets (h_dets holds max_batch frames)
+    for (int c = 0; c < nchunks; c++) {
+        const int b0 = c * chunk, n = std::min(chunk, batch - b0), bi = c & 1;
+        // staging area full: drain what has been produced so far
+        if (b0 + n - done_base > ctx->max_batch) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (int b = done_base; b < b0; b++) {
+                out_counts[b] = ctx->h_counts[b - done_base];
+                memcpy(out + (size_t)b * D, ctx->h_dets + (size_t)(b - done_base) * D, (size_t)out_counts[b] * sizeof(cb_detection));
+                for (int k = 0; k < out_counts[b]; k++) out[(size_t)b * D + k].frame = b;
+            }
+            done_base = b0;
+        }
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[bi], 0));
+        if (frame_stride == dfs) CK(cudaMemcpyAsync(bufs[bi], frames + (size_t)b0 * frame_stride, (size_t)n * frame_stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+        else CK(cudaMemcpy2DAsync(bufs[bi], dfs, frames + (size_t)b0 * frame_stride, frame_stride, bytes, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copied[bi], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[bi], 0));
+        Geom g;
+        int rc = make_geom(ctx, width, height, stride, dfs, n, g);
+        if (rc) return rc;
+        rc = run_pipeline(ctx, bufs[bi], g, ST_FULL);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_consumed[bi], ctx->stream));
+        const int off = b0 - done_base;
+        CK(cudaMemcpyAsync(ctx->h_dets + (size_t)off * D, ctx->d_dets, (size_t)n * D * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_counts + off, ctx->d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_chunk_err + c, ctx->d_small + 4 * (size_t)ctx->max_batch, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        acc.kernel_launches += ctx->timing.kernel_launches;
+        acc.threshold_launches += ctx->timing.threshold_launches;
+    }
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < nchunks; c++)
+        if (ctx->h_chunk_err[c]) { ctx->h_small[4 * (size_t)ctx->max_batch] = ctx->h_chunk_err[c]; return check_errflag(ctx); }
+    for (int b = done_base; b < batch; b++) {
+        out_counts[b] = ctx->h_counts[b - done_base];
+        memcpy(out + (size_t)b * D, ctx->h_dets + (size_t)(b - done_base) * D, (size_t)out_counts[b] * sizeof(cb_detection));
+        for (int k = 0; k < out_counts[b]; k++) out[(size_t)b * D + k].frame = b;
+    }
+    cudaEventElapsedTime(&acc.total_ms, ctx->ev[0], ctx->ev[7]);
+    ctx->timing = acc;
+    return CB_OK;
+}
+
 int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
                    cb_detection *out, int32_t *out_counts)
 {
     if (!ctx || !frames || !out || !out_counts) return CB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     if ((size_t)stride * height > ctx->max_npix) return fail(ctx, CB_ERR_ARG, "stride*height exceeds the context's frame capacity");
+    if (!ctx->family_set) return fail(ctx, CB_ERR_STATE, "no tag family set: call cb_set_family_tag36h11 first");
+    if (batch >= 64 && ctx->max_batch >= 32) {
+        Geom g;
+        int rc = make_geom(ctx, width, height, stride, frame_stride, 1, g);      // argument validation
+        if (rc) return rc;
+        return detect_gray_pipelined(ctx, frames, width, height, stride, frame_stride, batch, out, out_counts);
+    }
     cb_timing acc{};
     for (int b0 = 0; b0 < batch; b0 += ctx->max_batch) {
         const int n = std::min(ctx->max_batch, batch - b0);

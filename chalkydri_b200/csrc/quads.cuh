@@ -13,7 +13,7 @@
 // B200 mapping: the work is thousands of small, irregular, partly sequential jobs per frame (a c2 frame has ~700
 // clusters of 24..7000 points), so the design maximises the number of clusters in flight instead of the threads per
 // cluster.  Two persistent kernels pull (frame, cluster) items from device-side work lists:
-//   tier S: clusters of <= 512 points, ONE WARP per cluster (8 KB smem per warp, 24 warps per SM);
+//   tier S: clusters of <= 512 points, ONE WARP per cluster (10 KB smem per warp, 20 warps per SM);
 //   tier L: larger clusters, one 256-thread CTA per cluster (96 KB smem, 2 CTAs per SM; clusters above 6144 points
 //           run the same code out of a global scratch area).
 // A boundary point is fully described by its 32-bit scan key (pixel index, probe, gradient sign), so the only
@@ -187,7 +187,7 @@ struct QfScratch {       // per group (warp or CTA)
     int nkept;
     int taken[16];
     double thresh;
-    double stage[2][32][6];   // staging tiles of the sequential prefix pass
+    double stage[2][16][6];   // staging tiles of the sequential prefix pass
 };
 
 // Processes one cluster.  A and B are 8-byte-per-point work arrays (shared or global), lfps the 48-byte-per-point
@@ -279,10 +279,10 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
     G::sync();
     if (tid < 32) {
         double acc = 0;
-        for (int j0 = 0; j0 < n; j0 += 32) {
+        for (int j0 = 0; j0 < n; j0 += 16) {
             const int j = j0 + lane;
-            const int buf = (j0 >> 5) & 1;
-            if (j < n) {
+            const int buf = (j0 >> 4) & 1;
+            if (lane < 16 && j < n) {
                 const uint32_t xy = (uint32_t)src[j];
                 const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
                 const double W = Wd[j];
@@ -292,7 +292,7 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
             }
             __syncwarp();
             if (lane < 6) {
-                const int cnt = min(32, n - j0);
+                const int cnt = min(16, n - j0);
                 double *o = lfps + (size_t)j0 * 6 + lane;
 #pragma unroll 8
                 for (int k = 0; k < cnt; k++) {
@@ -423,9 +423,8 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
     G::sync();
     const int nk = S.nkept;
     if (nk < 4) return;   // (upstream's loops would simply find nothing)
-    // pair table: fit_line(kept[a], kept[c]) for a != c; lives in the (now dead) second work array, whose capacity is
-    // at least 24 points x 8 B x ... = QS_MAXN x 8 B = 4 KB in tier S and larger elsewhere (3200 B needed)
-    double (*p_err)[10] = reinterpret_cast<double (*)[10]>(dst);
+    // pair table: fit_line(kept[a], kept[c]) for a != c (3200 B); lives in the now dead work arrays
+    double (*p_err)[10] = reinterpret_cast<double (*)[10]>(A);    // A and B are adjacent (A first): >= 4 KB in every tier
     double (*p_mse)[10] = p_err + 10, (*p_nx)[10] = p_err + 20, (*p_ny)[10] = p_err + 30;
     for (int t = tid; t < nk * nk; t += NT) {
         const int a = t / nk, c = t % nk;
@@ -532,11 +531,12 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
     }
 }
 
-struct QsShared {
-    unsigned long long A[QS_WARPS][QS_MAXN];
-    unsigned long long B[QS_WARPS][QS_MAXN];
-    QfScratch S[QS_WARPS];
+struct QsWarp {
+    unsigned long long A[QS_MAXN];
+    unsigned long long B[QS_MAXN];   // directly after A: the pair table of the corner search spans both
+    QfScratch S;
 };
+struct QsShared { QsWarp w[QS_WARPS]; };
 
 // tier S: persistent warps, one cluster (<= QS_MAXN points) per warp at a time
 __global__ void __launch_bounds__(QS_WARPS * 32)
@@ -560,7 +560,7 @@ fit_quads_small_kernel(const uint8_t *__restrict__ in, const uint32_t *__restric
         const int n = (int)rec.count;
         if (n < 24 || n > QS_MAXN) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
-        fit_quad_cluster<32>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.A[wid], SH.B[wid], lfps_all + pbase * 6, SH.S[wid], rec, b,
+        fit_quad_cluster<32>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.w[wid].A, SH.w[wid].B, lfps_all + pbase * 6, SH.w[wid].S, rec, b,
                              quads, nquads, nquads_total, errflag, g, caps, prm);
         __syncwarp();
     }
