@@ -32,6 +32,9 @@ W, H, TAGS, BATCH = 1456, 1088, 8, 256        # BASELINE.json configs[1]
 WORKLOAD = "c2: 256 x 1456x1088 gray frames, 8 tag36h11 tags each (BASELINE.json configs[1])"
 METRIC = "frames/sec at 1/2/4/8 B200 (1456x1088 tag36h11, 8 tags/frame); p50 per-frame latency"
 UNIT = "frames/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of threshold_f2_tma_kernel over a 128-frame launch (ncu --set full), per frame;
+# the ternary map (0.25*W*H per frame) is only partly written back to DRAM inside the kernel (it stays in the 126 MB L2)
+NCU_TRAFFIC_BYTES_PER_FRAME = (110.668032e6 + 20.104960e6) / 128
 
 
 def make_frames(rank: int, batch: int = BATCH, unique: int = 16):
@@ -93,7 +96,7 @@ def run_reference(args, rank, world):
         return
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
-    sample = max(cores, 16)
+    sample = max(2 * cores, 32)
     frames, _ = make_frames(0, batch=sample, unique=min(sample, 16))
     for _ in range(args.warmup):
         po.detect_batch(frames[:cores], cap=64, nthreads=cores)
@@ -251,9 +254,10 @@ def main():
                     "ms_per_step_device_events": e2e_dev_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
-            "roofline": {"kernel": "threshold_f2_kernel (fused decimate + tile min/max + binarise)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "threshold_f2_tma_kernel (fused decimate + tile min/max + 3x3 dilate + binarise, TMA-staged)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "ms_per_launch": thr_ms,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_FRAME * BATCH,
+                         "traffic_source": "ncu --set full, profiles/r01_ncu_threshold_tma.txt: (dram read + write) / 128 frames", "ms_per_launch": thr_ms,
                          "algorithmic_bytes_per_launch": thr_bytes},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_ms_per_step_device_arm": wall_dev / args.steps * 1e3,

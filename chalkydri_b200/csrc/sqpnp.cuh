@@ -20,6 +20,7 @@ namespace cb {
 constexpr int SQ_MAX_TAGS = 16;
 constexpr int SQ_MAX_PTS = SQ_MAX_TAGS * 4;
 constexpr int SQ_WARPS = 4;
+constexpr int SQ_KP = 17;          // row pitch (doubles) of the 15x15 KKT system: odd, so that column accesses by 16 lanes are bank-conflict free
 
 struct SqWarpShared {
     double omega[81];       // column-major 9x9
@@ -29,7 +30,7 @@ struct SqWarpShared {
     double q_rt[27];        // column-major 9x3
     double temp[27];
     double q_tt[9], q_tt_inv[9];
-    double kkt[2][15 * 16]; // row-major 15x15 (pitch 16) per half-warp
+    double kkt[2][15 * SQ_KP]; // row-major 15x15 (pitch SQ_KP) per half-warp
     double rhs[2][16];
     double r[2][9];
     double cand_r[6][9];
@@ -293,10 +294,10 @@ __device__ double sq_optimize_half(SqWarpShared &S, int half, int hl, uint32_t h
     for (int it = 0; it < prm.max_iter; it++) {
         // ---- build the KKT system: row hl of [Omega J^T; J 0] and rhs = [-Omega r; -h] ----
         if (hl < 15) {
-            for (int c = 0; c < 15; c++) M[hl * 16 + c] = 0;
+            for (int c = 0; c < 15; c++) M[hl * SQ_KP + c] = 0;
             if (hl < 9) {
                 double acc = 0;
-                for (int j = 0; j < 9; j++) { const double o = om[j * 9 + hl]; M[hl * 16 + j] = o; acc += o * r[j]; }
+                for (int j = 0; j < 9; j++) { const double o = om[j * 9 + hl]; M[hl * SQ_KP + j] = o; acc += o * r[j]; }
                 b[hl] = -acc;
             }
         }
@@ -313,14 +314,14 @@ __device__ double sq_optimize_half(SqWarpShared &S, int half, int hl, uint32_t h
                 case 4: hval = c1[0] * c3[0] + c1[1] * c3[1] + c1[2] * c3[2]; for (int k = 0; k < 3; k++) { jr[k] = c3[k]; jr[6 + k] = c1[k]; } break;
                 default: hval = c2[0] * c3[0] + c2[1] * c3[1] + c2[2] * c3[2]; for (int k = 0; k < 3; k++) { jr[3 + k] = c3[k]; jr[6 + k] = c2[k]; } break;
             }
-            for (int j = 0; j < 9; j++) { M[(9 + hl) * 16 + j] = jr[j]; M[j * 16 + 9 + hl] = jr[j]; }
+            for (int j = 0; j < 9; j++) { M[(9 + hl) * SQ_KP + j] = jr[j]; M[j * SQ_KP + 9 + hl] = jr[j]; }
             b[9 + hl] = -hval;
         }
         __syncwarp(hmask);
         // ---- LU with partial pivoting (first maximum in row order), reciprocal-pivot multipliers ----
         bool singular = false;
         for (int i = 0; i < 15; i++) {
-            double best = (hl >= i && hl < 15) ? fabs(M[hl * 16 + i]) : -1.0;
+            double best = (hl >= i && hl < 15) ? fabs(M[hl * SQ_KP + i]) : -1.0;
             int piv = hl;
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
@@ -328,32 +329,32 @@ __device__ double sq_optimize_half(SqWarpShared &S, int half, int hl, uint32_t h
                 const int op = __shfl_xor_sync(hmask, piv, o, 16);
                 if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
             }
-            const double diag = M[piv * 16 + i];
+            const double diag = M[piv * SQ_KP + i];
             if (diag == 0) continue;
             if (piv != i) {
-                if (hl < 15) { const double t = M[i * 16 + hl]; M[i * 16 + hl] = M[piv * 16 + hl]; M[piv * 16 + hl] = t; }
+                if (hl < 15) { const double t = M[i * SQ_KP + hl]; M[i * SQ_KP + hl] = M[piv * SQ_KP + hl]; M[piv * SQ_KP + hl] = t; }
                 else { const double t = b[i]; b[i] = b[piv]; b[piv] = t; }
             }
             __syncwarp(hmask);
             const double inv_diag = 1.0 / diag;
             if (hl > i && hl < 15) {
-                const double coeff = M[hl * 16 + i] * inv_diag;
-                M[hl * 16 + i] = coeff;
-                for (int c = i + 1; c < 15; c++) M[hl * 16 + c] -= coeff * M[i * 16 + c];
+                const double coeff = M[hl * SQ_KP + i] * inv_diag;
+                M[hl * SQ_KP + i] = coeff;
+                for (int c = i + 1; c < 15; c++) M[hl * SQ_KP + c] -= coeff * M[i * SQ_KP + c];
             }
             __syncwarp(hmask);
         }
         // forward substitution L y = b (unit diagonal), then back substitution U x = y
         for (int i = 0; i < 15; i++) {
-            if (hl > i && hl < 15) b[hl] -= M[hl * 16 + i] * b[i];
+            if (hl > i && hl < 15) b[hl] -= M[hl * SQ_KP + i] * b[i];
             __syncwarp(hmask);
         }
         for (int i = 14; i >= 0; i--) {
-            const double diag = M[i * 16 + i];
+            const double diag = M[i * SQ_KP + i];
             if (diag == 0) { singular = true; break; }
             if (hl == i) b[i] = b[i] / diag;
             __syncwarp(hmask);
-            if (hl < i) b[hl] -= M[hl * 16 + i] * b[i];
+            if (hl < i) b[hl] -= M[hl * SQ_KP + i] * b[i];
             __syncwarp(hmask);
         }
         if (singular) break;

@@ -29,9 +29,26 @@ for l in dis:
         out.append((cur, m.group(2)))
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(csvtxt.split("\n")))
-h = rows[1]
+# the CSV holds one section per profiled kernel: "Kernel Name",<name> / header / instruction rows
+sections, cur_name, hdr, body = [], None, None, []
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        if cur_name is not None:
+            sections.append((cur_name, hdr, body))
+        cur_name, hdr, body = r[1] if len(r) > 1 else "", None, []
+    elif cur_name is not None and hdr is None and r:
+        hdr = r
+    elif cur_name is not None and r:
+        body.append(r)
+if cur_name is not None:
+    sections.append((cur_name, hdr, body))
+short = kern.split("_kernel")[0]
+sec = [x for x in sections if short in x[0]]
+if not sec:
+    sys.exit("kernel not found in report: " + ", ".join(x[0][:40] for x in sections))
+_, h, sass = sec[0]
 iS, iI = h.index("# Samples"), h.index("Instructions Executed")
-sass = [r for r in rows[2:] if len(r) > iI]
+sass = [r for r in sass if len(r) > iI]
 print("sass instrs: disasm", len(out), "ncu", len(sass))
 agg = defaultdict(lambda: [0, 0])
 for (cur, ins), r in zip(out, sass):
