@@ -91,6 +91,7 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
             const uint32_t rep1 = lab[(size_t)(y + dys[d]) * g.w + x + dxs[d]];
             key = rep0 < rep1 ? ((unsigned long long)rep1 << 32) | rep0 : ((unsigned long long)rep0 << 32) | rep1;
         }
+        if (__ballot_sync(full, emit[d]) == 0) continue;     // warp-uniform: nobody probes this direction
         const uint32_t peers = __match_any_sync(full, key);
         if (!emit[d]) continue;
         const int lane = threadIdx.x & 31;

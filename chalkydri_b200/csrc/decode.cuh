@@ -172,17 +172,29 @@ __device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q
                     const double x0 = alpha * (double)p[a][0] + (1 - alpha) * (double)p[bb][0];
                     const double y0 = alpha * (double)p[a][1] + (1 - alpha) * (double)p[bb][1];
                     double Mn = 0, Mcount = 0;
-                    for (double n = -range; n <= range; n += 0.25) {
-                        const double grange = 1;
-                        const int x1 = (int)(x0 + (n + grange) * nx), y1 = (int)(y0 + (n + grange) * ny);
-                        if (x1 < 0 || x1 >= W || y1 < 0 || y1 >= H) continue;
-                        const int x2 = (int)(x0 + (n - grange) * nx), y2 = (int)(y0 + (n - grange) * ny);
-                        if (x2 < 0 || x2 >= W || y2 < 0 || y2 >= H) continue;
-                        const int g1 = img[(size_t)y1 * stride + x1], g2 = img[(size_t)y2 * stride + x2];
-                        if (g1 < g2) continue;
-                        const double weight = (double)((g2 - g1) * (g2 - g1));
-                        Mn += weight * n;
-                        Mcount += weight;
+                    // upstream: for (double n = -range; n <= range; n += 0.25).  k*0.25 - range is exact in binary, so the steps are
+                    // enumerated by index; five steps (ten gathers) are kept in flight at a time.  weight and weight*n are exact
+                    // in double (integers times multiples of 1/4), so Mn / Mcount do not depend on the evaluation order.
+                    const int nsteps = (int)(range * 8.0) + 1;
+                    for (int i0 = 0; i0 < nsteps; i0 += 5) {
+                        int g1v[5], g2v[5];
+#pragma unroll
+                        for (int u = 0; u < 5; u++) {
+                            const double n = -range + 0.25 * (i0 + u);
+                            const int x1 = (int)(x0 + (n + 1) * nx), y1 = (int)(y0 + (n + 1) * ny);
+                            const int x2 = (int)(x0 + (n - 1) * nx), y2 = (int)(y0 + (n - 1) * ny);
+                            const bool ok = i0 + u < nsteps && !(x1 < 0 || x1 >= W || y1 < 0 || y1 >= H) && !(x2 < 0 || x2 >= W || y2 < 0 || y2 >= H);
+                            g1v[u] = -1; g2v[u] = 0;
+                            if (ok) { g1v[u] = img[(size_t)y1 * stride + x1]; g2v[u] = img[(size_t)y2 * stride + x2]; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 5; u++) {
+                            if (g1v[u] < g2v[u]) continue;          // also skips the out-of-range steps (g1 = -1)
+                            const double n = -range + 0.25 * (i0 + u);
+                            const double weight = (double)((g2v[u] - g1v[u]) * (g2v[u] - g1v[u]));
+                            Mn += weight * n;
+                            Mcount += weight;
+                        }
                     }
                     if (Mcount != 0) {
                         const double n0 = Mn / Mcount;

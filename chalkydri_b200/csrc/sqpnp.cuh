@@ -388,7 +388,7 @@ __device__ __forceinline__ double quad_form9(const double *om, const double *r)
     return e;
 }
 
-__global__ void __launch_bounds__(SQ_WARPS * 32)
+__global__ void __launch_bounds__(SQ_WARPS * 32, 4)
 sqpnp_kernel(const cb_iso3 *__restrict__ tags, const double *__restrict__ bearings, const int32_t *__restrict__ n_tags, int max_tags,
              const cb_iso3 *__restrict__ robot_to_cam_p, const double *__restrict__ gyro_arr, long long nprob, cb_pose *__restrict__ out,
              uint8_t *__restrict__ ok, SqParams prm)
