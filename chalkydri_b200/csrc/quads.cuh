@@ -14,7 +14,8 @@
 // clusters of 24..7000 points), so the design maximises the number of clusters in flight instead of the threads per
 // cluster.  Two persistent kernels pull (frame, cluster) items from device-side work lists:
 //   tier S: clusters of <= 512 points, ONE WARP per cluster (10 KB smem per warp, 20 warps per SM);
-//   tier L: larger clusters, one 256-thread CTA per cluster (96 KB smem, 2 CTAs per SM; clusters above 6144 points
+//   tier M: 513..2048 points, one 128-thread CTA per cluster (34 KB smem, 6 CTAs per SM);
+//   tier L: larger clusters, one 256-thread CTA per cluster (98 KB smem, 2 CTAs per SM; clusters above 6144 points
 //           run the same code out of a global scratch area).
 // A boundary point is fully described by its 32-bit scan key (pixel index, probe, gradient sign), so the only
 // per-point input is 4 bytes; sorting happens on packed (slope, scan key) 64-bit words in shared memory.
@@ -26,7 +27,7 @@ namespace cb {
 constexpr int QS_MAXN = 512;      // tier S: points per warp
 constexpr int QS_WARPS = 4;
 constexpr int QL_THREADS = 256;
-constexpr int QL_MAXN = 6144;     // tier L: points per CTA in shared memory
+constexpr int QL_MAXN = 6144;     // tier L: points per CTA in shared memory (tier M: 128 threads, 2048 points)
 
 struct LineFit { double Ex, Ey, nx, ny, err, mse; };
 
@@ -566,23 +567,27 @@ fit_quads_small_kernel(const uint8_t *__restrict__ in, const uint32_t *__restric
     }
 }
 
+template <int MAXN>
 struct QlShared {
-    unsigned long long A[QL_MAXN];
-    unsigned long long B[QL_MAXN];
+    unsigned long long A[MAXN];
+    unsigned long long B[MAXN];    // directly after A
     QfScratch S;
     int work;
 };
 
-// tier L: persistent CTAs, one cluster (> QS_MAXN points) per CTA at a time
-__global__ void __launch_bounds__(QL_THREADS)
-fit_quads_large_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ scankey, const ClusterRec *__restrict__ clusters,
-                       const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
-                       double *__restrict__ lfps_all, unsigned long long *__restrict__ scratch, QuadRec *__restrict__ quads,
-                       uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps,
-                       DetParams prm)
+// tiers M / L: persistent CTAs of NT threads, one cluster of (min_n, ...] points per CTA at a time; clusters above MAXN
+// points run out of the global scratch area.  Tier M (NT = 128, MAXN = 2048, 34 KB smem) keeps 6 CTAs per SM resident,
+// tier L (NT = 256, MAXN = 6144, 98 KB) two.
+template <int NT, int MAXN>
+__global__ void __launch_bounds__(NT)
+fit_quads_cta_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ scankey, const ClusterRec *__restrict__ clusters,
+                     const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
+                     double *__restrict__ lfps_all, unsigned long long *__restrict__ scratch, QuadRec *__restrict__ quads,
+                     uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps,
+                     DetParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    QlShared &SH = *reinterpret_cast<QlShared *>(smem_raw);
+    QlShared<MAXN> &SH = *reinterpret_cast<QlShared<MAXN> *>(smem_raw);
     const uint32_t total = *nwork;
     for (;;) {
         __syncthreads();
@@ -594,13 +599,15 @@ fit_quads_large_kernel(const uint8_t *__restrict__ in, const uint32_t *__restric
         const int b = item / caps.clusters_per_frame;
         const ClusterRec rec = clusters[item];
         const int n = (int)rec.count;
-        if (n <= QS_MAXN) continue;
+        if (n < 24) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         unsigned long long *A = SH.A, *B = SH.B;
-        if (n > QL_MAXN) { A = scratch + pbase * 2; B = A + n; }
-        fit_quad_cluster<QL_THREADS>(in + (size_t)b * g.frame_stride, scankey + pbase, n, A, B, lfps_all + pbase * 6, SH.S, rec, b, quads, nquads,
-                                     nquads_total, errflag, g, caps, prm);
+        if (n > MAXN) { A = scratch + pbase * 2; B = A + n; }
+        fit_quad_cluster<NT>(in + (size_t)b * g.frame_stride, scankey + pbase, n, A, B, lfps_all + pbase * 6, SH.S, rec, b, quads, nquads,
+                             nquads_total, errflag, g, caps, prm);
     }
 }
+
+constexpr int QM_THREADS = 128, QM_MAXN = 2048;
 
 }  // namespace cb
