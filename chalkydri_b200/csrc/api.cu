@@ -208,7 +208,7 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     ok = ok && alloc((void **)&ctx->d_labels, ctx->label_bytes) && alloc((void **)&ctx->d_sizes, ctx->label_bytes);
     ok = ok && alloc((void **)&ctx->d_table, B * c.slots_per_frame * sizeof(ClusterSlot));
     ok = ok && alloc((void **)&ctx->d_clusters, B * c.clusters_per_frame * sizeof(ClusterRec));
-    ok = ok && alloc((void **)&ctx->d_worklist, 3 * B * c.clusters_per_frame * sizeof(uint32_t));
+    ok = ok && alloc((void **)&ctx->d_worklist, 4 * B * c.clusters_per_frame * sizeof(uint32_t));
     ok = ok && alloc((void **)&ctx->d_scankey, B * c.points_per_frame * sizeof(uint32_t));
     ok = ok && alloc((void **)&ctx->d_lfps, B * c.points_per_frame * 6 * sizeof(double));
     ok = ok && alloc((void **)&ctx->d_scratch, B * c.points_per_frame * 2 * sizeof(unsigned long long));
@@ -227,7 +227,8 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ThrTmaWarp) * THR_TMA_WARPS)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM_THREADS, QM_MAXN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM_MAXN>)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM2_THREADS, QM2_MAXN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM2_MAXN>)) == cudaSuccess;
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
             uint16_t combos[210];
             int nc = 0;
@@ -315,8 +316,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     const DetParams &prm = ctx->prm;
     const int B = g.batch;
     int launches = 0, thr_launches = 0;
-    uint32_t *d_wl_large = ctx->d_worklist + (size_t)ctx->max_batch * caps.clusters_per_frame;
-    uint32_t *d_wl_medium = ctx->d_worklist + 2 * (size_t)ctx->max_batch * caps.clusters_per_frame;
+    const size_t wl_stride = (size_t)ctx->max_batch * caps.clusters_per_frame;       // four tier work lists, back to back
     uint32_t *d_ncl = ctx->d_small, *d_npt = ctx->d_small + ctx->max_batch, *d_nq = ctx->d_small + 2 * ctx->max_batch,
              *d_nraw = ctx->d_small + 3 * ctx->max_batch, *d_misc = ctx->d_small + 4 * ctx->max_batch;
     // misc: [0] errflag, [1] nwork, [2] work_counter, [3] nquads_total, [4] decode counter
@@ -393,25 +393,29 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         if (g.h > 2 && g.w > 2) {
             dim3 gc((g.w + 255) / 256, g.h - 2, B);
             cluster_pass_kernel<false><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
-            cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, d_misc + 1, d_wl_medium, d_misc + 7, d_wl_large, d_misc + 5,
-                                                     (uint32_t)QS_MAXN, (uint32_t)QM_MAXN, d_misc, g, caps, prm.min_cluster_pixels);
+            // misc: [0] error flags, [3] quads total, [4] decode counter, [8 + 2t] items of tier t, [9 + 2t] its work counter
+            cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, wl_stride,
+                                                                                            d_misc + 8, 2, (uint32_t)QS_MAXN, (uint32_t)QM1_MAXN,
+                                                                                            (uint32_t)QM2_MAXN, d_misc, g, caps, prm.min_cluster_pixels);
             cluster_pass_kernel<true><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
             launches += 3;
         }
         CK(cudaEventRecord(ctx->ev[4], st));
         // ---- A5 quad fitting ----
-        // tier L first (long jobs), then M, then S; misc: [1] n small, [2] small counter, [5] n large, [6] large counter,
-        // [7] n medium, [8] medium counter
+        // largest tier first (long jobs)
         fit_quads_cta_kernel<QL_THREADS, QL_MAXN><<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared<QL_MAXN>), st>>>(
-            d_frames, ctx->d_scankey, ctx->d_clusters, d_wl_large, d_misc + 5, d_misc + 6, ctx->d_lfps, ctx->d_scratch, ctx->d_quads, d_nq, d_misc + 3,
-            d_misc, g, caps, prm);
-        fit_quads_cta_kernel<QM_THREADS, QM_MAXN><<<ctx->num_sms * 6, QM_THREADS, sizeof(QlShared<QM_MAXN>), st>>>(
-            d_frames, ctx->d_scankey, ctx->d_clusters, d_wl_medium, d_misc + 7, d_misc + 8, ctx->d_lfps, ctx->d_scratch, ctx->d_quads, d_nq, d_misc + 3,
-            d_misc, g, caps, prm);
+            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist + 3 * wl_stride, d_misc + 14, d_misc + 15, ctx->d_lfps, ctx->d_scratch, ctx->d_quads,
+            d_nq, d_misc + 3, d_misc, g, caps, prm);
+        fit_quads_cta_kernel<QM2_THREADS, QM2_MAXN><<<1, QM2_THREADS, sizeof(QlShared<QM2_MAXN>), st>>>(
+            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist + 2 * wl_stride, d_misc + 12, d_misc + 13, ctx->d_lfps, ctx->d_scratch, ctx->d_quads,
+            d_nq, d_misc + 3, d_misc, g, caps, prm);
+        fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN><<<ctx->num_sms * 6, QM1_THREADS, sizeof(QlShared<QM1_MAXN>), st>>>(
+            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist + 1 * wl_stride, d_misc + 10, d_misc + 11, ctx->d_lfps, ctx->d_scratch, ctx->d_quads,
+            d_nq, d_misc + 3, d_misc, g, caps, prm);
         fit_quads_small_kernel<<<ctx->num_sms * 4, QS_WARPS * 32, sizeof(QsShared), st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist,
-                                                                                      d_misc + 1, d_misc + 2, ctx->d_lfps, ctx->d_quads, d_nq,
+                                                                                      d_misc + 8, d_misc + 9, ctx->d_lfps, ctx->d_quads, d_nq,
                                                                                       d_misc + 3, d_misc, g, caps, prm);
-        launches += 3;
+        launches += 4;
         CK(cudaEventRecord(ctx->ev[5], st));
     } else {
         CK(cudaEventRecord(ctx->ev[4], st));

@@ -132,10 +132,9 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
 // of its tier (one warp per small cluster, one CTA per large one).
 __global__ void __launch_bounds__(256)
 cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ clusters, uint32_t *__restrict__ nclusters,
-                      uint32_t *__restrict__ npoints, uint32_t *__restrict__ worklist_small, uint32_t *__restrict__ nwork_small,
-                      uint32_t *__restrict__ worklist_medium, uint32_t *__restrict__ nwork_medium, uint32_t *__restrict__ worklist_large,
-                      uint32_t *__restrict__ nwork_large, uint32_t small_max, uint32_t medium_max, uint32_t *__restrict__ errflag, Geom g,
-                      Caps caps, int min_cluster_pixels)
+                      uint32_t *__restrict__ npoints, uint32_t *__restrict__ worklists, size_t list_stride, uint32_t *__restrict__ nwork,
+                      int nwork_stride, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t *__restrict__ errflag, Geom g, Caps caps,
+                      int min_cluster_pixels)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -155,9 +154,8 @@ cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ 
     clusters[(size_t)b * caps.clusters_per_frame + ci] = r;
     slot->cluster = ci;
     const uint32_t item = (uint32_t)b * caps.clusters_per_frame + ci;
-    if (cnt > medium_max) worklist_large[atomicAdd(nwork_large, 1u)] = item;
-    else if (cnt > small_max) worklist_medium[atomicAdd(nwork_medium, 1u)] = item;
-    else worklist_small[atomicAdd(nwork_small, 1u)] = item;
+    const int tier = cnt <= t0 ? 0 : (cnt <= t1 ? 1 : (cnt <= t2 ? 2 : 3));     // work list of the quad-fitting tier
+    worklists[(size_t)tier * list_stride + atomicAdd(&nwork[tier * nwork_stride], 1u)] = item;
 }
 
 }  // namespace cb

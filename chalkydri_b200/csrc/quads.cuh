@@ -13,8 +13,8 @@
 // B200 mapping: the work is thousands of small, irregular, partly sequential jobs per frame (a c2 frame has ~700
 // clusters of 24..7000 points), so the design maximises the number of clusters in flight instead of the threads per
 // cluster.  Two persistent kernels pull (frame, cluster) items from device-side work lists:
-//   tier S: clusters of <= 512 points, ONE WARP per cluster (10 KB smem per warp, 20 warps per SM);
-//   tier M: 513..2048 points, one 128-thread CTA per cluster (34 KB smem, 6 CTAs per SM);
+//   tier S: clusters of <= 256 points, ONE WARP per cluster (6 KB smem per warp, 32 warps per SM);
+//   tier M: 257..2048 points, one 128-thread CTA per cluster (34 KB smem, 6 CTAs per SM);
 //   tier L: larger clusters, one 256-thread CTA per cluster (98 KB smem, 2 CTAs per SM; clusters above 6144 points
 //           run the same code out of a global scratch area).
 // A boundary point is fully described by its 32-bit scan key (pixel index, probe, gradient sign), so the only
@@ -24,8 +24,8 @@
 
 namespace cb {
 
-constexpr int QS_MAXN = 512;      // tier S: points per warp
-constexpr int QS_WARPS = 4;
+constexpr int QS_MAXN = 256;      // tier S: points per warp
+constexpr int QS_WARPS = 8;
 constexpr int QL_THREADS = 256;
 constexpr int QL_MAXN = 6144;     // tier L: points per CTA in shared memory (tier M: 128 threads, 2048 points)
 
@@ -608,6 +608,9 @@ fit_quads_cta_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict_
     }
 }
 
-constexpr int QM_THREADS = 128, QM_MAXN = 2048;
+// tiers: S (one warp, <= QS_MAXN) | M1 (128 threads, <= 2048) | M2 (spare slot: same bound as M1, so it stays empty) | L (256 threads, the rest).
+// Measured on the c2 workload (quad stage, ms per 256 frames): S512/L 24.6; S512/M2048/L 21.4; S256x8/M2048/L 18.7; S256/M1024(64 thr)/M3072/L 19.8.
+constexpr int QM1_THREADS = 128, QM1_MAXN = 2048;
+constexpr int QM2_THREADS = 128, QM2_MAXN = 2048;
 
 }  // namespace cb
