@@ -153,9 +153,11 @@ __device__ __forceinline__ void ptsort_emulate(T *&src, T *&dst, int n, int tid,
     Grp<NT>::sync();
     int maxd = 0;
     { int sz = n; while (sz > 5) { sz = sz - sz / 2; maxd++; } }
-    const int E = (n + NT - 1) / NT;
+    // elements per thread: at least 16 in the CTA tiers, so that the per-level fixed cost (node lookup + merge-path search)
+    // is amortised and warps without work stay idle instead of issuing that overhead for 2-3 elements each
+    const int E = NT == 32 ? (n + NT - 1) / NT : max(16, (n + NT - 1) / NT);
     for (int d = maxd - 1; d >= 0; d--) {
-        int p = tid * E;
+        int p = min(n, tid * E);
         const int p1 = min(n, p + E);
         while (p < p1) {
             int lo, hi;
@@ -167,10 +169,12 @@ __device__ __forceinline__ void ptsort_emulate(T *&src, T *&dst, int n, int tid,
             while (l < h) { const int m = (l + h) >> 1; if (key_of(src[lo + m]) < key_of(src[mid + k - m - 1])) l = m + 1; else h = m; }
             int ai = l, bi = k - l;
             T av = src[lo + min(ai, an - 1)], bv = src[mid + min(bi, bn - 1)];
-            for (; p < e; p++) {
-                const bool take_a = (bi >= bn) || (ai < an && key_of(av) < key_of(bv));
-                if (take_a) { dst[p] = av; ai++; if (ai < an) av = src[lo + ai]; }
-                else { dst[p] = bv; bi++; if (bi < bn) bv = src[mid + bi]; }
+            for (; p < e; p++) {      // branch-free step: lanes of a warp stay converged
+                const bool take_a = (bi >= bn) | ((ai < an) & (key_of(av) < key_of(bv)));
+                dst[p] = take_a ? av : bv;
+                ai += take_a ? 1 : 0; bi += take_a ? 0 : 1;
+                const T nv = src[take_a ? lo + min(ai, an - 1) : mid + min(bi, bn - 1)];
+                av = take_a ? nv : av; bv = take_a ? bv : nv;
             }
         }
         Grp<NT>::sync();

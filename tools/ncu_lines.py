@@ -3,8 +3,10 @@ usage: ncu_lines.py <report.ncu-rep> <kernel-substring> [top]"""
 import csv, re, subprocess, sys, os, tempfile
 from collections import defaultdict
 
+# usage: ncu_lines.py <report> <substring of the (mangled) kernel symbol> [top] [substring of the demangled name in the report]
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+name_filter = sys.argv[4] if len(sys.argv) > 4 else None
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "chalkydri_b200", "libchalkydri_b200.so")
 tmp = tempfile.mkdtemp()
@@ -42,11 +44,16 @@ for r in rows:
         body.append(r)
 if cur_name is not None:
     sections.append((cur_name, hdr, body))
-short = kern.split("_kernel")[0]
+short = name_filter if name_filter else kern.split("_kernel")[0]
 sec = [x for x in sections if short in x[0]]
 if not sec:
     sys.exit("kernel not found in report: " + ", ".join(x[0][:40] for x in sections))
-_, h, sass = sec[0]
+def _total(x):
+    hh = x[1]
+    ii = hh.index("Instructions Executed")
+    return sum(int(r[ii] or 0) for r in x[2] if len(r) > ii and (r[ii] or "0").isdigit())
+sec.sort(key=_total)
+_, h, sass = sec[-1]                  # the launch that did the most work
 iS, iI = h.index("# Samples"), h.index("Instructions Executed")
 sass = [r for r in sass if len(r) > iI]
 print("sass instrs: disasm", len(out), "ncu", len(sass))
