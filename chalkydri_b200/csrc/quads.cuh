@@ -197,9 +197,14 @@ struct QfScratch {       // per group (warp or CTA)
 
 // Processes one cluster.  A and B are 8-byte-per-point work arrays (shared or global), lfps the 48-byte-per-point
 // prefix-moment array (global).  Every thread of the group must call it; control flow is group-uniform.
-template <int NT>
-__device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t *__restrict__ K, int n, unsigned long long *A,
-                                 unsigned long long *B, double *__restrict__ lfps, QfScratch &S, const ClusterRec &rec, int b,
+// PHASE 0: everything.  PHASE 1: up to and including the slope sort; the sorted points (packed px | py << 16) replace the
+// cluster's scan keys in global memory and rejected clusters get cursor = 0xffffffff.  PHASE 2: the rest, starting from
+// those sorted points.  Splitting the work into two kernels halves the instruction footprint of each (the one-warp-per-
+// cluster tier is instruction-fetch bound when every warp of an SM sits in a different part of a 100 KB kernel).
+template <int NT, int PHASE>
+__device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__restrict__ K, int n, unsigned long long *A,
+                                 unsigned long long *B, double *__restrict__ lfps, QfScratch &S, const ClusterRec &rec,
+                                 ClusterRec *__restrict__ rec_global, int b,
                                  QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
                                  uint32_t *__restrict__ errflag, const Geom &g, const Caps &caps, const DetParams &prm)
 {
@@ -207,6 +212,9 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
     const int tid = G::tid();
     const int lane = threadIdx.x & 31;
 
+    int reversed_border = 0;
+    unsigned long long *src, *dst;
+    if (PHASE != 2) {
     // ---- scan keys -> work array; bounding box ----------------------------------------------------------------
     uint32_t *k0 = reinterpret_cast<uint32_t *>(A), *k1 = k0 + n;      // two u32 halves of A for the scan-order sort
     int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
@@ -221,7 +229,7 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
     xmax = G::reduce(xmax, [](int a, int c) { return max(a, c); }, S.red_i);
     ymin = G::reduce(ymin, [](int a, int c) { return min(a, c); }, S.red_i);
     ymax = G::reduce(ymax, [](int a, int c) { return max(a, c); }, S.red_i);
-    if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) return;
+    if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) { if (PHASE == 1 && tid == 0) rec_global->cursor = 0xffffffffu; return; }
     const float cx = (float)((xmin + xmax) * 0.5 + 0.05118);
     const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
     G::sync();
@@ -236,8 +244,8 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
         dot += dx * (float)gx + dy * (float)gy;
     }
     dot = G::reduce(dot, [](float a, float c) { return a + c; }, S.red_f);
-    const int reversed_border = dot < 0.f;
-    if (reversed_border) return;                   // tag36h11 has a normal border only
+    reversed_border = dot < 0.f;
+    if (reversed_border) { if (PHASE == 1 && tid == 0) rec_global->cursor = 0xffffffffu; return; }   // tag36h11 has a normal border only
     G::sync();
 
     // ---- restore scan order: merge sort of the (unique) scan keys -------------------------------------------------
@@ -262,8 +270,17 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, const uint32_t
     G::sync();
 
     // ---- ptsort() on the slope keys -------------------------------------------------------------------------------
-    unsigned long long *src = B, *dst = A;
+    src = B; dst = A;
     ptsort_emulate<NT>(src, dst, n, tid, [](unsigned long long v) { return (uint32_t)(v >> 32); });
+    if (PHASE == 1) {
+        for (int j = tid; j < n; j += NT) K[j] = (uint32_t)src[j];
+        return;
+    }
+    } else {
+        src = A; dst = B;
+        for (int j = tid; j < n; j += NT) A[j] = K[j];
+        G::sync();
+    }
     // src: sorted (slope key, packed px | py << 16).  ---- compute_lfps -----------------------------------------------------------
     // per-point weight (parallel), then the sequential prefix: each block of 32 points is expanded into its six
     // terms by 32 lanes, staged in shared memory, and accumulated in order by lanes 0..5 of the first warp.
@@ -544,8 +561,9 @@ struct QsWarp {
 struct QsShared { QsWarp w[QS_WARPS]; };
 
 // tier S: persistent warps, one cluster (<= QS_MAXN points) per warp at a time
+template <int PHASE>
 __global__ void __launch_bounds__(QS_WARPS * 32)
-fit_quads_small_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ scankey, const ClusterRec *__restrict__ clusters,
+fit_quads_small_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters,
                        const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
                        double *__restrict__ lfps_all, QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads,
                        uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm)
@@ -564,8 +582,10 @@ fit_quads_small_kernel(const uint8_t *__restrict__ in, const uint32_t *__restric
         const ClusterRec rec = clusters[item];
         const int n = (int)rec.count;
         if (n < 24 || n > QS_MAXN) continue;
+        if (PHASE == 2 && rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
-        fit_quad_cluster<32>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.w[wid].A, SH.w[wid].B, lfps_all + pbase * 6, SH.w[wid].S, rec, b,
+        fit_quad_cluster<32, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.w[wid].A, SH.w[wid].B, lfps_all + pbase * 6, SH.w[wid].S, rec,
+                                    clusters + item, b,
                              quads, nquads, nquads_total, errflag, g, caps, prm);
         __syncwarp();
     }
@@ -582,9 +602,9 @@ struct QlShared {
 // tiers M / L: persistent CTAs of NT threads, one cluster of (min_n, ...] points per CTA at a time; clusters above MAXN
 // points run out of the global scratch area.  Tier M (NT = 128, MAXN = 2048, 34 KB smem) keeps 6 CTAs per SM resident,
 // tier L (NT = 256, MAXN = 6144, 98 KB) two.
-template <int NT, int MAXN>
+template <int NT, int MAXN, int PHASE>
 __global__ void __launch_bounds__(NT)
-fit_quads_cta_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ scankey, const ClusterRec *__restrict__ clusters,
+fit_quads_cta_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters,
                      const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
                      double *__restrict__ lfps_all, unsigned long long *__restrict__ scratch, QuadRec *__restrict__ quads,
                      uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps,
@@ -604,10 +624,11 @@ fit_quads_cta_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict_
         const ClusterRec rec = clusters[item];
         const int n = (int)rec.count;
         if (n < 24) continue;
+        if (PHASE == 2 && rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         unsigned long long *A = SH.A, *B = SH.B;
         if (n > MAXN) { A = scratch + pbase * 2; B = A + n; }
-        fit_quad_cluster<NT>(in + (size_t)b * g.frame_stride, scankey + pbase, n, A, B, lfps_all + pbase * 6, SH.S, rec, b, quads, nquads,
+        fit_quad_cluster<NT, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, A, B, lfps_all + pbase * 6, SH.S, rec, clusters + item, b, quads, nquads,
                              nquads_total, errflag, g, caps, prm);
     }
 }
