@@ -216,21 +216,21 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     ok = ok && alloc((void **)&ctx->d_raw, B * c.quads_per_frame * sizeof(RawDet));
     ok = ok && alloc((void **)&ctx->d_dets, B * c.dets_per_frame * sizeof(cb_detection));
     ok = ok && alloc((void **)&ctx->d_counts, B * sizeof(int32_t));
-    ok = ok && alloc((void **)&ctx->d_small, (4 * B + 32) * sizeof(uint32_t));
+    ok = ok && alloc((void **)&ctx->d_small, (4 * B + 48) * sizeof(uint32_t));
     ok = ok && cudaMallocHost((void **)&ctx->h_dets, B * c.dets_per_frame * sizeof(cb_detection)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&ctx->h_counts, B * sizeof(int32_t)) == cudaSuccess;
-    ok = ok && cudaMallocHost((void **)&ctx->h_small, (4 * B + 32) * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&ctx->h_small, (4 * B + 48) * sizeof(uint32_t)) == cudaSuccess;
     if (ok) {
         ok = ok && cudaMemcpyToSymbol(c_codes, kHostCodes, sizeof(kHostCodes)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ThrTmaWarp) * THR_TMA_WARPS)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
+#define CB_QUAD_ATTR(PH)                                                                                                                                              \
+        ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel<PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;              \
+        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess; \
+        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
+        CB_QUAD_ATTR(1) CB_QUAD_ATTR(2) CB_QUAD_ATTR(3) CB_QUAD_ATTR(4)
+#undef CB_QUAD_ATTR
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
             uint16_t combos[210];
             int nc = 0;
@@ -322,7 +322,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     uint32_t *d_ncl = ctx->d_small, *d_npt = ctx->d_small + ctx->max_batch, *d_nq = ctx->d_small + 2 * ctx->max_batch,
              *d_nraw = ctx->d_small + 3 * ctx->max_batch, *d_misc = ctx->d_small + 4 * ctx->max_batch;
     // misc: [0] errflag, [1] nwork, [2] work_counter, [3] nquads_total, [4] decode counter
-    CK(cudaMemsetAsync(ctx->d_small, 0, (4 * (size_t)ctx->max_batch + 32) * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(ctx->d_small, 0, (4 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), st));
     CK(cudaEventRecord(ctx->ev[1], st));
     // ---- A1+A2 threshold ----
     const bool fast = g.f == 2 && (g.stride % 16 == 0) && (g.frame_stride % 16 == 0) && ((uintptr_t)d_frames % 16 == 0) && g.tw > 0 && g.th > 0;
@@ -404,7 +404,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         }
         CK(cudaEventRecord(ctx->ev[4], st));
         // ---- A5 quad fitting ----
-        // two phases (sort | fit), largest tier first inside each (long jobs); work counters of phase 2 live at misc[17 + 2t]
+        // two phases (sort | fit), largest tier first inside each (long jobs); work counters of phase p live at misc[1 + 8p + 2t]
 #define CB_LAUNCH_QUAD_PHASE(PH, CNT_BASE)                                                                                                        \
         fit_quads_cta_kernel<QL_THREADS, QL_MAXN, PH><<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared<QL_MAXN>), st>>>(                              \
             d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist + 3 * wl_stride, d_misc + 14, d_misc + (CNT_BASE) + 6, ctx->d_lfps, ctx->d_scratch, \
@@ -417,8 +417,10 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
                                                                                           d_nq, d_misc + 3, d_misc, g, caps, prm);
         CB_LAUNCH_QUAD_PHASE(1, 9)
         CB_LAUNCH_QUAD_PHASE(2, 17)
+        CB_LAUNCH_QUAD_PHASE(3, 25)
+        CB_LAUNCH_QUAD_PHASE(4, 33)
 #undef CB_LAUNCH_QUAD_PHASE
-        launches += 6;
+        launches += 12;
         CK(cudaEventRecord(ctx->ev[5], st));
     } else {
         CK(cudaEventRecord(ctx->ev[4], st));
@@ -469,7 +471,7 @@ static int detect_device_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom 
     const size_t B = g.batch;
     CK(cudaMemcpyAsync(ctx->h_dets, ctx->d_dets, B * ctx->caps.dets_per_frame * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (4 * (size_t)ctx->max_batch + 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (4 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev[7], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     finish_timing(ctx, timed_h2d, true);
@@ -691,7 +693,7 @@ static int tap_common(cb_ctx *ctx, const uint8_t *frames, int width, int height,
     if (rc) return rc;
     rc = run_pipeline(ctx, ctx->d_in, g, stage);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (4 * (size_t)ctx->max_batch + 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (4 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev[7], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     finish_timing(ctx, true, true);

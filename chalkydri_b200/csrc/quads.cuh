@@ -197,10 +197,13 @@ struct QfScratch {       // per group (warp or CTA)
 
 // Processes one cluster.  A and B are 8-byte-per-point work arrays (shared or global), lfps the 48-byte-per-point
 // prefix-moment array (global).  Every thread of the group must call it; control flow is group-uniform.
-// PHASE 0: everything.  PHASE 1: up to and including the slope sort; the sorted points (packed px | py << 16) replace the
-// cluster's scan keys in global memory and rejected clusters get cursor = 0xffffffff.  PHASE 2: the rest, starting from
-// those sorted points.  Splitting the work into two kernels halves the instruction footprint of each (the one-warp-per-
-// cluster tier is instruction-fetch bound when every warp of an SM sits in a different part of a 100 KB kernel).
+// The work on a cluster is cut into four phases, each its own kernel (per tier), because the one-warp-per-cluster tier is
+// instruction-fetch bound when every warp of an SM sits in a different part of a 100 KB kernel (ncu: stall_no_instruction):
+//   PHASE 1: bounding box, border polarity (rejected clusters get cursor = 0xffffffff), scan-order sort; the sorted scan
+//            keys replace the unsorted ones in global memory;
+//   PHASE 2: slopes, ptsort() emulation; the sorted points (px | py << 16) replace the keys;
+//   PHASE 3: per-point weights and the sequential prefix moments (global lfps array);
+//   PHASE 4: window errors, maxima, corner search, corner / area / convexity tests.
 template <int NT, int PHASE>
 __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__restrict__ K, int n, unsigned long long *A,
                                  unsigned long long *B, double *__restrict__ lfps, QfScratch &S, const ClusterRec &rec,
@@ -212,75 +215,70 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__re
     const int tid = G::tid();
     const int lane = threadIdx.x & 31;
 
-    int reversed_border = 0;
-    unsigned long long *src, *dst;
-    if (PHASE != 2) {
-    // ---- scan keys -> work array; bounding box ----------------------------------------------------------------
-    uint32_t *k0 = reinterpret_cast<uint32_t *>(A), *k1 = k0 + n;      // two u32 halves of A for the scan-order sort
-    int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
-    for (int i = tid; i < n; i += NT) {
-        const uint32_t key = K[i];
-        k0[i] = key;
-        int px, py, gx, gy;
-        decode_point(key, g.w, px, py, gx, gy);
-        xmin = min(xmin, px); xmax = max(xmax, px); ymin = min(ymin, py); ymax = max(ymax, py);
-    }
-    xmin = G::reduce(xmin, [](int a, int c) { return min(a, c); }, S.red_i);
-    xmax = G::reduce(xmax, [](int a, int c) { return max(a, c); }, S.red_i);
-    ymin = G::reduce(ymin, [](int a, int c) { return min(a, c); }, S.red_i);
-    ymax = G::reduce(ymax, [](int a, int c) { return max(a, c); }, S.red_i);
-    if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) { if (PHASE == 1 && tid == 0) rec_global->cursor = 0xffffffffu; return; }
-    const float cx = (float)((xmin + xmax) * 0.5 + 0.05118);
-    const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
-    G::sync();
-    // border polarity (upstream: dot = sum dx*gx + dy*gy, reversed_border = dot < 0).  Only the sign is used and the
-    // sum does not depend on the order of the points beyond float rounding, so it is evaluated before any sorting:
-    // about half of all clusters (white blobs inside black) are rejected here.
-    float dot = 0.f;
-    for (int i = tid; i < n; i += NT) {
-        int px, py, gx, gy;
-        decode_point(k0[i], g.w, px, py, gx, gy);
-        const float dx = (float)px - cx, dy = (float)py - cy;
-        dot += dx * (float)gx + dy * (float)gy;
-    }
-    dot = G::reduce(dot, [](float a, float c) { return a + c; }, S.red_f);
-    reversed_border = dot < 0.f;
-    if (reversed_border) { if (PHASE == 1 && tid == 0) rec_global->cursor = 0xffffffffu; return; }   // tag36h11 has a normal border only
-    G::sync();
-
-    // ---- restore scan order: merge sort of the (unique) scan keys -------------------------------------------------
-    {
-        uint32_t *ssrc = k0, *sdst = k1;
-        ptsort_emulate<NT>(ssrc, sdst, n, tid, [](uint32_t v) { return v; });
-        k0 = ssrc;   // sorted keys
-    }
-    // ---- slopes in scan order (upstream fit_quad step 1) ---------------------------------------------------------
-    for (int j = tid; j < n; j += NT) {
-        const uint32_t key = k0[j];
-        int px, py, gx, gy;
-        decode_point(key, g.w, px, py, gx, gy);
-        float dx = (float)px - cx, dy = (float)py - cy;
-        float quadrant;
-        if (dy > 0) quadrant = dx > 0 ? 65536.f : 131072.f; else quadrant = dx > 0 ? 0.f : -65536.f;
-        if (dy < 0) { dy = -dy; dx = -dx; }
-        if (dx < 0) { const float t = dx; dx = dy; dy = -t; }
-        const float slope = quadrant + dy / dx;
-        B[j] = ((unsigned long long)float_orderable(slope) << 32) | (uint32_t)px | ((uint32_t)py << 16);
-    }
-    G::sync();
-
-    // ---- ptsort() on the slope keys -------------------------------------------------------------------------------
-    src = B; dst = A;
-    ptsort_emulate<NT>(src, dst, n, tid, [](unsigned long long v) { return (uint32_t)(v >> 32); });
-    if (PHASE == 1) {
-        for (int j = tid; j < n; j += NT) K[j] = (uint32_t)src[j];
+    const int reversed_border = 0;          // reversed clusters never get past phase 1 (tag36h11 has a normal border only)
+    unsigned long long *src = A, *dst = B;
+    if (PHASE == 1 || PHASE == 2) {
+        // ---- scan keys -> work array; bounding box -------------------------------------------------------------
+        uint32_t *k0 = reinterpret_cast<uint32_t *>(A), *k1 = k0 + n;      // two u32 halves of A for the scan-order sort
+        int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
+        for (int i = tid; i < n; i += NT) {
+            const uint32_t key = K[i];
+            k0[i] = key;
+            int px, py, gx, gy;
+            decode_point(key, g.w, px, py, gx, gy);
+            xmin = min(xmin, px); xmax = max(xmax, px); ymin = min(ymin, py); ymax = max(ymax, py);
+        }
+        xmin = G::reduce(xmin, [](int a, int c) { return min(a, c); }, S.red_i);
+        xmax = G::reduce(xmax, [](int a, int c) { return max(a, c); }, S.red_i);
+        ymin = G::reduce(ymin, [](int a, int c) { return min(a, c); }, S.red_i);
+        ymax = G::reduce(ymax, [](int a, int c) { return max(a, c); }, S.red_i);
+        const float cx = (float)((xmin + xmax) * 0.5 + 0.05118);
+        const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
+        G::sync();
+        if (PHASE == 1) {
+            if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) { if (tid == 0) rec_global->cursor = 0xffffffffu; return; }
+            // border polarity (upstream: dot = sum dx*gx + dy*gy, reversed_border = dot < 0).  Only the sign is used and the
+            // sum does not depend on the order of the points beyond float rounding, so it is evaluated before any sorting.
+            float dot = 0.f;
+            for (int i = tid; i < n; i += NT) {
+                int px, py, gx, gy;
+                decode_point(k0[i], g.w, px, py, gx, gy);
+                const float dx = (float)px - cx, dy = (float)py - cy;
+                dot += dx * (float)gx + dy * (float)gy;
+            }
+            dot = G::reduce(dot, [](float a, float c) { return a + c; }, S.red_f);
+            if (dot < 0.f) { if (tid == 0) rec_global->cursor = 0xffffffffu; return; }
+            G::sync();
+            // ---- restore scan order: merge sort of the (unique) scan keys; the sorted keys replace the unsorted ones ----
+            uint32_t *ssrc = k0, *sdst = k1;
+            ptsort_emulate<NT>(ssrc, sdst, n, tid, [](uint32_t v) { return v; });
+            for (int j = tid; j < n; j += NT) K[j] = ssrc[j];
+            return;
+        }
+        // ---- PHASE 2: slopes in scan order (upstream fit_quad step 1), then ptsort() on the slope keys ----------------
+        for (int j = tid; j < n; j += NT) {
+            const uint32_t key = k0[j];
+            int px, py, gx, gy;
+            decode_point(key, g.w, px, py, gx, gy);
+            float dx = (float)px - cx, dy = (float)py - cy;
+            float quadrant;
+            if (dy > 0) quadrant = dx > 0 ? 65536.f : 131072.f; else quadrant = dx > 0 ? 0.f : -65536.f;
+            if (dy < 0) { dy = -dy; dx = -dx; }
+            if (dx < 0) { const float t = dx; dx = dy; dy = -t; }
+            const float slope = quadrant + dy / dx;
+            B[j] = ((unsigned long long)float_orderable(slope) << 32) | (uint32_t)px | ((uint32_t)py << 16);
+        }
+        G::sync();
+        src = B; dst = A;
+        ptsort_emulate<NT>(src, dst, n, tid, [](unsigned long long v) { return (uint32_t)(v >> 32); });
+        for (int j = tid; j < n; j += NT) K[j] = (uint32_t)src[j];      // sorted points (px | py << 16) replace the keys
         return;
     }
-    } else {
-        src = A; dst = B;
+    if (PHASE == 3) {
         for (int j = tid; j < n; j += NT) A[j] = K[j];
         G::sync();
     }
+    if (PHASE == 3) {
     // src: sorted (slope key, packed px | py << 16).  ---- compute_lfps -----------------------------------------------------------
     // per-point weight (parallel), then the sequential prefix: each block of 32 points is expanded into its six
     // terms by 32 lanes, staged in shared memory, and accumulated in order by lanes 0..5 of the first warp.
@@ -327,7 +325,10 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__re
     }
     G::sync();
 
-    // ---- quad_segment_maxima -------------------------------------------------------------------------------------
+        return;
+    }
+
+    // ---- PHASE 4: quad_segment_maxima ---------------------------------------------------------------------------
     const int ksz = min(20, n / 12);
     if (ksz < 2) return;
     double *errs = reinterpret_cast<double *>(src);   // sorted keys are no longer needed
@@ -582,7 +583,7 @@ fit_quads_small_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ sc
         const ClusterRec rec = clusters[item];
         const int n = (int)rec.count;
         if (n < 24 || n > QS_MAXN) continue;
-        if (PHASE == 2 && rec.cursor == 0xffffffffu) continue;
+        if (PHASE >= 2 && rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         fit_quad_cluster<32, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.w[wid].A, SH.w[wid].B, lfps_all + pbase * 6, SH.w[wid].S, rec,
                                     clusters + item, b,
@@ -624,7 +625,7 @@ fit_quads_cta_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scan
         const ClusterRec rec = clusters[item];
         const int n = (int)rec.count;
         if (n < 24) continue;
-        if (PHASE == 2 && rec.cursor == 0xffffffffu) continue;
+        if (PHASE >= 2 && rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         unsigned long long *A = SH.A, *B = SH.B;
         if (n > MAXN) { A = scratch + pbase * 2; B = A + n; }
