@@ -229,7 +229,7 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel<PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;              \
         ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess; \
         ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
-        CB_QUAD_ATTR(1) CB_QUAD_ATTR(2) CB_QUAD_ATTR(3) CB_QUAD_ATTR(4)
+        CB_QUAD_ATTR(1) CB_QUAD_ATTR(2) CB_QUAD_ATTR(4)
 #undef CB_QUAD_ATTR
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
             uint16_t combos[210];
@@ -417,10 +417,11 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
                                                                                           d_nq, d_misc + 3, d_misc, g, caps, prm);
         CB_LAUNCH_QUAD_PHASE(1, 9)
         CB_LAUNCH_QUAD_PHASE(2, 17)
-        CB_LAUNCH_QUAD_PHASE(3, 25)
+        lfps_kernel<<<ctx->num_sms * 6, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 25,
+                                                                  ctx->d_lfps, g, caps);
         CB_LAUNCH_QUAD_PHASE(4, 33)
 #undef CB_LAUNCH_QUAD_PHASE
-        launches += 12;
+        launches += 10;
         CK(cudaEventRecord(ctx->ev[5], st));
     } else {
         CK(cudaEventRecord(ctx->ev[4], st));

@@ -634,6 +634,86 @@ fit_quads_cta_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scan
     }
 }
 
+// ---- phase 3 for every tier: per-point weights + sequential prefix moments, ONE WARP per cluster --------------------
+// The prefix is a dependent chain (one DADD per point and moment) that only six lanes can work on, so threads beyond a
+// warp only add barrier waits; what matters is the number of clusters in flight.  This kernel needs no per-point shared
+// memory (8 warps share 24 KB of staging tiles), so every SM keeps 48+ chains going.  The gradient taps of the next 32
+// points are issued before the current 32 are accumulated, so the gathers hide behind the chain.
+constexpr int LF_WARPS = 8;
+__global__ void __launch_bounds__(LF_WARPS * 32)
+lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const ClusterRec *__restrict__ clusters,
+            const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork /* stride 2, 4 tiers */,
+            uint32_t *__restrict__ work_counter, double *__restrict__ lfps_all, Geom g, Caps caps)
+{
+    __shared__ double stage[LF_WARPS][2][32][6];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t full = 0xffffffffu;
+    const uint32_t cnt_t[4] = {nwork[0], nwork[2], nwork[4], nwork[6]};
+    const uint32_t total = cnt_t[0] + cnt_t[1] + cnt_t[2] + cnt_t[3];
+    for (;;) {
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(work_counter, 1u);
+        wi = __shfl_sync(full, wi, 0);
+        if (wi >= total) return;
+        int t = 3;                                   // largest tier first
+        while (wi >= cnt_t[t]) { wi -= cnt_t[t]; t--; }
+        const uint32_t item = worklists[(size_t)t * wl_stride + wi];
+        const int b = item / caps.clusters_per_frame;
+        const ClusterRec rec = clusters[item];
+        if (rec.cursor == 0xffffffffu || rec.count < 24) continue;
+        const int n = (int)rec.count;
+        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
+        const uint32_t *XY = sorted_xy + pbase;
+        double *lfps = lfps_all + pbase * 6;
+        const uint8_t *img = in + (size_t)b * g.frame_stride;
+        // raw taps of one point: left/right/up/down neighbours of the decimated pixel, -1 = no gradient (W = 1)
+        int gl = -1, gr = 0, gu = 0, gd = 0;
+        uint32_t xy = 0;
+        auto issue = [&](int j) {
+            gl = -1;
+            if (j < n) {
+                xy = XY[j];
+                const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
+                const double x = px * .5 + 0.5, y = py * .5 + 0.5;
+                const int ix = (int)x, iy = (int)y;
+                if (ix > 0 && ix + 1 < g.w && iy > 0 && iy + 1 < g.h) {
+                    const uint8_t *row = img + (size_t)(iy * g.f) * g.stride;
+                    gl = row[(ix - 1) * g.f]; gr = row[(ix + 1) * g.f];
+                    gu = row[(ptrdiff_t)ix * g.f - (ptrdiff_t)g.f * g.stride]; gd = row[(ptrdiff_t)ix * g.f + (ptrdiff_t)g.f * g.stride];
+                }
+            }
+        };
+        issue(lane);
+        double acc = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane, buf = (j0 >> 5) & 1;
+            if (j < n) {
+                double W = 1;
+                if (gl >= 0) {
+                    const int grad_x = gr - gl, grad_y = gd - gu;
+                    W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
+                }
+                const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
+                const double fx = px * .5 + 0.5, fy = py * .5 + 0.5;
+                double *tt = stage[wid][buf][lane];
+                tt[0] = W * fx; tt[1] = W * fy; tt[2] = W * fx * fx; tt[3] = W * fx * fy; tt[4] = W * fy * fy; tt[5] = W;
+            }
+            __syncwarp();
+            issue(j0 + 32 + lane);                   // gathers of the next block fly while this block is accumulated
+            if (lane < 6) {
+                const int cnt = min(32, n - j0);
+                double *o = lfps + (size_t)j0 * 6 + lane;
+#pragma unroll 8
+                for (int k = 0; k < cnt; k++) {
+                    acc += stage[wid][buf][k][lane];
+                    o[(size_t)k * 6] = acc;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // tiers: S (one warp, <= QS_MAXN) | M1 (128 threads, <= 2048) | M2 (spare slot: same bound as M1, so it stays empty) | L (256 threads, the rest).
 // Measured on the c2 workload (quad stage, ms per 256 frames): S512/L 24.6; S512/M2048/L 21.4; S256x8/M2048/L 18.7; S256/M1024(64 thr)/M3072/L 19.8.
 constexpr int QM1_THREADS = 128, QM1_MAXN = 2048;
