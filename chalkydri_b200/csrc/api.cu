@@ -225,12 +225,16 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ThrTmaWarp) * THR_TMA_WARPS)) == cudaSuccess;
-#define CB_QUAD_ATTR(PH)                                                                                                                                              \
-        ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel<PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;              \
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess; \
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
-        CB_QUAD_ATTR(1) CB_QUAD_ATTR(2) CB_QUAD_ATTR(4)
-#undef CB_QUAD_ATTR
+        ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
+#define CB_SORT_ATTR(W)                                                                                                                                  \
+        ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<SORT_S(W), 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SortShared<SORT_S(W)>::BYTES) == cudaSuccess; \
+        ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<SORT_M(W), 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SortShared<SORT_M(W)>::BYTES) == cudaSuccess; \
+        ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<SORT_L1(W), 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SortShared<SORT_L1(W)>::BYTES) == cudaSuccess; \
+        ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<SORT_L2(W), 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SortShared<SORT_L2(W)>::BYTES) == cudaSuccess;
+        CB_SORT_ATTR(1) CB_SORT_ATTR(2)
+#undef CB_SORT_ATTR
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
             uint16_t combos[210];
             int nc = 0;
@@ -397,31 +401,39 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             cluster_pass_kernel<false><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
             // misc: [0] error flags, [3] quads total, [4] decode counter, [8 + 2t] items of tier t, [9 + 2t] its work counter
             cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, wl_stride,
-                                                                                            d_misc + 8, 2, (uint32_t)QS_MAXN, (uint32_t)QM1_MAXN,
-                                                                                            (uint32_t)QM2_MAXN, d_misc, g, caps, prm.min_cluster_pixels);
+                                                                                            d_misc + 8, 2, (uint32_t)QT0, (uint32_t)QT1,
+                                                                                            (uint32_t)QT2, d_misc, g, caps, prm.min_cluster_pixels);
             cluster_pass_kernel<true><<<gc, 256, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
             launches += 3;
         }
         CK(cudaEventRecord(ctx->ev[4], st));
         // ---- A5 quad fitting ----
-        // two phases (sort | fit), largest tier first inside each (long jobs); work counters of phase p live at misc[1 + 8p + 2t]
-#define CB_LAUNCH_QUAD_PHASE(PH, CNT_BASE)                                                                                                        \
-        fit_quads_cta_kernel<QL_THREADS, QL_MAXN, PH><<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared<QL_MAXN>), st>>>(                              \
-            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist + 3 * wl_stride, d_misc + 14, d_misc + (CNT_BASE) + 6, ctx->d_lfps, ctx->d_scratch, \
-            ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);                                                                                 \
-        fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, PH><<<ctx->num_sms * 6, QM1_THREADS, sizeof(QlShared<QM1_MAXN>), st>>>(                          \
-            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist + 1 * wl_stride, d_misc + 10, d_misc + (CNT_BASE) + 2, ctx->d_lfps, ctx->d_scratch, \
-            ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);                                                                                 \
-        fit_quads_small_kernel<PH><<<ctx->num_sms * 4, QS_WARPS * 32, sizeof(QsShared), st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, \
-                                                                                          d_misc + 8, d_misc + (CNT_BASE), ctx->d_lfps, ctx->d_quads, \
-                                                                                          d_nq, d_misc + 3, d_misc, g, caps, prm);
-        CB_LAUNCH_QUAD_PHASE(1, 9)
-        CB_LAUNCH_QUAD_PHASE(2, 17)
-        lfps_kernel<<<ctx->num_sms * 6, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 25,
+        // sort #1 | sort #2 | prefix moments | fit, largest tier first inside each (long jobs).
+        // misc: [8 + 2t] items of tier t; work counters: [16..19] sort #1, [20..23] sort #2, [24] moments, [26..28] fit
+#define CB_LAUNCH_SORT(W, CNT)                                                                                                                    \
+        sort_clusters_kernel<SORT_L2(W), 3, 3><<<ctx->num_sms * 1, 512, SortShared<SORT_L2(W)>::BYTES, st>>>(                                   \
+            ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + (CNT) + 3, ctx->d_scratch, g, caps, prm);           \
+        sort_clusters_kernel<SORT_L1(W), 2, 2><<<ctx->num_sms * 3, 256, SortShared<SORT_L1(W)>::BYTES, st>>>(                                   \
+            ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + (CNT) + 2, ctx->d_scratch, g, caps, prm);           \
+        sort_clusters_kernel<SORT_M(W), 1, 1><<<ctx->num_sms * 6, 128, SortShared<SORT_M(W)>::BYTES, st>>>(                                     \
+            ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + (CNT) + 1, ctx->d_scratch, g, caps, prm);           \
+        sort_clusters_kernel<SORT_S(W), 0, 0><<<ctx->num_sms * 4, SORT_WARPS * 32, SortShared<SORT_S(W)>::BYTES, st>>>(                         \
+            ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + (CNT), ctx->d_scratch, g, caps, prm);
+        CB_LAUNCH_SORT(1, 16)
+        CB_LAUNCH_SORT(2, 20)
+#undef CB_LAUNCH_SORT
+        lfps_kernel<<<ctx->num_sms * 6, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 24,
                                                                   ctx->d_lfps, g, caps);
-        CB_LAUNCH_QUAD_PHASE(4, 33)
-#undef CB_LAUNCH_QUAD_PHASE
-        launches += 10;
+        fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 2, 3><<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared<QL_MAXN>), st>>>(
+            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 28, ctx->d_lfps, ctx->d_scratch,
+            ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
+        fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 1><<<ctx->num_sms * 6, QM1_THREADS, sizeof(QlShared<QM1_MAXN>), st>>>(
+            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 27, ctx->d_lfps, ctx->d_scratch,
+            ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
+        fit_quads_small_kernel<4><<<ctx->num_sms * 4, QS_WARPS * 32, sizeof(QsShared), st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist,
+                                                                                          d_misc + 8, d_misc + 26, ctx->d_lfps, ctx->d_quads,
+                                                                                          d_nq, d_misc + 3, d_misc, g, caps, prm);
+        launches += 12;
         CK(cudaEventRecord(ctx->ev[5], st));
     } else {
         CK(cudaEventRecord(ctx->ev[4], st));

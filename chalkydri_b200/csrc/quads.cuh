@@ -21,6 +21,7 @@
 // per-point input is 4 bytes; sorting happens on packed (slope, scan key) 64-bit words in shared memory.
 #pragma once
 #include "common.cuh"
+#include "sort.cuh"
 
 namespace cb {
 
@@ -30,23 +31,6 @@ constexpr int QL_THREADS = 256;
 constexpr int QL_MAXN = 6144;     // tier L: points per CTA in shared memory (tier M: 128 threads, 2048 points)
 
 struct LineFit { double Ex, Ey, nx, ny, err, mse; };
-
-__device__ __forceinline__ uint32_t float_orderable(float f)
-{
-    uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-
-// scan key layout (clusters.cuh): (pixel index << 3) | (probe << 1) | (v1 > v0)
-__device__ __forceinline__ void decode_point(uint32_t key, int w, int &px, int &py, int &gx, int &gy)
-{
-    const uint32_t pix = key >> 3;
-    const int d = (key >> 1) & 3, s = key & 1;
-    const int x = pix % w, y = pix / w;
-    const int dx = d == 2 ? -1 : (d == 1 ? 0 : 1), dy = d == 0 ? 0 : 1;
-    const int dv = s ? 255 : -255;
-    px = 2 * x + dx; py = 2 * y + dy; gx = dx * dv; gy = dy * dv;
-}
 
 // fit_line() on prefix moments lfps[j*6 + {Mx,My,Mxx,Mxy,Myy,W}]
 __device__ __forceinline__ void fit_line(const double *__restrict__ lfps, int sz, int i0, int i1, bool want_params, LineFit &o)
@@ -86,101 +70,9 @@ __device__ __forceinline__ void fit_line(const double *__restrict__ lfps, int sz
     o.mse = eig_small;
 }
 
-// node of ptsort()'s recursion tree that contains position i at depth d; false when the branch ended in a leaf earlier
-__device__ __forceinline__ bool ptsort_node(int n, int i, int d, int &lo, int &hi)
-{
-    lo = 0; hi = n;
-    for (int k = 0; k < d; k++) {
-        if (hi - lo <= 5) return false;
-        const int mid = lo + (hi - lo) / 2;
-        if (i < mid) hi = mid; else lo = mid;
-    }
-    return true;
-}
-
-__device__ __forceinline__ uint32_t hi32(unsigned long long v) { return (uint32_t)(v >> 32); }
-
 // 4-subsets of {0..9} packed (m0<<12|m1<<8|m2<<4|m3), in colex order so that the subsets of {0..k-1} are the first
 // C(k,4) entries; filled by the host (api.cu)
 __constant__ uint16_t c_combos[210];
-
-// group abstraction: NT = 32 (one warp) or 256 (one CTA) working on one cluster
-template <int NT>
-struct Grp {
-    static __device__ __forceinline__ int tid() { return NT == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
-    static __device__ __forceinline__ void sync() { if (NT == 32) __syncwarp(); else __syncthreads(); }
-    template <typename T, typename Op>
-    static __device__ __forceinline__ T reduce(T v, Op op, T *scratch)
-    {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (NT == 32) return v;
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        __syncthreads();
-        if (lane == 0) scratch[wid] = v;
-        __syncthreads();
-        T r = scratch[0];
-#pragma unroll
-        for (int k = 1; k < NT / 32; k++) r = op(r, scratch[k]);
-        return r;
-    }
-};
-
-
-// Emulation of upstream ptsort() on an array of packed words whose sort key is key_of(word):
-//   recursion tree split at sz/2, leaves of <= 5 elements sorted by upstream's networks (swap only when strictly
-//   greater), every internal node merged with "take from the first half only when strictly smaller".
-// Parallelisation: leaves one thread each; every level is a merge-path pass -- each thread owns a contiguous chunk of
-// the output, finds its split of the two input runs with one binary search and then merges sequentially, so the work is
-// O(n log n) compare-moves instead of a binary search per element per level.  Used for both sorts (the scan-key sort has
-// unique keys, so any merge tree gives the same result).
-template <int NT, typename T, typename KeyOf>
-__device__ __forceinline__ void ptsort_emulate(T *&src, T *&dst, int n, int tid, KeyOf key_of)
-{
-    for (int i = tid; i < n; i += NT) {
-        int lo = 0, hi = n;
-        while (hi - lo > 5) { const int mid = lo + (hi - lo) / 2; if (i < mid) hi = mid; else lo = mid; }
-        if (i != lo) continue;
-        const int sz = hi - lo;
-        T *a = src + lo;
-#define QF_SWAP(x, y) if (key_of(a[x]) > key_of(a[y])) { const T t = a[x]; a[x] = a[y]; a[y] = t; }
-        if (sz == 2) { QF_SWAP(0, 1); }
-        else if (sz == 3) { QF_SWAP(0, 1); QF_SWAP(1, 2); QF_SWAP(0, 1); }
-        else if (sz == 4) { QF_SWAP(0, 1); QF_SWAP(2, 3); QF_SWAP(0, 2); QF_SWAP(1, 3); QF_SWAP(1, 2); }
-        else if (sz == 5) { QF_SWAP(0, 1); QF_SWAP(3, 4); QF_SWAP(2, 4); QF_SWAP(2, 3); QF_SWAP(0, 3); QF_SWAP(0, 2); QF_SWAP(1, 4); QF_SWAP(1, 3); QF_SWAP(1, 2); }
-#undef QF_SWAP
-    }
-    Grp<NT>::sync();
-    int maxd = 0;
-    { int sz = n; while (sz > 5) { sz = sz - sz / 2; maxd++; } }
-    // elements per thread: at least 16 in the CTA tiers, so that the per-level fixed cost (node lookup + merge-path search)
-    // is amortised and warps without work stay idle instead of issuing that overhead for 2-3 elements each
-    const int E = NT == 32 ? (n + NT - 1) / NT : max(16, (n + NT - 1) / NT);
-    for (int d = maxd - 1; d >= 0; d--) {
-        int p = min(n, tid * E);
-        const int p1 = min(n, p + E);
-        while (p < p1) {
-            int lo, hi;
-            const bool internal = ptsort_node(n, p, d, lo, hi) && hi - lo > 5;
-            const int e = min(hi, p1);
-            if (!internal) { for (; p < e; p++) dst[p] = src[p]; continue; }
-            const int mid = lo + (hi - lo) / 2, an = mid - lo, bn = hi - mid, k = p - lo;
-            int l = max(0, k - bn), h = min(k, an);
-            while (l < h) { const int m = (l + h) >> 1; if (key_of(src[lo + m]) < key_of(src[mid + k - m - 1])) l = m + 1; else h = m; }
-            int ai = l, bi = k - l;
-            T av = src[lo + min(ai, an - 1)], bv = src[mid + min(bi, bn - 1)];
-            for (; p < e; p++) {      // branch-free step: lanes of a warp stay converged
-                const bool take_a = (bi >= bn) | ((ai < an) & (key_of(av) < key_of(bv)));
-                dst[p] = take_a ? av : bv;
-                ai += take_a ? 1 : 0; bi += take_a ? 0 : 1;
-                const T nv = src[take_a ? lo + min(ai, an - 1) : mid + min(bi, bn - 1)];
-                av = take_a ? nv : av; bv = take_a ? bv : nv;
-            }
-        }
-        Grp<NT>::sync();
-        T *t = src; src = dst; dst = t;
-    }
-}
 
 struct QfScratch {       // per group (warp or CTA)
     double red_d[8];
@@ -215,119 +107,8 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__re
     const int tid = G::tid();
     const int lane = threadIdx.x & 31;
 
-    const int reversed_border = 0;          // reversed clusters never get past phase 1 (tag36h11 has a normal border only)
+    const int reversed_border = 0;          // reversed clusters never get past sort #1 (tag36h11 has a normal border only)
     unsigned long long *src = A, *dst = B;
-    if (PHASE == 1 || PHASE == 2) {
-        // ---- scan keys -> work array; bounding box -------------------------------------------------------------
-        uint32_t *k0 = reinterpret_cast<uint32_t *>(A), *k1 = k0 + n;      // two u32 halves of A for the scan-order sort
-        int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
-        for (int i = tid; i < n; i += NT) {
-            const uint32_t key = K[i];
-            k0[i] = key;
-            int px, py, gx, gy;
-            decode_point(key, g.w, px, py, gx, gy);
-            xmin = min(xmin, px); xmax = max(xmax, px); ymin = min(ymin, py); ymax = max(ymax, py);
-        }
-        xmin = G::reduce(xmin, [](int a, int c) { return min(a, c); }, S.red_i);
-        xmax = G::reduce(xmax, [](int a, int c) { return max(a, c); }, S.red_i);
-        ymin = G::reduce(ymin, [](int a, int c) { return min(a, c); }, S.red_i);
-        ymax = G::reduce(ymax, [](int a, int c) { return max(a, c); }, S.red_i);
-        const float cx = (float)((xmin + xmax) * 0.5 + 0.05118);
-        const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
-        G::sync();
-        if (PHASE == 1) {
-            if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) { if (tid == 0) rec_global->cursor = 0xffffffffu; return; }
-            // border polarity (upstream: dot = sum dx*gx + dy*gy, reversed_border = dot < 0).  Only the sign is used and the
-            // sum does not depend on the order of the points beyond float rounding, so it is evaluated before any sorting.
-            float dot = 0.f;
-            for (int i = tid; i < n; i += NT) {
-                int px, py, gx, gy;
-                decode_point(k0[i], g.w, px, py, gx, gy);
-                const float dx = (float)px - cx, dy = (float)py - cy;
-                dot += dx * (float)gx + dy * (float)gy;
-            }
-            dot = G::reduce(dot, [](float a, float c) { return a + c; }, S.red_f);
-            if (dot < 0.f) { if (tid == 0) rec_global->cursor = 0xffffffffu; return; }
-            G::sync();
-            // ---- restore scan order: merge sort of the (unique) scan keys; the sorted keys replace the unsorted ones ----
-            uint32_t *ssrc = k0, *sdst = k1;
-            ptsort_emulate<NT>(ssrc, sdst, n, tid, [](uint32_t v) { return v; });
-            for (int j = tid; j < n; j += NT) K[j] = ssrc[j];
-            return;
-        }
-        // ---- PHASE 2: slopes in scan order (upstream fit_quad step 1), then ptsort() on the slope keys ----------------
-        for (int j = tid; j < n; j += NT) {
-            const uint32_t key = k0[j];
-            int px, py, gx, gy;
-            decode_point(key, g.w, px, py, gx, gy);
-            float dx = (float)px - cx, dy = (float)py - cy;
-            float quadrant;
-            if (dy > 0) quadrant = dx > 0 ? 65536.f : 131072.f; else quadrant = dx > 0 ? 0.f : -65536.f;
-            if (dy < 0) { dy = -dy; dx = -dx; }
-            if (dx < 0) { const float t = dx; dx = dy; dy = -t; }
-            const float slope = quadrant + dy / dx;
-            B[j] = ((unsigned long long)float_orderable(slope) << 32) | (uint32_t)px | ((uint32_t)py << 16);
-        }
-        G::sync();
-        src = B; dst = A;
-        ptsort_emulate<NT>(src, dst, n, tid, [](unsigned long long v) { return (uint32_t)(v >> 32); });
-        for (int j = tid; j < n; j += NT) K[j] = (uint32_t)src[j];      // sorted points (px | py << 16) replace the keys
-        return;
-    }
-    if (PHASE == 3) {
-        for (int j = tid; j < n; j += NT) A[j] = K[j];
-        G::sync();
-    }
-    if (PHASE == 3) {
-    // src: sorted (slope key, packed px | py << 16).  ---- compute_lfps -----------------------------------------------------------
-    // per-point weight (parallel), then the sequential prefix: each block of 32 points is expanded into its six
-    // terms by 32 lanes, staged in shared memory, and accumulated in order by lanes 0..5 of the first warp.
-    double *Wd = reinterpret_cast<double *>(dst);
-    for (int j = tid; j < n; j += NT) {
-        const uint32_t xy = (uint32_t)src[j];
-        const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
-        const double x = px * .5 + 0.5, y = py * .5 + 0.5;
-        const int ix = (int)x, iy = (int)y;
-        double W = 1;
-        if (ix > 0 && ix + 1 < g.w && iy > 0 && iy + 1 < g.h) {
-            const int grad_x = (int)img[(size_t)(iy * g.f) * g.stride + (ix + 1) * g.f] - (int)img[(size_t)(iy * g.f) * g.stride + (ix - 1) * g.f];
-            const int grad_y = (int)img[(size_t)((iy + 1) * g.f) * g.stride + ix * g.f] - (int)img[(size_t)((iy - 1) * g.f) * g.stride + ix * g.f];
-            W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
-        }
-        Wd[j] = W;
-    }
-    G::sync();
-    if (tid < 32) {
-        double acc = 0;
-        for (int j0 = 0; j0 < n; j0 += 16) {
-            const int j = j0 + lane;
-            const int buf = (j0 >> 4) & 1;
-            if (lane < 16 && j < n) {
-                const uint32_t xy = (uint32_t)src[j];
-                const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
-                const double W = Wd[j];
-                const double fx = px * .5 + 0.5, fy = py * .5 + 0.5;
-                double *t = S.stage[buf][lane];
-                t[0] = W * fx; t[1] = W * fy; t[2] = W * fx * fx; t[3] = W * fx * fy; t[4] = W * fy * fy; t[5] = W;
-            }
-            __syncwarp();
-            if (lane < 6) {
-                const int cnt = min(16, n - j0);
-                double *o = lfps + (size_t)j0 * 6 + lane;
-#pragma unroll 8
-                for (int k = 0; k < cnt; k++) {
-                    acc += S.stage[buf][k][lane];
-                    o[(size_t)k * 6] = acc;
-                }
-            }
-            // tile `buf` is rewritten two rounds later, after another __syncwarp(): lanes 0..5 are done with it by then
-        }
-    }
-    G::sync();
-
-        return;
-    }
-
     // ---- PHASE 4: quad_segment_maxima ---------------------------------------------------------------------------
     const int ksz = min(20, n / 12);
     if (ksz < 2) return;
@@ -561,7 +342,7 @@ struct QsWarp {
 };
 struct QsShared { QsWarp w[QS_WARPS]; };
 
-// tier S: persistent warps, one cluster (<= QS_MAXN points) per warp at a time
+// tier S: persistent warps, one cluster (<= QS_MAXN points, work list 0) per warp at a time
 template <int PHASE>
 __global__ void __launch_bounds__(QS_WARPS * 32)
 fit_quads_small_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters,
@@ -583,7 +364,7 @@ fit_quads_small_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ sc
         const ClusterRec rec = clusters[item];
         const int n = (int)rec.count;
         if (n < 24 || n > QS_MAXN) continue;
-        if (PHASE >= 2 && rec.cursor == 0xffffffffu) continue;
+        if (rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         fit_quad_cluster<32, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.w[wid].A, SH.w[wid].B, lfps_all + pbase * 6, SH.w[wid].S, rec,
                                     clusters + item, b,
@@ -600,32 +381,31 @@ struct QlShared {
     int work;
 };
 
-// tiers M / L: persistent CTAs of NT threads, one cluster of (min_n, ...] points per CTA at a time; clusters above MAXN
-// points run out of the global scratch area.  Tier M (NT = 128, MAXN = 2048, 34 KB smem) keeps 6 CTAs per SM resident,
-// tier L (NT = 256, MAXN = 6144, 98 KB) two.
-template <int NT, int MAXN, int PHASE>
+// tiers M / L: persistent CTAs of NT threads, one cluster from work lists T_LO..T_HI per CTA at a time; clusters above
+// MAXN points run out of the global scratch area.  Tier M (NT = 128, MAXN = 2048, 34 KB smem) keeps 6 CTAs per SM
+// resident, tier L (NT = 256, MAXN = 6144, 98 KB) two.
+template <int NT, int MAXN, int PHASE, int T_LO, int T_HI>
 __global__ void __launch_bounds__(NT)
 fit_quads_cta_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters,
-                     const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
+                     const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork,
+                     uint32_t *__restrict__ work_counter,
                      double *__restrict__ lfps_all, unsigned long long *__restrict__ scratch, QuadRec *__restrict__ quads,
                      uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps,
                      DetParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     QlShared<MAXN> &SH = *reinterpret_cast<QlShared<MAXN> *>(smem_raw);
-    const uint32_t total = *nwork;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) SH.work = (int)atomicAdd(work_counter, 1u);
         __syncthreads();
-        const uint32_t wi = (uint32_t)SH.work;
-        if (wi >= total) return;
-        const uint32_t item = worklist[wi];
+        uint32_t item;
+        if (!tier_item<T_LO, T_HI>((uint32_t)SH.work, nwork, worklists, wl_stride, item)) return;
         const int b = item / caps.clusters_per_frame;
         const ClusterRec rec = clusters[item];
         const int n = (int)rec.count;
         if (n < 24) continue;
-        if (PHASE >= 2 && rec.cursor == 0xffffffffu) continue;
+        if (rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         unsigned long long *A = SH.A, *B = SH.B;
         if (n > MAXN) { A = scratch + pbase * 2; B = A + n; }
@@ -717,6 +497,11 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
 // tiers: S (one warp, <= QS_MAXN) | M1 (128 threads, <= 2048) | M2 (spare slot: same bound as M1, so it stays empty) | L (256 threads, the rest).
 // Measured on the c2 workload (quad stage, ms per 256 frames): S512/L 24.6; S512/M2048/L 21.4; S256x8/M2048/L 18.7; S256/M1024(64 thr)/M3072/L 19.8.
 constexpr int QM1_THREADS = 128, QM1_MAXN = 2048;
-constexpr int QM2_THREADS = 128, QM2_MAXN = 2048;
+// tier limits of the four work lists, and the sort kernels' (threads, elements per thread, shared-memory points) per tier
+constexpr int QT0 = 256, QT1 = 2048, QT2 = 4096;
+#define SORT_S(W) 32, 8, QT0, W
+#define SORT_M(W) 128, 16, QT1, W
+#define SORT_L1(W) 256, 16, QT2, W
+#define SORT_L2(W) 512, 16, 8192, W
 
 }  // namespace cb
