@@ -226,14 +226,11 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ThrTmaWarp) * THR_TMA_WARPS)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
-#define CB_SORT_ATTR(W)                                                                                                                                  \
-        ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<SORT_S(W), 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SortShared<SORT_S(W)>::BYTES) == cudaSuccess; \
-        ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<SORT_M(W), 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SortShared<SORT_M(W)>::BYTES) == cudaSuccess; \
-        ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<SORT_L1(W), 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SortShared<SORT_L1(W)>::BYTES) == cudaSuccess; \
-        ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<SORT_L2(W), 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SortShared<SORT_L2(W)>::BYTES) == cudaSuccess;
-        CB_SORT_ATTR(1) CB_SORT_ATTR(2)
+        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
+#define CB_SORT_ATTR(CFG) ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::BYTES) == cudaSuccess;
+        CB_SORT_ATTR(SortS8<1>) CB_SORT_ATTR(SortS16<1>) CB_SORT_ATTR(SortM<1>) CB_SORT_ATTR(SortL1<1>) CB_SORT_ATTR(SortL2<1>)
+        CB_SORT_ATTR(SortS8<2>) CB_SORT_ATTR(SortS16<2>) CB_SORT_ATTR(SortM<2>) CB_SORT_ATTR(SortL1<2>) CB_SORT_ATTR(SortL2<2>)
 #undef CB_SORT_ATTR
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
             uint16_t combos[210];
@@ -409,31 +406,32 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         CK(cudaEventRecord(ctx->ev[4], st));
         // ---- A5 quad fitting ----
         // sort #1 | sort #2 | prefix moments | fit, largest tier first inside each (long jobs).
-        // misc: [8 + 2t] items of tier t; work counters: [16..19] sort #1, [20..23] sort #2, [24] moments, [26..28] fit
+        // misc: [8 + 2t] items of tier t; work counters: [16..20] sort #1, [21..25] sort #2, [26] moments, [27..29] fit
+#define CB_LAUNCH_SORT1(CFG, GRID, CNT)                                                                                                          \
+        sort_clusters_kernel<CFG><<<ctx->num_sms * (GRID), CFG::THREADS, CFG::BYTES, st>>>(ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, \
+                                                                                         d_misc + (CNT), ctx->d_scratch, g, caps, prm);
 #define CB_LAUNCH_SORT(W, CNT)                                                                                                                    \
-        sort_clusters_kernel<SORT_L2(W), 3, 3><<<ctx->num_sms * 1, 512, SortShared<SORT_L2(W)>::BYTES, st>>>(                                   \
-            ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + (CNT) + 3, ctx->d_scratch, g, caps, prm);           \
-        sort_clusters_kernel<SORT_L1(W), 2, 2><<<ctx->num_sms * 3, 256, SortShared<SORT_L1(W)>::BYTES, st>>>(                                   \
-            ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + (CNT) + 2, ctx->d_scratch, g, caps, prm);           \
-        sort_clusters_kernel<SORT_M(W), 1, 1><<<ctx->num_sms * 6, 128, SortShared<SORT_M(W)>::BYTES, st>>>(                                     \
-            ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + (CNT) + 1, ctx->d_scratch, g, caps, prm);           \
-        sort_clusters_kernel<SORT_S(W), 0, 0><<<ctx->num_sms * 4, SORT_WARPS * 32, SortShared<SORT_S(W)>::BYTES, st>>>(                         \
-            ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + (CNT), ctx->d_scratch, g, caps, prm);
+        CB_LAUNCH_SORT1(SortL2<W>, 1, (CNT) + 4)                                                                                                 \
+        CB_LAUNCH_SORT1(SortL1<W>, 3, (CNT) + 3)                                                                                                 \
+        CB_LAUNCH_SORT1(SortM<W>, 6, (CNT) + 2)                                                                                                  \
+        CB_LAUNCH_SORT1(SortS16<W>, 3, (CNT) + 1)                                                                                                \
+        CB_LAUNCH_SORT1(SortS8<W>, 4, (CNT))
         CB_LAUNCH_SORT(1, 16)
-        CB_LAUNCH_SORT(2, 20)
+        CB_LAUNCH_SORT(2, 21)
 #undef CB_LAUNCH_SORT
-        lfps_kernel<<<ctx->num_sms * 6, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 24,
+#undef CB_LAUNCH_SORT1
+        lfps_kernel<<<ctx->num_sms * 6, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 26,
                                                                   ctx->d_lfps, g, caps);
-        fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 2, 3><<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared<QL_MAXN>), st>>>(
+        fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 3, 3><<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared<QL_MAXN>), st>>>(
+            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 29, ctx->d_lfps, ctx->d_scratch,
+            ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
+        fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 2><<<ctx->num_sms * 6, QM1_THREADS, sizeof(QlShared<QM1_MAXN>), st>>>(
             d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 28, ctx->d_lfps, ctx->d_scratch,
             ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
-        fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 1><<<ctx->num_sms * 6, QM1_THREADS, sizeof(QlShared<QM1_MAXN>), st>>>(
-            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 27, ctx->d_lfps, ctx->d_scratch,
-            ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
         fit_quads_small_kernel<4><<<ctx->num_sms * 4, QS_WARPS * 32, sizeof(QsShared), st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist,
-                                                                                          d_misc + 8, d_misc + 26, ctx->d_lfps, ctx->d_quads,
+                                                                                          d_misc + 8, d_misc + 27, ctx->d_lfps, ctx->d_quads,
                                                                                           d_nq, d_misc + 3, d_misc, g, caps, prm);
-        launches += 12;
+        launches += 14;
         CK(cudaEventRecord(ctx->ev[5], st));
     } else {
         CK(cudaEventRecord(ctx->ev[4], st));

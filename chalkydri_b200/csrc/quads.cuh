@@ -498,10 +498,12 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
 // Measured on the c2 workload (quad stage, ms per 256 frames): S512/L 24.6; S512/M2048/L 21.4; S256x8/M2048/L 18.7; S256/M1024(64 thr)/M3072/L 19.8.
 constexpr int QM1_THREADS = 128, QM1_MAXN = 2048;
 // tier limits of the four work lists, and the sort kernels' (threads, elements per thread, shared-memory points) per tier
-constexpr int QT0 = 256, QT1 = 2048, QT2 = 4096;
-#define SORT_S(W) 32, 8, QT0, W
-#define SORT_M(W) 128, 16, QT1, W
-#define SORT_L1(W) 256, 16, QT2, W
-#define SORT_L2(W) 512, 16, 8192, W
+constexpr int QT0 = 256, QT1 = 512, QT2 = 2048;
+// the five kernels of each sort: <NT, E, MAXN, WHICH, T_LO, T_HI, NMIN, NMAX>
+template <int W> using SortS8 = SortCfg<32, 8, QT0, W, 0, 0, 0, QT0>;
+template <int W> using SortS16 = SortCfg<32, 16, QT1, W, 1, 1, 0, QT1>;
+template <int W> using SortM = SortCfg<128, 16, QT2, W, 2, 2, 0, QT2>;
+template <int W> using SortL1 = SortCfg<256, 16, 4096, W, 3, 3, 0, 4096>;
+template <int W> using SortL2 = SortCfg<512, 16, 8192, W, 3, 3, 4097, (1 << 30)>;
 
 }  // namespace cb

@@ -298,24 +298,30 @@ __device__ __forceinline__ bool tier_item(uint32_t wi, const uint32_t *__restric
 
 template <int E> constexpr int sort_padded(int n) { return n + n / E + 1; }
 
-// WHICH = 1: sort_scan_cluster on u32, WHICH = 2: sort_slope_cluster on u64.  NT = 32: SORT_WARPS clusters per CTA.
+// Configuration of one sort kernel.  WHICH = 1: sort_scan_cluster on u32, WHICH = 2: sort_slope_cluster on u64.
+// NT = 32: SORT_WARPS clusters per CTA, one per warp; otherwise one cluster per CTA of NT threads.  The kernel pulls from
+// work lists T_LO..T_HI and processes the clusters of NMIN..NMAX points (several kernels can share one list); above MAXN
+// points the work arrays live in the global scratch area.
 constexpr int SORT_WARPS = 8;
-template <int NT, int E, int MAXN, int WHICH>
-struct SortShared {
+template <int NT_, int E_, int MAXN_, int WHICH_, int T_LO_, int T_HI_, int NMIN_, int NMAX_>
+struct SortCfg {
+    static constexpr int NT = NT_, E = E_, MAXN = MAXN_, WHICH = WHICH_, T_LO = T_LO_, T_HI = T_HI_, NMIN = NMIN_, NMAX = NMAX_;
     static constexpr int GROUPS = NT == 32 ? SORT_WARPS : 1;
+    static constexpr int THREADS = NT * GROUPS;
     static constexpr int ELEM = WHICH == 1 ? 4 : 8;
     static constexpr size_t ARRAY_BYTES = ((size_t)sort_padded<E>(MAXN) * ELEM + 15) / 16 * 16;
     static constexpr size_t GROUP_BYTES = 2 * ARRAY_BYTES + (sizeof(SortScratch) + 15) / 16 * 16;
     static constexpr size_t BYTES = GROUPS * GROUP_BYTES;
 };
 
-template <int NT, int E, int MAXN, int WHICH, int T_LO, int T_HI>
-__global__ void __launch_bounds__(NT == 32 ? SORT_WARPS * 32 : NT)
+template <typename C>
+__global__ void __launch_bounds__(C::THREADS)
 sort_clusters_kernel(uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ worklists,
                      size_t wl_stride, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
                      unsigned long long *__restrict__ scratch, Geom g, Caps caps, DetParams prm)
 {
-    typedef SortShared<NT, E, MAXN, WHICH> SH;
+    typedef C SH;
+    constexpr int NT = C::NT, E = C::E, MAXN = C::MAXN, WHICH = C::WHICH, T_LO = C::T_LO, T_HI = C::T_HI, NMIN = C::NMIN, NMAX = C::NMAX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = NT == 32 ? (int)(threadIdx.x >> 5) : 0;
     unsigned char *base = smem_raw + (size_t)grp * SH::GROUP_BYTES;
@@ -338,7 +344,7 @@ sort_clusters_kernel(uint32_t *__restrict__ scankey, ClusterRec *__restrict__ cl
         const int b = item / caps.clusters_per_frame;
         const ClusterRec rec = clusters[item];
         const int n = (int)rec.count;
-        if (n < 24) continue;
+        if (n < 24 || n < NMIN || n > NMAX) continue;
         if (WHICH == 2 && rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         if (WHICH == 1) {
