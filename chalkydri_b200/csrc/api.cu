@@ -59,7 +59,8 @@ struct cb_ctx {
     ClusterRec *d_clusters = nullptr;
     uint32_t *d_worklist = nullptr;
     uint32_t *d_scankey = nullptr;
-    double *d_lfps = nullptr;
+    double *d_errs = nullptr;       // window errors, 8 B per point
+    double *d_cp = nullptr;         // prefix-moment checkpoints, 48 B per LF_CP points
     unsigned long long *d_scratch = nullptr;
     QuadRec *d_quads = nullptr;
     RawDet *d_raw = nullptr;
@@ -132,7 +133,7 @@ void cb_destroy(cb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
-                    ctx->d_table, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_lfps, ctx->d_scratch,
+                    ctx->d_table, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
                     ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
@@ -199,7 +200,7 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     Caps &c = ctx->caps;
     c.slots_per_frame = next_pow2((uint32_t)std::max<size_t>(1024, dpix / 8));
     c.clusters_per_frame = (uint32_t)std::max<size_t>(2048, dpix / 128);
-    c.points_per_frame = (uint32_t)std::max<size_t>(65536, dpix + dpix / 2);   // noisy frames emit ~0.85 points / pixel
+    c.points_per_frame = (uint32_t)((std::max<size_t>(65536, dpix + dpix / 2) + 7) / 8 * 8);   // noisy frames emit ~0.85 points / pixel
     c.quads_per_frame = (uint32_t)std::max<size_t>(2048, dpix / 32);   // pure-noise frames produce thousands of candidate quads
     c.dets_per_frame = (uint32_t)max_dets_per_frame;
     ok = ok && alloc((void **)&ctx->d_in, ctx->in_bytes + 64);
@@ -210,7 +211,8 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     ok = ok && alloc((void **)&ctx->d_clusters, B * c.clusters_per_frame * sizeof(ClusterRec));
     ok = ok && alloc((void **)&ctx->d_worklist, 4 * B * c.clusters_per_frame * sizeof(uint32_t));
     ok = ok && alloc((void **)&ctx->d_scankey, B * c.points_per_frame * sizeof(uint32_t));
-    ok = ok && alloc((void **)&ctx->d_lfps, B * c.points_per_frame * 6 * sizeof(double));
+    ok = ok && alloc((void **)&ctx->d_errs, B * c.points_per_frame * sizeof(double));
+    ok = ok && alloc((void **)&ctx->d_cp, B * c.points_per_frame / LF_CP * 6 * sizeof(double));
     ok = ok && alloc((void **)&ctx->d_scratch, B * c.points_per_frame * 2 * sizeof(unsigned long long));
     ok = ok && alloc((void **)&ctx->d_quads, B * c.quads_per_frame * sizeof(QuadRec));
     ok = ok && alloc((void **)&ctx->d_raw, B * c.quads_per_frame * sizeof(RawDet));
@@ -420,16 +422,16 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         CB_LAUNCH_SORT(2, 21)
 #undef CB_LAUNCH_SORT
 #undef CB_LAUNCH_SORT1
-        lfps_kernel<<<ctx->num_sms * 6, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 26,
-                                                                  ctx->d_lfps, g, caps);
+        lfps_kernel<<<ctx->num_sms * 8, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 26,
+                                                                  ctx->d_errs, ctx->d_cp, g, caps);
         fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 3, 3><<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared<QL_MAXN>), st>>>(
-            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 29, ctx->d_lfps, ctx->d_scratch,
+            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 29, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
             ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
         fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 2><<<ctx->num_sms * 6, QM1_THREADS, sizeof(QlShared<QM1_MAXN>), st>>>(
-            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 28, ctx->d_lfps, ctx->d_scratch,
+            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 28, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
             ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
         fit_quads_small_kernel<4><<<ctx->num_sms * 4, QS_WARPS * 32, sizeof(QsShared), st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist,
-                                                                                          d_misc + 8, d_misc + 27, ctx->d_lfps, ctx->d_quads,
+                                                                                          d_misc + 8, d_misc + 27, ctx->d_errs, ctx->d_cp, ctx->d_quads,
                                                                                           d_nq, d_misc + 3, d_misc, g, caps, prm);
         launches += 14;
         CK(cudaEventRecord(ctx->ev[5], st));

@@ -147,7 +147,7 @@ cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ 
     if (cnt < minsz || cnt > maxsz) return;          // slot->cluster stays 0xffffffff
     const uint32_t ci = atomicAdd(&nclusters[b], 1u);
     if (ci >= caps.clusters_per_frame) { atomicOr(errflag, ERR_CLUSTERS_FULL); return; }
-    const uint32_t off = atomicAdd(&npoints[b], cnt);
+    const uint32_t off = atomicAdd(&npoints[b], (cnt + 7u) & ~7u);   // 8-aligned: one checkpoint slot per 8 points (quads.cuh LF_CP)
     if (off + cnt > caps.points_per_frame) { atomicOr(errflag, ERR_POINTS_FULL); return; }
     ClusterRec r;
     r.key = slot->key; r.offset = off; r.count = cnt; r.cursor = 0; r.pad = 0;

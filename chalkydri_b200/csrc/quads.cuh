@@ -32,24 +32,21 @@ constexpr int QL_MAXN = 6144;     // tier L: points per CTA in shared memory (ti
 
 struct LineFit { double Ex, Ey, nx, ny, err, mse; };
 
-// fit_line() on prefix moments lfps[j*6 + {Mx,My,Mxx,Mxy,Myy,W}]
-__device__ __forceinline__ void fit_line(const double *__restrict__ lfps, int sz, int i0, int i1, bool want_params, LineFit &o)
+// One entry of upstream's prefix-moment array lfps[] (struct line_fit_pt).
+struct M6 { double Mx, My, Mxx, Mxy, Myy, W; };
+
+// fit_line() given the (at most) three entries of lfps[] it reads: a = lfps[i1], p = lfps[i0 - 1], l = lfps[sz - 1].
+//   mode 0: i0 == 0 < i1 (a alone), mode 1: 0 < i0 < i1 (a - p), mode 2: i0 > i1, the range wraps ((l - p) + a).
+// N = number of points in the range.
+__device__ __forceinline__ void fit_line_m(const M6 &a, const M6 &p, const M6 &l, int mode, int N, bool want_params, LineFit &o)
 {
     double Mx, My, Mxx, Myy, Mxy, W;
-    int N;
-    const double *a = lfps + (size_t)i1 * 6;
-    if (i0 < i1) {
-        N = i1 - i0 + 1;
-        Mx = a[0]; My = a[1]; Mxx = a[2]; Mxy = a[3]; Myy = a[4]; W = a[5];
-        if (i0 > 0) {
-            const double *p = lfps + (size_t)(i0 - 1) * 6;
-            Mx -= p[0]; My -= p[1]; Mxx -= p[2]; Mxy -= p[3]; Myy -= p[4]; W -= p[5];
-        }
+    if (mode != 2) {
+        Mx = a.Mx; My = a.My; Mxx = a.Mxx; Mxy = a.Mxy; Myy = a.Myy; W = a.W;
+        if (mode == 1) { Mx -= p.Mx; My -= p.My; Mxx -= p.Mxx; Mxy -= p.Mxy; Myy -= p.Myy; W -= p.W; }
     } else {
-        const double *l = lfps + (size_t)(sz - 1) * 6, *p = lfps + (size_t)(i0 - 1) * 6;
-        Mx = l[0] - p[0]; My = l[1] - p[1]; Mxx = l[2] - p[2]; Mxy = l[3] - p[3]; Myy = l[4] - p[4]; W = l[5] - p[5];
-        Mx += a[0]; My += a[1]; Mxx += a[2]; Mxy += a[3]; Myy += a[4]; W += a[5];
-        N = sz - i0 + i1 + 1;
+        Mx = l.Mx - p.Mx; My = l.My - p.My; Mxx = l.Mxx - p.Mxx; Mxy = l.Mxy - p.Mxy; Myy = l.Myy - p.Myy; W = l.W - p.W;
+        Mx += a.Mx; My += a.My; Mxx += a.Mxx; Mxy += a.Mxy; Myy += a.Myy; W += a.W;
     }
     const double Ex = Mx / W, Ey = My / W;
     const double Cxx = Mxx / W - Ex * Ex, Cxy = Mxy / W - Ex * Ey, Cyy = Myy / W - Ey * Ey;
@@ -70,6 +67,40 @@ __device__ __forceinline__ void fit_line(const double *__restrict__ lfps, int sz
     o.mse = eig_small;
 }
 
+// The six terms point xy = px | py << 16 adds to the prefix moments (upstream compute_lfps): gradient-magnitude weight
+// from the full-resolution image around the decimated pixel.
+__device__ __forceinline__ void point_terms(const uint8_t *__restrict__ img, uint32_t xy, const Geom &g, double t[6])
+{
+    const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
+    const double x = px * .5 + 0.5, y = py * .5 + 0.5;
+    const int ix = (int)x, iy = (int)y;
+    double W = 1;
+    if (ix > 0 && ix + 1 < g.w && iy > 0 && iy + 1 < g.h) {
+        const uint8_t *row = img + (size_t)(iy * g.f) * g.stride;
+        const int grad_x = (int)row[(ix + 1) * g.f] - (int)row[(ix - 1) * g.f];
+        const int grad_y = (int)row[(ptrdiff_t)ix * g.f + (ptrdiff_t)g.f * g.stride] - (int)row[(ptrdiff_t)ix * g.f - (ptrdiff_t)g.f * g.stride];
+        W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
+    }
+    t[0] = W * x; t[1] = W * y; t[2] = W * x * x; t[3] = W * x * y; t[4] = W * y * y; t[5] = W;
+}
+
+// lfps[idx] rebuilt from the checkpoint before it (every LF_CP-th entry is kept) plus at most LF_CP - 1 replayed points;
+// the additions happen in the same order as in the sequential pass, so the value is the same.
+constexpr int LF_CP = 8;
+__device__ __forceinline__ void replay_entry(const uint8_t *__restrict__ img, const uint32_t *__restrict__ XY, const double *__restrict__ cp,
+                                             int idx, const Geom &g, double acc[6])
+{
+    const int blk = idx / LF_CP;
+#pragma unroll
+    for (int m = 0; m < 6; m++) acc[m] = blk > 0 ? cp[(size_t)(blk - 1) * 6 + m] : 0.0;
+    for (int j = blk * LF_CP; j <= idx; j++) {
+        double t[6];
+        point_terms(img, XY[j], g, t);
+#pragma unroll
+        for (int m = 0; m < 6; m++) acc[m] += t[m];
+    }
+}
+
 // 4-subsets of {0..9} packed (m0<<12|m1<<8|m2<<4|m3), in colex order so that the subsets of {0..k-1} are the first
 // C(k,4) entries; filled by the host (api.cu)
 __constant__ uint16_t c_combos[210];
@@ -84,7 +115,7 @@ struct QfScratch {       // per group (warp or CTA)
     int nkept;
     int taken[16];
     double thresh;
-    double stage[2][16][6];   // staging tiles of the sequential prefix pass
+    M6 ent[21];               // prefix-moment entries of the kept maxima
 };
 
 // Processes one cluster.  A and B are 8-byte-per-point work arrays (shared or global), lfps the 48-byte-per-point
@@ -98,7 +129,7 @@ struct QfScratch {       // per group (warp or CTA)
 //   PHASE 4: window errors, maxima, corner search, corner / area / convexity tests.
 template <int NT, int PHASE>
 __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__restrict__ K, int n, unsigned long long *A,
-                                 unsigned long long *B, double *__restrict__ lfps, QfScratch &S, const ClusterRec &rec,
+                                 unsigned long long *B, const double *__restrict__ errs_g, const double *__restrict__ cp, QfScratch &S, const ClusterRec &rec,
                                  ClusterRec *__restrict__ rec_global, int b,
                                  QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
                                  uint32_t *__restrict__ errflag, const Geom &g, const Caps &caps, const DetParams &prm)
@@ -112,15 +143,9 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__re
     // ---- PHASE 4: quad_segment_maxima ---------------------------------------------------------------------------
     const int ksz = min(20, n / 12);
     if (ksz < 2) return;
-    double *errs = reinterpret_cast<double *>(src);   // sorted keys are no longer needed
-    double *ysm = reinterpret_cast<double *>(dst);    // neither are the weights
-    for (int i = tid; i < n; i += NT) {
-        LineFit lf;
-        int i0 = i - ksz; if (i0 < 0) i0 += n;
-        int i1 = i + ksz; if (i1 >= n) i1 -= n;
-        fit_line(lfps, n, i0, i1, false, lf);
-        errs[i] = lf.err;
-    }
+    double *errs = reinterpret_cast<double *>(src);
+    double *ysm = reinterpret_cast<double *>(dst);
+    for (int i = tid; i < n; i += NT) errs[i] = errs_g[i];      // window errors (lfps_kernel)
     G::sync();
     for (int iy = tid; iy < n; iy += NT) {
         double acc = 0;
@@ -230,11 +255,28 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__re
     // pair table: fit_line(kept[a], kept[c]) for a != c (3200 B); lives in the now dead work arrays
     double (*p_err)[10] = reinterpret_cast<double (*)[10]>(A);    // A and B are adjacent (A first): >= 4 KB in every tier
     double (*p_mse)[10] = p_err + 10, (*p_nx)[10] = p_err + 20, (*p_ny)[10] = p_err + 30;
+    // the prefix-moment entries the corner search reads: lfps[kept[m]], lfps[kept[m] - 1], lfps[n - 1]
+    if (tid <= 2 * nk) {
+        const int idx = tid == 2 * nk ? n - 1 : S.kept[tid >> 1] - (tid & 1);
+        if (idx >= 0) {
+            double acc[6];
+            replay_entry(img, K, cp, idx, g, acc);
+            M6 &e = S.ent[tid];
+            e.Mx = acc[0]; e.My = acc[1]; e.Mxx = acc[2]; e.Mxy = acc[3]; e.Myy = acc[4]; e.W = acc[5];
+        }
+    }
+    G::sync();
+    // fit_line(lfps, n, kept[a], kept[c]) on the cached entries
+    auto fit_kept = [&](int a, int c, LineFit &lf) {
+        const int i0 = S.kept[a], i1 = S.kept[c];
+        if (i0 < i1) fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], i0 > 0 ? 1 : 0, i1 - i0 + 1, true, lf);
+        else fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], 2, n - i0 + i1 + 1, true, lf);
+    };
     for (int t = tid; t < nk * nk; t += NT) {
         const int a = t / nk, c = t % nk;
         if (a == c) continue;
         LineFit lf;
-        fit_line(lfps, n, S.kept[a], S.kept[c], true, lf);
+        fit_kept(a, c, lf);
         p_err[a][c] = lf.err; p_mse[a][c] = lf.mse; p_nx[a][c] = lf.nx; p_ny[a][c] = lf.ny;
     }
     G::sync();
@@ -270,13 +312,11 @@ __device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__re
     // ---- corners, area and convexity tests (one thread) -------------------------------------------------------------
     if (tid == 0) {
         const int mi[4] = {(best_combo >> 12) & 15, (best_combo >> 8) & 15, (best_combo >> 4) & 15, best_combo & 15};
-        int indices[4];
-        for (int i = 0; i < 4; i++) indices[i] = S.kept[mi[i]];
         double lines[4][4];
         bool good = true;
         for (int i = 0; i < 4 && good; i++) {
             LineFit lf;
-            fit_line(lfps, n, indices[i], indices[(i + 1) & 3], true, lf);
+            fit_kept(mi[i], mi[(i + 1) & 3], lf);
             lines[i][0] = lf.Ex; lines[i][1] = lf.Ey; lines[i][2] = lf.nx; lines[i][3] = lf.ny;
             if (lf.mse > (double)prm.max_line_fit_mse) good = false;
         }
@@ -347,7 +387,7 @@ template <int PHASE>
 __global__ void __launch_bounds__(QS_WARPS * 32)
 fit_quads_small_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters,
                        const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
-                       double *__restrict__ lfps_all, QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads,
+                       const double *__restrict__ errs_all, const double *__restrict__ cp_all, QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads,
                        uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -366,7 +406,7 @@ fit_quads_small_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ sc
         if (n < 24 || n > QS_MAXN) continue;
         if (rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
-        fit_quad_cluster<32, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.w[wid].A, SH.w[wid].B, lfps_all + pbase * 6, SH.w[wid].S, rec,
+        fit_quad_cluster<32, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.w[wid].A, SH.w[wid].B, errs_all + pbase, cp_all + (pbase / LF_CP) * 6, SH.w[wid].S, rec,
                                     clusters + item, b,
                              quads, nquads, nquads_total, errflag, g, caps, prm);
         __syncwarp();
@@ -389,7 +429,7 @@ __global__ void __launch_bounds__(NT)
 fit_quads_cta_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters,
                      const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork,
                      uint32_t *__restrict__ work_counter,
-                     double *__restrict__ lfps_all, unsigned long long *__restrict__ scratch, QuadRec *__restrict__ quads,
+                     const double *__restrict__ errs_all, const double *__restrict__ cp_all, unsigned long long *__restrict__ scratch, QuadRec *__restrict__ quads,
                      uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps,
                      DetParams prm)
 {
@@ -409,42 +449,55 @@ fit_quads_cta_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scan
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         unsigned long long *A = SH.A, *B = SH.B;
         if (n > MAXN) { A = scratch + pbase * 2; B = A + n; }
-        fit_quad_cluster<NT, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, A, B, lfps_all + pbase * 6, SH.S, rec, clusters + item, b, quads, nquads,
+        fit_quad_cluster<NT, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, A, B, errs_all + pbase, cp_all + (pbase / LF_CP) * 6, SH.S, rec, clusters + item, b, quads, nquads,
                              nquads_total, errflag, g, caps, prm);
     }
 }
 
-// ---- phase 3 for every tier: per-point weights + sequential prefix moments, ONE WARP per cluster --------------------
-// The prefix is a dependent chain (one DADD per point and moment) that only six lanes can work on, so threads beyond a
-// warp only add barrier waits; what matters is the number of clusters in flight.  This kernel needs no per-point shared
-// memory (8 warps share 24 KB of staging tiles), so every SM keeps 48+ chains going.  The gradient taps of the next 32
-// points are issued before the current 32 are accumulated, so the gathers hide behind the chain.
-constexpr int LF_WARPS = 8;
+// ---- prefix moments + window errors for every tier: ONE WARP per cluster ------------------------------------------------
+// upstream compute_lfps() + the first loop of quad_segment_maxima().  The prefix is a dependent chain (one DADD per point
+// and moment) that only six lanes can work on, so what matters is the number of clusters in flight, not the threads per
+// cluster.  Writing the whole 48-byte-per-point prefix array and reading it back for the window errors was the largest
+// HBM stream of the detector, so the array never leaves the SM:
+//   * the prefix of the last 96 points lives in a shared-memory ring (moment-major, pitch 97: the six chain lanes and the
+//     32 window lanes are both bank-conflict free); the window error errs[i] = fit_line(i - ksz, i + ksz) only needs
+//     entries i + ksz and i - ksz - 1, i.e. at most 41 back, and is emitted as soon as entry i + ksz exists;
+//   * the 2 ksz windows that wrap around the ends are done last, from the ring (tail) and a copy of the first 2 ksz
+//     entries (head);
+//   * every LF_CP-th entry is written to global memory as a checkpoint (6 bytes per point); the fit kernel rebuilds the
+//     <= 21 entries the corner search needs by replaying <= LF_CP - 1 points from a checkpoint.
+// The gradient taps of the next 32 points are issued before the current 32 are accumulated.
+constexpr int LF_WARPS = 4;
+constexpr int LF_RING = 96, LF_PITCH = 97, LF_HEAD = 40, LF_HPITCH = 41;
+struct LfWarp {
+    double ring[6][LF_PITCH];
+    double head[6][LF_HPITCH];
+};
 __global__ void __launch_bounds__(LF_WARPS * 32)
 lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const ClusterRec *__restrict__ clusters,
             const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork /* stride 2, 4 tiers */,
-            uint32_t *__restrict__ work_counter, double *__restrict__ lfps_all, Geom g, Caps caps)
+            uint32_t *__restrict__ work_counter, double *__restrict__ errs_all, double *__restrict__ cp_all, Geom g, Caps caps)
 {
-    __shared__ double stage[LF_WARPS][2][32][6];
+    __shared__ LfWarp sh[LF_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t full = 0xffffffffu;
-    const uint32_t cnt_t[4] = {nwork[0], nwork[2], nwork[4], nwork[6]};
-    const uint32_t total = cnt_t[0] + cnt_t[1] + cnt_t[2] + cnt_t[3];
+    double (*ring)[LF_PITCH] = sh[wid].ring;
+    double (*head)[LF_HPITCH] = sh[wid].head;
     for (;;) {
         uint32_t wi = 0;
         if (lane == 0) wi = atomicAdd(work_counter, 1u);
         wi = __shfl_sync(full, wi, 0);
-        if (wi >= total) return;
-        int t = 3;                                   // largest tier first
-        while (wi >= cnt_t[t]) { wi -= cnt_t[t]; t--; }
-        const uint32_t item = worklists[(size_t)t * wl_stride + wi];
+        uint32_t item;
+        if (!tier_item<0, 3>(wi, nwork, worklists, wl_stride, item)) return;
         const int b = item / caps.clusters_per_frame;
         const ClusterRec rec = clusters[item];
         if (rec.cursor == 0xffffffffu || rec.count < 24) continue;
         const int n = (int)rec.count;
-        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
+        const int ksz = min(20, n / 12);
+        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;     // multiple of LF_CP
         const uint32_t *XY = sorted_xy + pbase;
-        double *lfps = lfps_all + pbase * 6;
+        double *errs = errs_all + pbase;
+        double *cp = cp_all + (pbase / LF_CP) * 6;
         const uint8_t *img = in + (size_t)b * g.frame_stride;
         // raw taps of one point: left/right/up/down neighbours of the decimated pixel, -1 = no gradient (W = 1)
         int gl = -1, gr = 0, gu = 0, gd = 0;
@@ -463,10 +516,14 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
                 }
             }
         };
+        auto ring_entry = [&](int idx, M6 &e) {
+            const int s = idx % LF_RING;
+            e.Mx = ring[0][s]; e.My = ring[1][s]; e.Mxx = ring[2][s]; e.Mxy = ring[3][s]; e.Myy = ring[4][s]; e.W = ring[5][s];
+        };
         issue(lane);
         double acc = 0;
         for (int j0 = 0; j0 < n; j0 += 32) {
-            const int j = j0 + lane, buf = (j0 >> 5) & 1;
+            const int j = j0 + lane, s0 = j0 % LF_RING, s = s0 + lane;
             if (j < n) {
                 double W = 1;
                 if (gl >= 0) {
@@ -475,20 +532,52 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
                 }
                 const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
                 const double fx = px * .5 + 0.5, fy = py * .5 + 0.5;
-                double *tt = stage[wid][buf][lane];
-                tt[0] = W * fx; tt[1] = W * fy; tt[2] = W * fx * fx; tt[3] = W * fx * fy; tt[4] = W * fy * fy; tt[5] = W;
+                ring[0][s] = W * fx; ring[1][s] = W * fy; ring[2][s] = W * fx * fx; ring[3][s] = W * fx * fy; ring[4][s] = W * fy * fy; ring[5][s] = W;
             }
             __syncwarp();
             issue(j0 + 32 + lane);                   // gathers of the next block fly while this block is accumulated
             if (lane < 6) {
                 const int cnt = min(32, n - j0);
-                double *o = lfps + (size_t)j0 * 6 + lane;
+                double *r = &ring[lane][s0];
+                double *c = cp + (size_t)(j0 / LF_CP) * 6 + lane;
 #pragma unroll 8
                 for (int k = 0; k < cnt; k++) {
-                    acc += stage[wid][buf][k][lane];
-                    o[(size_t)k * 6] = acc;
+                    acc += r[k];
+                    r[k] = acc;
+                    if ((k & (LF_CP - 1)) == LF_CP - 1) c[(size_t)(k / LF_CP) * 6] = acc;
                 }
             }
+            __syncwarp();
+            if (j < n) {
+                if (j < 2 * ksz) {
+#pragma unroll
+                    for (int m = 0; m < 6; m++) head[m][j] = ring[m][s];
+                } else {
+                    // window centred on i = j - ksz: i0 = j - 2 ksz >= 0, i1 = j
+                    M6 a, p;
+                    ring_entry(j, a);
+                    p = a;
+                    const int i0 = j - 2 * ksz;
+                    if (i0 > 0) ring_entry(i0 - 1, p);
+                    LineFit lf;
+                    fit_line_m(a, p, p, i0 > 0 ? 1 : 0, 2 * ksz + 1, false, lf);
+                    errs[j - ksz] = lf.err;
+                }
+            }
+            __syncwarp();                            // the next block overwrites the oldest third of the ring
+        }
+        // windows that wrap: i in [0, ksz) and [n - ksz, n)
+        for (int t = lane; t < 2 * ksz; t += 32) {
+            const int i = t < ksz ? t : n - 2 * ksz + t;
+            int i0 = i - ksz; if (i0 < 0) i0 += n;
+            int i1 = i + ksz; if (i1 >= n) i1 -= n;
+            M6 a, p, l;
+            a.Mx = head[0][i1]; a.My = head[1][i1]; a.Mxx = head[2][i1]; a.Mxy = head[3][i1]; a.Myy = head[4][i1]; a.W = head[5][i1];
+            ring_entry(i0 - 1, p);
+            ring_entry(n - 1, l);
+            LineFit lf;
+            fit_line_m(a, p, l, 2, n - i0 + i1 + 1, false, lf);
+            errs[i] = lf.err;
         }
         __syncwarp();
     }
