@@ -227,9 +227,6 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ThrTmaWarp) * THR_TMA_WARPS)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QsShared)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QL_MAXN>)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QlShared<QM1_MAXN>)) == cudaSuccess;
 #define CB_SORT_ATTR(CFG) ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::BYTES) == cudaSuccess;
         CB_SORT_ATTR(SortS8<1>) CB_SORT_ATTR(SortS16<1>) CB_SORT_ATTR(SortM<1>) CB_SORT_ATTR(SortL1<1>) CB_SORT_ATTR(SortL2<1>)
         CB_SORT_ATTR(SortS8<2>) CB_SORT_ATTR(SortS16<2>) CB_SORT_ATTR(SortM<2>) CB_SORT_ATTR(SortL1<2>) CB_SORT_ATTR(SortL2<2>)
@@ -408,7 +405,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         CK(cudaEventRecord(ctx->ev[4], st));
         // ---- A5 quad fitting ----
         // sort #1 | sort #2 | prefix moments | fit, largest tier first inside each (long jobs).
-        // misc: [8 + 2t] items of tier t; work counters: [16..20] sort #1, [21..25] sort #2, [26] moments, [27..29] fit
+        // misc: [8 + 2t] items of tier t; work counters: [16..20] sort #1, [21..25] sort #2, [26] moments, [27] fit
 #define CB_LAUNCH_SORT1(CFG, GRID, CNT)                                                                                                          \
         sort_clusters_kernel<CFG><<<ctx->num_sms * (GRID), CFG::THREADS, CFG::BYTES, st>>>(ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, \
                                                                                          d_misc + (CNT), ctx->d_scratch, g, caps, prm);
@@ -424,16 +421,9 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
 #undef CB_LAUNCH_SORT1
         lfps_kernel<<<ctx->num_sms * 8, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 26,
                                                                   ctx->d_errs, ctx->d_cp, g, caps);
-        fit_quads_cta_kernel<QL_THREADS, QL_MAXN, 4, 3, 3><<<ctx->num_sms * 2, QL_THREADS, sizeof(QlShared<QL_MAXN>), st>>>(
-            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 29, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
-            ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
-        fit_quads_cta_kernel<QM1_THREADS, QM1_MAXN, 4, 1, 2><<<ctx->num_sms * 6, QM1_THREADS, sizeof(QlShared<QM1_MAXN>), st>>>(
-            d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 28, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
-            ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
-        fit_quads_small_kernel<4><<<ctx->num_sms * 4, QS_WARPS * 32, sizeof(QsShared), st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist,
-                                                                                          d_misc + 8, d_misc + 27, ctx->d_errs, ctx->d_cp, ctx->d_quads,
-                                                                                          d_nq, d_misc + 3, d_misc, g, caps, prm);
-        launches += 14;
+        fit_quads_kernel<<<ctx->num_sms * 8, FQ_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 27,
+                                                                       ctx->d_errs, ctx->d_cp, ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
+        launches += 12;
         CK(cudaEventRecord(ctx->ev[5], st));
     } else {
         CK(cudaEventRecord(ctx->ev[4], st));

@@ -4,31 +4,28 @@
 // double arithmetic below follows upstream operation by operation (the library is built with --fmad=false), and
 // every order-dependent accumulation keeps upstream's order:
 //   * points are first put back into scan order (y, x, probe) -- the order upstream's hash map appends them in;
-//   * ptsort()'s merge sort is emulated exactly: same recursive split (sz/2), same 2..5 element sorting networks
-//     at the leaves, merges that take from the SECOND half on ties -- done as parallel rank merges;
-//   * the line-fit prefix moments are accumulated sequentially (six lanes, one per moment), fed 32 points at a time
-//     through a small shared-memory staging tile so that the dependent chain is one DADD per point;
+//   * ptsort()'s result is reproduced exactly: its leaf networks are emulated, the merges are replaced by a sort on a
+//     composite key that has the same order (sort.cuh);
+//   * the line-fit prefix moments are accumulated sequentially (six lanes, one per moment), 32 points at a time
+//     through a shared-memory ring, so that the dependent chain is one DADD per point;
 //   * the 4-corner search evaluates all <=210 subsets in parallel and keeps the first minimum in loop order.
 //
 // B200 mapping: the work is thousands of small, irregular, partly sequential jobs per frame (a c2 frame has ~700
 // clusters of 24..7000 points), so the design maximises the number of clusters in flight instead of the threads per
-// cluster.  Two persistent kernels pull (frame, cluster) items from device-side work lists:
-//   tier S: clusters of <= 256 points, ONE WARP per cluster (6 KB smem per warp, 32 warps per SM);
-//   tier M: 257..2048 points, one 128-thread CTA per cluster (34 KB smem, 6 CTAs per SM);
-//   tier L: larger clusters, one 256-thread CTA per cluster (98 KB smem, 2 CTAs per SM; clusters above 6144 points
-//           run the same code out of a global scratch area).
+// cluster.  Persistent kernels pull (frame, cluster) items from four device-side work lists (by cluster size):
+//   sort #1, sort #2 (sort.cuh): five kernels each -- one warp per cluster up to 512 points, CTAs of 128 / 256 / 512
+//           threads above -- on a register-blocked merge-path sort in shared memory;
+//   lfps_kernel: prefix moments + window errors, one warp per cluster of any size, the prefix array stays in a
+//           shared-memory ring;
+//   fit_quads_kernel: maxima, corner search, quad tests, one warp per cluster of any size.
 // A boundary point is fully described by its 32-bit scan key (pixel index, probe, gradient sign), so the only
-// per-point input is 4 bytes; sorting happens on packed (slope, scan key) 64-bit words in shared memory.
+// per-point input is 4 bytes; per point the stage moves 4 B (keys) + 4 B (sorted points) + 8 B (window error) + 6 B
+// (checkpoints) through global memory.
 #pragma once
 #include "common.cuh"
 #include "sort.cuh"
 
 namespace cb {
-
-constexpr int QS_MAXN = 256;      // tier S: points per warp
-constexpr int QS_WARPS = 8;
-constexpr int QL_THREADS = 256;
-constexpr int QL_MAXN = 6144;     // tier L: points per CTA in shared memory (tier M: 128 threads, 2048 points)
 
 struct LineFit { double Ex, Ey, nx, ny, err, mse; };
 
@@ -105,352 +102,239 @@ __device__ __forceinline__ void replay_entry(const uint8_t *__restrict__ img, co
 // C(k,4) entries; filled by the host (api.cu)
 __constant__ uint16_t c_combos[210];
 
-struct QfScratch {       // per group (warp or CTA)
-    double red_d[8];
-    int red_i[8];
-    float red_f[8];
-    uint32_t w_cnt[8];
-    int nmax;
-    int kept[16];
-    int nkept;
-    int taken[16];
-    double thresh;
-    M6 ent[21];               // prefix-moment entries of the kept maxima
+// ---- maxima, corner search, corner / area / convexity tests: ONE WARP per cluster, every tier ------------------------------
+// upstream quad_segment_maxima() from its second loop on, and the rest of fit_quad().  After the window errors exist the
+// only per-point work left is a 7-tap smoothing and a local-maximum test, which stream through a 40-entry tile; all that
+// follows works on <= 10 maxima.  So a cluster of any size needs one warp and ~7 KB of shared memory, no barriers:
+//   * smoothed errors and local maxima, 32 points per step (wrap-around by modular loads of the global errs array);
+//   * the best max_nmaxima + 1 maxima are kept in a sorted list, one per lane (insertion by shuffle) -- upstream's
+//     "threshold = element [max_nmaxima] of the descending sort, keep err > threshold";
+//   * the <= 21 prefix-moment entries the kept maxima refer to are rebuilt from checkpoints (replay_entry);
+//   * pair table fit_line(kept[a], kept[c]), <= 210 four-subsets evaluated in parallel, first minimum in loop order;
+//   * line intersections on four lanes, area and convexity on one.
+constexpr int FQ_WARPS = 4;
+struct FqWarp {
+    double et[40];          // window errors of points j0 - 4 .. j0 + 35 (indices wrapped)
+    double ys[34];          // smoothed errors of points j0 - 1 .. j0 + 32
+    M6 ent[21];             // lfps[kept[m]], lfps[kept[m] - 1] (m < 10), lfps[n - 1]
+    double p_err[10][10], p_mse[10][10], p_nx[10][10], p_ny[10][10], p_ex[10][10], p_ey[10][10];
+    double lines[4][4];
+    float qp[4][2];
+    int kept[10];
 };
 
-// Processes one cluster.  A and B are 8-byte-per-point work arrays (shared or global), lfps the 48-byte-per-point
-// prefix-moment array (global).  Every thread of the group must call it; control flow is group-uniform.
-// The work on a cluster is cut into four phases, each its own kernel (per tier), because the one-warp-per-cluster tier is
-// instruction-fetch bound when every warp of an SM sits in a different part of a 100 KB kernel (ncu: stall_no_instruction):
-//   PHASE 1: bounding box, border polarity (rejected clusters get cursor = 0xffffffff), scan-order sort; the sorted scan
-//            keys replace the unsorted ones in global memory;
-//   PHASE 2: slopes, ptsort() emulation; the sorted points (px | py << 16) replace the keys;
-//   PHASE 3: per-point weights and the sequential prefix moments (global lfps array);
-//   PHASE 4: window errors, maxima, corner search, corner / area / convexity tests.
-template <int NT, int PHASE>
-__device__ void fit_quad_cluster(const uint8_t *__restrict__ img, uint32_t *__restrict__ K, int n, unsigned long long *A,
-                                 unsigned long long *B, const double *__restrict__ errs_g, const double *__restrict__ cp, QfScratch &S, const ClusterRec &rec,
-                                 ClusterRec *__restrict__ rec_global, int b,
-                                 QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
-                                 uint32_t *__restrict__ errflag, const Geom &g, const Caps &caps, const DetParams &prm)
+__global__ void __launch_bounds__(FQ_WARPS * 32)
+fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const ClusterRec *__restrict__ clusters,
+                 const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork /* stride 2, 4 tiers */,
+                 uint32_t *__restrict__ work_counter, const double *__restrict__ errs_all, const double *__restrict__ cp_all,
+                 QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
+                 uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm)
 {
-    typedef Grp<NT> G;
-    const int tid = G::tid();
-    const int lane = threadIdx.x & 31;
-
+    __shared__ FqWarp sh[FQ_WARPS];
+    const int lane = threadIdx.x & 31, tid = lane;
+    const uint32_t full = 0xffffffffu;
+    FqWarp &S = sh[threadIdx.x >> 5];
     const int reversed_border = 0;          // reversed clusters never get past sort #1 (tag36h11 has a normal border only)
-    unsigned long long *src = A, *dst = B;
-    // ---- PHASE 4: quad_segment_maxima ---------------------------------------------------------------------------
-    const int ksz = min(20, n / 12);
-    if (ksz < 2) return;
-    double *errs = reinterpret_cast<double *>(src);
-    double *ysm = reinterpret_cast<double *>(dst);
-    for (int i = tid; i < n; i += NT) errs[i] = errs_g[i];      // window errors (lfps_kernel)
-    G::sync();
-    for (int iy = tid; iy < n; iy += NT) {
-        double acc = 0;
-#pragma unroll
-        for (int i = 0; i < 7; i++) {
-            int q = iy + i - 3;
-            if (q < 0) q += n; else if (q >= n) q -= n;
-            acc += errs[q] * prm.smooth_f[i];
-        }
-        ysm[iy] = acc;
-    }
-    G::sync();
-    // local maxima, collected in index order (two maxima are never adjacent, so there are at most n/2)
-    int *maxima = reinterpret_cast<int *>(errs);
-    double *maxima_errs = reinterpret_cast<double *>(errs) + (n + 3) / 4;
-    if (tid == 0) S.nmax = 0;
-    G::sync();
-    for (int i0 = 0; i0 < n; i0 += NT) {
-        const int i = i0 + tid;
-        bool is_max = false;
-        double e = 0;
-        if (i < n) {
-            e = ysm[i];
-            const int nx = i + 1 == n ? 0 : i + 1, pv = i == 0 ? n - 1 : i - 1;
-            is_max = e > ysm[nx] && e > ysm[pv];
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, is_max);
-        int base;
-        if (NT == 32) {
-            base = S.nmax;
-        } else {
-            const int wid = threadIdx.x >> 5;
-            if (lane == 0) S.w_cnt[wid] = __popc(bal);
-            __syncthreads();
-            base = S.nmax;
-            for (int k = 0; k < wid; k++) base += S.w_cnt[k];
-        }
-        if (is_max) {
-            const int pos = base + __popc(bal & ((1u << lane) - 1));
-            maxima[pos] = i;
-            maxima_errs[pos] = e;
-        }
-        G::sync();
-        if (tid == 0) {
-            if (NT == 32) S.nmax += __popc(bal);
-            else { int t = 0; for (int k = 0; k < NT / 32; k++) t += S.w_cnt[k]; S.nmax += t; }
-        }
-        G::sync();
-    }
-    const int nmaxima = S.nmax;
-    if (nmaxima < 4) return;
-    // keep only the best max_nmaxima: maxima_thresh = element [max_nmaxima] of the descending sort, found by
-    // max_nmaxima + 1 rounds of "largest not yet taken" (ties -> lowest position, one element per round)
-    const int max_nmaxima = min(prm.max_nmaxima, 10);
-    if (nmaxima > max_nmaxima) {
-        for (int r = 0; r <= max_nmaxima; r++) {
-            double best = 0;
-            int bpos = 1 << 30;       // 1<<30 = nothing found yet
-            for (int m = tid; m < nmaxima; m += NT) {
-                bool tk = false;
-                for (int q = 0; q < r; q++) tk |= (S.taken[q] == m);
-                if (tk) continue;
-                const double e = maxima_errs[m];
-                if (bpos == (1 << 30) || e > best) { best = e; bpos = m; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
-                if (op != (1 << 30) && (bpos == (1 << 30) || ob > best || (ob == best && op < bpos))) { best = ob; bpos = op; }
-            }
-            if (NT != 32) {
-                const int wid = threadIdx.x >> 5;
-                __syncthreads();
-                if (lane == 0) { S.red_d[wid] = best; S.red_i[wid] = bpos; }
-                __syncthreads();
-                best = S.red_d[0]; bpos = S.red_i[0];
-                for (int k = 1; k < NT / 32; k++) {
-                    const double ob = S.red_d[k]; const int op = S.red_i[k];
-                    if (op != (1 << 30) && (bpos == (1 << 30) || ob > best || (ob == best && op < bpos))) { best = ob; bpos = op; }
-                }
-            }
-            G::sync();
-            if (tid == 0) { S.taken[r] = bpos; S.thresh = best; }
-            G::sync();
-        }
-        if (tid == 0) {
-            int out = 0;
-            const double th = S.thresh;
-            // the kept maxima are among the positions taken in the first max_nmaxima rounds; emit them in index order
-            int pos[10];
-            for (int q = 0; q < max_nmaxima; q++) pos[q] = S.taken[q];
-            for (int a = 1; a < max_nmaxima; a++) { const int t = pos[a]; int c = a; while (c > 0 && pos[c - 1] > t) { pos[c] = pos[c - 1]; c--; } pos[c] = t; }
-            for (int q = 0; q < max_nmaxima; q++) {
-                if (maxima_errs[pos[q]] <= th) continue;
-                S.kept[out++] = maxima[pos[q]];
-            }
-            S.nkept = out;
-        }
-    } else if (tid == 0) {
-        for (int m = 0; m < nmaxima; m++) S.kept[m] = maxima[m];
-        S.nkept = nmaxima;
-    }
-    G::sync();
-    const int nk = S.nkept;
-    if (nk < 4) return;   // (upstream's loops would simply find nothing)
-    // pair table: fit_line(kept[a], kept[c]) for a != c (3200 B); lives in the now dead work arrays
-    double (*p_err)[10] = reinterpret_cast<double (*)[10]>(A);    // A and B are adjacent (A first): >= 4 KB in every tier
-    double (*p_mse)[10] = p_err + 10, (*p_nx)[10] = p_err + 20, (*p_ny)[10] = p_err + 30;
-    // the prefix-moment entries the corner search reads: lfps[kept[m]], lfps[kept[m] - 1], lfps[n - 1]
-    if (tid <= 2 * nk) {
-        const int idx = tid == 2 * nk ? n - 1 : S.kept[tid >> 1] - (tid & 1);
-        if (idx >= 0) {
-            double acc[6];
-            replay_entry(img, K, cp, idx, g, acc);
-            M6 &e = S.ent[tid];
-            e.Mx = acc[0]; e.My = acc[1]; e.Mxx = acc[2]; e.Mxy = acc[3]; e.Myy = acc[4]; e.W = acc[5];
-        }
-    }
-    G::sync();
-    // fit_line(lfps, n, kept[a], kept[c]) on the cached entries
-    auto fit_kept = [&](int a, int c, LineFit &lf) {
-        const int i0 = S.kept[a], i1 = S.kept[c];
-        if (i0 < i1) fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], i0 > 0 ? 1 : 0, i1 - i0 + 1, true, lf);
-        else fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], 2, n - i0 + i1 + 1, true, lf);
-    };
-    for (int t = tid; t < nk * nk; t += NT) {
-        const int a = t / nk, c = t % nk;
-        if (a == c) continue;
-        LineFit lf;
-        fit_kept(a, c, lf);
-        p_err[a][c] = lf.err; p_mse[a][c] = lf.mse; p_nx[a][c] = lf.nx; p_ny[a][c] = lf.ny;
-    }
-    G::sync();
-    // 4-corner search; (m0,m1,m2,m3) packed big-endian orders like upstream's loop nest, so the minimum over
-    // (err, packed) is upstream's "first minimum"
-    double best_err = __longlong_as_double(0x7ff0000000000000ll);
-    int best_combo = 1 << 30;
-    {
-        const double max_mse = (double)prm.max_line_fit_mse;
-        const int ncomb = nk * (nk - 1) * (nk - 2) * (nk - 3) / 24;
-        for (int ci = tid; ci < ncomb; ci += NT) {
-            const int pk = c_combos[ci];
-            const int m0 = pk >> 12, m1 = (pk >> 8) & 15, m2 = (pk >> 4) & 15, m3 = pk & 15;
-            if (p_mse[m0][m1] > max_mse) continue;
-            if (p_mse[m1][m2] > max_mse) continue;
-            const double dt = p_nx[m0][m1] * p_nx[m1][m2] + p_ny[m0][m1] * p_ny[m1][m2];
-            if (fabs(dt) > prm.cos_critical_rad) continue;
-            if (p_mse[m2][m3] > max_mse) continue;
-            if (p_mse[m3][m0] > max_mse) continue;
-            const double err = p_err[m0][m1] + p_err[m1][m2] + p_err[m2][m3] + p_err[m3][m0];
-            if (err < best_err || (err == best_err && pk < best_combo)) { best_err = err; best_combo = pk; }
-        }
-    }
-    {
-        const double bmin = G::reduce(best_err, [](double a, double c) { return a < c ? a : c; }, S.red_d);
-        int cand = (best_err == bmin && best_combo != (1 << 30)) ? best_combo : (1 << 30);
-        cand = G::reduce(cand, [](int a, int c) { return min(a, c); }, S.red_i);
-        best_err = bmin; best_combo = cand;
-    }
-    if (best_combo == (1 << 30)) return;
-    if (!(best_err / n < (double)prm.max_line_fit_mse)) return;
-
-    // ---- corners, area and convexity tests (one thread) -------------------------------------------------------------
-    if (tid == 0) {
-        const int mi[4] = {(best_combo >> 12) & 15, (best_combo >> 8) & 15, (best_combo >> 4) & 15, best_combo & 15};
-        double lines[4][4];
-        bool good = true;
-        for (int i = 0; i < 4 && good; i++) {
-            LineFit lf;
-            fit_kept(mi[i], mi[(i + 1) & 3], lf);
-            lines[i][0] = lf.Ex; lines[i][1] = lf.Ey; lines[i][2] = lf.nx; lines[i][3] = lf.ny;
-            if (lf.mse > (double)prm.max_line_fit_mse) good = false;
-        }
-        float qp[4][2];
-        for (int i = 0; i < 4 && good; i++) {
-            const double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
-            const double A10 = -lines[i][2], A11 = lines[(i + 1) & 3][2];
-            const double B0 = -lines[i][0] + lines[(i + 1) & 3][0];
-            const double B1 = -lines[i][1] + lines[(i + 1) & 3][1];
-            const double det = A00 * A11 - A10 * A01;
-            const double W00 = A11 / det, W01 = -A01 / det;
-            if (fabs(det) < 0.001) { good = false; break; }
-            const double L0 = W00 * B0 + W01 * B1;
-            qp[i][0] = (float)(lines[i][0] + L0 * A00);
-            qp[i][1] = (float)(lines[i][1] + L0 * A10);
-        }
-        if (good) {
-            double area = 0, length[3], p;
-            for (int i = 0; i < 3; i++) {
-                const int a = i, c = (i + 1) % 3;
-                const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
-                length[i] = sqrt(ddx * ddx + ddy * ddy);
-            }
-            p = (length[0] + length[1] + length[2]) / 2;
-            area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
-            const int idxs[4] = {2, 3, 0, 2};
-            for (int i = 0; i < 3; i++) {
-                const int a = idxs[i], c = idxs[i + 1];
-                const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
-                length[i] = sqrt(ddx * ddx + ddy * ddy);
-            }
-            p = (length[0] + length[1] + length[2]) / 2;
-            area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
-            if (area < 0.95 * prm.min_tag_width * prm.min_tag_width) good = false;
-        }
-        if (good) {
-            for (int i = 0; i < 4; i++) {
-                const int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
-                const double dx1 = (double)qp[i1][0] - (double)qp[i0][0], dy1 = (double)qp[i1][1] - (double)qp[i0][1];
-                const double dx2 = (double)qp[i2][0] - (double)qp[i1][0], dy2 = (double)qp[i2][1] - (double)qp[i1][1];
-                const double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
-                if ((cos_dtheta > prm.cos_critical_rad || cos_dtheta < -prm.cos_critical_rad) || dx1 * dy2 < dy1 * dx2) { good = false; break; }
-            }
-        }
-        if (good) {
-            const uint32_t qf = atomicAdd(&nquads[b], 1u);
-            if (qf >= caps.quads_per_frame) atomicOr(errflag, ERR_QUADS_FULL);
-            else {
-                const uint32_t qi = atomicAdd(nquads_total, 1u);   // < batch * quads_per_frame by construction
-                QuadRec q;
-                for (int i = 0; i < 4; i++) { q.p[i][0] = qp[i][0]; q.p[i][1] = qp[i][1]; }
-                q.reversed_border = reversed_border; q.npoints = n; q.key = rec.key; q.frame = b; q.pad = 0;
-                quads[qi] = q;
-            }
-        }
-    }
-}
-
-struct QsWarp {
-    unsigned long long A[QS_MAXN];
-    unsigned long long B[QS_MAXN];   // directly after A: the pair table of the corner search spans both
-    QfScratch S;
-};
-struct QsShared { QsWarp w[QS_WARPS]; };
-
-// tier S: persistent warps, one cluster (<= QS_MAXN points, work list 0) per warp at a time
-template <int PHASE>
-__global__ void __launch_bounds__(QS_WARPS * 32)
-fit_quads_small_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters,
-                       const uint32_t *__restrict__ worklist, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
-                       const double *__restrict__ errs_all, const double *__restrict__ cp_all, QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads,
-                       uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    QsShared &SH = *reinterpret_cast<QsShared *>(smem_raw);
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t total = *nwork;
     for (;;) {
+        __syncwarp();
         uint32_t wi = 0;
         if (lane == 0) wi = atomicAdd(work_counter, 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= total) return;
-        const uint32_t item = worklist[wi];
-        const int b = item / caps.clusters_per_frame;
-        const ClusterRec rec = clusters[item];
-        const int n = (int)rec.count;
-        if (n < 24 || n > QS_MAXN) continue;
-        if (rec.cursor == 0xffffffffu) continue;
-        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
-        fit_quad_cluster<32, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, SH.w[wid].A, SH.w[wid].B, errs_all + pbase, cp_all + (pbase / LF_CP) * 6, SH.w[wid].S, rec,
-                                    clusters + item, b,
-                             quads, nquads, nquads_total, errflag, g, caps, prm);
-        __syncwarp();
-    }
-}
-
-template <int MAXN>
-struct QlShared {
-    unsigned long long A[MAXN];
-    unsigned long long B[MAXN];    // directly after A
-    QfScratch S;
-    int work;
-};
-
-// tiers M / L: persistent CTAs of NT threads, one cluster from work lists T_LO..T_HI per CTA at a time; clusters above
-// MAXN points run out of the global scratch area.  Tier M (NT = 128, MAXN = 2048, 34 KB smem) keeps 6 CTAs per SM
-// resident, tier L (NT = 256, MAXN = 6144, 98 KB) two.
-template <int NT, int MAXN, int PHASE, int T_LO, int T_HI>
-__global__ void __launch_bounds__(NT)
-fit_quads_cta_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters,
-                     const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork,
-                     uint32_t *__restrict__ work_counter,
-                     const double *__restrict__ errs_all, const double *__restrict__ cp_all, unsigned long long *__restrict__ scratch, QuadRec *__restrict__ quads,
-                     uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total, uint32_t *__restrict__ errflag, Geom g, Caps caps,
-                     DetParams prm)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    QlShared<MAXN> &SH = *reinterpret_cast<QlShared<MAXN> *>(smem_raw);
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) SH.work = (int)atomicAdd(work_counter, 1u);
-        __syncthreads();
+        wi = __shfl_sync(full, wi, 0);
         uint32_t item;
-        if (!tier_item<T_LO, T_HI>((uint32_t)SH.work, nwork, worklists, wl_stride, item)) return;
+        if (!tier_item<0, 3>(wi, nwork, worklists, wl_stride, item)) return;
         const int b = item / caps.clusters_per_frame;
         const ClusterRec rec = clusters[item];
+        if (rec.cursor == 0xffffffffu || rec.count < 24) continue;
         const int n = (int)rec.count;
-        if (n < 24) continue;
-        if (rec.cursor == 0xffffffffu) continue;
+        const int ksz = min(20, n / 12);
+        if (ksz < 2) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
-        unsigned long long *A = SH.A, *B = SH.B;
-        if (n > MAXN) { A = scratch + pbase * 2; B = A + n; }
-        fit_quad_cluster<NT, PHASE>(in + (size_t)b * g.frame_stride, scankey + pbase, n, A, B, errs_all + pbase, cp_all + (pbase / LF_CP) * 6, SH.S, rec, clusters + item, b, quads, nquads,
-                             nquads_total, errflag, g, caps, prm);
+        const double *errs = errs_all + pbase;
+
+        // ---- smoothed errors, local maxima, running top list (descending error; ties: lower index first) ----
+        double te = __longlong_as_double(0xfff0000000000000ll);
+        int ti = 1 << 30, nm = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            for (int t = lane; t < 40; t += 32) {
+                int idx = j0 - 4 + t;
+                if (idx < 0) idx += n;
+                while (idx >= n) idx -= n;
+                S.et[t] = errs[idx];
+            }
+            __syncwarp();
+            for (int u = lane; u < 34; u += 32) {
+                double acc = 0;
+#pragma unroll
+                for (int i = 0; i < 7; i++) acc += S.et[u + i] * prm.smooth_f[i];
+                S.ys[u] = acc;
+            }
+            __syncwarp();
+            bool is_max = false;
+            double e = 0;
+            if (j0 + lane < n) {
+                e = S.ys[lane + 1];
+                is_max = e > S.ys[lane + 2] && e > S.ys[lane];
+            }
+            uint32_t bal = __ballot_sync(full, is_max);
+            nm += __popc(bal);
+            while (bal) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const double ev = __shfl_sync(full, e, src);
+                const int pos = __popc(__ballot_sync(full, lane < 11 && te >= ev));
+                const double up_te = __shfl_up_sync(full, te, 1);
+                const int up_ti = __shfl_up_sync(full, ti, 1);
+                if (lane == pos) { te = ev; ti = j0 + src; }
+                else if (lane > pos) { te = up_te; ti = up_ti; }
+            }
+            __syncwarp();
+        }
+        if (nm < 4) continue;
+        const int max_nmaxima = min(prm.max_nmaxima, 10);
+        bool keep;
+        if (nm > max_nmaxima) {
+            const double thresh = __shfl_sync(full, te, max_nmaxima);
+            keep = lane < max_nmaxima && te > thresh;
+        } else {
+            keep = lane < nm;
+        }
+        const uint32_t kb = __ballot_sync(full, keep);
+        const int nk = __popc(kb);
+        {
+            int rank = 0;
+            for (int q = 0; q < 11; q++) {
+                const int oi = __shfl_sync(full, ti, q);
+                if ((kb >> q) & 1) rank += oi < ti ? 1 : 0;
+            }
+            if (keep) S.kept[rank] = ti;
+        }
+        __syncwarp();
+        if (nk < 4) continue;   // (upstream's loops would simply find nothing)
+
+        // ---- the prefix-moment entries the corner search reads: lfps[kept[m]], lfps[kept[m] - 1], lfps[n - 1] ----
+        if (tid <= 2 * nk) {
+            const int idx = tid == 2 * nk ? n - 1 : S.kept[tid >> 1] - (tid & 1);
+            if (idx >= 0) {
+                double acc[6];
+                replay_entry(in + (size_t)b * g.frame_stride, sorted_xy + pbase, cp_all + (pbase / LF_CP) * 6, idx, g, acc);
+                M6 &e = S.ent[tid];
+                e.Mx = acc[0]; e.My = acc[1]; e.Mxx = acc[2]; e.Mxy = acc[3]; e.Myy = acc[4]; e.W = acc[5];
+            }
+        }
+        __syncwarp();
+        // pair table: fit_line(lfps, n, kept[a], kept[c]) for a != c
+        for (int t = tid; t < nk * nk; t += 32) {
+            const int a = t / nk, c = t % nk;
+            if (a == c) continue;
+            const int i0 = S.kept[a], i1 = S.kept[c];
+            LineFit lf;
+            if (i0 < i1) fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], i0 > 0 ? 1 : 0, i1 - i0 + 1, true, lf);
+            else fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], 2, n - i0 + i1 + 1, true, lf);
+            S.p_err[a][c] = lf.err; S.p_mse[a][c] = lf.mse; S.p_nx[a][c] = lf.nx; S.p_ny[a][c] = lf.ny;
+            S.p_ex[a][c] = lf.Ex; S.p_ey[a][c] = lf.Ey;
+        }
+        __syncwarp();
+        // 4-corner search; (m0,m1,m2,m3) packed big-endian orders like upstream's loop nest, so the minimum over
+        // (err, packed) is upstream's "first minimum"
+        double best_err = __longlong_as_double(0x7ff0000000000000ll);
+        int best_combo = 1 << 30;
+        {
+            const double max_mse = (double)prm.max_line_fit_mse;
+            const int ncomb = nk * (nk - 1) * (nk - 2) * (nk - 3) / 24;
+            for (int ci = tid; ci < ncomb; ci += 32) {
+                const int pk = c_combos[ci];
+                const int m0 = pk >> 12, m1 = (pk >> 8) & 15, m2 = (pk >> 4) & 15, m3 = pk & 15;
+                if (S.p_mse[m0][m1] > max_mse) continue;
+                if (S.p_mse[m1][m2] > max_mse) continue;
+                const double dt = S.p_nx[m0][m1] * S.p_nx[m1][m2] + S.p_ny[m0][m1] * S.p_ny[m1][m2];
+                if (fabs(dt) > prm.cos_critical_rad) continue;
+                if (S.p_mse[m2][m3] > max_mse) continue;
+                if (S.p_mse[m3][m0] > max_mse) continue;
+                const double err = S.p_err[m0][m1] + S.p_err[m1][m2] + S.p_err[m2][m3] + S.p_err[m3][m0];
+                if (err < best_err || (err == best_err && pk < best_combo)) { best_err = err; best_combo = pk; }
+            }
+        }
+        {
+            double bmin = best_err;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(full, bmin, o); bmin = ob < bmin ? ob : bmin; }
+            int cand = (best_err == bmin && best_combo != (1 << 30)) ? best_combo : (1 << 30);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(full, cand, o));
+            best_err = bmin; best_combo = cand;
+        }
+        if (best_combo == (1 << 30)) continue;
+        if (!(best_err / n < (double)prm.max_line_fit_mse)) continue;
+
+        // ---- corners (four lanes), area and convexity tests (one lane) -----------------------------------------------
+        const int mi[4] = {(best_combo >> 12) & 15, (best_combo >> 8) & 15, (best_combo >> 4) & 15, best_combo & 15};
+        bool bad = false;
+        if (tid < 4) {
+            const int a = mi[tid], c = mi[(tid + 1) & 3];
+            S.lines[tid][0] = S.p_ex[a][c]; S.lines[tid][1] = S.p_ey[a][c]; S.lines[tid][2] = S.p_nx[a][c]; S.lines[tid][3] = S.p_ny[a][c];
+            bad = S.p_mse[a][c] > (double)prm.max_line_fit_mse;
+        }
+        if (__any_sync(full, bad)) continue;
+        if (tid < 4) {
+            const int i = tid;
+            const double A00 = S.lines[i][3], A01 = -S.lines[(i + 1) & 3][3];
+            const double A10 = -S.lines[i][2], A11 = S.lines[(i + 1) & 3][2];
+            const double B0 = -S.lines[i][0] + S.lines[(i + 1) & 3][0];
+            const double B1 = -S.lines[i][1] + S.lines[(i + 1) & 3][1];
+            const double det = A00 * A11 - A10 * A01;
+            const double W00 = A11 / det, W01 = -A01 / det;
+            if (fabs(det) < 0.001) bad = true;
+            else {
+                const double L0 = W00 * B0 + W01 * B1;
+                S.qp[i][0] = (float)(S.lines[i][0] + L0 * A00);
+                S.qp[i][1] = (float)(S.lines[i][1] + L0 * A10);
+            }
+        }
+        if (__any_sync(full, bad)) continue;
+        if (tid == 0) {
+            float qp[4][2];
+            for (int i = 0; i < 4; i++) { qp[i][0] = S.qp[i][0]; qp[i][1] = S.qp[i][1]; }
+            bool good = true;
+            if (good) {
+                double area = 0, length[3], p;
+                for (int i = 0; i < 3; i++) {
+                    const int a = i, c = (i + 1) % 3;
+                    const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
+                    length[i] = sqrt(ddx * ddx + ddy * ddy);
+                }
+                p = (length[0] + length[1] + length[2]) / 2;
+                area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
+                const int idxs[4] = {2, 3, 0, 2};
+                for (int i = 0; i < 3; i++) {
+                    const int a = idxs[i], c = idxs[i + 1];
+                    const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
+                    length[i] = sqrt(ddx * ddx + ddy * ddy);
+                }
+                p = (length[0] + length[1] + length[2]) / 2;
+                area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
+                if (area < 0.95 * prm.min_tag_width * prm.min_tag_width) good = false;
+            }
+            if (good) {
+                for (int i = 0; i < 4; i++) {
+                    const int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
+                    const double dx1 = (double)qp[i1][0] - (double)qp[i0][0], dy1 = (double)qp[i1][1] - (double)qp[i0][1];
+                    const double dx2 = (double)qp[i2][0] - (double)qp[i1][0], dy2 = (double)qp[i2][1] - (double)qp[i1][1];
+                    const double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
+                    if ((cos_dtheta > prm.cos_critical_rad || cos_dtheta < -prm.cos_critical_rad) || dx1 * dy2 < dy1 * dx2) { good = false; break; }
+                }
+            }
+            if (good) {
+                const uint32_t qf = atomicAdd(&nquads[b], 1u);
+                if (qf >= caps.quads_per_frame) atomicOr(errflag, ERR_QUADS_FULL);
+                else {
+                    const uint32_t qi = atomicAdd(nquads_total, 1u);   // < batch * quads_per_frame by construction
+                    QuadRec q;
+                    for (int i = 0; i < 4; i++) { q.p[i][0] = qp[i][0]; q.p[i][1] = qp[i][1]; }
+                    q.reversed_border = reversed_border; q.npoints = n; q.key = rec.key; q.frame = b; q.pad = 0;
+                    quads[qi] = q;
+                }
+            }
+        }
     }
 }
 
@@ -583,9 +467,6 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
     }
 }
 
-// tiers: S (one warp, <= QS_MAXN) | M1 (128 threads, <= 2048) | M2 (spare slot: same bound as M1, so it stays empty) | L (256 threads, the rest).
-// Measured on the c2 workload (quad stage, ms per 256 frames): S512/L 24.6; S512/M2048/L 21.4; S256x8/M2048/L 18.7; S256/M1024(64 thr)/M3072/L 19.8.
-constexpr int QM1_THREADS = 128, QM1_MAXN = 2048;
 // tier limits of the four work lists, and the sort kernels' (threads, elements per thread, shared-memory points) per tier
 constexpr int QT0 = 256, QT1 = 512, QT2 = 2048;
 // the five kernels of each sort: <NT, E, MAXN, WHICH, T_LO, T_HI, NMIN, NMAX>
