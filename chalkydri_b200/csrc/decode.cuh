@@ -10,7 +10,8 @@
 
 namespace cb {
 
-__constant__ unsigned long long c_codes[kNumCodes];
+// read with a different index per lane, so it lives in global memory (L1) instead of the constant bank
+__device__ unsigned long long c_codes[kNumCodes];
 __constant__ int c_bit_x[36];
 __constant__ int c_bit_y[36];
 
@@ -250,8 +251,9 @@ __device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q
     GrayModel wm = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, bm = wm;
     {
         const float wab = 8.f;
-        double s_tagx[2], s_tagy[2];
-        int s_v[2], s_flag[2];   // flag: 0 skip, 1 white, 2 black
+        // the 64 border samples in upstream's loop order: tag coordinates, pixel value, flag (0 skip, 1 white, 2 black)
+        double *s_tagx = values, *s_tagy = values + 64;
+        int *s_v = reinterpret_cast<int *>(values + 128), *s_flag = s_v + 64;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int k = lane + 32 * h, pi = k >> 3, i = k & 7;
@@ -272,23 +274,34 @@ __device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q
             double px, py;
             homography_project(Hq, tagx, tagy, &px, &py);
             const int ix = (int)px, iy = (int)py;
-            s_tagx[h] = tagx; s_tagy[h] = tagy; s_v[h] = 0; s_flag[h] = 0;
+            int sv = 0, sf = 0;
             if (!(ix < 0 || iy < 0 || ix >= W || iy >= H)) {
-                s_v[h] = img[(size_t)iy * stride + ix];
-                s_flag[h] = is_white ? 1 : 2;
+                sv = img[(size_t)iy * stride + ix];
+                sf = is_white ? 1 : 2;
             }
+            s_tagx[k] = tagx; s_tagy[k] = tagy; s_v[k] = sv; s_flag[k] = sf;
         }
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-            for (int k = 0; k < 32; k++) {
-                const int fl = __shfl_sync(full, s_flag[h], k);
-                const double x = __shfl_sync(full, s_tagx[h], k), y = __shfl_sync(full, s_tagy[h], k);
-                const double gray = (double)__shfl_sync(full, s_v[h], k);
-                if (fl == 0) continue;
-                GrayModel &gm = fl == 1 ? wm : bm;
-                gm.A00 += x * x; gm.A01 += x * y; gm.A02 += x; gm.A11 += y * y; gm.A12 += y; gm.A22 += 1;
-                gm.B0 += x * gray; gm.B1 += y * gray; gm.B2 += gray;
-            }
+        __syncwarp();
+        // The nine sums of each model are independent chains whose terms are all products of two of {x, y, gray, 1}
+        // (x * 1 and 1 * 1 are exact), so lane a (white) / 16 + a (black) accumulates sum a over the samples in order.
+        const int a = lane & 15, my_flag = lane < 16 ? 1 : 2;
+        const int su = (a == 0 || a == 1 || a == 2 || a == 6) ? 0 : ((a == 3 || a == 4 || a == 7) ? 1 : (a == 8 ? 2 : 3));
+        const int sw = a == 0 ? 0 : ((a == 1 || a == 3) ? 1 : ((a == 6 || a == 7) ? 2 : 3));
+        double acc = 0;
+#pragma unroll 4
+        for (int k = 0; k < 64; k++) {
+            const double x = s_tagx[k], y = s_tagy[k], gray = (double)s_v[k];
+            const double u = su == 0 ? x : (su == 1 ? y : (su == 2 ? gray : 1.0));
+            const double w = sw == 0 ? x : (sw == 1 ? y : (sw == 2 ? gray : 1.0));
+            if (s_flag[k] == my_flag) acc += u * w;
+        }
+        wm.A00 = __shfl_sync(full, acc, 0); wm.A01 = __shfl_sync(full, acc, 1); wm.A02 = __shfl_sync(full, acc, 2);
+        wm.A11 = __shfl_sync(full, acc, 3); wm.A12 = __shfl_sync(full, acc, 4); wm.A22 = __shfl_sync(full, acc, 5);
+        wm.B0 = __shfl_sync(full, acc, 6); wm.B1 = __shfl_sync(full, acc, 7); wm.B2 = __shfl_sync(full, acc, 8);
+        bm.A00 = __shfl_sync(full, acc, 16); bm.A01 = __shfl_sync(full, acc, 17); bm.A02 = __shfl_sync(full, acc, 18);
+        bm.A11 = __shfl_sync(full, acc, 19); bm.A12 = __shfl_sync(full, acc, 20); bm.A22 = __shfl_sync(full, acc, 21);
+        bm.B0 = __shfl_sync(full, acc, 22); bm.B1 = __shfl_sync(full, acc, 23); bm.B2 = __shfl_sync(full, acc, 24);
+        __syncwarp();
     }
     gm_solve(wm);
     gm_solve(bm);
@@ -350,7 +363,7 @@ __device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q
         for (int ridx = 0; ridx < 4; ridx++) {
             int best = 1 << 30;   // (id << 8) | hamming, smallest id first
             for (int c = lane; c < kNumCodes; c += 32) {
-                const int d = __popcll(rc ^ c_codes[c]);
+                const int d = __popcll(rc ^ __ldg(&c_codes[c]));
                 if (d <= prm.bits_corrected) { best = min(best, (c << 8) | d); }
             }
 #pragma unroll
@@ -392,7 +405,7 @@ decode_quads_kernel(const uint8_t *__restrict__ in, const QuadRec *__restrict__ 
                     uint32_t *__restrict__ counter, RawDet *__restrict__ raw, uint32_t *__restrict__ nraw, Geom g, Caps caps,
                     DetParams prm, DecodeConst dc)
 {
-    __shared__ double s_values[DEC_WARPS][100];
+    __shared__ double s_values[DEC_WARPS][192];   // 10x10 bit grid; before that the 64 border samples (2 x 64 doubles + 2 x 64 ints)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t total = *nquads_total;
     for (;;) {
