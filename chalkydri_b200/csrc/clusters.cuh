@@ -53,75 +53,160 @@ __device__ __forceinline__ uint32_t slot_find(const ClusterSlot *tab, uint32_t n
     return 0xffffffffu;
 }
 
-// One thread per pixel.  SCATTER = false: count; true: write points of selected clusters.
+// One CTA per 64x16-pixel tile, one thread per pixel and step (4 steps).  SCATTER = false: count; true: write the points of
+// selected clusters.  The points of one cluster inside a tile (a stretch of boundary, typically 30..100 points) are first
+// aggregated in a 256-entry shared-memory table -- lanes with the same key elect a leader (match.any), the leader bumps the
+// tile-local count -- so the global table sees one probe and one atomic per (tile, cluster) instead of one per warp row and
+// probe direction.  In the scatter pass the tile-local count doubles as the rank of the point inside the tile's share of
+// the cluster, and one atomicAdd on the cluster's cursor reserves that share.
+constexpr int CL_TW = 64, CL_TH = 16, CL_THREADS = 256, CL_PER = CL_TW * CL_TH / CL_THREADS, CL_CAP = 256, CL_PROBES = 24;
+struct ClShared {
+    unsigned long long key[CL_CAP];
+    uint32_t cnt[CL_CAP];
+    uint32_t base[CL_CAP];
+};
+
+// find-or-insert in the tile table; -1 when no free entry is found within CL_PROBES probes (the caller goes to the global table)
+__device__ __forceinline__ int tile_insert(ClShared &S, unsigned long long key, uint32_t h)
+{
+    uint32_t s = h % (CL_CAP - 1);      // entry CL_CAP - 1 = 0xff stays unused: it is the "no entry" mark of the per-point word
+    for (int probe = 0; probe < CL_PROBES; probe++) {
+        const unsigned long long cur = *((volatile unsigned long long *)&S.key[s]);
+        if (cur == key) return (int)s;
+        if (cur == EMPTY_KEY) {
+            const unsigned long long old = atomicCAS(&S.key[s], EMPTY_KEY, key);
+            if (old == EMPTY_KEY || old == key) return (int)s;
+        }
+        s = s + 1 == CL_CAP - 1 ? 0 : s + 1;
+    }
+    return -1;
+}
+
 template <bool SCATTER>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CL_THREADS)
 cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, ClusterSlot *__restrict__ table,
                     ClusterRec *__restrict__ clusters, uint32_t *__restrict__ scankey, uint32_t *__restrict__ errflag, Geom g, Caps caps)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y + 1, b = blockIdx.z;
-    const uint8_t *m = mark + (size_t)b * g.h * g.tp;
-    const bool inside = x >= 1 && x <= g.w - 2 && y <= g.h - 2;
-    uint32_t v0 = 127;
-    if (inside) v0 = m[(size_t)y * g.tp + x];
+    __shared__ ClShared S;
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * CL_TW, y0 = 1 + blockIdx.y * CL_TH;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t full = 0xffffffffu;
-    // all lanes stay in the loop so that the warp-aggregation below sees a full mask
-    uint32_t vn[4] = {127, 127, 127, 127};
-    bool emit[4] = {false, false, false, false};
-    if (v0 != 127) {
-        const uint8_t *r0 = m + (size_t)y * g.tp, *r1 = r0 + g.tp;
-        vn[0] = r0[x + 1]; vn[1] = r1[x]; vn[2] = r1[x - 1]; vn[3] = r1[x + 1];
-        const uint32_t vprev = r0[x - 1];
-        const bool connected_last = (x - 1 >= 1) && vprev != 127 && (vprev + vn[1] == 255);
-        emit[0] = v0 + vn[0] == 255;
-        emit[1] = v0 + vn[1] == 255;
-        emit[2] = (v0 + vn[2] == 255) && !connected_last;
-        emit[3] = v0 + vn[3] == 255;
-    }
+    const uint8_t *m = mark + (size_t)b * g.h * g.tp;
     const uint32_t *lab = labels + (size_t)b * g.npix;
     ClusterSlot *tab = table + (size_t)b * caps.slots_per_frame;
-    uint32_t rep0 = 0;
-    if (emit[0] | emit[1] | emit[2] | emit[3]) rep0 = lab[(size_t)y * g.w + x];
+    for (int e = threadIdx.x; e < CL_CAP; e += CL_THREADS) { S.key[e] = EMPTY_KEY; S.cnt[e] = 0; }
+    __syncthreads();
+    // per step and probe: tile entry (8 bits, 0xff = none) | rank inside the tile entry << 8 | gradient sign << 31
+    uint32_t ent[CL_PER][4];
     const int dxs[4] = {1, 0, -1, 1}, dys[4] = {0, 1, 1, 1};
 #pragma unroll
-    for (int d = 0; d < 4; d++) {
-        unsigned long long key = EMPTY_KEY;
-        if (emit[d]) {
-            const uint32_t rep1 = lab[(size_t)(y + dys[d]) * g.w + x + dxs[d]];
-            key = rep0 < rep1 ? ((unsigned long long)rep1 << 32) | rep0 : ((unsigned long long)rep0 << 32) | rep1;
+    for (int it = 0; it < CL_PER; it++) {
+        const int x = x0 + (wid & 1) * 32 + lane, y = y0 + it * (CL_THREADS / CL_TW) + (wid >> 1);
+        const bool inside = x >= 1 && x <= g.w - 2 && y <= g.h - 2;
+        uint32_t v0 = 127;
+        if (inside) v0 = m[(size_t)y * g.tp + x];
+        uint32_t vn[4] = {127, 127, 127, 127};
+        bool emit[4] = {false, false, false, false};
+        if (v0 != 127) {
+            const uint8_t *r0 = m + (size_t)y * g.tp, *r1 = r0 + g.tp;
+            vn[0] = r0[x + 1]; vn[1] = r1[x]; vn[2] = r1[x - 1]; vn[3] = r1[x + 1];
+            const uint32_t vprev = r0[x - 1];
+            const bool connected_last = (x - 1 >= 1) && vprev != 127 && (vprev + vn[1] == 255);
+            emit[0] = v0 + vn[0] == 255;
+            emit[1] = v0 + vn[1] == 255;
+            emit[2] = (v0 + vn[2] == 255) && !connected_last;
+            emit[3] = v0 + vn[3] == 255;
         }
-        if (__ballot_sync(full, emit[d]) == 0) continue;     // warp-uniform: nobody probes this direction
-        const uint32_t peers = __match_any_sync(full, key);
-        if (!emit[d]) continue;
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(peers) - 1;
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1));
-        if (!SCATTER) {
-            if (lane == leader) {
-                uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
-                if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
-                else atomicAdd(&tab[s].count, (uint32_t)__popc(peers));
+        uint32_t rep0 = 0;
+        if (emit[0] | emit[1] | emit[2] | emit[3]) rep0 = lab[(size_t)y * g.w + x];
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            ent[it][d] = 0xffu;
+            unsigned long long key = EMPTY_KEY;
+            if (emit[d]) {
+                const uint32_t rep1 = lab[(size_t)(y + dys[d]) * g.w + x + dxs[d]];
+                key = rep0 < rep1 ? ((unsigned long long)rep1 << 32) | rep0 : ((unsigned long long)rep0 << 32) | rep1;
             }
-        } else {
-            uint32_t pos = 0xffffffffu;
+            if (__ballot_sync(full, emit[d]) == 0) continue;     // warp-uniform: nobody probes this direction
+            const uint32_t peers = __match_any_sync(full, key);
+            if (!emit[d]) continue;
+            const int leader = __ffs(peers) - 1;
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1)), npeers = __popc(peers);
+            const uint32_t sign = vn[d] > v0 ? 1u : 0u;
+            int e = -1;
+            uint32_t r0 = 0;
             if (lane == leader) {
-                uint32_t s = slot_find(tab, caps.slots_per_frame, key);
-                if (s != 0xffffffffu) {
-                    uint32_t c = tab[s].cluster;
-                    if (c != 0xffffffffu) {
-                        ClusterRec *cr = clusters + (size_t)b * caps.clusters_per_frame + c;
-                        pos = cr->offset + atomicAdd(&cr->cursor, (uint32_t)__popc(peers));
+                e = tile_insert(S, key, hash_key(key));
+                if (e >= 0) r0 = atomicAdd(&S.cnt[e], npeers);
+            }
+            e = __shfl_sync(peers, e, leader);
+            r0 = __shfl_sync(peers, r0, leader);
+            if (e >= 0) {
+                ent[it][d] = (uint32_t)e | ((r0 + rank) << 8) | (sign << 31);
+                continue;
+            }
+            // tile table full (a tile crossed by > ~200 clusters): straight to the global table
+            if (!SCATTER) {
+                if (lane == leader) {
+                    const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
+                    if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
+                    else atomicAdd(&tab[s].count, npeers);
+                }
+            } else {
+                uint32_t pos = 0xffffffffu;
+                if (lane == leader) {
+                    const uint32_t s = slot_find(tab, caps.slots_per_frame, key);
+                    if (s != 0xffffffffu) {
+                        const uint32_t c = tab[s].cluster;
+                        if (c != 0xffffffffu) {
+                            ClusterRec *cr = clusters + (size_t)b * caps.clusters_per_frame + c;
+                            pos = cr->offset + atomicAdd(&cr->cursor, npeers);
+                        }
                     }
                 }
+                pos = __shfl_sync(peers, pos, leader);
+                if (pos != 0xffffffffu)
+                    scankey[(size_t)b * caps.points_per_frame + pos + rank] = ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | sign;
             }
-            pos = __shfl_sync(peers, pos, leader);
-            if (pos != 0xffffffffu) {
-                pos += rank;
-                // a boundary point is fully described by (pixel, probe, gradient sign): 2x+dx, 2y+dy, g = d*(v1-v0)
-                const size_t o = (size_t)b * caps.points_per_frame + pos;
-                scankey[o] = ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | (vn[d] > v0 ? 1u : 0u);
+        }
+    }
+    __syncthreads();
+    // one global probe + atomic per (tile, cluster)
+    for (int e = threadIdx.x; e < CL_CAP; e += CL_THREADS) {
+        const unsigned long long key = S.key[e];
+        if (key == EMPTY_KEY) continue;
+        if (!SCATTER) {
+            const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
+            if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
+            else atomicAdd(&tab[s].count, S.cnt[e]);
+        } else {
+            uint32_t base = 0xffffffffu;
+            const uint32_t s = slot_find(tab, caps.slots_per_frame, key);
+            if (s != 0xffffffffu) {
+                const uint32_t c = tab[s].cluster;
+                if (c != 0xffffffffu) {
+                    ClusterRec *cr = clusters + (size_t)b * caps.clusters_per_frame + c;
+                    base = cr->offset + atomicAdd(&cr->cursor, S.cnt[e]);
+                }
             }
+            S.base[e] = base;
+        }
+    }
+    if (!SCATTER) return;
+    __syncthreads();
+    // a boundary point is fully described by (pixel, probe, gradient sign): 2x+dx, 2y+dy, g = d*(v1-v0)
+#pragma unroll
+    for (int it = 0; it < CL_PER; it++) {
+        const int x = x0 + (wid & 1) * 32 + lane, y = y0 + it * (CL_THREADS / CL_TW) + (wid >> 1);
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const uint32_t en = ent[it][d];
+            if ((en & 0xffu) == 0xffu) continue;
+            const uint32_t base = S.base[en & 0xffu];
+            if (base == 0xffffffffu) continue;
+            scankey[(size_t)b * caps.points_per_frame + base + ((en >> 8) & 0x7fffffu)] =
+                ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | (en >> 31);
         }
     }
 }

@@ -169,6 +169,7 @@ __device__ __forceinline__ void block_sort(T *&src, T *&dst, int n, int tid)
 }
 
 struct SortScratch {      // per group (warp or CTA)
+    double red_d[16];
     int red_i[16];
     float red_f[16];
     int work;
@@ -199,20 +200,41 @@ __device__ __forceinline__ void sort_scan_cluster(uint32_t *__restrict__ K, int 
     const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
     G::sync();
     if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) { if (tid == 0) rec_global->cursor = 0xffffffffu; return; }
-    // border polarity (upstream: dot = sum dx*gx + dy*gy, reversed_border = dot < 0).  Only the sign is used and the sum
-    // does not depend on the order of the points beyond float rounding, so it is evaluated before any sorting.
-    float dot = 0.f;
+    // border polarity (upstream: float dot = sum over the points IN SCAN ORDER of dx*gx + dy*gy; reversed_border = dot < 0).
+    // The per-point terms are independent and evaluated exactly as upstream does; only the float accumulation is order
+    // dependent.  Its result differs from the exact sum S of the terms by at most (n - 1) * 2^-24 * sum|t|, so when |S|
+    // clears twice that bound the sign is known before any sorting (the usual case, and half of all clusters end here).
+    // Otherwise (thin, nearly symmetric clusters whose terms cancel) the chain is replayed in scan order after the sort.
+    double sum = 0, sum_abs = 0;
     for (int i = tid; i < n; i += NT) {
         int px, py, gx, gy;
         decode_point(A[sidx<E, PAD>(i)], g.w, px, py, gx, gy);
         const float dx = (float)px - cx, dy = (float)py - cy;
-        dot += dx * (float)gx + dy * (float)gy;
+        const float t = dx * (float)gx + dy * (float)gy;
+        sum += (double)t; sum_abs += fabs((double)t);
     }
-    dot = G::reduce(dot, [](float a, float c) { return a + c; }, S.red_f);
-    if (dot < 0.f) { if (tid == 0) rec_global->cursor = 0xffffffffu; return; }
+    sum = G::reduce(sum, [](double a, double c) { return a + c; }, S.red_d);
+    sum_abs = G::reduce(sum_abs, [](double a, double c) { return a + c; }, S.red_d);
+    const bool certain = fabs(sum) > 2.0 * (double)n * 5.9604644775390625e-8 * sum_abs;
+    if (certain && sum < 0) { if (tid == 0) rec_global->cursor = 0xffffffffu; return; }
     G::sync();
     uint32_t *src = A, *dst = B;
     block_sort<NT, E, PAD>(src, dst, n, tid);
+    if (!certain) {
+        if (tid == 0) {
+            float dot = 0.f;
+            for (int i = 0; i < n; i++) {
+                int px, py, gx, gy;
+                decode_point(src[sidx<E, PAD>(i)], g.w, px, py, gx, gy);
+                const float dx = (float)px - cx, dy = (float)py - cy;
+                dot += dx * (float)gx + dy * (float)gy;
+            }
+            S.work = dot < 0.f ? 1 : 0;
+            if (dot < 0.f) rec_global->cursor = 0xffffffffu;
+        }
+        G::sync();
+        if (S.work) return;
+    }
     for (int j = tid; j < n; j += NT) K[j] = src[sidx<E, PAD>(j)];
 }
 
