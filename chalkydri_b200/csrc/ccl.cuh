@@ -92,6 +92,7 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
     const int lane = threadIdx.x & 31;
     constexpr int PER = CCL_TW * CCL_TH / CCL_THREADS;
     uint32_t masks[PER];
+    uint8_t runlen[PER];
 #pragma unroll
     for (int k = 0; k < PER; k++) {
         const int i = threadIdx.x + k * CCL_THREADS;
@@ -103,6 +104,9 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
         const uint32_t starts = __ballot_sync(0xffffffffu, !(m & LINK_LEFT) || lane == 0);
         const int start_lane = 31 - __clz(starts & ((2u << lane) - 1u));
         L[i] = (uint32_t)(i - lane + start_lane);
+        // run starts remember the length of their run inside this 32-pixel segment (0 for every other pixel)
+        const uint32_t higher = lane == 31 ? 0u : starts & ~((2u << lane) - 1u);
+        runlen[k] = start_lane == lane ? (uint8_t)((higher ? __ffs(higher) - 1 : 32) - lane) : (uint8_t)0;
         Ms[i] = (uint8_t)m;
         Cnt[i] = 0;
     }
@@ -121,18 +125,42 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
         if ((m & LINK_UPRIGHT) && ly > 0 && lx < CCL_TW - 1) uf_union(L, i, i - CCL_TW + 1);
     }
     __syncthreads();
-    uint32_t roots[PER];
+    // pointer jumping over the run starts: parallel hooking leaves chains as long as the component is tall (a start per
+    // row), and a divergent walk costs the warp its longest chain; three uniform rounds cut the depth eightfold
+#pragma unroll 1
+    for (int round = 0; round < 3; round++) {
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int i = threadIdx.x + k * CCL_THREADS;
+            if (runlen[k]) {
+                const uint32_t p = L[i];
+                const uint32_t pp = L[p];
+                if (pp != p) L[i] = pp;
+            }
+        }
+        __syncthreads();
+    }
+    // Only run starts can be tree nodes (every other pixel still points at the start of its run), so only they walk to
+    // the root; they compress their own link and credit the run's pixels to the root.  After that every pixel is two
+    // loads away from its root.
 #pragma unroll
     for (int k = 0; k < PER; k++) {
         const int i = threadIdx.x + k * CCL_THREADS;
         const int lx = i % CCL_TW, ly = i / CCL_TW;
         const bool in = (x0 + lx < g.w) && (y0 + ly < g.h);
-        const uint32_t r = in ? uf_find(L, (uint32_t)i) : 0xffffffffu;
-        roots[k] = r;
-        const uint32_t peers = __match_any_sync(0xffffffffu, r);
-        if (in && lane == __ffs(peers) - 1) atomicAdd(&Cnt[r], (uint32_t)__popc(peers));
+        if (runlen[k] && in) {
+            const uint32_t r = uf_find(L, (uint32_t)i);
+            if (r != (uint32_t)i) L[i] = r;
+            atomicAdd(&Cnt[r], (uint32_t)runlen[k]);
+        }
     }
     __syncthreads();
+    uint32_t roots[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int i = threadIdx.x + k * CCL_THREADS;
+        roots[k] = L[L[i]];
+    }
     const uint32_t base = (uint32_t)b * g.npix;
 #pragma unroll
     for (int k = 0; k < PER; k++) {
