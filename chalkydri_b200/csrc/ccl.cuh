@@ -6,7 +6,7 @@
 // edge set -- and therefore the partition -- is identical; only the tree shape differs (roots are the smallest
 // pixel index of each component, which is also the canonical form the oracle reports).
 //
-// B200 mapping: latency / atomic bound.  Pass 1 resolves 64x16-pixel tiles in shared memory (atomicMin
+// B200 mapping: latency / atomic bound.  Pass 1 resolves 256x16-pixel tiles in shared memory (atomicMin
 // union-find on 32-bit smem words), pass 2 stitches tile borders with global atomicMin, pass 3 flattens every
 // pixel to its root and histograms component sizes with warp-aggregated atomics (match.any on the label).
 #pragma once
@@ -14,7 +14,7 @@
 
 namespace cb {
 
-constexpr int CCL_TW = 64, CCL_TH = 16, CCL_THREADS = 256;
+constexpr int CCL_TW = 256, CCL_TH = 16, CCL_THREADS = 256;   // 8 warps x (32-column strip), 16 rows
 
 enum : uint32_t { LINK_LEFT = 1, LINK_UP = 2, LINK_UPLEFT = 4, LINK_UPRIGHT = 8 };
 
@@ -76,91 +76,86 @@ __device__ __forceinline__ void uf_union(uint32_t *L, uint32_t a, uint32_t b)
 }
 
 // pass 1: tile-local union-find in shared memory, then write global labels (index of the local root) and the local
-// component sizes.  Horizontal runs are labelled without atomics (ballot of run starts inside each 32-pixel row
-// segment); vertical links that are implied by the neighbouring column of the same two runs are skipped, so the
-// number of smem atomics is about one per run overlap instead of one per pixel.
+// component sizes.  A CTA resolves a 256x16-pixel tile.  Each warp first labels its own 32-column strip top-down, one
+// row per step: the row's horizontal runs are labelled without atomics (ballot of run starts), runs are hooked to the
+// runs of the previous row (vertical links implied by the neighbouring column of the same two runs are skipped), and
+// the row is compressed at once -- every pixel points at its current root before the next row starts, so the walks of
+// the union-find stay one or two hops long instead of growing with the height of the component.  The seven strip
+// borders are stitched afterwards, then every pixel is flattened and the run starts credit their run to the root.
 template <int MODE>
 __global__ void __launch_bounds__(CCL_THREADS)
 ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, Geom g)
 {
     __shared__ uint32_t L[CCL_TW * CCL_TH];
     __shared__ uint32_t Cnt[CCL_TW * CCL_TH];
-    __shared__ uint8_t Ms[CCL_TW * CCL_TH];
+    __shared__ uint8_t Rl[CCL_TW * CCL_TH];     // run length at run starts, 0 elsewhere
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * CCL_TW, y0 = blockIdx.y * CCL_TH;
     const uint8_t *t = thresh + (size_t)b * g.h * g.tp;
-    const int lane = threadIdx.x & 31;
-    constexpr int PER = CCL_TW * CCL_TH / CCL_THREADS;
-    uint32_t masks[PER];
-    uint8_t runlen[PER];
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int i = threadIdx.x + k * CCL_THREADS;
-        const int lx = i % CCL_TW, ly = i / CCL_TW;
-        const int x = x0 + lx, y = y0 + ly;
-        uint32_t m = 0;
-        if (x < g.w && y < g.h) m = link_mask<MODE>(t, g.tp, g.w, x, y);
-        masks[k] = m;
-        const uint32_t starts = __ballot_sync(0xffffffffu, !(m & LINK_LEFT) || lane == 0);
-        const int start_lane = 31 - __clz(starts & ((2u << lane) - 1u));
-        L[i] = (uint32_t)(i - lane + start_lane);
-        // run starts remember the length of their run inside this 32-pixel segment (0 for every other pixel)
-        const uint32_t higher = lane == 31 ? 0u : starts & ~((2u << lane) - 1u);
-        runlen[k] = start_lane == lane ? (uint8_t)((higher ? __ffs(higher) - 1 : 32) - lane) : (uint8_t)0;
-        Ms[i] = (uint8_t)m;
-        Cnt[i] = 0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int i = threadIdx.x + k * CCL_THREADS;
-        const int lx = i % CCL_TW, ly = i / CCL_TW;
-        const uint32_t m = masks[k];
-        if (lane == 0 && (m & LINK_LEFT) && lx > 0) uf_union(L, i, i - 1);      // run continues across the 32-pixel segment
-        if ((m & LINK_UP) && ly > 0) {
-            const bool implied = (m & LINK_LEFT) && lx > 0 && (Ms[i - 1] & LINK_UP) && (Ms[i - CCL_TW] & LINK_LEFT);
-            if (!implied) uf_union(L, i, i - CCL_TW);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t full = 0xffffffffu;
+    {
+        const int lx = wid * 32 + lane, x = x0 + lx;
+        uint32_t m_prev = 0;
+        for (int ly = 0; ly < CCL_TH; ly++) {
+            const int y = y0 + ly, i = ly * CCL_TW + lx;
+            uint32_t m = 0;
+            if (x < g.w && y < g.h) m = link_mask<MODE>(t, g.tp, g.w, x, y);
+            const uint32_t starts = __ballot_sync(full, !(m & LINK_LEFT) || lane == 0);
+            const int start_lane = 31 - __clz(starts & ((2u << lane) - 1u));
+            const uint32_t higher = lane == 31 ? 0u : starts & ~((2u << lane) - 1u);
+            L[i] = (uint32_t)(i - lane + start_lane);
+            Cnt[i] = 0;
+            Rl[i] = start_lane == lane ? (uint8_t)((higher ? __ffs(higher) - 1 : 32) - lane) : (uint8_t)0;
+            const uint32_t m_left = __shfl_up_sync(full, m, 1);
+            __syncwarp();
+            if (ly > 0) {
+                if (m & LINK_UP) {
+                    const bool implied = (m & LINK_LEFT) && lane > 0 && (m_left & LINK_UP) && (m_prev & LINK_LEFT);
+                    if (!implied) uf_union(L, i, i - CCL_TW);
+                }
+                if ((m & LINK_UPLEFT) && lane > 0) uf_union(L, i, i - CCL_TW - 1);
+                if ((m & LINK_UPRIGHT) && lane < 31) uf_union(L, i, i - CCL_TW + 1);
+                __syncwarp();
+                uint32_t r = 0;
+                if (start_lane == lane) r = uf_find(L, (uint32_t)i);
+                r = __shfl_sync(full, r, start_lane);
+                L[i] = r;
+                __syncwarp();
+            }
+            m_prev = m;
         }
-        if ((m & LINK_UPLEFT) && ly > 0 && lx > 0) uf_union(L, i, i - CCL_TW - 1);
-        if ((m & LINK_UPRIGHT) && ly > 0 && lx < CCL_TW - 1) uf_union(L, i, i - CCL_TW + 1);
     }
     __syncthreads();
-    // pointer jumping over the run starts: parallel hooking leaves chains as long as the component is tall (a start per
-    // row), and a divergent walk costs the warp its longest chain; three uniform rounds cut the depth eightfold
-#pragma unroll 1
-    for (int round = 0; round < 3; round++) {
-#pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int i = threadIdx.x + k * CCL_THREADS;
-            if (runlen[k]) {
-                const uint32_t p = L[i];
-                const uint32_t pp = L[p];
-                if (pp != p) L[i] = pp;
+    // strip borders: columns 32k (left link, up-left link) and 32k - 1 (up-right link), k = 1..7
+    if (threadIdx.x < 2 * 7 * CCL_TH) {
+        const int side = threadIdx.x / (7 * CCL_TH), rem = threadIdx.x % (7 * CCL_TH);
+        const int k = rem / CCL_TH + 1, ly = rem % CCL_TH;
+        const int lx = side == 0 ? 32 * k : 32 * k - 1;
+        const int x = x0 + lx, y = y0 + ly, i = ly * CCL_TW + lx;
+        if (x < g.w && y < g.h) {
+            const uint32_t m = link_mask<MODE>(t, g.tp, g.w, x, y);
+            if (side == 0) {
+                if (m & LINK_LEFT) uf_union(L, i, i - 1);
+                if ((m & LINK_UPLEFT) && ly > 0) uf_union(L, i, i - CCL_TW - 1);
+            } else {
+                if ((m & LINK_UPRIGHT) && ly > 0) uf_union(L, i, i - CCL_TW + 1);
             }
         }
-        __syncthreads();
-    }
-    // Only run starts can be tree nodes (every other pixel still points at the start of its run), so only they walk to
-    // the root; they compress their own link and credit the run's pixels to the root.  After that every pixel is two
-    // loads away from its root.
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int i = threadIdx.x + k * CCL_THREADS;
-        const int lx = i % CCL_TW, ly = i / CCL_TW;
-        const bool in = (x0 + lx < g.w) && (y0 + ly < g.h);
-        if (runlen[k] && in) {
-            const uint32_t r = uf_find(L, (uint32_t)i);
-            if (r != (uint32_t)i) L[i] = r;
-            atomicAdd(&Cnt[r], (uint32_t)runlen[k]);
-        }
     }
     __syncthreads();
+    constexpr int PER = CCL_TW * CCL_TH / CCL_THREADS;
     uint32_t roots[PER];
 #pragma unroll
     for (int k = 0; k < PER; k++) {
         const int i = threadIdx.x + k * CCL_THREADS;
-        roots[k] = L[L[i]];
+        const uint32_t r = uf_find(L, (uint32_t)i);
+        roots[k] = r;
+        const uint32_t rl = Rl[i];
+        const int lx = i % CCL_TW, ly = i / CCL_TW;
+        if (rl && x0 + lx < g.w && y0 + ly < g.h) atomicAdd(&Cnt[r], rl);
     }
+    __syncthreads();
     const uint32_t base = (uint32_t)b * g.npix;
 #pragma unroll
     for (int k = 0; k < PER; k++) {
