@@ -53,6 +53,34 @@ __device__ __forceinline__ uint32_t link_mask(const uint8_t *__restrict__ t, int
     return m;
 }
 
+// the same from the six pixel values (v = (x,y); the others by offset); has_up = false leaves only the LEFT bit
+template <int MODE>
+__device__ __forceinline__ uint32_t link_mask_vals(int w, int x, bool has_up, uint32_t v, uint32_t v_m1_0, uint32_t v_m1_m1,
+                                                   uint32_t v_0_m1, uint32_t v_1_m1)
+{
+    if (x < 1 || x > w - 2) return 0;
+    const uint32_t SKIP = MODE == 0 ? 127u : 2u, WHITE = MODE == 0 ? 255u : 1u;
+    if (v == SKIP) return 0;
+    uint32_t m = 0;
+    if (v_m1_0 == v) m |= LINK_LEFT;
+    if (has_up) {
+        if (MODE == 0) {
+            if (v_0_m1 == v && (x == 1 || !((v_m1_0 == v_m1_m1) && (v_m1_m1 == v_0_m1)))) m |= LINK_UP;
+            if (v == WHITE) {
+                if (v_m1_m1 == v && (x == 1 || !(v_m1_0 == v_m1_m1 || v_0_m1 == v_m1_m1))) m |= LINK_UPLEFT;
+                if (v_1_m1 == v && !(v_0_m1 == v_1_m1)) m |= LINK_UPRIGHT;
+            }
+        } else {
+            if (v_0_m1 == v) m |= LINK_UP;
+            if (v == WHITE) {
+                if (v_m1_m1 == v) m |= LINK_UPLEFT;
+                if (v_1_m1 == v) m |= LINK_UPRIGHT;
+            }
+        }
+    }
+    return m;
+}
+
 template <typename T>
 __device__ __forceinline__ uint32_t uf_find(const T *L, uint32_t i)
 {
@@ -88,7 +116,6 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
 {
     __shared__ uint32_t L[CCL_TW * CCL_TH];
     __shared__ uint32_t Cnt[CCL_TW * CCL_TH];
-    __shared__ uint8_t Rl[CCL_TW * CCL_TH];     // run length at run starts, 0 elsewhere
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * CCL_TW, y0 = blockIdx.y * CCL_TH;
     const uint8_t *t = thresh + (size_t)b * g.h * g.tp;
@@ -97,16 +124,28 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
     {
         const int lx = wid * 32 + lane, x = x0 + lx;
         uint32_t m_prev = 0;
+        // pixel values of the previous row at x - 1, x, x + 1 stay in registers; a row costs one byte load per lane plus the
+        // two halo columns (lanes 0 and 31).  Columns beyond the pitch never reach a link (x > w - 2 gives mask 0).
+        uint32_t u_l = 0, u_c = 0, u_r = 0;
+        const int xl = max(x - 1, 0), xr = min(x + 1, g.tp - 1), xc = min(x, g.tp - 1);
         for (int ly = 0; ly < CCL_TH; ly++) {
             const int y = y0 + ly, i = ly * CCL_TW + lx;
-            uint32_t m = 0;
-            if (x < g.w && y < g.h) m = link_mask<MODE>(t, g.tp, g.w, x, y);
+            uint32_t m = 0, v_c = 0, v_l = 0, v_r = 0;
+            if (y < g.h) {
+                const uint8_t *row = t + (size_t)y * g.tp;
+                v_c = row[xc];
+                v_l = __shfl_up_sync(full, v_c, 1);
+                v_r = __shfl_down_sync(full, v_c, 1);
+                if (lane == 0) v_l = row[xl];
+                if (lane == 31) v_r = row[xr];
+                if (x < g.w) m = link_mask_vals<MODE>(g.w, x, ly > 0, v_c, v_l, u_l, u_c, u_r);
+            }
+            u_l = v_l; u_c = v_c; u_r = v_r;
             const uint32_t starts = __ballot_sync(full, !(m & LINK_LEFT) || lane == 0);
             const int start_lane = 31 - __clz(starts & ((2u << lane) - 1u));
             const uint32_t higher = lane == 31 ? 0u : starts & ~((2u << lane) - 1u);
             L[i] = (uint32_t)(i - lane + start_lane);
-            Cnt[i] = 0;
-            Rl[i] = start_lane == lane ? (uint8_t)((higher ? __ffs(higher) - 1 : 32) - lane) : (uint8_t)0;
+            Cnt[i] = start_lane == lane ? (uint32_t)((higher ? __ffs(higher) - 1 : 32) - lane) : 0u;   // run length at run starts
             const uint32_t m_left = __shfl_up_sync(full, m, 1);
             __syncwarp();
             if (ly > 0) {
@@ -151,9 +190,13 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
         const int i = threadIdx.x + k * CCL_THREADS;
         const uint32_t r = uf_find(L, (uint32_t)i);
         roots[k] = r;
-        const uint32_t rl = Rl[i];
-        const int lx = i % CCL_TW, ly = i / CCL_TW;
-        if (rl && x0 + lx < g.w && y0 + ly < g.h) atomicAdd(&Cnt[r], rl);
+        // run starts that are not the root hand their run to the root (a start's count is only ever added to by others
+        // when it IS the root, so the value read here is still its own run length)
+        if (r != (uint32_t)i) {
+            const uint32_t rl = Cnt[i];
+            const int lx = i % CCL_TW, ly = i / CCL_TW;
+            if (rl && x0 + lx < g.w && y0 + ly < g.h) atomicAdd(&Cnt[r], rl);
+        }
     }
     __syncthreads();
     const uint32_t base = (uint32_t)b * g.npix;
