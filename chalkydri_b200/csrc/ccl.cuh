@@ -259,7 +259,8 @@ __global__ void ccl_merge_kernel(const uint8_t *__restrict__ thresh, uint32_t *_
 
 // pass 3: flatten every pixel to its root; local roots that were merged into another root add their local
 // component size to it (a few atomics per component instead of one per pixel).  sizes[root] ends up as the full size.
-__global__ void ccl_flatten_kernel(uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, uint32_t total)
+constexpr int FLAT_PER = 1;   // (four interleaved walks per thread measured slower: every thread then waits for its longest chain)
+__global__ void __launch_bounds__(256) ccl_flatten_kernel(uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, uint32_t total)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -272,19 +273,31 @@ __global__ void ccl_flatten_kernel(uint32_t *__restrict__ labels, uint32_t *__re
 }
 
 // component-size gate of gradient_clusters(): pixels of components smaller than 25 become 127 ("ignore")
-__global__ void ccl_mark_kernel(const uint8_t *__restrict__ thresh, const uint32_t *__restrict__ labels,
-                                const uint32_t *__restrict__ sizes, uint8_t *__restrict__ mark, Geom g)
+constexpr int MARK_PER = 4;
+__global__ void __launch_bounds__(256) ccl_mark_kernel(const uint8_t *__restrict__ thresh, const uint32_t *__restrict__ labels,
+                                                       const uint32_t *__restrict__ sizes, uint8_t *__restrict__ mark, Geom g)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= g.w) return;
-    const size_t ti = (size_t)b * g.h * g.tp + (size_t)y * g.tp + x;
-    uint8_t v = thresh[ti];
-    if (v != 127) {
-        const uint32_t root = labels[(size_t)b * g.npix + (size_t)y * g.w + x];
-        if (sizes[root] < 25) v = 127;
+    const size_t trow = (size_t)b * g.h * g.tp + (size_t)y * g.tp, lrow = (size_t)b * g.npix + (size_t)y * g.w;
+    uint8_t v[MARK_PER];
+    uint32_t root[MARK_PER];
+#pragma unroll
+    for (int k = 0; k < MARK_PER; k++) {
+        const int x = (blockIdx.x * MARK_PER + k) * 256 + threadIdx.x;
+        v[k] = 127; root[k] = 0;
+        if (x < g.w) {
+            v[k] = thresh[trow + x];
+            if (v[k] != 127) root[k] = labels[lrow + x];
+        }
     }
-    mark[ti] = v;
+#pragma unroll
+    for (int k = 0; k < MARK_PER; k++)
+        if (v[k] != 127 && sizes[root[k]] < 25) v[k] = 127;
+#pragma unroll
+    for (int k = 0; k < MARK_PER; k++) {
+        const int x = (blockIdx.x * MARK_PER + k) * 256 + threadIdx.x;
+        if (x < g.w) mark[trow + x] = v[k];
+    }
 }
 
 }  // namespace cb
