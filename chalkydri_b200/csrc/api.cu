@@ -539,9 +539,33 @@ static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, 
     const size_t bytes = (size_t)stride * height;
     const size_t dfs = (bytes + 15) / 16 * 16;
     const int half = ctx->max_batch / 2;
-    int chunk = std::max(16, std::min(half, (batch + 3) / 4));
-    chunk = std::min(chunk, half);
-    const int nchunks = (batch + chunk - 1) / chunk;
+    // The first copy cannot overlap anything and small chunks run the kernels less efficiently, so the chunks ramp up
+    // steeply: batch/8, 3 batch/8, then half the context's capacity (measured best on the c2 workload: 32 | 96 | 128
+    // frames, against 4 x 64 and 2 x 128).  End to end the call costs about one small copy plus all kernels.
+    std::vector<int> cstart;
+    {
+        const int s1 = std::max(8, std::min(half, batch / 8));
+        int b0 = 0, k = 0;
+        while (b0 < batch) {
+            const int sz = k == 0 ? s1 : (k == 1 ? std::min(half, 3 * s1) : half);
+            cstart.push_back(b0);
+            b0 += std::min(sz, batch - b0);
+            k++;
+        }
+    }
+    if (const char *e = getenv("CB_E2E_CHUNKS")) {     // experiment hook: explicit chunk sizes "32,96,128" (each <= max_batch / 2)
+        cstart.clear();
+        int b0 = 0;
+        for (const char *p = e; *p && b0 < batch;) {
+            const int sz = std::max(1, std::min(half, atoi(p)));
+            cstart.push_back(b0); b0 += std::min(sz, batch - b0);
+            while (*p && *p != ',') p++;
+            if (*p == ',') p++;
+            if (!*p) while (b0 < batch) { cstart.push_back(b0); b0 += std::min(sz, batch - b0); }
+        }
+    }
+    cstart.push_back(batch);
+    const int nchunks = (int)cstart.size() - 1;
     if (nchunks > 4096) return fail(ctx, CB_ERR_ARG, "too many chunks");
     uint8_t *bufs[2] = {ctx->d_in, ctx->d_in + (size_t)half * dfs};
     cb_timing acc{};
@@ -550,7 +574,7 @@ static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, 
     CK(cudaEventRecord(ctx->ev_consumed[1], ctx->stream));
     int done_base = 0;    // first frame of the group currently staged in h_dets (h_dets holds max_batch frames)
     for (int c = 0; c < nchunks; c++) {
-        const int b0 = c * chunk, n = std::min(chunk, batch - b0), bi = c & 1;
+        const int b0 = cstart[c], n = cstart[c + 1] - b0, bi = c & 1;
         // staging area full: drain what has been produced so far
         if (b0 + n - done_base > ctx->max_batch) {
             CK(cudaStreamSynchronize(ctx->stream));
