@@ -40,6 +40,8 @@ struct cb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;           // H2D of the next chunk overlaps the kernels of the current one
     cudaEvent_t ev_copied[2]{}, ev_consumed[2]{};
+    cudaStream_t tier_stream[4]{};                 // the size tiers of the two cluster sorts run side by side
+    cudaEvent_t ev_fork = nullptr, ev_tier[4]{};
     uint32_t *h_chunk_err = nullptr;              // pinned: error flag of every chunk of a pipelined call
     std::string err;
     bool family_set = false;
@@ -142,6 +144,8 @@ void cb_destroy(cb_ctx *ctx)
     if (ctx->h_chunk_err) cudaFreeHost(ctx->h_chunk_err);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 4; i++) { if (ctx->tier_stream[i]) cudaStreamDestroy(ctx->tier_stream[i]); if (ctx->ev_tier[i]) cudaEventDestroy(ctx->ev_tier[i]); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -186,6 +190,8 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 4; i++) ok = ok && cudaStreamCreateWithFlags(&ctx->tier_stream[i], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_tier[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2; i++) ok = ok && cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&ctx->h_chunk_err, 4096 * sizeof(uint32_t)) == cudaSuccess;
     for (auto &ev : ctx->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
@@ -406,19 +412,28 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         // ---- A5 quad fitting ----
         // sort #1 | sort #2 | prefix moments | fit, largest tier first inside each (long jobs).
         // misc: [8 + 2t] items of tier t; work counters: [16..20] sort #1, [21..25] sort #2, [26] moments, [27] fit
-#define CB_LAUNCH_SORT1(CFG, GRID, CNT)                                                                                                          \
-        sort_clusters_kernel<CFG><<<ctx->num_sms * (GRID), CFG::THREADS, CFG::BYTES, st>>>(ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, \
-                                                                                         d_misc + (CNT), ctx->d_scratch, g, caps, prm);
-#define CB_LAUNCH_SORT(W, CNT)                                                                                                                    \
-        CB_LAUNCH_SORT1(SortL2<W>, 1, (CNT) + 4)                                                                                                 \
-        CB_LAUNCH_SORT1(SortL1<W>, 3, (CNT) + 3)                                                                                                 \
-        CB_LAUNCH_SORT1(SortM<W>, 6, (CNT) + 2)                                                                                                  \
-        CB_LAUNCH_SORT1(SortS16<W>, 3, (CNT) + 1)                                                                                                \
-        CB_LAUNCH_SORT1(SortS8<W>, 4, (CNT))
-        CB_LAUNCH_SORT(1, 16)
-        CB_LAUNCH_SORT(2, 21)
-#undef CB_LAUNCH_SORT
+        // Each tier's sort #2 only depends on the same tier's sort #1, so the five tiers run as five independent chains (the
+        // main stream plus four side streams): a tier with few, large CTAs no longer leaves the rest of the SMs idle.
+#define CB_LAUNCH_SORT1(CFG, GRID, CNT, STREAM)                                                                                                  \
+        sort_clusters_kernel<CFG><<<ctx->num_sms * (GRID), CFG::THREADS, CFG::BYTES, STREAM>>>(ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, \
+                                                                                             d_misc + (CNT), ctx->d_scratch, g, caps, prm);
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        for (int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(ctx->tier_stream[i], ctx->ev_fork, 0));
+        CB_LAUNCH_SORT1(SortL2<1>, 1, 20, st)
+        CB_LAUNCH_SORT1(SortL2<2>, 1, 25, st)
+        CB_LAUNCH_SORT1(SortL1<1>, 3, 19, ctx->tier_stream[0])
+        CB_LAUNCH_SORT1(SortL1<2>, 3, 24, ctx->tier_stream[0])
+        CB_LAUNCH_SORT1(SortM<1>, 6, 18, ctx->tier_stream[1])
+        CB_LAUNCH_SORT1(SortM<2>, 6, 23, ctx->tier_stream[1])
+        CB_LAUNCH_SORT1(SortS16<1>, 3, 17, ctx->tier_stream[2])
+        CB_LAUNCH_SORT1(SortS16<2>, 3, 22, ctx->tier_stream[2])
+        CB_LAUNCH_SORT1(SortS8<1>, 4, 16, ctx->tier_stream[3])
+        CB_LAUNCH_SORT1(SortS8<2>, 4, 21, ctx->tier_stream[3])
 #undef CB_LAUNCH_SORT1
+        for (int i = 0; i < 4; i++) {
+            CK(cudaEventRecord(ctx->ev_tier[i], ctx->tier_stream[i]));
+            CK(cudaStreamWaitEvent(st, ctx->ev_tier[i], 0));
+        }
         lfps_kernel<<<ctx->num_sms * 8, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 26,
                                                                   ctx->d_errs, ctx->d_cp, g, caps);
         fit_quads_kernel<<<ctx->num_sms * 8, FQ_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 27,
