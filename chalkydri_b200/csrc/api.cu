@@ -387,17 +387,17 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             launches++;
         }
         const uint32_t total = (uint32_t)B * g.npix;
-        ccl_flatten_kernel<<<(total + 256 * FLAT_PER - 1) / (256 * FLAT_PER), 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, total);
-        launches++;
+        ccl_flatten_roots_kernel<<<(total + 255) / 256, 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, total);
+        dim3 gfin((g.w + 256 * MARK_PER - 1) / (256 * MARK_PER), g.h, B);
+        ccl_finish_kernel<<<gfin, 256, 0, st>>>(ctx->d_thresh, ctx->d_labels, ctx->d_sizes, ctx->d_mark, g);
+        launches += 2;
     }
     CK(cudaEventRecord(ctx->ev[3], st));
     if (stage >= ST_QUADS) {
         // ---- A4 gradient clusters ----
-        dim3 gmark((g.w + 256 * MARK_PER - 1) / (256 * MARK_PER), g.h, B);
-        ccl_mark_kernel<<<gmark, 256, 0, st>>>(ctx->d_thresh, ctx->d_labels, ctx->d_sizes, ctx->d_mark, g);
         const size_t nslots = (size_t)B * caps.slots_per_frame;
         table_init_kernel<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(ctx->d_table, nslots);
-        launches += 2;
+        launches += 1;
         if (g.h > 2 && g.w > 2) {
             dim3 gc((g.w + CL_TW - 1) / CL_TW, (g.h - 2 + CL_TH - 1) / CL_TH, B);
             cluster_pass_kernel<false><<<gc, CL_THREADS, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);

@@ -272,10 +272,28 @@ __global__ void __launch_bounds__(256) ccl_flatten_kernel(uint32_t *__restrict__
     }
 }
 
-// component-size gate of gradient_clusters(): pixels of components smaller than 25 become 127 ("ignore")
+// pass 3, detector variant, in two uniform steps instead of a pointer chase per pixel:
+//   (a) only local roots (the pixels pass 1 left with a non-zero local size) walk to their final root, link straight to it
+//       and add their local size to it;
+//   (b) every pixel is then exactly two loads from its final root; the same kernel applies the component-size gate of
+//       gradient_clusters() (pixels of components smaller than 25 become 127, "ignore") -- sizes[] is final because (a)
+//       is a separate launch.
+__global__ void __launch_bounds__(256) ccl_flatten_roots_kernel(uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, uint32_t total)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t c = sizes[i];
+    if (c == 0) return;
+    const uint32_t root = uf_find(labels, i);
+    if (root != i) {
+        labels[i] = root;
+        atomicAdd(&sizes[root], c);
+    }
+}
+
 constexpr int MARK_PER = 4;
-__global__ void __launch_bounds__(256) ccl_mark_kernel(const uint8_t *__restrict__ thresh, const uint32_t *__restrict__ labels,
-                                                       const uint32_t *__restrict__ sizes, uint8_t *__restrict__ mark, Geom g)
+__global__ void __launch_bounds__(256) ccl_finish_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labels,
+                                                         const uint32_t *__restrict__ sizes, uint8_t *__restrict__ mark, Geom g)
 {
     const int y = blockIdx.y, b = blockIdx.z;
     const size_t trow = (size_t)b * g.h * g.tp + (size_t)y * g.tp, lrow = (size_t)b * g.npix + (size_t)y * g.w;
@@ -284,19 +302,19 @@ __global__ void __launch_bounds__(256) ccl_mark_kernel(const uint8_t *__restrict
 #pragma unroll
     for (int k = 0; k < MARK_PER; k++) {
         const int x = (blockIdx.x * MARK_PER + k) * 256 + threadIdx.x;
-        v[k] = 127; root[k] = 0;
-        if (x < g.w) {
-            v[k] = thresh[trow + x];
-            if (v[k] != 127) root[k] = labels[lrow + x];
-        }
+        v[k] = 127; root[k] = 0xffffffffu;
+        if (x < g.w) { v[k] = thresh[trow + x]; root[k] = labels[lrow + x]; }
     }
 #pragma unroll
     for (int k = 0; k < MARK_PER; k++)
-        if (v[k] != 127 && sizes[root[k]] < 25) v[k] = 127;
+        if (root[k] != 0xffffffffu) root[k] = labels[root[k]];       // the local root's link is final after step (a)
 #pragma unroll
     for (int k = 0; k < MARK_PER; k++) {
         const int x = (blockIdx.x * MARK_PER + k) * 256 + threadIdx.x;
-        if (x < g.w) mark[trow + x] = v[k];
+        if (x >= g.w) continue;
+        labels[lrow + x] = root[k];
+        if (v[k] != 127 && sizes[root[k]] < 25) v[k] = 127;
+        mark[trow + x] = v[k];
     }
 }
 
