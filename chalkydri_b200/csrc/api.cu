@@ -58,6 +58,9 @@ struct cb_ctx {
     uint8_t *d_tmin = nullptr, *d_tmax = nullptr;    size_t tile_bytes = 0;
     uint32_t *d_labels = nullptr, *d_sizes = nullptr; size_t label_bytes = 0;
     ClusterSlot *d_table = nullptr;
+    uint4 *d_ent = nullptr;                    // per-point words of the cluster count pass, 16 B per decimated pixel
+    unsigned long long *d_tile_keys = nullptr;  // per-tile tables of the count pass
+    uint32_t *d_tile_cnt = nullptr;
     ClusterRec *d_clusters = nullptr;
     uint32_t *d_worklist = nullptr;
     uint32_t *d_scankey = nullptr;
@@ -135,7 +138,7 @@ void cb_destroy(cb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
-                    ctx->d_table, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
+                    ctx->d_table, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
                     ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
@@ -206,6 +209,8 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     Caps &c = ctx->caps;
     c.slots_per_frame = next_pow2((uint32_t)std::max<size_t>(1024, dpix / 8));
     c.clusters_per_frame = (uint32_t)std::max<size_t>(2048, dpix / 128);
+    c.tile_probes = CL_PROBES;
+    if (const char *e = getenv("CB_TILE_PROBES")) c.tile_probes = (uint32_t)std::max(1, std::min(CL_CAP, atoi(e)));   // test hook
     c.points_per_frame = (uint32_t)((std::max<size_t>(65536, dpix + dpix / 2) + 7) / 8 * 8);   // noisy frames emit ~0.85 points / pixel
     c.quads_per_frame = (uint32_t)std::max<size_t>(2048, dpix / 32);   // pure-noise frames produce thousands of candidate quads
     c.dets_per_frame = (uint32_t)max_dets_per_frame;
@@ -214,6 +219,13 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     ok = ok && alloc((void **)&ctx->d_tmin, ctx->tile_bytes) && alloc((void **)&ctx->d_tmax, ctx->tile_bytes);
     ok = ok && alloc((void **)&ctx->d_labels, ctx->label_bytes) && alloc((void **)&ctx->d_sizes, ctx->label_bytes);
     ok = ok && alloc((void **)&ctx->d_table, B * c.slots_per_frame * sizeof(ClusterSlot));
+    {
+        const size_t dw = (size_t)ctx->max_w / 2 + 1, dh = (size_t)ctx->max_h / 2 + 1;      // decimated size bound (quad_decimate = 2)
+        const size_t tiles = ((dw + CL_TW - 1) / CL_TW) * ((dh + CL_TH - 1) / CL_TH);
+        ok = ok && alloc((void **)&ctx->d_ent, B * dw * dh * sizeof(uint4));
+        ok = ok && alloc((void **)&ctx->d_tile_keys, B * tiles * CL_CAP * sizeof(unsigned long long));
+        ok = ok && alloc((void **)&ctx->d_tile_cnt, B * tiles * CL_CAP * sizeof(uint32_t));
+    }
     ok = ok && alloc((void **)&ctx->d_clusters, B * c.clusters_per_frame * sizeof(ClusterRec));
     ok = ok && alloc((void **)&ctx->d_worklist, 4 * B * c.clusters_per_frame * sizeof(uint32_t));
     ok = ok && alloc((void **)&ctx->d_scankey, B * c.points_per_frame * sizeof(uint32_t));
@@ -400,12 +412,14 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         launches += 1;
         if (g.h > 2 && g.w > 2) {
             dim3 gc((g.w + CL_TW - 1) / CL_TW, (g.h - 2 + CL_TH - 1) / CL_TH, B);
-            cluster_pass_kernel<false><<<gc, CL_THREADS, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
+            cluster_pass_kernel<false><<<gc, CL_THREADS, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, ctx->d_ent,
+                                                                  ctx->d_tile_keys, ctx->d_tile_cnt, g, caps);
             // misc: [0] error flags, [3] quads total, [4] decode counter, [8 + 2t] items of tier t, [9 + 2t] its work counter
             cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, wl_stride,
                                                                                             d_misc + 8, 2, (uint32_t)QT0, (uint32_t)QT1,
                                                                                             (uint32_t)QT2, d_misc, g, caps, prm.min_cluster_pixels);
-            cluster_pass_kernel<true><<<gc, CL_THREADS, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, g, caps);
+            cluster_scatter_kernel<<<gc, CL_THREADS, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, ctx->d_ent, ctx->d_tile_keys,
+                                                               ctx->d_tile_cnt, g, caps);
             launches += 3;
         }
         CK(cudaEventRecord(ctx->ev[4], st));

@@ -67,25 +67,31 @@ struct ClShared {
 };
 
 // find-or-insert in the tile table; -1 when no free entry is found within CL_PROBES probes (the caller goes to the global table)
-__device__ __forceinline__ int tile_insert(ClShared &S, unsigned long long key, uint32_t h)
+__device__ __forceinline__ int tile_insert(ClShared &S, unsigned long long key, uint32_t h, int max_probes)
 {
-    uint32_t s = h % (CL_CAP - 1);      // entry CL_CAP - 1 = 0xff stays unused: it is the "no entry" mark of the per-point word
-    for (int probe = 0; probe < CL_PROBES; probe++) {
+    uint32_t s = h % (CL_CAP - 2);      // entries 0xfe / 0xff stay unused: they are the "overflow" / "no entry" marks of the per-point word
+    for (int probe = 0; probe < max_probes; probe++) {
         const unsigned long long cur = *((volatile unsigned long long *)&S.key[s]);
         if (cur == key) return (int)s;
         if (cur == EMPTY_KEY) {
             const unsigned long long old = atomicCAS(&S.key[s], EMPTY_KEY, key);
             if (old == EMPTY_KEY || old == key) return (int)s;
         }
-        s = s + 1 == CL_CAP - 1 ? 0 : s + 1;
+        s = s + 1 == CL_CAP - 2 ? 0 : s + 1;
     }
     return -1;
 }
 
+// The count pass also saves what the scatter pass would have to recompute: the per-point words (16 bytes per pixel) and
+// the tile's table (keys, counts), so the scatter pass (cluster_scatter_kernel) only reserves the tile's share of each
+// selected cluster and streams the points out.  SCATTER = true is the self-contained scatter pass (kept as a reference
+// path; the detector runs count + cluster_scatter_kernel).
+constexpr uint32_t CL_ENT_OVERFLOW = 0xfeu;     // point that did not get a tile entry: the scatter pass looks its cluster up itself
 template <bool SCATTER>
 __global__ void __launch_bounds__(CL_THREADS)
 cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, ClusterSlot *__restrict__ table,
-                    ClusterRec *__restrict__ clusters, uint32_t *__restrict__ scankey, uint32_t *__restrict__ errflag, Geom g, Caps caps)
+                    ClusterRec *__restrict__ clusters, uint32_t *__restrict__ scankey, uint32_t *__restrict__ errflag,
+                    uint4 *__restrict__ ent_out, unsigned long long *__restrict__ tile_keys, uint32_t *__restrict__ tile_cnt, Geom g, Caps caps)
 {
     __shared__ ClShared S;
     const int b = blockIdx.z;
@@ -137,7 +143,7 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
             int e = -1;
             uint32_t r0 = 0;
             if (lane == leader) {
-                e = tile_insert(S, key, hash_key(key));
+                e = tile_insert(S, key, hash_key(key), (int)caps.tile_probes);
                 if (e >= 0) r0 = atomicAdd(&S.cnt[e], npeers);
             }
             e = __shfl_sync(peers, e, leader);
@@ -148,6 +154,7 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
             }
             // tile table full (a tile crossed by > ~200 clusters): straight to the global table
             if (!SCATTER) {
+                ent[it][d] = CL_ENT_OVERFLOW | (sign << 31);
                 if (lane == leader) {
                     const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
                     if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
@@ -170,11 +177,15 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
                     scankey[(size_t)b * caps.points_per_frame + pos + rank] = ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | sign;
             }
         }
+        if (!SCATTER && ent_out && x < g.w && y <= g.h - 2)
+            ent_out[(size_t)b * g.npix + (size_t)y * g.w + x] = make_uint4(ent[it][0], ent[it][1], ent[it][2], ent[it][3]);
     }
     __syncthreads();
     // one global probe + atomic per (tile, cluster)
+    const size_t tile = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     for (int e = threadIdx.x; e < CL_CAP; e += CL_THREADS) {
         const unsigned long long key = S.key[e];
+        if (!SCATTER && tile_keys) { tile_keys[tile * CL_CAP + e] = key; tile_cnt[tile * CL_CAP + e] = S.cnt[e]; }
         if (key == EMPTY_KEY) continue;
         if (!SCATTER) {
             const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
@@ -207,6 +218,72 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
             if (base == 0xffffffffu) continue;
             scankey[(size_t)b * caps.points_per_frame + base + ((en >> 8) & 0x7fffffu)] =
                 ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | (en >> 31);
+        }
+    }
+}
+
+// Scatter pass on the saved results of the count pass: per tile, one global probe + one atomicAdd on the cluster cursor per
+// table entry, then every point goes to (share of its entry) + (its rank inside the tile).
+__global__ void __launch_bounds__(CL_THREADS)
+cluster_scatter_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, const ClusterSlot *__restrict__ table,
+                       ClusterRec *__restrict__ clusters, uint32_t *__restrict__ scankey, const uint4 *__restrict__ ent_in,
+                       const unsigned long long *__restrict__ tile_keys, const uint32_t *__restrict__ tile_cnt, Geom g, Caps caps)
+{
+    __shared__ uint32_t s_base[CL_CAP];
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * CL_TW, y0 = 1 + blockIdx.y * CL_TH;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const ClusterSlot *tab = table + (size_t)b * caps.slots_per_frame;
+    const size_t tile = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    // issue the per-point loads before the table work
+    uint4 en[CL_PER];
+#pragma unroll
+    for (int it = 0; it < CL_PER; it++) {
+        const int x = x0 + (wid & 1) * 32 + lane, y = y0 + it * (CL_THREADS / CL_TW) + (wid >> 1);
+        en[it] = make_uint4(0xffu, 0xffu, 0xffu, 0xffu);
+        if (x >= 1 && x <= g.w - 2 && y <= g.h - 2) en[it] = ent_in[(size_t)b * g.npix + (size_t)y * g.w + x];
+    }
+    for (int e = threadIdx.x; e < CL_CAP; e += CL_THREADS) {
+        const unsigned long long key = tile_keys[tile * CL_CAP + e];
+        uint32_t base = 0xffffffffu;
+        if (key != EMPTY_KEY) {
+            const uint32_t s = slot_find(tab, caps.slots_per_frame, key);
+            if (s != 0xffffffffu) {
+                const uint32_t c = tab[s].cluster;
+                if (c != 0xffffffffu) {
+                    ClusterRec *cr = clusters + (size_t)b * caps.clusters_per_frame + c;
+                    base = cr->offset + atomicAdd(&cr->cursor, tile_cnt[tile * CL_CAP + e]);
+                }
+            }
+        }
+        s_base[e] = base;
+    }
+    __syncthreads();
+    const int dxs[4] = {1, 0, -1, 1}, dys[4] = {0, 1, 1, 1};
+#pragma unroll
+    for (int it = 0; it < CL_PER; it++) {
+        const int x = x0 + (wid & 1) * 32 + lane, y = y0 + it * (CL_THREADS / CL_TW) + (wid >> 1);
+        const uint32_t w4[4] = {en[it].x, en[it].y, en[it].z, en[it].w};
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const uint32_t w = w4[d], e = w & 0xffu;
+            if (e == 0xffu) continue;
+            const uint32_t word = ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | (w >> 31);
+            if (e != CL_ENT_OVERFLOW) {
+                const uint32_t base = s_base[e];
+                if (base != 0xffffffffu) scankey[(size_t)b * caps.points_per_frame + base + ((w >> 8) & 0x7fffffu)] = word;
+                continue;
+            }
+            // the tile table was full when this point was counted: look its cluster up directly
+            const uint32_t *lab = labels + (size_t)b * g.npix;
+            const uint32_t rep0 = lab[(size_t)y * g.w + x], rep1 = lab[(size_t)(y + dys[d]) * g.w + x + dxs[d]];
+            const unsigned long long key = rep0 < rep1 ? ((unsigned long long)rep1 << 32) | rep0 : ((unsigned long long)rep0 << 32) | rep1;
+            const uint32_t s = slot_find(tab, caps.slots_per_frame, key);
+            if (s == 0xffffffffu) continue;
+            const uint32_t c = tab[s].cluster;
+            if (c == 0xffffffffu) continue;
+            ClusterRec *cr = clusters + (size_t)b * caps.clusters_per_frame + c;
+            scankey[(size_t)b * caps.points_per_frame + cr->offset + atomicAdd(&cr->cursor, 1u)] = word;
         }
     }
 }

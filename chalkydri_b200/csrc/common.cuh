@@ -64,6 +64,7 @@ struct Caps {
     uint32_t points_per_frame;
     uint32_t quads_per_frame;
     uint32_t dets_per_frame;
+    uint32_t tile_probes;         // probe limit of the per-tile cluster table (clusters.cuh); lowered by tests to force the overflow path
 };
 
 // error flag bits written by kernels

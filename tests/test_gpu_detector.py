@@ -68,6 +68,57 @@ def test_stages_bit_exact(oracle, W, H, tags, seed, edge):
     det.close()
 
 
+def _axis_aligned_frame(W=1280, H=720):
+    """Pixel-replicated upright tags (every edge axis aligned: whole runs of points share one slope key), plus thin
+    symmetric outlines whose border-polarity sum cancels to ~0 (the sign then depends on the summation order)."""
+    img = np.full((H, W), 150, np.uint8)
+    x = 40
+    for k, (tag_id, cell) in enumerate([(3, 8), (17, 12), (101, 6), (250, 16), (586, 10), (42, 5)]):
+        pat = np.kron(synth.tag_pattern(tag_id), np.ones((cell, cell), np.uint8))
+        n = pat.shape[0]
+        y = 30 + (k % 2) * 330
+        img[y:y + n, x:x + n] = np.where(pat > 0, 230, 25)
+        x += n + 30
+    for k in range(6):                                      # outlines 2 / 4 px thick, several sizes
+        x0, y0, sz, th = 60 + k * 180, 560, 60 + 14 * k, 2 + 2 * (k % 2)
+        img[y0:y0 + sz, x0:x0 + sz] = 30
+        img[y0 + th:y0 + sz - th, x0 + th:x0 + sz - th] = 150
+    img[700:704, 100:1100] = 20                            # long thin lines
+    img[100:620, 1240:1243] = 235
+    return img
+
+
+def test_axis_aligned_tags_slope_ties_and_thin_outlines(oracle):
+    """ptsort()'s order among equal slope keys and the sign of near-cancelling polarity sums must match upstream exactly."""
+    frame = _axis_aligned_frame()
+    det = make_detector(1280, 720, 2)
+    frames = np.stack([frame, np.ascontiguousarray(frame[::-1, ::-1])])       # second frame: 180 degree turn, other tie patterns
+    q, qc, _ = det.quads(frames)
+    out, counts = det.detect_batch(frames)
+    for b in range(2):
+        ref, taps = oracle.detect(frames[b], taps=True)
+        assert qc[b] == taps["nquads"] and qc[b] >= 6
+        gq, oq = canon_quads(q[b, :qc[b]]), canon_quads(taps["quads"]["p"])
+        assert np.abs(np.array(gq) - np.array(oq)).max() < 1e-4
+        assert_same_detections(out[b, :counts[b]], ref)
+        assert len(ref) >= 5
+    det.close()
+
+
+def test_cluster_tile_table_overflow_path(oracle, monkeypatch):
+    """CB_TILE_PROBES=1 makes every hash collision in the per-tile cluster table take the overflow path (global table)."""
+    monkeypatch.setenv("CB_TILE_PROBES", "1")
+    frames, _ = synth.render_batch(1456, 1088, 2, 8, seed=2, edge_px=(40, 200))
+    det = make_detector(1456, 1088, 2)
+    q, qc, _ = det.quads(frames)
+    for b in range(2):
+        _, taps = oracle.detect(frames[b], taps=True)
+        assert qc[b] == taps["nquads"]
+        gq, oq = canon_quads(q[b, :qc[b]]), canon_quads(taps["quads"]["p"])
+        assert np.abs(np.array(gq) - np.array(oq)).max() < 1e-4
+    det.close()
+
+
 def test_strided_frame_with_partial_tiles(oracle):
     """stride != width and w, h not multiples of 4: vector loads + upstream's remainder rule (last full tile, never 127)."""
     from chalkydri_b200.detector import Image
