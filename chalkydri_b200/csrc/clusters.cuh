@@ -21,8 +21,10 @@ constexpr unsigned long long EMPTY_KEY = ~0ull;
 
 __device__ __forceinline__ uint32_t hash_key(unsigned long long k)
 {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-    return (uint32_t)k;
+    // two 32-bit multiplies (the 64-bit finaliser this replaces was ~10 % of the count pass' instructions)
+    uint32_t h = (uint32_t)k * 0x9E3779B1u ^ (uint32_t)(k >> 32) * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+    return h;
 }
 
 // find-or-insert; returns slot index inside the frame's sub-table or 0xffffffff when the table is full
