@@ -244,7 +244,7 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaMemcpyToSymbol(c_codes, kHostCodes, sizeof(kHostCodes)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ThrTmaWarp) * THR_TMA_WARPS)) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, thr_tma_warp_bytes(THR_TMA_ROWB) * THR_TMA_WARPS) == cudaSuccess;
 #define CB_SORT_ATTR(CFG) ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::BYTES) == cudaSuccess;
         CB_SORT_ATTR(SortS8<1>) CB_SORT_ATTR(SortS16<1>) CB_SORT_ATTR(SortM<1>) CB_SORT_ATTR(SortL1<1>) CB_SORT_ATTR(SortL2<1>)
         CB_SORT_ATTR(SortS8<2>) CB_SORT_ATTR(SortS16<2>) CB_SORT_ATTR(SortM<2>) CB_SORT_ATTR(SortL1<2>) CB_SORT_ATTR(SortL2<2>)
@@ -355,14 +355,31 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             RollPlan plan;
             plan.strips = (g.tw + THR_ROLL_MAXIW - 1) / THR_ROLL_MAXIW;
             plan.iw = ((g.tw + plan.strips - 1) / plan.strips + 3) / 4 * 4;
-            const long long target_warps = (long long)ctx->num_sms * 24;
-            int ysegs = (int)((target_warps + (long long)plan.strips * B - 1) / ((long long)plan.strips * B));
-            ysegs = std::max(1, std::min(ysegs, std::max(1, g.th / 8)));
-            plan.seg_rows = (g.th + ysegs - 1) / ysegs;
-            plan.ysegs = (g.th + plan.seg_rows - 1) / plan.seg_rows;
+            // Every warp does the same work (seg_rows + 2 halo tile rows, plus the fill of its TMA ring), and an SM holds 3 CTAs
+            // of 4 warps (66 KB of ring each), so the launch runs in ceil(warps / resident) equal waves: pick the segment
+            // count that minimises waves x (rows per warp).  (A fixed "24 warps per SM" target gave 2.02 waves -> 3 rounds.)
+            {
+                const int nlanes_max = (plan.iw + 3 + 3) / 4;                                 // lanes that hold data: iw inner tiles + 3 halo, 4 tiles per lane
+                plan.rowb = std::min(THR_TMA_ROWB, (nlanes_max * 32 + 127) / 128 * 128);
+                plan.warp_bytes = thr_tma_warp_bytes(plan.rowb);
+                const int ctas_per_sm = std::max(1, std::min(5, (int)((227 * 1024) / (plan.warp_bytes * THR_TMA_WARPS + 1024))));   // 5: register limit (87 regs)
+                const long long resident = (long long)ctx->num_sms * ctas_per_sm * THR_TMA_WARPS;
+                const int max_segs = std::max(1, g.th / 8);
+                long long best_cost = -1;
+                int best = 1;
+                for (int ys = 1; ys <= max_segs; ys++) {
+                    const int rows = (g.th + ys - 1) / ys, segs = (g.th + rows - 1) / rows;
+                    if (segs != ys) continue;
+                    const long long warps = (long long)plan.strips * segs * B;
+                    const long long cost = ((warps + resident - 1) / resident) * (rows + 2 + THR_TMA_STAGES);
+                    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ys; }
+                }
+                plan.seg_rows = (g.th + best - 1) / best;
+                plan.ysegs = (g.th + plan.seg_rows - 1) / plan.seg_rows;
+            }
             const long long warps = (long long)plan.strips * plan.ysegs * B;
             const int wt = (g.w % 4 || g.h % 4) ? 1 : 0;
-            threshold_f2_tma_kernel<<<(unsigned)((warps + THR_TMA_WARPS - 1) / THR_TMA_WARPS), THR_TMA_WARPS * 32, sizeof(ThrTmaWarp) * THR_TMA_WARPS, st>>>(
+            threshold_f2_tma_kernel<<<(unsigned)((warps + THR_TMA_WARPS - 1) / THR_TMA_WARPS), THR_TMA_WARPS * 32, (size_t)plan.warp_bytes * THR_TMA_WARPS, st>>>(
                     d_frames, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g, prm.min_white_black_diff, plan, wt);
         }
         launches++; thr_launches++;

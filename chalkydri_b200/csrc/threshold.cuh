@@ -143,7 +143,7 @@ threshold_f2_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, u
 }
 
 constexpr int THR_ROLL_MAXIW = 124;      // inner tiles per strip (32 lanes x 4 tiles minus 2 + 2 halo tiles)
-struct RollPlan { int strips, iw, ysegs, seg_rows; };
+struct RollPlan { int strips, iw, ysegs, seg_rows, rowb, warp_bytes; };   // rowb: ring row pitch (bytes), warp_bytes: ring + barriers per warp
 
 // ---- TMA-staged streaming variant (default) ----------------------------------------------------------------------
 // The CTA-tiled kernel above serialises load / exchange / dilate / store phases behind block barriers, so with 3 CTAs per
@@ -161,11 +161,15 @@ struct RollPlan { int strips, iw, ysegs, seg_rows; };
 //   * no block barrier; the only redundancy is one halo tile row at each end of a segment.
 constexpr int THR_TMA_WARPS = 4, THR_TMA_STAGES = 4, THR_TMA_ROWB = 1024;
 
-struct __align__(128) ThrTmaWarp {
-    uint8_t buf[THR_TMA_STAGES][4][THR_TMA_ROWB];
-    unsigned long long bar[THR_TMA_STAGES];
-    unsigned long long pad[12];
+// per-warp shared memory: THR_TMA_STAGES x 4 rows x plan.rowb bytes, then the stages' mbarriers.  The row pitch follows the
+// strip width (768 B for the c2 frame instead of the 1 KB maximum), which is what decides how many warps fit an SM.
+struct ThrTmaWarp {
+    uint8_t *buf;
+    unsigned long long *bar;
+    int rowb;
+    __device__ __forceinline__ uint8_t *row(int stage, int dy) const { return buf + (size_t)(stage * 4 + dy) * rowb; }
 };
+__host__ __device__ inline int thr_tma_warp_bytes(int rowb) { return THR_TMA_STAGES * 4 * rowb + 128; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -201,7 +205,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 
 // lane 0: start the copies of tile row rr (4 even input rows, `nbytes` bytes starting at byte x0s) into `stage`
-__device__ __forceinline__ void thr_tma_issue(ThrTmaWarp &W, int stage, const uint8_t *__restrict__ img, const Geom &g, int rr, int x0s, int nbytes)
+__device__ __forceinline__ void thr_tma_issue(const ThrTmaWarp &W, int stage, const uint8_t *__restrict__ img, const Geom &g, int rr, int x0s, int nbytes)
 {
     const int xs = max(x0s, 0), xe = min(x0s + nbytes, g.stride);
     const int n = xe - xs;
@@ -212,7 +216,7 @@ __device__ __forceinline__ void thr_tma_issue(ThrTmaWarp &W, int stage, const ui
     mbar_expect_tx(&W.bar[stage], total);
     for (int dy = 0; dy < 4; dy++) {
         const int y = rr * 4 + dy;
-        if (y < g.h) tma_load_1d(&W.buf[stage][dy][xs - x0s], img + (size_t)(2 * y) * g.stride + xs, (uint32_t)n, &W.bar[stage]);
+        if (y < g.h) tma_load_1d(W.row(stage, dy) + (xs - x0s), img + (size_t)(2 * y) * g.stride + xs, (uint32_t)n, &W.bar[stage]);
     }
 }
 
@@ -221,7 +225,10 @@ threshold_f2_tma_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ ou
                         Geom g, int min_diff, RollPlan plan, int write_tiles)
 {
     extern __shared__ __align__(128) unsigned char thr_smem[];
-    ThrTmaWarp &W = reinterpret_cast<ThrTmaWarp *>(thr_smem)[threadIdx.x >> 5];
+    ThrTmaWarp W;
+    W.buf = thr_smem + (size_t)(threadIdx.x >> 5) * plan.warp_bytes;
+    W.bar = reinterpret_cast<unsigned long long *>(W.buf + THR_TMA_STAGES * 4 * plan.rowb);
+    W.rowb = plan.rowb;
     const int lane = threadIdx.x & 31;
     const long long widx = (long long)blockIdx.x * THR_TMA_WARPS + (threadIdx.x >> 5);
     const long long per_frame = (long long)plan.strips * plan.ysegs;
@@ -285,7 +292,7 @@ threshold_f2_tma_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ ou
             for (int k = 0; k < 4; k++) px_prev[dy][k] = px_cur[dy][k];
             uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
             if (lane_on) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(&W.buf[stage][dy][lane * 32]);
+                const uint4 *p = reinterpret_cast<const uint4 *>(W.row(stage, dy) + lane * 32);
                 v0 = p[0]; v1 = p[1];
             }
             const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
