@@ -154,12 +154,15 @@ fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ so
         // ---- smoothed errors, local maxima, running top list (descending error; ties: lower index first) ----
         double te = __longlong_as_double(0xfff0000000000000ll);
         int ti = 1 << 30, nm = 0;
+        // tile loads run one step ahead of their use (the errs array comes from L2 / HBM)
+        auto load_err = [&](int idx) { if (idx < 0) idx += n; while (idx >= n) idx -= n; return errs[idx]; };
+        double pre0 = load_err(-4 + lane), pre1 = lane < 8 ? load_err(-4 + 32 + lane) : 0.0;
         for (int j0 = 0; j0 < n; j0 += 32) {
-            for (int t = lane; t < 40; t += 32) {
-                int idx = j0 - 4 + t;
-                if (idx < 0) idx += n;
-                while (idx >= n) idx -= n;
-                S.et[t] = errs[idx];
+            S.et[lane] = pre0;
+            if (lane < 8) S.et[32 + lane] = pre1;
+            if (j0 + 32 < n) {
+                pre0 = load_err(j0 + 32 - 4 + lane);
+                if (lane < 8) pre1 = load_err(j0 + 32 - 4 + 32 + lane);
             }
             __syncwarp();
             for (int u = lane; u < 34; u += 32) {
@@ -385,11 +388,14 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
         const uint8_t *img = in + (size_t)b * g.frame_stride;
         // raw taps of one point: left/right/up/down neighbours of the decimated pixel, -1 = no gradient (W = 1)
         int gl = -1, gr = 0, gu = 0, gd = 0;
-        uint32_t xy = 0;
+        // xy: the point whose taps are in flight; xy_ahead: the point one block further (its load is issued a whole block
+        // before its taps need it, so the tap addresses never wait for it)
+        uint32_t xy = 0, xy_ahead = lane < n ? XY[lane] : 0u;
         auto issue = [&](int j) {
             gl = -1;
+            xy = xy_ahead;
+            if (j + 32 < n) xy_ahead = XY[j + 32];
             if (j < n) {
-                xy = XY[j];
                 const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
                 const double x = px * .5 + 0.5, y = py * .5 + 0.5;
                 const int ix = (int)x, iy = (int)y;
