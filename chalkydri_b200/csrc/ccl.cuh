@@ -123,7 +123,7 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
     const uint32_t full = 0xffffffffu;
     {
         const int lx = wid * 32 + lane, x = x0 + lx;
-        uint32_t m_prev = 0;
+        uint32_t m_prev = 0, r_prev = 0;
         // pixel values of the previous row at x - 1, x, x + 1 stay in registers; a row costs one byte load per lane plus the
         // two halo columns (lanes 0 and 31).  Columns beyond the pitch never reach a link (x > w - 2 gives mask 0).
         uint32_t u_l = 0, u_c = 0, u_r = 0;
@@ -144,23 +144,32 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
             const uint32_t starts = __ballot_sync(full, !(m & LINK_LEFT) || lane == 0);
             const int start_lane = 31 - __clz(starts & ((2u << lane) - 1u));
             const uint32_t higher = lane == 31 ? 0u : starts & ~((2u << lane) - 1u);
-            L[i] = (uint32_t)(i - lane + start_lane);
+            const uint32_t my_start = (uint32_t)(i - lane + start_lane);
+            L[i] = my_start;
             Cnt[i] = start_lane == lane ? (uint32_t)((higher ? __ffs(higher) - 1 : 32) - lane) : 0u;   // run length at run starts
             const uint32_t m_left = __shfl_up_sync(full, m, 1);
+            // roots the three upper neighbours had when their row was compressed: unions start from them and from this run's
+            // start instead of from the pixels, which saves a hop per walk
+            const uint32_t r_ul = __shfl_up_sync(full, r_prev, 1), r_ur = __shfl_down_sync(full, r_prev, 1);
             __syncwarp();
             if (ly > 0) {
-                if (m & LINK_UP) {
-                    const bool implied = (m & LINK_LEFT) && lane > 0 && (m_left & LINK_UP) && (m_prev & LINK_LEFT);
-                    if (!implied) uf_union(L, i, i - CCL_TW);
-                }
-                if ((m & LINK_UPLEFT) && lane > 0) uf_union(L, i, i - CCL_TW - 1);
-                if ((m & LINK_UPRIGHT) && lane < 31) uf_union(L, i, i - CCL_TW + 1);
+                const uint32_t NONE = 0xffffffffu;
+                const bool up = (m & LINK_UP) && !((m & LINK_LEFT) && lane > 0 && (m_left & LINK_UP) && (m_prev & LINK_LEFT));
+                const bool ul = (m & LINK_UPLEFT) && lane > 0, ur = (m & LINK_UPRIGHT) && lane < 31;
+                // upstream's guards make UP exclude both diagonals, so two rounds cover a pixel's links (CAT: three)
+                const uint32_t t1 = up ? r_prev : (ul ? r_ul : NONE);
+                if (t1 != NONE) uf_union(L, my_start, t1);
+                if (ur) uf_union(L, my_start, r_ur);
+                if (MODE == 1 && up && ul) uf_union(L, my_start, r_ul);
                 __syncwarp();
                 uint32_t r = 0;
-                if (start_lane == lane) r = uf_find(L, (uint32_t)i);
+                if (start_lane == lane) r = uf_find(L, my_start);
                 r = __shfl_sync(full, r, start_lane);
                 L[i] = r;
+                r_prev = r;
                 __syncwarp();
+            } else {
+                r_prev = my_start;
             }
             m_prev = m;
         }
@@ -184,21 +193,28 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
     }
     __syncthreads();
     constexpr int PER = CCL_TW * CCL_TH / CCL_THREADS;
+    // final flatten in two steps: run starts (Cnt != 0; the only possible tree nodes) walk to the root, link straight to it
+    // and hand it their run length; then every pixel is two loads from its root
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int i = threadIdx.x + k * CCL_THREADS;
+        const uint32_t rl = Cnt[i];
+        if (rl == 0) continue;
+        const uint32_t r = uf_find(L, (uint32_t)i);
+        if (r != (uint32_t)i) {
+            // (a start's count is only ever added to by others when it IS the root, so rl is still its own run length)
+            L[i] = r;
+            const int lx = i % CCL_TW, ly = i / CCL_TW;
+            if (x0 + lx < g.w && y0 + ly < g.h) atomicAdd(&Cnt[r], rl);
+        }
+    }
+    __syncthreads();
     uint32_t roots[PER];
 #pragma unroll
     for (int k = 0; k < PER; k++) {
         const int i = threadIdx.x + k * CCL_THREADS;
-        const uint32_t r = uf_find(L, (uint32_t)i);
-        roots[k] = r;
-        // run starts that are not the root hand their run to the root (a start's count is only ever added to by others
-        // when it IS the root, so the value read here is still its own run length)
-        if (r != (uint32_t)i) {
-            const uint32_t rl = Cnt[i];
-            const int lx = i % CCL_TW, ly = i / CCL_TW;
-            if (rl && x0 + lx < g.w && y0 + ly < g.h) atomicAdd(&Cnt[r], rl);
-        }
+        roots[k] = L[L[i]];
     }
-    __syncthreads();
     const uint32_t base = (uint32_t)b * g.npix;
 #pragma unroll
     for (int k = 0; k < PER; k++) {
