@@ -142,6 +142,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner / debug lines off stdout (one JSON line there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from chalkydri_b200 import capi
