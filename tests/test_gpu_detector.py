@@ -105,6 +105,31 @@ def test_axis_aligned_tags_slope_ties_and_thin_outlines(oracle):
     det.close()
 
 
+def test_huge_cluster_uses_global_work_arrays(oracle):
+    """A cluster above 8192 points (here the outline of a 4000x2300 rectangle, ~12.6 k points, below upstream's
+    3(2w+2h) cap) no longer fits the largest shared-memory tier: both sorts run out of the global scratch arrays."""
+    H, W = 2592, 4608
+    rng = np.random.default_rng(7)
+    img = np.full((H, W), 170, np.uint8)
+    img[140:2440, 300:4300] = 40
+    img[400:700, 800:1100] = 200                           # some structure inside, plus a tag so the decode stage has work
+    pat = np.kron(synth.tag_pattern(5), np.ones((24, 24), np.uint8))
+    img[1000:1240, 2000:2240] = np.where(pat > 0, 235, 20)
+    img = np.clip(img.astype(np.int16) + rng.integers(-1, 2, img.shape), 0, 255).astype(np.uint8)
+    det = make_detector(W, H, 1, 64)
+    q, qc, _ = det.quads(img[None])
+    out, counts = det.detect_batch(img[None])
+    ref, taps = oracle.detect(img, taps=True, pts_cap=8_000_000)
+    _, sizes = np.unique(taps["pts_cluster"][:taps["npoints"]], return_counts=True)
+    assert sizes.max() > 8192, "the fixture no longer produces a cluster above the shared-memory tiers"
+    assert qc[0] == taps["nquads"] and qc[0] >= 2
+    gq, oq = canon_quads(q[0, :qc[0]]), canon_quads(taps["quads"]["p"])
+    assert np.abs(np.array(gq) - np.array(oq)).max() < 1e-4
+    assert_same_detections(out[0, :counts[0]], ref)
+    assert 5 in ref["id"].tolist()
+    det.close()
+
+
 def test_cluster_tile_table_overflow_path(oracle, monkeypatch):
     """CB_TILE_PROBES=1 makes every hash collision in the per-tile cluster table take the overflow path (global table)."""
     monkeypatch.setenv("CB_TILE_PROBES", "1")
