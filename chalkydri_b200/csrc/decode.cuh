@@ -400,7 +400,7 @@ __device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q
 }
 
 // persistent warps pull candidate quads from the batch-wide list
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__(DEC_WARPS * 32, 6)
 decode_quads_kernel(const uint8_t *__restrict__ in, const QuadRec *__restrict__ quads, const uint32_t *__restrict__ nquads_total,
                     uint32_t *__restrict__ counter, RawDet *__restrict__ raw, uint32_t *__restrict__ nraw, Geom g, Caps caps,
                     DetParams prm, DecodeConst dc)
