@@ -24,6 +24,7 @@
 #pragma once
 #include "common.cuh"
 #include "sort.cuh"
+#include "divby.cuh"
 
 namespace cb {
 
@@ -45,8 +46,9 @@ __device__ __forceinline__ void fit_line_m(const M6 &a, const M6 &p, const M6 &l
         Mx = l.Mx - p.Mx; My = l.My - p.My; Mxx = l.Mxx - p.Mxx; Mxy = l.Mxy - p.Mxy; Myy = l.Myy - p.Myy; W = l.W - p.W;
         Mx += a.Mx; My += a.My; Mxx += a.Mxx; Mxy += a.Mxy; Myy += a.Myy; W += a.W;
     }
-    const double Ex = Mx / W, Ey = My / W;
-    const double Cxx = Mxx / W - Ex * Ex, Cxy = Mxy / W - Ex * Ey, Cyy = Myy / W - Ey * Ey;
+    const DivBy by_w(W);
+    const double Ex = by_w(Mx), Ey = by_w(My);
+    const double Cxx = by_w(Mxx) - Ex * Ex, Cxy = by_w(Mxy) - Ex * Ey, Cyy = by_w(Myy) - Ey * Ey;
     const float disc = sqrtf((float)((Cxx - Cyy) * (Cxx - Cyy) + 4 * Cxy * Cxy));
     const double eig_small = 0.5 * (Cxx + Cyy - disc);
     if (want_params) {
@@ -58,7 +60,7 @@ __device__ __forceinline__ void fit_line_m(const M6 &a, const M6 &p, const M6 &l
         if (M1 > M2) { nx = nx1; ny = ny1; M = M1; } else { nx = nx2; ny = ny2; M = M2; }
         const double length = sqrtf((float)M);
         if (fabs(length) < 1e-12) { o.nx = 0; o.ny = 0; }
-        else { o.nx = nx / length; o.ny = ny / length; }
+        else { const DivBy by_len(length); o.nx = by_len(nx); o.ny = by_len(ny); }
     }
     o.err = N * eig_small;
     o.mse = eig_small;

@@ -130,6 +130,17 @@ def test_huge_cluster_uses_global_work_arrays(oracle):
     det.close()
 
 
+def test_shared_reciprocal_division_is_the_compilers_division(tmp_path):
+    """fit_line() divides five moments by one weight through cb::DivBy; it must equal a / b bit for bit (2e10 pairs)."""
+    import subprocess, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "divby_check")
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "--fmad=false", "-O3", "-I",
+                           os.path.join(root, "chalkydri_b200", "csrc"), "-o", exe, os.path.join(root, "tests", "cuda", "divby_check.cu")])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_cluster_tile_table_overflow_path(oracle, monkeypatch):
     """CB_TILE_PROBES=1 makes every hash collision in the per-tile cluster table take the overflow path (global table)."""
     monkeypatch.setenv("CB_TILE_PROBES", "1")
