@@ -416,7 +416,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             launches++;
         }
         const uint32_t total = (uint32_t)B * g.npix;
-        ccl_flatten_roots_kernel<<<(total + 255) / 256, 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, total);
+        ccl_flatten_roots_kernel<<<(total + 256 * ROOTS_PER - 1) / (256 * ROOTS_PER), 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, total);
         dim3 gfin((g.w + 256 * MARK_PER - 1) / (256 * MARK_PER), g.h, B);
         ccl_finish_kernel<<<gfin, 256, 0, st>>>(ctx->d_thresh, ctx->d_labels, ctx->d_sizes, ctx->d_mark, g);
         launches += 2;

@@ -294,16 +294,30 @@ __global__ void __launch_bounds__(256) ccl_flatten_kernel(uint32_t *__restrict__
 //   (b) every pixel is then exactly two loads from its final root; the same kernel applies the component-size gate of
 //       gradient_clusters() (pixels of components smaller than 25 become 127, "ignore") -- sizes[] is final because (a)
 //       is a separate launch.
+// Four pixels per thread: almost every thread only reads four zeros and leaves, so the launch is a quarter as many waves of
+// the pointer chase's latency.
+constexpr int ROOTS_PER = 4;
 __global__ void __launch_bounds__(256) ccl_flatten_roots_kernel(uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, uint32_t total)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const uint32_t c = sizes[i];
-    if (c == 0) return;
-    const uint32_t root = uf_find(labels, i);
-    if (root != i) {
-        labels[i] = root;
-        atomicAdd(&sizes[root], c);
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * ROOTS_PER;
+    if (i0 >= total) return;
+    uint32_t c[ROOTS_PER];
+    if (i0 + ROOTS_PER <= total && (reinterpret_cast<uintptr_t>(sizes) & 15) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(sizes + i0);
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < ROOTS_PER; k++) c[k] = i0 + k < total ? sizes[i0 + k] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < ROOTS_PER; k++) {
+        if (c[k] == 0) continue;
+        const uint32_t i = i0 + k;
+        const uint32_t root = uf_find(labels, i);
+        if (root != i) {
+            labels[i] = root;
+            atomicAdd(&sizes[root], c[k]);
+        }
     }
 }
 

@@ -348,7 +348,7 @@ fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ so
 // and moment) that only six lanes can work on, so what matters is the number of clusters in flight, not the threads per
 // cluster.  Writing the whole 48-byte-per-point prefix array and reading it back for the window errors was the largest
 // HBM stream of the detector, so the array never leaves the SM:
-//   * the prefix of the last 96 points lives in a shared-memory ring (moment-major, pitch 97: the six chain lanes and the
+//   * the prefix of the last 96 points lives in a shared-memory ring (moment-major, pitch 98: the six chain lanes and the
 //     32 window lanes are both bank-conflict free); the window error errs[i] = fit_line(i - ksz, i + ksz) only needs
 //     entries i + ksz and i - ksz - 1, i.e. at most 41 back, and is emitted as soon as entry i + ksz exists;
 //   * the 2 ksz windows that wrap around the ends are done last, from the ring (tail) and a copy of the first 2 ksz
@@ -357,8 +357,8 @@ fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ so
 //     <= 21 entries the corner search needs by replaying <= LF_CP - 1 points from a checkpoint.
 // The gradient taps of the next 32 points are issued before the current 32 are accumulated.
 constexpr int LF_WARPS = 4;
-constexpr int LF_RING = 96, LF_PITCH = 97, LF_HEAD = 40, LF_HPITCH = 41;
-struct LfWarp {
+constexpr int LF_RING = 96, LF_PITCH = 98, LF_HEAD = 40, LF_HPITCH = 41;   // pitch 98: rows 16-byte aligned, chain lanes 4 banks apart
+struct __align__(16) LfWarp {
     double ring[6][LF_PITCH];
     double head[6][LF_HPITCH];
 };
@@ -432,11 +432,24 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
                 const int cnt = min(32, n - j0);
                 double *r = &ring[lane][s0];
                 double *c = cp + (size_t)(j0 / LF_CP) * 6 + lane;
+                if (cnt == 32) {
+                    // full block: 128-bit shared-memory accesses, the additions stay one dependent chain
+                    double2 *r2 = reinterpret_cast<double2 *>(r);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        double2 v = r2[k];
+                        acc += v.x; v.x = acc;
+                        acc += v.y; v.y = acc;
+                        r2[k] = v;
+                        if ((k & (LF_CP / 2 - 1)) == LF_CP / 2 - 1) c[(size_t)(k / (LF_CP / 2)) * 6] = acc;
+                    }
+                } else {
 #pragma unroll 8
-                for (int k = 0; k < cnt; k++) {
-                    acc += r[k];
-                    r[k] = acc;
-                    if ((k & (LF_CP - 1)) == LF_CP - 1) c[(size_t)(k / LF_CP) * 6] = acc;
+                    for (int k = 0; k < cnt; k++) {
+                        acc += r[k];
+                        r[k] = acc;
+                        if ((k & (LF_CP - 1)) == LF_CP - 1) c[(size_t)(k / LF_CP) * 6] = acc;
+                    }
                 }
             }
             __syncwarp();
