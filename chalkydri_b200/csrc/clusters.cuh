@@ -302,24 +302,50 @@ cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ 
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    if (s >= caps.slots_per_frame) return;
-    ClusterSlot *slot = table + (size_t)b * caps.slots_per_frame + s;
-    if (slot->key == EMPTY_KEY) return;
-    const uint32_t cnt = slot->count;
+    const int lane = threadIdx.x & 31;
+    const uint32_t full = 0xffffffffu, lt = (1u << lane) - 1u;
+    // (slots_per_frame is a power of two >= 1024, so whole warps are in range together)
+    ClusterSlot *slot = table + (size_t)b * caps.slots_per_frame + min(s, caps.slots_per_frame - 1);
     const uint32_t maxsz = 3u * (2u * g.w + 2u * g.h);
     const uint32_t minsz = (uint32_t)max(24, min_cluster_pixels);
-    if (cnt < minsz || cnt > maxsz) return;          // slot->cluster stays 0xffffffff
-    const uint32_t ci = atomicAdd(&nclusters[b], 1u);
-    if (ci >= caps.clusters_per_frame) { atomicOr(errflag, ERR_CLUSTERS_FULL); return; }
-    const uint32_t off = atomicAdd(&npoints[b], (cnt + 7u) & ~7u);   // 8-aligned: one checkpoint slot per 8 points (quads.cuh LF_CP)
-    if (off + cnt > caps.points_per_frame) { atomicOr(errflag, ERR_POINTS_FULL); return; }
+    unsigned long long key = EMPTY_KEY;
+    uint32_t cnt = 0;
+    if (s < caps.slots_per_frame) { key = slot->key; if (key != EMPTY_KEY) cnt = slot->count; }
+    const bool sel = key != EMPTY_KEY && cnt >= minsz && cnt <= maxsz;          // otherwise slot->cluster stays 0xffffffff
+    // the three allocations are warp-aggregated: the batch-wide tier counters would otherwise take one atomic per cluster
+    const uint32_t m = __ballot_sync(full, sel);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    const uint32_t padded = sel ? (cnt + 7u) & ~7u : 0u;        // 8-aligned: one checkpoint slot per 8 points (quads.cuh LF_CP)
+    uint32_t scan = padded;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(full, scan, o); if (lane >= o) scan += v; }
+    const uint32_t total = __shfl_sync(full, scan, 31);
+    uint32_t ci0 = 0, off0 = 0;
+    if (lane == leader) { ci0 = atomicAdd(&nclusters[b], (uint32_t)__popc(m)); off0 = atomicAdd(&npoints[b], total); }
+    ci0 = __shfl_sync(full, ci0, leader); off0 = __shfl_sync(full, off0, leader);
+    const uint32_t ci = ci0 + __popc(m & lt), off = off0 + scan - padded;
+    const int tier = cnt <= t0 ? 0 : (cnt <= t1 ? 1 : (cnt <= t2 ? 2 : 3));     // work list of the quad-fitting tier
+    bool ok = sel;
+    if (ok && ci >= caps.clusters_per_frame) { atomicOr(errflag, ERR_CLUSTERS_FULL); ok = false; }
+    if (ok && off + cnt > caps.points_per_frame) { atomicOr(errflag, ERR_POINTS_FULL); ok = false; }
+    uint32_t pos = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const uint32_t mt = __ballot_sync(full, ok && tier == t);
+        if (mt == 0) continue;
+        const int ld = __ffs(mt) - 1;
+        uint32_t p0 = 0;
+        if (lane == ld) p0 = atomicAdd(&nwork[t * nwork_stride], (uint32_t)__popc(mt));
+        p0 = __shfl_sync(full, p0, ld);
+        if (ok && tier == t) pos = p0 + __popc(mt & lt);
+    }
+    if (!ok) return;
     ClusterRec r;
-    r.key = slot->key; r.offset = off; r.count = cnt; r.cursor = 0; r.pad = 0;
+    r.key = key; r.offset = off; r.count = cnt; r.cursor = 0; r.pad = 0;
     clusters[(size_t)b * caps.clusters_per_frame + ci] = r;
     slot->cluster = ci;
-    const uint32_t item = (uint32_t)b * caps.clusters_per_frame + ci;
-    const int tier = cnt <= t0 ? 0 : (cnt <= t1 ? 1 : (cnt <= t2 ? 2 : 3));     // work list of the quad-fitting tier
-    worklists[(size_t)tier * list_stride + atomicAdd(&nwork[tier * nwork_stride], 1u)] = item;
+    worklists[(size_t)tier * list_stride + pos] = (uint32_t)b * caps.clusters_per_frame + ci;
 }
 
 }  // namespace cb
