@@ -142,8 +142,20 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner / debug lines off stdout (one JSON line there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION and up) with printf when the communicator comes up; stdout must
+        # carry exactly one JSON line, so fd 1 points at stderr until the first collective has run.
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from chalkydri_b200 import capi
     from chalkydri_b200.detector import DetectorBuilder, DET_DTYPE
