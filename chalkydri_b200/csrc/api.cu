@@ -590,7 +590,8 @@ static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, 
     // frames, against 4 x 64 and 2 x 128).  End to end the call costs about one small copy plus all kernels.
     std::vector<int> cstart;
     {
-        const int s1 = std::max(8, std::min(half, batch / 8));
+        const int min_first = (int)std::max<size_t>(1, ((size_t)16 << 20) / std::max<size_t>(bytes, 1));   // a first copy of >= 16 MB
+        const int s1 = std::max(std::min(8, std::max(min_first, 1)), std::min(half, batch / 8));
         int b0 = 0, k = 0;
         while (b0 < batch) {
             const int sz = k == 0 ? s1 : (k == 1 ? std::min(half, 3 * s1) : half);
@@ -670,7 +671,8 @@ int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, in
     CK(cudaSetDevice(ctx->device));
     if ((size_t)stride * height > ctx->max_npix) return fail(ctx, CB_ERR_ARG, "stride*height exceeds the context's frame capacity");
     if (!ctx->family_set) return fail(ctx, CB_ERR_STATE, "no tag family set: call cb_set_family_tag36h11 first");
-    if (batch >= 64 && ctx->max_batch >= 32) {
+    // pipelined (copy of chunk i+1 under the kernels of chunk i) when there is enough to overlap: many frames, or few large ones
+    if (ctx->max_batch >= 8 && batch >= 8 && (batch >= 64 || (size_t)batch * stride * height >= ((size_t)128 << 20))) {
         Geom g;
         int rc = make_geom(ctx, width, height, stride, frame_stride, 1, g);      // argument validation
         if (rc) return rc;
