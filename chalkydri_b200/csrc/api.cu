@@ -478,7 +478,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     if (stage >= ST_FULL) {
         // ---- A6-A9 refine, homography, decode, reconcile ----
         decode_quads_kernel<<<ctx->num_sms * 6, DEC_WARPS * 32, 0, st>>>(d_frames, ctx->d_quads, d_misc + 3, d_misc + 4, ctx->d_raw, d_nraw, g, caps, prm, ctx->dc);
-        reconcile_kernel<<<(B + 63) / 64, 64, 0, st>>>(ctx->d_raw, d_nraw, ctx->d_dets, ctx->d_counts, caps, B);
+        reconcile_kernel<<<(B + REC_WARPS - 1) / REC_WARPS, REC_WARPS * 32, 0, st>>>(ctx->d_raw, d_nraw, ctx->d_dets, ctx->d_counts, caps, B);
         launches += 2;
     }
     CK(cudaEventRecord(ctx->ev[6], st));

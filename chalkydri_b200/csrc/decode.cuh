@@ -474,47 +474,100 @@ __device__ __forceinline__ bool det_less(const cb_detection &a, const cb_detecti
     return a.c[1] < b.c[1];
 }
 
-__global__ void reconcile_kernel(RawDet *__restrict__ raw, const uint32_t *__restrict__ nraw, cb_detection *__restrict__ out,
-                                 int32_t *__restrict__ counts, Caps caps, int batch)
+// One warp per frame.  The bookkeeping (a handful of detections) runs on lane 0 over an index permutation in shared memory
+// instead of moving 176-byte records around global memory; the surviving records are copied out by the whole warp.
+// Frames with more raw detections than REC_MAX fall back to lane 0 working on the records in place.
+constexpr int REC_WARPS = 4, REC_MAX = 128;
+__global__ void __launch_bounds__(REC_WARPS * 32)
+reconcile_kernel(RawDet *__restrict__ raw, const uint32_t *__restrict__ nraw, cb_detection *__restrict__ out,
+                 int32_t *__restrict__ counts, Caps caps, int batch)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint16_t s_idx[REC_WARPS][REC_MAX];
+    __shared__ int s_n[REC_WARPS];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * REC_WARPS + wid;
     if (b >= batch) return;
     RawDet *r = raw + (size_t)b * caps.quads_per_frame;
     int n = (int)min(nraw[b], caps.quads_per_frame);
-    // The decode kernel appends in arbitrary order; upstream's outcome depends on list order only through the
-    // swap-remove bookkeeping, not through which detection of an overlapping pair survives.  Put the list into a
-    // canonical order first so the result is deterministic.
-    for (int i = 1; i < n; i++) {
-        RawDet t = r[i];
-        int j = i;
-        while (j > 0 && det_less(t.d, r[j - 1].d)) { r[j] = r[j - 1]; j--; }
-        r[j] = t;
-    }
-    for (int i0 = 0; i0 < n; i0++) {
-        for (int i1 = i0 + 1; i1 < n; i1++) {
-            const cb_detection &d0 = r[i0].d, &d1 = r[i1].d;
-            if (d0.id != d1.id) continue;
-            if (!polygons_overlap(d0.p, d1.p)) continue;
-            int pref = 0;
-            pref = prefer_smaller(pref, d0.hamming, d1.hamming);
-            pref = prefer_smaller(pref, -d0.decision_margin, -d1.decision_margin);
-            for (int i = 0; i < 4; i++) {
-                pref = prefer_smaller(pref, d0.p[i][0], d1.p[i][0]);
-                pref = prefer_smaller(pref, d0.p[i][1], d1.p[i][1]);
+    const bool indexed = n <= REC_MAX;
+    uint16_t *ix = s_idx[wid];
+    if (lane == 0) {
+        // The decode kernel appends in arbitrary order; upstream's outcome depends on list order only through the
+        // swap-remove bookkeeping, not through which detection of an overlapping pair survives.  Put the list into a
+        // canonical order first so the result is deterministic.
+        if (indexed) {
+            for (int i = 0; i < n; i++) ix[i] = (uint16_t)i;
+            for (int i = 1; i < n; i++) {
+                const uint16_t t = ix[i];
+                int j = i;
+                while (j > 0 && det_less(r[t].d, r[ix[j - 1]].d)) { ix[j] = ix[j - 1]; j--; }
+                ix[j] = t;
             }
-            if (pref < 0) { r[i1] = r[n - 1]; n--; i1--; }
-            else { r[i0] = r[n - 1]; n--; i0--; break; }
+            for (int i0 = 0; i0 < n; i0++) {
+                for (int i1 = i0 + 1; i1 < n; i1++) {
+                    const cb_detection &d0 = r[ix[i0]].d, &d1 = r[ix[i1]].d;
+                    if (d0.id != d1.id) continue;
+                    if (!polygons_overlap(d0.p, d1.p)) continue;
+                    int pref = 0;
+                    pref = prefer_smaller(pref, d0.hamming, d1.hamming);
+                    pref = prefer_smaller(pref, -d0.decision_margin, -d1.decision_margin);
+                    for (int i = 0; i < 4; i++) {
+                        pref = prefer_smaller(pref, d0.p[i][0], d1.p[i][0]);
+                        pref = prefer_smaller(pref, d0.p[i][1], d1.p[i][1]);
+                    }
+                    if (pref < 0) { ix[i1] = ix[n - 1]; n--; i1--; }
+                    else { ix[i0] = ix[n - 1]; n--; i0--; break; }
+                }
+            }
+            for (int i = 1; i < n; i++) {
+                const uint16_t t = ix[i];
+                int j = i;
+                while (j > 0 && det_less(r[t].d, r[ix[j - 1]].d)) { ix[j] = ix[j - 1]; j--; }
+                ix[j] = t;
+            }
+        } else {
+            for (int i = 1; i < n; i++) {
+                RawDet t = r[i];
+                int j = i;
+                while (j > 0 && det_less(t.d, r[j - 1].d)) { r[j] = r[j - 1]; j--; }
+                r[j] = t;
+            }
+            for (int i0 = 0; i0 < n; i0++) {
+                for (int i1 = i0 + 1; i1 < n; i1++) {
+                    const cb_detection &d0 = r[i0].d, &d1 = r[i1].d;
+                    if (d0.id != d1.id) continue;
+                    if (!polygons_overlap(d0.p, d1.p)) continue;
+                    int pref = 0;
+                    pref = prefer_smaller(pref, d0.hamming, d1.hamming);
+                    pref = prefer_smaller(pref, -d0.decision_margin, -d1.decision_margin);
+                    for (int i = 0; i < 4; i++) {
+                        pref = prefer_smaller(pref, d0.p[i][0], d1.p[i][0]);
+                        pref = prefer_smaller(pref, d0.p[i][1], d1.p[i][1]);
+                    }
+                    if (pref < 0) { r[i1] = r[n - 1]; n--; i1--; }
+                    else { r[i0] = r[n - 1]; n--; i0--; break; }
+                }
+            }
+            for (int i = 1; i < n; i++) {
+                RawDet t = r[i];
+                int j = i;
+                while (j > 0 && det_less(t.d, r[j - 1].d)) { r[j] = r[j - 1]; j--; }
+                r[j] = t;
+            }
         }
+        s_n[wid] = n;
     }
-    for (int i = 1; i < n; i++) {
-        RawDet t = r[i];
-        int j = i;
-        while (j > 0 && det_less(t.d, r[j - 1].d)) { r[j] = r[j - 1]; j--; }
-        r[j] = t;
-    }
+    __syncwarp();
+    n = s_n[wid];
     const int m = min(n, (int)caps.dets_per_frame);
-    for (int i = 0; i < m; i++) out[(size_t)b * caps.dets_per_frame + i] = r[i].d;
-    counts[b] = m;
+    static_assert(sizeof(cb_detection) % 4 == 0, "record copy works on 32-bit words");
+    constexpr int WORDS = (int)(sizeof(cb_detection) / 4);
+    uint32_t *o = reinterpret_cast<uint32_t *>(out + (size_t)b * caps.dets_per_frame);
+    for (int i = 0; i < m; i++) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&r[indexed ? ix[i] : i].d);
+        for (int w = lane; w < WORDS; w += 32) o[(size_t)i * WORDS + w] = src[w];
+    }
+    if (lane == 0) counts[b] = m;
 }
 
 }  // namespace cb
