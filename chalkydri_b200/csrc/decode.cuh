@@ -36,40 +36,70 @@ __device__ __forceinline__ void homography_project(const double *H, double x, do
     *oy = yy / zz;
 }
 
-__device__ bool homography_compute2(const double c[4][4], double *H)
+// homography_compute2(): 8x9 Gaussian elimination with partial pivoting, executed by a full warp.  Lane j (0..8) keeps
+// column j of the system in registers (no 72-double local array); the pivot search of column `col` runs on lane col, the
+// multipliers are broadcast by shuffle, and every element sees exactly the operations of the sequential code
+// (f = A[i][col] / A[col][col]; A[i][j] -= f * A[col][j]; back substitution summed in ascending i).
+__device__ __forceinline__ bool homography_compute2(const double c[4][4], double *H)
 {
-    double A[72];
+    const uint32_t full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double a[8];
+#pragma unroll
     for (int i = 0; i < 4; i++) {
-        double *r0 = &A[(2 * i) * 9], *r1 = &A[(2 * i + 1) * 9];
-        r0[0] = c[i][0]; r0[1] = c[i][1]; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0;
-        r0[6] = -c[i][0] * c[i][2]; r0[7] = -c[i][1] * c[i][2]; r0[8] = c[i][2];
-        r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = c[i][0]; r1[4] = c[i][1]; r1[5] = 1;
-        r1[6] = -c[i][0] * c[i][3]; r1[7] = -c[i][1] * c[i][3]; r1[8] = c[i][3];
+        const double cx = c[i][0], cy = c[i][1], cz = c[i][2], cw = c[i][3];
+        double r0, r1;
+        switch (lane) {
+            case 0: r0 = cx; r1 = 0; break;
+            case 1: r0 = cy; r1 = 0; break;
+            case 2: r0 = 1; r1 = 0; break;
+            case 3: r0 = 0; r1 = cx; break;
+            case 4: r0 = 0; r1 = cy; break;
+            case 5: r0 = 0; r1 = 1; break;
+            case 6: r0 = -cx * cz; r1 = -cx * cw; break;
+            case 7: r0 = -cy * cz; r1 = -cy * cw; break;
+            case 8: r0 = cz; r1 = cw; break;
+            default: r0 = 0; r1 = 0; break;
+        }
+        a[2 * i] = r0; a[2 * i + 1] = r1;
     }
     const double epsilon = 1e-10;
+#pragma unroll
     for (int col = 0; col < 8; col++) {
         double max_val = 0;
         int max_val_idx = -1;
+#pragma unroll
         for (int row = col; row < 8; row++) {
-            const double val = fabs(A[row * 9 + col]);
+            const double val = fabs(a[row]);
             if (val > max_val) { max_val = val; max_val_idx = row; }
         }
+        max_val = __shfl_sync(full, max_val, col);
+        max_val_idx = __shfl_sync(full, max_val_idx, col);
         if (max_val_idx < 0) return false;
         if (max_val < epsilon) return false;
-        if (max_val_idx != col)
-            for (int i = col; i < 9; i++) { const double t = A[col * 9 + i]; A[col * 9 + i] = A[max_val_idx * 9 + i]; A[max_val_idx * 9 + i] = t; }
+        if (max_val_idx != col) {
+#pragma unroll
+            for (int row = col + 1; row < 8; row++)
+                if (row == max_val_idx) { const double t = a[col]; a[col] = a[row]; a[row] = t; }
+        }
+        const double pivot = __shfl_sync(full, a[col], col);
+#pragma unroll
         for (int i = col + 1; i < 8; i++) {
-            const double f = A[i * 9 + col] / A[col * 9 + col];
-            A[i * 9 + col] = 0;
-            for (int j = col + 1; j < 9; j++) A[i * 9 + j] -= f * A[col * 9 + j];
+            const double f = __shfl_sync(full, a[i], col) / pivot;
+            if (lane == col) a[i] = 0;
+            else if (lane > col) a[i] -= f * a[col];
         }
     }
+    double x[8];
+#pragma unroll
     for (int col = 7; col >= 0; col--) {
         double sum = 0;
-        for (int i = col + 1; i < 8; i++) sum += A[col * 9 + i] * A[i * 9 + 8];
-        A[col * 9 + 8] = (A[col * 9 + 8] - sum) / A[col * 9 + col];
+#pragma unroll
+        for (int i = col + 1; i < 8; i++) sum += __shfl_sync(full, a[col], i) * x[i];
+        x[col] = (__shfl_sync(full, a[col], 8) - sum) / __shfl_sync(full, a[col], col);
     }
-    for (int i = 0; i < 8; i++) H[i] = A[i * 9 + 8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) H[i] = x[i];
     H[8] = 1;
     return true;
 }
