@@ -369,21 +369,25 @@ sort_clusters_kernel(uint32_t *__restrict__ scankey, ClusterRec *__restrict__ cl
         if (n < 24 || n < NMIN || n > NMAX) continue;
         if (WHICH == 2 && rec.cursor == 0xffffffffu) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
+        // NMAX <= MAXN: the global-memory variant is never needed (and not compiled into the kernel).
+        // (A half-E variant for the small clusters of the one-warp tiers measured slower: twice the code in the kernel.)
+        constexpr bool NEVER_GLOBAL = NMAX <= MAXN;
+        constexpr int EH = E;
         if (WHICH == 1) {
-            if (n <= MAXN)
-                sort_scan_cluster<NT, E, true>(scankey + pbase, n, reinterpret_cast<uint32_t *>(base),
-                                               reinterpret_cast<uint32_t *>(base + SH::ARRAY_BYTES), S, clusters + item, g, prm);
+            uint32_t *A = reinterpret_cast<uint32_t *>(base), *B = reinterpret_cast<uint32_t *>(base + SH::ARRAY_BYTES);
+            if (EH != E && n <= MAXN / 2) sort_scan_cluster<NT, EH, true>(scankey + pbase, n, A, B, S, clusters + item, g, prm);
+            else if (NEVER_GLOBAL || n <= MAXN) sort_scan_cluster<NT, E, true>(scankey + pbase, n, A, B, S, clusters + item, g, prm);
             else {
-                uint32_t *A = reinterpret_cast<uint32_t *>(scratch + pbase * 2);
-                sort_scan_cluster<NT, E, false>(scankey + pbase, n, A, A + n, S, clusters + item, g, prm);
+                uint32_t *GA = reinterpret_cast<uint32_t *>(scratch + pbase * 2);
+                sort_scan_cluster<NT, E, false>(scankey + pbase, n, GA, GA + n, S, clusters + item, g, prm);
             }
         } else {
-            if (n <= MAXN)
-                sort_slope_cluster<NT, E, true>(scankey + pbase, n, reinterpret_cast<unsigned long long *>(base),
-                                                reinterpret_cast<unsigned long long *>(base + SH::ARRAY_BYTES), S, g);
+            unsigned long long *A = reinterpret_cast<unsigned long long *>(base), *B = reinterpret_cast<unsigned long long *>(base + SH::ARRAY_BYTES);
+            if (EH != E && n <= MAXN / 2) sort_slope_cluster<NT, EH, true>(scankey + pbase, n, A, B, S, g);
+            else if (NEVER_GLOBAL || n <= MAXN) sort_slope_cluster<NT, E, true>(scankey + pbase, n, A, B, S, g);
             else {
-                unsigned long long *A = scratch + pbase * 2;
-                sort_slope_cluster<NT, E, false>(scankey + pbase, n, A, A + n, S, g);
+                unsigned long long *GA = scratch + pbase * 2;
+                sort_slope_cluster<NT, E, false>(scankey + pbase, n, GA, GA + n, S, g);
             }
         }
         if (NT == 32) __syncwarp();
