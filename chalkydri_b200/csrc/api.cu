@@ -429,8 +429,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         launches += 1;
         if (g.h > 2 && g.w > 2) {
             dim3 gc((g.w + CL_TW - 1) / CL_TW, (g.h - 2 + CL_TH - 1) / CL_TH, B);
-            cluster_pass_kernel<false><<<gc, CL_THREADS, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, ctx->d_clusters, ctx->d_scankey, d_misc, ctx->d_ent,
-                                                                  ctx->d_tile_keys, ctx->d_tile_cnt, g, caps);
+            cluster_count_kernel<<<gc, CL_THREADS, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, d_misc, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, g, caps);
             // misc: [0] error flags, [3] quads total, [4] decode counter, [8 + 2t] items of tier t, [9 + 2t] its work counter
             cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, wl_stride,
                                                                                             d_misc + 8, 2, (uint32_t)QT0, (uint32_t)QT1,

@@ -55,8 +55,7 @@ __device__ __forceinline__ uint32_t slot_find(const ClusterSlot *tab, uint32_t n
     return 0xffffffffu;
 }
 
-// One CTA per 64x16-pixel tile, one thread per pixel and step (4 steps).  SCATTER = false: count; true: write the points of
-// selected clusters.  The points of one cluster inside a tile (a stretch of boundary, typically 30..100 points) are first
+// One CTA per 64x16-pixel tile, one thread per pixel and step (4 steps).  The points of one cluster inside a tile (a stretch of boundary, typically 30..100 points) are first
 // aggregated in a 256-entry shared-memory table -- lanes with the same key elect a leader (match.any), the leader bumps the
 // tile-local count -- so the global table sees one probe and one atomic per (tile, cluster) instead of one per warp row and
 // probe direction.  In the scatter pass the tile-local count doubles as the rank of the point inside the tile's share of
@@ -65,7 +64,6 @@ constexpr int CL_TW = 64, CL_TH = 16, CL_THREADS = 256, CL_PER = CL_TW * CL_TH /
 struct ClShared {
     unsigned long long key[CL_CAP];
     uint32_t cnt[CL_CAP];
-    uint32_t base[CL_CAP];
 };
 
 // find-or-insert in the tile table; -1 when no free entry is found within CL_PROBES probes (the caller goes to the global table)
@@ -84,16 +82,15 @@ __device__ __forceinline__ int tile_insert(ClShared &S, unsigned long long key, 
     return -1;
 }
 
-// The count pass also saves what the scatter pass would have to recompute: the per-point words (16 bytes per pixel) and
+// The count pass also saves what the scatter pass would otherwise recompute: the per-point words (16 bytes per pixel) and
 // the tile's table (keys, counts), so the scatter pass (cluster_scatter_kernel) only reserves the tile's share of each
-// selected cluster and streams the points out.  SCATTER = true is the self-contained scatter pass (kept as a reference
-// path; the detector runs count + cluster_scatter_kernel).
+// selected cluster and streams the points out.  The step loop is kept rolled: unrolled four times the kernel was 66 KB of
+// code and stalled on instruction fetch.
 constexpr uint32_t CL_ENT_OVERFLOW = 0xfeu;     // point that did not get a tile entry: the scatter pass looks its cluster up itself
-template <bool SCATTER>
 __global__ void __launch_bounds__(CL_THREADS)
-cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, ClusterSlot *__restrict__ table,
-                    ClusterRec *__restrict__ clusters, uint32_t *__restrict__ scankey, uint32_t *__restrict__ errflag,
-                    uint4 *__restrict__ ent_out, unsigned long long *__restrict__ tile_keys, uint32_t *__restrict__ tile_cnt, Geom g, Caps caps)
+cluster_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, ClusterSlot *__restrict__ table,
+                     uint32_t *__restrict__ errflag, uint4 *__restrict__ ent_out, unsigned long long *__restrict__ tile_keys,
+                     uint32_t *__restrict__ tile_cnt, Geom g, Caps caps)
 {
     __shared__ ClShared S;
     const int b = blockIdx.z;
@@ -105,12 +102,11 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
     ClusterSlot *tab = table + (size_t)b * caps.slots_per_frame;
     for (int e = threadIdx.x; e < CL_CAP; e += CL_THREADS) { S.key[e] = EMPTY_KEY; S.cnt[e] = 0; }
     __syncthreads();
-    // per step and probe: tile entry (8 bits, 0xff = none) | rank inside the tile entry << 8 | gradient sign << 31
-    uint32_t ent[CL_PER][4];
     const int dxs[4] = {1, 0, -1, 1}, dys[4] = {0, 1, 1, 1};
-#pragma unroll
+    const int x = x0 + (wid & 1) * 32 + lane;
+#pragma unroll 1
     for (int it = 0; it < CL_PER; it++) {
-        const int x = x0 + (wid & 1) * 32 + lane, y = y0 + it * (CL_THREADS / CL_TW) + (wid >> 1);
+        const int y = y0 + it * (CL_THREADS / CL_TW) + (wid >> 1);
         const bool inside = x >= 1 && x <= g.w - 2 && y <= g.h - 2;
         uint32_t v0 = 127;
         if (inside) v0 = m[(size_t)y * g.tp + x];
@@ -128,9 +124,11 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
         }
         uint32_t rep0 = 0;
         if (emit[0] | emit[1] | emit[2] | emit[3]) rep0 = lab[(size_t)y * g.w + x];
+        // per probe: tile entry (8 bits, 0xff = none, 0xfe = overflow) | rank inside the tile entry << 8 | gradient sign << 31
+        uint32_t ent[4];
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-            ent[it][d] = 0xffu;
+            ent[d] = 0xffu;
             unsigned long long key = EMPTY_KEY;
             if (emit[d]) {
                 const uint32_t rep1 = lab[(size_t)(y + dys[d]) * g.w + x + dxs[d]];
@@ -151,76 +149,30 @@ cluster_pass_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict
             e = __shfl_sync(peers, e, leader);
             r0 = __shfl_sync(peers, r0, leader);
             if (e >= 0) {
-                ent[it][d] = (uint32_t)e | ((r0 + rank) << 8) | (sign << 31);
+                ent[d] = (uint32_t)e | ((r0 + rank) << 8) | (sign << 31);
                 continue;
             }
             // tile table full (a tile crossed by > ~200 clusters): straight to the global table
-            if (!SCATTER) {
-                ent[it][d] = CL_ENT_OVERFLOW | (sign << 31);
-                if (lane == leader) {
-                    const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
-                    if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
-                    else atomicAdd(&tab[s].count, npeers);
-                }
-            } else {
-                uint32_t pos = 0xffffffffu;
-                if (lane == leader) {
-                    const uint32_t s = slot_find(tab, caps.slots_per_frame, key);
-                    if (s != 0xffffffffu) {
-                        const uint32_t c = tab[s].cluster;
-                        if (c != 0xffffffffu) {
-                            ClusterRec *cr = clusters + (size_t)b * caps.clusters_per_frame + c;
-                            pos = cr->offset + atomicAdd(&cr->cursor, npeers);
-                        }
-                    }
-                }
-                pos = __shfl_sync(peers, pos, leader);
-                if (pos != 0xffffffffu)
-                    scankey[(size_t)b * caps.points_per_frame + pos + rank] = ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | sign;
+            ent[d] = CL_ENT_OVERFLOW | (sign << 31);
+            if (lane == leader) {
+                const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
+                if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
+                else atomicAdd(&tab[s].count, npeers);
             }
         }
-        if (!SCATTER && ent_out && x < g.w && y <= g.h - 2)
-            ent_out[(size_t)b * g.npix + (size_t)y * g.w + x] = make_uint4(ent[it][0], ent[it][1], ent[it][2], ent[it][3]);
+        if (x < g.w && y <= g.h - 2) ent_out[(size_t)b * g.npix + (size_t)y * g.w + x] = make_uint4(ent[0], ent[1], ent[2], ent[3]);
     }
     __syncthreads();
     // one global probe + atomic per (tile, cluster)
     const size_t tile = ((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     for (int e = threadIdx.x; e < CL_CAP; e += CL_THREADS) {
         const unsigned long long key = S.key[e];
-        if (!SCATTER && tile_keys) { tile_keys[tile * CL_CAP + e] = key; tile_cnt[tile * CL_CAP + e] = S.cnt[e]; }
+        tile_keys[tile * CL_CAP + e] = key;
+        tile_cnt[tile * CL_CAP + e] = S.cnt[e];
         if (key == EMPTY_KEY) continue;
-        if (!SCATTER) {
-            const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
-            if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
-            else atomicAdd(&tab[s].count, S.cnt[e]);
-        } else {
-            uint32_t base = 0xffffffffu;
-            const uint32_t s = slot_find(tab, caps.slots_per_frame, key);
-            if (s != 0xffffffffu) {
-                const uint32_t c = tab[s].cluster;
-                if (c != 0xffffffffu) {
-                    ClusterRec *cr = clusters + (size_t)b * caps.clusters_per_frame + c;
-                    base = cr->offset + atomicAdd(&cr->cursor, S.cnt[e]);
-                }
-            }
-            S.base[e] = base;
-        }
-    }
-    if (!SCATTER) return;
-    __syncthreads();
-    // a boundary point is fully described by (pixel, probe, gradient sign): 2x+dx, 2y+dy, g = d*(v1-v0)
-#pragma unroll
-    for (int it = 0; it < CL_PER; it++) {
-        const int x = x0 + (wid & 1) * 32 + lane, y = y0 + it * (CL_THREADS / CL_TW) + (wid >> 1);
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-            const uint32_t en = ent[it][d];
-            if ((en & 0xffu) == 0xffu) continue;
-            const uint32_t base = S.base[en & 0xffu];
-            if (base == 0xffffffffu) continue;
-            scankey[(size_t)b * caps.points_per_frame + base + ((en >> 8) & 0x7fffffu)] =
-                ((uint32_t)(y * g.w + x) << 3) | ((uint32_t)d << 1) | (en >> 31);
-        }
+        const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
+        if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
+        else atomicAdd(&tab[s].count, S.cnt[e]);
     }
 }
 
