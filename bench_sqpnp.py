@@ -1,7 +1,7 @@
 """BASELINE configs[4]: batched SQPnP pose solve for 1M tag corner sets vs the CPU solver (oracle restatement)."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from chalkydri_b200.solver import SqPnP
 from tests.sqpnp_problems import make_problems
 

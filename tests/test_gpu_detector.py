@@ -142,10 +142,10 @@ def test_shared_reciprocal_division_is_the_compilers_division(tmp_path):
 
 
 def test_randomised_frames_match_oracle(oracle):
-    """tools/fuzz_parity.py: odd sizes, random shapes / lines / noise / replicated tags; every stage compared with the oracle."""
+    """tests/fuzz_parity.py: odd sizes, random shapes / lines / noise / replicated tags; every stage compared with the oracle."""
     import subprocess, os, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "16", "2024"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_parity.py"), "16", "2024"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
