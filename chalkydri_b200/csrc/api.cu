@@ -49,6 +49,16 @@ struct cb_ctx {
     DecodeConst dc{};
     int sq_max_iter = 15;
     double sq_tol_sq = 1e-16;
+    // fused detect -> pose (cb_detect_pose_gray): field layout, camera, per-frame SQPnP problems
+    int32_t *d_field_ids = nullptr;
+    cb_iso3 *d_field_poses = nullptr;
+    int n_field = 0;
+    double *d_cam9 = nullptr;            // 9 intrinsics, then robot_to_cam (cb_iso3) behind them
+    bool camera_set = false;
+    uint8_t *d_pose_buf = nullptr;       // [tags | bearings | n_tags | gyro | poses | ok] for pose_cap frames
+    int pose_cap = 0;
+    bool pose_active = false;            // run_pipeline appends the chunk's problems at frame pose_frame_base
+    int pose_frame_base = 0;
     int num_sms = 148;
 
     // device buffers (sized for max_batch frames of max_w x max_h at decimation >= 1)
@@ -141,6 +151,7 @@ void cb_destroy(cb_ctx *ctx)
                     ctx->d_table, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
                     ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : {(void *)ctx->d_field_ids, (void *)ctx->d_field_poses, (void *)ctx->d_cam9, (void *)ctx->d_pose_buf}) if (p) cudaFree(p);
     if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -329,6 +340,29 @@ static int make_geom(cb_ctx *ctx, int width, int height, int stride, size_t fram
 
 // Runs the device pipeline on `d_frames` (device memory) up to `stage`.  Events: ev[1] start, ev[2] after threshold,
 // ev[3] after ccl, ev[4] after clusters, ev[5] after quads, ev[6] after decode+reconcile.
+// layout of d_pose_buf for pose_cap frames
+struct PoseBufs { cb_iso3 *tags; double *bearings; int32_t *n_tags; double *gyro; cb_pose *poses; uint8_t *ok; };
+static PoseBufs pose_bufs(cb_ctx *ctx)
+{
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t n = (size_t)ctx->pose_cap;
+    uint8_t *p = ctx->d_pose_buf;
+    PoseBufs b;
+    b.tags = (cb_iso3 *)p; p += up(n * SQ_MAX_TAGS * sizeof(cb_iso3));
+    b.bearings = (double *)p; p += up(n * SQ_MAX_TAGS * 12 * sizeof(double));
+    b.n_tags = (int32_t *)p; p += up(n * sizeof(int32_t));
+    b.gyro = (double *)p; p += up(n * sizeof(double));
+    b.poses = (cb_pose *)p; p += up(n * sizeof(cb_pose));
+    b.ok = p;
+    return b;
+}
+static size_t pose_buf_bytes(size_t n)
+{
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    return up(n * SQ_MAX_TAGS * sizeof(cb_iso3)) + up(n * SQ_MAX_TAGS * 12 * sizeof(double)) + up(n * sizeof(int32_t)) + up(n * sizeof(double)) +
+           up(n * sizeof(cb_pose)) + up(n);
+}
+
 static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int stage)
 {
     cudaStream_t st = ctx->stream;
@@ -479,6 +513,13 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         decode_quads_kernel<<<ctx->num_sms * 6, DEC_WARPS * 32, 0, st>>>(d_frames, ctx->d_quads, d_misc + 3, d_misc + 4, ctx->d_raw, d_nraw, g, caps, prm, ctx->dc);
         reconcile_kernel<<<(B + REC_WARPS - 1) / REC_WARPS, REC_WARPS * 32, 0, st>>>(ctx->d_raw, d_nraw, ctx->d_dets, ctx->d_counts, caps, B);
         launches += 2;
+        if (ctx->pose_active) {
+            PoseBufs pb = pose_bufs(ctx);
+            assemble_pose_problems_kernel<<<(B + 63) / 64, 64, 0, st>>>(ctx->d_dets, ctx->d_counts, (int)caps.dets_per_frame, ctx->d_field_ids, ctx->d_field_poses,
+                                                                         ctx->n_field, ctx->d_cam9, pb.gyro, SQ_MAX_TAGS, pb.tags, pb.bearings, pb.n_tags,
+                                                                         ctx->pose_frame_base, B);
+            launches++;
+        }
     }
     CK(cudaEventRecord(ctx->ev[6], st));
     CK(cudaGetLastError());
@@ -639,6 +680,7 @@ static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, 
         Geom g;
         int rc = make_geom(ctx, width, height, stride, dfs, n, g);
         if (rc) return rc;
+        ctx->pose_frame_base = b0;
         rc = run_pipeline(ctx, bufs[bi], g, ST_FULL);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_consumed[bi], ctx->stream));
@@ -686,6 +728,7 @@ int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, in
         Geom g;
         rc = make_geom(ctx, width, height, stride, dfs, n, g);
         if (rc) return rc;
+        ctx->pose_frame_base = b0;
         rc = detect_device_chunk(ctx, ctx->d_in, g, out + (size_t)b0 * ctx->caps.dets_per_frame, out_counts + b0, true);
         if (rc) return rc;
         for (int i = 0; i < n; i++)

@@ -648,15 +648,12 @@ sqpnp_kernel(const cb_iso3 *__restrict__ tags, const double *__restrict__ bearin
     }
 }
 
-// OpenCV-5 un-projection (crates/apriltags/src/lib.rs:316-321): one thread per pixel
-__global__ void unproject_opencv5_kernel(const double *__restrict__ params, const double *__restrict__ px, long long n,
-                                         double *__restrict__ bearings, uint8_t *__restrict__ ok)
+// OpenCV-5 un-projection (crates/apriltags/src/lib.rs:316-321): pixel -> bearing (x, y, 1) by fixed-point undistortion
+__device__ __forceinline__ bool unproject_opencv5(const double *__restrict__ params, double u, double v, double out[3])
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     const double fx = params[0], fy = params[1], cx = params[2], cy = params[3], k1 = params[4], k2 = params[5], p1 = params[6],
                  p2 = params[7], k3 = params[8];
-    const double xd = (px[2 * i] - cx) / fx, yd = (px[2 * i + 1] - cy) / fy;
+    const double xd = (u - cx) / fx, yd = (v - cy) / fy;
     double x = xd, y = yd;
     bool good = false;
     for (int it = 0; it < 100; it++) {
@@ -670,9 +667,56 @@ __global__ void unproject_opencv5_kernel(const double *__restrict__ params, cons
         x = xn; y = yn;
         if (e < 1e-24) { good = true; break; }
     }
-    if (!good || !isfinite(x) || !isfinite(y)) { ok[i] = 0; bearings[3 * i] = bearings[3 * i + 1] = bearings[3 * i + 2] = 0; return; }
-    bearings[3 * i] = x; bearings[3 * i + 1] = y; bearings[3 * i + 2] = 1.0;
-    ok[i] = 1;
+    if (!good || !isfinite(x) || !isfinite(y)) { out[0] = out[1] = out[2] = 0; return false; }
+    out[0] = x; out[1] = y; out[2] = 1.0;
+    return true;
+}
+
+// one thread per pixel
+__global__ void unproject_opencv5_kernel(const double *__restrict__ params, const double *__restrict__ px, long long n,
+                                         double *__restrict__ bearings, uint8_t *__restrict__ ok)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double b[3];
+    ok[i] = unproject_opencv5(params, px[2 * i], px[2 * i + 1], b) ? 1 : 0;
+    bearings[3 * i] = b[0]; bearings[3 * i + 1] = b[1]; bearings[3 * i + 2] = b[2];
+}
+
+// The body of AprilTags::process between detect() and solve_robot_pose() (crates/apriltags/src/lib.rs:303-327), one thread per
+// frame: detections in list order; tags missing from the field layout are skipped (:306-308); a tag is used only if all four
+// corners un-project (:324-327).  Writes frame b's SQPnP problem (tags, 4 bearings per tag, tag count); no gyro reading (NaN) or
+// no usable tag leaves the count at 0, which the solver answers with "None".  At most max_tags tags are used.
+__global__ void assemble_pose_problems_kernel(const cb_detection *__restrict__ dets, const int32_t *__restrict__ counts, int dets_per_frame,
+                                              const int32_t *__restrict__ field_ids, const cb_iso3 *__restrict__ field_poses, int n_field,
+                                              const double *__restrict__ cam9, const double *__restrict__ gyro, int max_tags,
+                                              cb_iso3 *__restrict__ tags, double *__restrict__ bearings, int32_t *__restrict__ n_tags,
+                                              int frame_base, int n_frames)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const int b = frame_base + f;
+    int used = 0;
+    const double gy = gyro[b];
+    if (gy == gy) {
+        const cb_detection *d = dets + (size_t)f * dets_per_frame;
+        const int n = counts[f];
+        for (int k = 0; k < n && used < max_tags; k++) {
+            int t = -1;
+            for (int q = 0; q < n_field; q++)
+                if (field_ids[q] == d[k].id) { t = q; break; }
+            if (t < 0) continue;
+            double br[4][3];
+            bool all = true;
+            for (int c = 0; c < 4; c++) all = unproject_opencv5(cam9, d[k].p[c][0], d[k].p[c][1], br[c]) && all;
+            if (!all) continue;
+            tags[(size_t)b * max_tags + used] = field_poses[t];
+            double *o = bearings + ((size_t)b * max_tags + used) * 12;
+            for (int c = 0; c < 4; c++) { o[3 * c] = br[c][0]; o[3 * c + 1] = br[c][1]; o[3 * c + 2] = br[c][2]; }
+            used++;
+        }
+    }
+    n_tags[b] = used;
 }
 
 }  // namespace cb

@@ -77,6 +77,58 @@ class AprilTags:
                 cam.append(bearings)
         return world, cam
 
+    def _configure_device_path(self):
+        """field layout + camera into the context once (cb_set_field / cb_set_camera)."""
+        if getattr(self, "_device_path_ready", False):
+            return
+        from . import capi
+        L = capi.lib()
+        ids = np.array(sorted(self.tags), np.int32)
+        poses = np.array([self.tags[int(i)] for i in ids], ISO_DTYPE)
+        self.detector._check(L.cb_set_field(self.detector.ctx, capi.ptr(ids), capi.ptr(poses), len(ids)))
+        r2c = None if self.robot_to_cam is None else np.ascontiguousarray(np.array(self.robot_to_cam, ISO_DTYPE))
+        self.detector._check(L.cb_set_camera(self.detector.ctx, capi.ptr(np.ascontiguousarray(self.cam_params, np.float64)),
+                                             None if r2c is None else capi.ptr(r2c)))
+        self._device_path_ready = True
+
+    def process_batch(self, now_us: int, frame_times_us, grays: np.ndarray, gyro=None):
+        """`process` for a batch of frames in ONE library call (cb_detect_pose_gray): detections never leave the device between
+        detect, field lookup, un-projection and the per-frame SQPnP.  gyro: per-frame yaw (None / NaN = no reading, like
+        comm.gyro_angle() == None); default: comm.gyro_angle() for every frame.  Publishes and returns per frame what `process`
+        would: (RobotPose, VisionUncertainty) or None."""
+        from . import capi
+        from .capi import DET_DTYPE, POSE_DTYPE
+        self._configure_device_path()
+        L = capi.lib()
+        grays = np.ascontiguousarray(grays)
+        B, H, W = grays.shape
+        if gyro is None:
+            gy = self.comm.gyro_angle()
+            gyro = [gy] * B
+        gy = np.array([np.nan if v is None else float(v) for v in gyro], np.float64)
+        out = np.zeros((B, 64), DET_DTYPE); counts = np.zeros(B, np.int32)
+        poses = np.zeros(B, POSE_DTYPE); ok = np.zeros(B, np.uint8); ntags = np.zeros(B, np.int32)
+        self.detector._check(L.cb_detect_pose_gray(self.detector.ctx, capi.ptr(grays), W, H, W, H * W, B, capi.ptr(gy), SIGN_FLIP_CONST,
+                                                   capi.ptr(out), capi.ptr(counts), capi.ptr(poses), capi.ptr(ok), capi.ptr(ntags)))
+        results = []
+        for b in range(B):
+            ts = now_us - int(frame_times_us[b])
+            if ok[b]:
+                rot = poses[b]["rot"].reshape(3, 3).T          # column-major like nalgebra
+                pos, std = poses[b]["pos"], poses[b]["std_devs"]
+                pose = RobotPose(pos[0], pos[1], euler_angles(rot)[2])
+                unc = VisionUncertainty(std[0], std[1], std[2])
+                self.comm.publish(self.cam_id, min(int(counts[b]), 255), ts, pose, unc)
+                results.append((pose, unc))
+                continue
+            now_ms = now_us // 1000
+            if self.last_time is None or (now_ms - self.last_time) > 5:
+                self.comm.publish(self.cam_id, 0, ts, RobotPose(), VisionUncertainty())
+                self.last_time = now_ms
+            results.append(None)
+        self.last_batch = (out, counts, poses, ok, ntags)
+        return results
+
     def process(self, now_us: int, frame_time_us: int, gray: np.ndarray):
         out, counts = self.detector.detect_batch(np.ascontiguousarray(gray)[None])
         dets = out[0, :counts[0]]

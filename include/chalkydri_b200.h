@@ -119,6 +119,22 @@ int cb_sqpnp_batch(cb_ctx *ctx, const cb_iso3 *tags, const double *bearings, con
 int cb_sqpnp_batch_device(cb_ctx *ctx, const cb_iso3 *tags, const double *bearings, const int32_t *n_tags, int max_tags,
                           const cb_iso3 *robot_to_cam, const double *gyro, double sign_change_error, int64_t n,
                           cb_pose *out, uint8_t *ok);
+/* ---- row B0, AprilTags::process on the device (crates/apriltags/src/lib.rs:293-379): detect -> field lookup -> un-project ->
+ *      one multi-tag SQPnP per frame, without the detections leaving the device in between.
+ *  cb_set_field: the tag layout of field.json (AprilTagFieldLayout, crates/apriltags/src/field_layout.rs:18-44); tags not in
+ *      it are skipped like lib.rs:306-308.
+ *  cb_set_camera: OpenCVModel5 intrinsics {fx, fy, cx, cy, k1, k2, p1, p2, k3} (lib.rs:232-233) and the robot->camera
+ *      transform from cb_create_solver_camera_transform; NULL = identity (lib.rs:333).
+ *  cb_detect_pose_gray: host frames in; detection lists like cb_detect_gray, plus per frame the Some((rot, pos, std_devs)) of
+ *      solve_robot_pose in poses[b] with pose_ok[b] = 1, or pose_ok[b] = 0 for None (no detections, no usable tag, solver
+ *      None) and for gyro[b] = NaN (comm.gyro_angle() == None, lib.rs:329).  pose_tags (optional): tags used per frame.
+ *      At most 16 tags per frame enter the solver. ---- */
+int cb_set_field(cb_ctx *ctx, const int32_t *ids, const cb_iso3 *poses, int n);
+int cb_set_camera(cb_ctx *ctx, const double *params9, const cb_iso3 *robot_to_cam);
+int cb_detect_pose_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
+                        const double *gyro, double sign_change_error, cb_detection *out, int32_t *out_counts, cb_pose *poses,
+                        uint8_t *pose_ok, int32_t *pose_tags);
+
 /* SqPnP::create_solver_camera_transform (lib.rs:430-461); host-side scalar helper */
 int cb_create_solver_camera_transform(double fwd_m, double left_m, double up_m, double roll_deg, double pitch_deg,
                                       double yaw_deg, cb_iso3 *out);
