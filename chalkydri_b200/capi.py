@@ -20,7 +20,10 @@ DET_DTYPE = np.dtype([("frame", "<i4"), ("id", "<i4"), ("hamming", "<i4"), ("dec
                       ("H", "<f8", (9,)), ("c", "<f8", (2,)), ("p", "<f8", (4, 2))])
 ISO_DTYPE = np.dtype([("t", "<f8", (3,)), ("q", "<f8", (4,))])
 POSE_DTYPE = np.dtype([("rot", "<f8", (9,)), ("pos", "<f8", (3,)), ("std_devs", "<f8", (3,))])
-assert DET_DTYPE.itemsize == 168 and ISO_DTYPE.itemsize == 56 and POSE_DTYPE.itemsize == 120
+# struct VisionMeasurement (crates/whacknet/src/lib.rs:40-66)
+VISION_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("rot", "<f8"), ("std_x", "<f8"), ("std_y", "<f8"), ("std_rot", "<f8"), ("ts", "<u8"),
+                         ("camera_id", "u1"), ("tag_count", "u1"), ("reserved", "u1", (6,))])
+assert DET_DTYPE.itemsize == 168 and ISO_DTYPE.itemsize == 56 and POSE_DTYPE.itemsize == 120 and VISION_DTYPE.itemsize == 64
 
 
 class Timing(C.Structure):
@@ -36,7 +39,7 @@ class Timing(C.Structure):
 EXPORTS = ["cb_create", "cb_destroy", "cb_last_error", "cb_set_family_tag36h11", "cb_set_params", "cb_detect_gray",
            "cb_detect_gray_device", "cb_detect_rgb", "cb_detect_yuyv", "cb_decimated_size", "cb_threshold", "cb_labels",
            "cb_quads", "cb_get_timing", "cb_sqpnp_set", "cb_sqpnp_batch", "cb_sqpnp_batch_device",
-           "cb_create_solver_camera_transform", "cb_unproject_opencv5", "cb_set_field", "cb_set_camera", "cb_detect_pose_gray", "cb_cat_calc_otsu", "cb_cat_thresh",
+           "cb_create_solver_camera_transform", "cb_unproject_opencv5", "cb_set_field", "cb_set_camera", "cb_detect_pose_gray", "cb_pack_vision_measurements", "cb_cat_calc_otsu", "cb_cat_thresh",
            "cb_cat_detect_corners", "cb_cat_check_edges", "cb_cat_connected_components", "cb_host_alloc", "cb_host_free",
            "cb_device_alloc", "cb_device_free", "cb_memcpy_h2d", "cb_memcpy_d2h", "cb_device_count", "cb_version"]
 
@@ -75,6 +78,7 @@ def lib():
         L.cb_sqpnp_batch_device.argtypes = [vp, vp, vp, vp, i32, vp, vp, f64, i64, vp, vp]
         L.cb_create_solver_camera_transform.argtypes = [f64] * 6 + [vp]
         L.cb_unproject_opencv5.argtypes = [vp, vp, vp, i64, vp, vp]
+        L.cb_pack_vision_measurements.argtypes = [vp, vp, vp, vp, C.c_uint8, i32, vp]
         L.cb_set_field.argtypes = [vp, vp, vp, i32]
         L.cb_set_camera.argtypes = [vp, vp, vp]
         L.cb_detect_pose_gray.argtypes = [vp, vp, i32, i32, i32, sz, i32, vp, f64, vp, vp, vp, vp, vp]

@@ -135,6 +135,22 @@ int cb_detect_pose_gray(cb_ctx *ctx, const uint8_t *frames, int width, int heigh
                         const double *gyro, double sign_change_error, cb_detection *out, int32_t *out_counts, cb_pose *poses,
                         uint8_t *pose_ok, int32_t *pose_tags);
 
+/* ---- output contract of the task: the 64-byte record whacknet sends to the robot controller
+ *      (struct VisionMeasurement, crates/whacknet/src/lib.rs:40-66; the reference's one test checks its size, :92-95) ---- */
+typedef struct {
+    double x, y, rot;             /* RobotPose (whacknet/src/lib.rs:17-26): position x, y and yaw */
+    double std_x, std_y, std_rot; /* VisionUncertainty (:29-38) */
+    uint64_t ts;                  /* microseconds */
+    uint8_t camera_id;
+    uint8_t tag_count;
+    uint8_t reserved[6];
+} cb_vision_measurement;
+/* What AprilTags::process publishes for frame i (crates/apriltags/src/lib.rs:340-376): pose_ok[i] != 0 -> {x = pos[0],
+ * y = pos[1], rot = Rotation3::euler_angles().2, the three std-devs, tag_count = min(det_counts[i], 255)}; otherwise the
+ * heartbeat record (default pose and uncertainty, tag_count 0).  Host-side arithmetic only; ts_us[i] is copied through. */
+int cb_pack_vision_measurements(const cb_pose *poses, const uint8_t *pose_ok, const int32_t *det_counts, const uint64_t *ts_us,
+                                uint8_t camera_id, int n, cb_vision_measurement *out);
+
 /* SqPnP::create_solver_camera_transform (lib.rs:430-461); host-side scalar helper */
 int cb_create_solver_camera_transform(double fwd_m, double left_m, double up_m, double roll_deg, double pitch_deg,
                                       double yaw_deg, cb_iso3 *out);

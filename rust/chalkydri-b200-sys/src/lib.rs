@@ -55,12 +55,26 @@ unsafe extern "C" {
     pub fn cb_create_solver_camera_transform(fwd: f64, left: f64, up: f64, roll_deg: f64, pitch_deg: f64, yaw_deg: f64,
                                              out: *mut cb_iso3) -> c_int;
     pub fn cb_unproject_opencv5(ctx: *mut cb_ctx, params9: *const f64, px: *const f64, n: i64, bearings: *mut f64, ok: *mut u8) -> c_int;
+    pub fn cb_pack_vision_measurements(poses: *const cb_pose, pose_ok: *const u8, det_counts: *const i32, ts_us: *const u64, camera_id: u8,
+                                       n: c_int, out: *mut cb_vision_measurement) -> c_int;
     // AprilTags::process on the device: field layout + camera once, then frames in -> detections and poses out
     pub fn cb_set_field(ctx: *mut cb_ctx, ids: *const i32, poses: *const cb_iso3, n: c_int) -> c_int;
     pub fn cb_set_camera(ctx: *mut cb_ctx, params9: *const f64, robot_to_cam: *const cb_iso3) -> c_int;
     pub fn cb_detect_pose_gray(ctx: *mut cb_ctx, frames: *const u8, width: c_int, height: c_int, stride: c_int, frame_stride: usize,
                                batch: c_int, gyro: *const f64, sign_change_error: f64, out: *mut cb_detection, out_counts: *mut i32,
                                poses: *mut cb_pose, pose_ok: *mut u8, pose_tags: *mut i32) -> c_int;
+}
+
+/// whacknet's 64-byte wire record (crates/whacknet/src/lib.rs:40-66)
+#[repr(C)]
+#[derive(Debug, Default, Clone, Copy)]
+pub struct cb_vision_measurement {
+    pub x: f64, pub y: f64, pub rot: f64,
+    pub std_x: f64, pub std_y: f64, pub std_rot: f64,
+    pub ts: u64,
+    pub camera_id: u8,
+    pub tag_count: u8,
+    pub reserved: [u8; 6],
 }
 
 #[derive(Debug)]

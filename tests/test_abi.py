@@ -40,6 +40,31 @@ def test_record_layouts():
     assert C.sizeof(capi.Timing) == 9 * 4 + 8
 
 
+def test_vision_measurement_contract(lib):
+    """The reference's one test: size_of::<VisionMeasurement>() == 64 (crates/whacknet/src/lib.rs:92-95); plus what
+    AprilTags::process publishes per frame (crates/apriltags/src/lib.rs:340-376)."""
+    from chalkydri_b200 import capi
+    from chalkydri_b200.solver import euler_angles
+    assert capi.VISION_DTYPE.itemsize == 64
+    poses = np.zeros(3, capi.POSE_DTYPE)
+    a = 0.7
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    poses[0]["rot"] = R.T.reshape(-1)                       # column-major
+    poses[0]["pos"] = (1.5, -2.25, 0.3)
+    poses[0]["std_devs"] = (0.01, 0.02, 0.03)
+    poses[2] = poses[0]
+    ok = np.array([1, 0, 1], np.uint8)
+    counts = np.array([3, 5, 400], np.int32)
+    ts = np.array([10, 20, 30], np.uint64)
+    out = np.zeros(3, capi.VISION_DTYPE)
+    assert lib.cb_pack_vision_measurements(capi.ptr(poses), capi.ptr(ok), capi.ptr(counts), capi.ptr(ts), 7, 3, capi.ptr(out)) == 0
+    assert out["ts"].tolist() == [10, 20, 30] and out["camera_id"].tolist() == [7, 7, 7]
+    assert out["tag_count"].tolist() == [3, 0, 255]                      # None -> heartbeat record; count saturates like u8::MAX
+    assert out[0]["x"] == 1.5 and out[0]["y"] == -2.25 and abs(out[0]["rot"] - euler_angles(R)[2]) < 1e-15
+    assert (out[0]["std_x"], out[0]["std_y"], out[0]["std_rot"]) == (0.01, 0.02, 0.03)
+    assert out[1]["x"] == 0 and out[1]["rot"] == 0 and out[1]["std_x"] == 0
+
+
 def test_version_and_no_cpu_fallback(lib):
     assert b"sm_100a" in lib.cb_version()
     import torch
