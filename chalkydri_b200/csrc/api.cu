@@ -57,8 +57,11 @@ struct cb_ctx {
     bool camera_set = false;
     uint8_t *d_pose_buf = nullptr;       // [tags | bearings | n_tags | gyro | poses | ok] for pose_cap frames
     int pose_cap = 0;
-    bool pose_active = false;            // run_pipeline appends the chunk's problems at frame pose_frame_base
+    bool pose_active = false;            // run_pipeline appends the chunk's problems at frame pose_frame_base ...
     int pose_frame_base = 0;
+    double pose_sign_change_error = 0;   // ... and solves them on pose_stream, under the kernels of the next chunk
+    cudaStream_t pose_stream = nullptr;
+    cudaEvent_t ev_pose_ready = nullptr, ev_pose_done = nullptr;
     int num_sms = 148;
 
     // device buffers (sized for max_batch frames of max_w x max_h at decimation >= 1)
@@ -158,6 +161,9 @@ void cb_destroy(cb_ctx *ctx)
     if (ctx->h_chunk_err) cudaFreeHost(ctx->h_chunk_err);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->pose_stream) cudaStreamDestroy(ctx->pose_stream);
+    if (ctx->ev_pose_ready) cudaEventDestroy(ctx->ev_pose_ready);
+    if (ctx->ev_pose_done) cudaEventDestroy(ctx->ev_pose_done);
     for (int i = 0; i < 4; i++) { if (ctx->tier_stream[i]) cudaStreamDestroy(ctx->tier_stream[i]); if (ctx->ev_tier[i]) cudaEventDestroy(ctx->ev_tier[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -204,6 +210,8 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->pose_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_pose_ready, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_pose_done, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 4; i++) ok = ok && cudaStreamCreateWithFlags(&ctx->tier_stream[i], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_tier[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2; i++) ok = ok && cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
@@ -340,6 +348,8 @@ static int make_geom(cb_ctx *ctx, int width, int height, int stride, size_t fram
 
 // Runs the device pipeline on `d_frames` (device memory) up to `stage`.  Events: ev[1] start, ev[2] after threshold,
 // ev[3] after ccl, ev[4] after clusters, ev[5] after quads, ev[6] after decode+reconcile.
+static int sqpnp_launch(cb_ctx *ctx, const cb_iso3 *d_tags, const double *d_bear, const int32_t *d_nt, int max_tags, const cb_iso3 *d_r2c,
+                        const double *d_gyro, double sign_change_error, int64_t n, cb_pose *d_out, uint8_t *d_ok, cudaStream_t stream = nullptr);
 // layout of d_pose_buf for pose_cap frames
 struct PoseBufs { cb_iso3 *tags; double *bearings; int32_t *n_tags; double *gyro; cb_pose *poses; uint8_t *ok; };
 static PoseBufs pose_bufs(cb_ctx *ctx)
@@ -518,7 +528,16 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             assemble_pose_problems_kernel<<<(B + 63) / 64, 64, 0, st>>>(ctx->d_dets, ctx->d_counts, (int)caps.dets_per_frame, ctx->d_field_ids, ctx->d_field_poses,
                                                                          ctx->n_field, ctx->d_cam9, pb.gyro, SQ_MAX_TAGS, pb.tags, pb.bearings, pb.n_tags,
                                                                          ctx->pose_frame_base, B);
-            launches++;
+            // a few hundred problems are one latency-bound wave of warps (~2 ms): solved on a side stream they disappear
+            // behind the next chunk's detection kernels
+            CK(cudaEventRecord(ctx->ev_pose_ready, st));
+            CK(cudaStreamWaitEvent(ctx->pose_stream, ctx->ev_pose_ready, 0));
+            const size_t o = (size_t)ctx->pose_frame_base;
+            int prc = sqpnp_launch(ctx, pb.tags + o * SQ_MAX_TAGS, pb.bearings + o * SQ_MAX_TAGS * 12, pb.n_tags + o, SQ_MAX_TAGS,
+                                   (const cb_iso3 *)(ctx->d_cam9 + 9), pb.gyro + o, ctx->pose_sign_change_error, B, pb.poses + o, pb.ok + o,
+                                   ctx->pose_stream);
+            if (prc) return prc;
+            launches += 2;
         }
     }
     CK(cudaEventRecord(ctx->ev[6], st));
