@@ -184,24 +184,34 @@ __device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q
     // ---- refine_edges ----------------------------------------------------------------------------------
     if (prm.refine_edges) {
         double lines[4][4];
-        for (int edge = 0; edge < 4; edge++) {
+        // Two edges at a time, one per half-warp (a tag edge below ~136 px has 16 samples, which would leave half of a warp
+        // idle): lanes 0..15 take edge 2*pass, lanes 16..31 edge 2*pass + 1, sixteen samples per step each.
+        const int half = lane >> 4, hl = lane & 15;
+        for (int pass = 0; pass < 2; pass++) {
+            const int edge = 2 * pass + half;
             const int a = edge, bb = (edge + 1) & 3;
-            double nx = (double)p[bb][1] - (double)p[a][1];
-            double ny = -(double)p[bb][0] + (double)p[a][0];
+            // (p[][] is indexed with a lane-dependent edge: select instead of dynamic indexing)
+            const double pax = (double)(a == 0 ? p[0][0] : a == 1 ? p[1][0] : a == 2 ? p[2][0] : p[3][0]);
+            const double pay = (double)(a == 0 ? p[0][1] : a == 1 ? p[1][1] : a == 2 ? p[2][1] : p[3][1]);
+            const double pbx = (double)(bb == 0 ? p[0][0] : bb == 1 ? p[1][0] : bb == 2 ? p[2][0] : p[3][0]);
+            const double pby = (double)(bb == 0 ? p[0][1] : bb == 1 ? p[1][1] : bb == 2 ? p[2][1] : p[3][1]);
+            double nx = pby - pay;
+            double ny = -pbx + pax;
             const double mag = sqrt(nx * nx + ny * ny);
             nx /= mag; ny /= mag;
             if (q.reversed_border) { nx = -nx; ny = -ny; }
             const int nsamples = max(16, (int)(mag / 8));
+            const int nsamples_max = max(nsamples, __shfl_xor_sync(full, nsamples, 16));
             double Mx = 0, My = 0, Mxx = 0, Mxy = 0, Myy = 0, N = 0;
             const double range = (double)prm.quad_decimate + 1;
-            for (int s0 = 0; s0 < nsamples; s0 += 32) {
-                const int s = s0 + lane;
+            for (int s0 = 0; s0 < nsamples_max; s0 += 16) {
+                const int s = s0 + hl;
                 double bestx = 0, besty = 0;
                 int have = 0;
                 if (s < nsamples) {
                     const double alpha = (1.0 + s) / (nsamples + 1);
-                    const double x0 = alpha * (double)p[a][0] + (1 - alpha) * (double)p[bb][0];
-                    const double y0 = alpha * (double)p[a][1] + (1 - alpha) * (double)p[bb][1];
+                    const double x0 = alpha * pax + (1 - alpha) * pbx;
+                    const double y0 = alpha * pay + (1 - alpha) * pby;
                     double Mn = 0, Mcount = 0;
                     // upstream: for (double n = -range; n <= range; n += 0.25).  k*0.25 - range is exact in binary, so the steps are
                     // enumerated by index; five steps (ten gathers) are kept in flight at a time.  weight and weight*n are exact
@@ -233,11 +243,11 @@ __device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q
                         have = 1;
                     }
                 }
-                // replay the accumulation in sample order (uniform across lanes)
-                const int cnt = min(32, nsamples - s0);
-                for (int k = 0; k < cnt; k++) {
-                    const int hv = __shfl_sync(full, have, k);
-                    const double bx = __shfl_sync(full, bestx, k), by = __shfl_sync(full, besty, k);
+                // replay the accumulation in sample order inside each half-warp (samples beyond an edge's count have have = 0)
+                for (int k = 0; k < 16; k++) {
+                    const int src = (lane & 16) | k;
+                    const int hv = __shfl_sync(full, have, src);
+                    const double bx = __shfl_sync(full, bestx, src), by = __shfl_sync(full, besty, src);
                     if (hv) { Mx += bx; My += by; Mxx += bx * bx; Mxy += bx * by; Myy += by * by; N++; }
                 }
             }
@@ -246,7 +256,11 @@ __device__ void decode_one_quad(const uint8_t *__restrict__ in, const QuadRec &q
             const double normal_theta = .5 * atan2f((float)(-2 * Cxy), (float)(Cyy - Cxx));
             nx = cosf((float)normal_theta);
             ny = sinf((float)normal_theta);
-            lines[edge][0] = Ex; lines[edge][1] = Ey; lines[edge][2] = nx; lines[edge][3] = ny;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                lines[2 * pass + h][0] = __shfl_sync(full, Ex, 16 * h); lines[2 * pass + h][1] = __shfl_sync(full, Ey, 16 * h);
+                lines[2 * pass + h][2] = __shfl_sync(full, nx, 16 * h); lines[2 * pass + h][3] = __shfl_sync(full, ny, 16 * h);
+            }
         }
         for (int i = 0; i < 4; i++) {
             const double A00 = lines[i][3], A01 = -lines[(i + 1) & 3][3];
