@@ -154,7 +154,7 @@ fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ so
         const double *errs = errs_all + pbase;
 
         // ---- smoothed errors, local maxima, running top list (descending error; ties: lower index first) ----
-        double te = __longlong_as_double(0xfff0000000000000ll);
+        double te = __longlong_as_double(0xfff0000000000000ll), t11 = te;     // t11: error of the 11th list entry (-inf while the list is short)
         int ti = 1 << 30, nm = 0;
         // tile loads run one step ahead of their use (the errs array comes from L2 / HBM)
         auto load_err = [&](int idx) { if (idx < 0) idx += n; while (idx >= n) idx -= n; return errs[idx]; };
@@ -180,8 +180,9 @@ fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ so
                 e = S.ys[lane + 1];
                 is_max = e > S.ys[lane + 2] && e > S.ys[lane];
             }
-            uint32_t bal = __ballot_sync(full, is_max);
-            nm += __popc(bal);
+            nm += __popc(__ballot_sync(full, is_max));
+            // only maxima above the current 11th best can enter the list (an equal error with a later index cannot)
+            uint32_t bal = __ballot_sync(full, is_max && e > t11);
             while (bal) {
                 const int src = __ffs(bal) - 1;
                 bal &= bal - 1;
@@ -191,6 +192,7 @@ fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ so
                 const int up_ti = __shfl_up_sync(full, ti, 1);
                 if (lane == pos) { te = ev; ti = j0 + src; }
                 else if (lane > pos) { te = up_te; ti = up_ti; }
+                t11 = __shfl_sync(full, te, 10);
             }
             __syncwarp();
         }
