@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def result(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -129,7 +129,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
