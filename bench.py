@@ -51,16 +51,40 @@ def make_frames(rank: int, batch: int = BATCH, unique: int = 16):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML (the library behind nvidia-smi; a query takes
+    microseconds, so the region gets dozens of samples), falling back to the nvidia-smi command line of the profiling recipe."""
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
-        self.gpu, self.samples, self.reasons, self.stop_flag, self.max_mhz = gpu_index, [], set(), False, None
+        self.gpu, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.source = gpu_index, [], set(), False, None, None
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # CUDA_VISIBLE_DEVICES remaps ordinals: resolve the physical device through its UUID / PCI bus id when torch knows it
+        try:
+            import torch
+            h = nv.nvmlDeviceGetHandleByPciBusId(torch.cuda.get_device_properties(self.gpu).pci_bus_id.encode()) \
+                if hasattr(torch.cuda.get_device_properties(self.gpu), "pci_bus_id") else nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
+        while not self.stop_flag:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for n, b in bits.items():
+                if r & b:
+                    self.reasons.add(n)
+            time.sleep(0.01)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
@@ -74,9 +98,15 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.02)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def result(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 def cpu_baseline(frames: np.ndarray, seconds_target: float = 12.0):
