@@ -650,7 +650,7 @@ static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, 
     std::vector<int> cstart;
     {
         const int min_first = (int)std::max<size_t>(1, ((size_t)16 << 20) / std::max<size_t>(bytes, 1));   // a first copy of >= 16 MB
-        const int s1 = std::max(std::min(8, std::max(min_first, 1)), std::min(half, batch / 8));
+        const int s1 = std::min(half, std::max(std::min(8, std::max(min_first, 1)), batch / 8));      // never more than one buffer half
         int b0 = 0, k = 0;
         while (b0 < batch) {
             const int sz = k == 0 ? s1 : (k == 1 ? std::min(half, 3 * s1) : half);

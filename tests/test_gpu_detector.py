@@ -149,6 +149,17 @@ def test_randomised_frames_match_oracle(oracle):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_small_capacity_context_large_batch(oracle):
+    """A context with room for 8 frames fed 72: the pipelined host path must never put more than half its capacity in flight."""
+    frames, _ = synth.render_batch(640, 480, 72, 2, seed=5, unique=6, edge_px=(50, 110))
+    det = make_detector(640, 480, 8)
+    out, counts = det.detect_batch(frames)
+    for b in (0, 1, 5, 7, 8, 30, 71):
+        assert_same_detections(out[b, :counts[b]], oracle.detect(frames[b]))
+    assert counts.sum() >= 72
+    det.close()
+
+
 def test_cluster_tile_table_overflow_path(oracle, monkeypatch):
     """CB_TILE_PROBES=1 makes every hash collision in the per-tile cluster table take the overflow path (global table)."""
     monkeypatch.setenv("CB_TILE_PROBES", "1")
