@@ -48,6 +48,7 @@ struct cb_ctx {
     DetParams prm{};
     DecodeConst dc{};
     int sq_max_iter = 15;
+    bool sq_attr_set = false;
     double sq_tol_sq = 1e-16;
     // fused detect -> pose (cb_detect_pose_gray): field layout, camera, per-frame SQPnP problems
     int32_t *d_field_ids = nullptr;
