@@ -4,13 +4,17 @@
 // Python (chalkydri_b200/*.py).  Names, argument meaning and failure behaviour follow
 //   apriltag::{DetectorBuilder, Detector, Detection}   /root/reference/crates/apriltags/src/lib.rs:19,258-261,301-314
 //   chalkydri_sqpnp::SqPnP                              /root/reference/crates/chalkydri_sqpnp/src/lib.rs:183-304,430-461
+//   the Copper task AprilTags (new / process)           /root/reference/crates/apriltags/src/lib.rs:166-379
 // Config errors throw (the reference unwrap()s / panics), the solver returns std::optional (the reference: Option).
 #pragma once
 #include <array>
+#include <cmath>
 #include <cstdint>
+#include <functional>
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "chalkydri_b200.h"
@@ -77,6 +81,7 @@ class Detector {
     }
     cb_timing timing() const { cb_timing t; cb_get_timing(ctx_, &t); return t; }
     cb_ctx *ctx() { return ctx_; }
+    int max_dets() const { return max_dets_; }
 
   private:
     void check(int rc) { if (rc != CB_OK) throw Error(rc, cb_last_error(ctx_)); }
@@ -150,6 +155,71 @@ class SqPnP {
     cb_ctx *ctx_ = nullptr;
     int max_iter_ = 15;
     double tol_ = 1e-8;
+};
+
+// ---- whacknet/src/lib.rs:17-38 ----
+struct RobotPose { double x = 0, y = 0, rot = 0; };
+struct VisionUncertainty { double x = 0, y = 0, rot = 0; };
+
+// What the task needs from whacknet::Comm (whacknet/src/lib.rs:152-178): the gyro reading and the publish call.
+struct Comm {
+    std::function<std::optional<double>()> gyro_angle;
+    std::function<void(uint8_t cam_id, uint8_t tag_count, uint64_t ts_us, const RobotPose &, const VisionUncertainty &)> publish;
+};
+
+// Mirror of the Copper sink task `AprilTags` (crates/apriltags/src/lib.rs:166-379) on the fused device call: detect, field
+// lookup, un-projection and the multi-tag SQPnP run inside cb_detect_pose_gray; this class keeps the task's publish / heartbeat
+// rules (lib.rs:340-376).
+class AprilTags {
+  public:
+    // field: tag id -> pose (field.json, field_layout.rs:18-44); calib: OpenCVModel5 {fx, fy, cx, cy, k1, k2, p1, p2, k3}
+    // (lib.rs:232-233); robot_to_cam: SqPnP::create_solver_camera_transform(...) or nullopt (lib.rs:277-290)
+    AprilTags(const DetectorBuilder &builder, const std::vector<std::pair<int32_t, cb_iso3>> &field, const std::array<double, 9> &calib,
+              std::optional<cb_iso3> robot_to_cam, uint8_t cam_id, Comm comm)
+        : det_(builder.build()), cam_id_(cam_id), comm_(std::move(comm))
+    {
+        std::vector<int32_t> ids;
+        std::vector<cb_iso3> poses;
+        for (const auto &kv : field) { ids.push_back(kv.first); poses.push_back(kv.second); }
+        check(cb_set_field(det_.ctx(), ids.data(), poses.data(), (int)ids.size()));
+        check(cb_set_camera(det_.ctx(), calib.data(), robot_to_cam ? &*robot_to_cam : nullptr));
+    }
+
+    // process(clock.now(), tov, image) -> the pose it published, if any
+    std::optional<std::pair<RobotPose, VisionUncertainty>> process(uint64_t now_us, uint64_t frame_time_us, const Image &image)
+    {
+        constexpr double SIGN_FLIP_CONST = 600.0;                                 // crates/apriltags/src/lib.rs:6
+        const std::optional<double> gyro = comm_.gyro_angle ? comm_.gyro_angle() : std::nullopt;
+        const double g = gyro ? *gyro : std::nan("");
+        std::vector<cb_detection> dets((size_t)det_.max_dets());
+        int32_t count = 0, used = 0;
+        cb_pose pose{};
+        uint8_t ok = 0;
+        check(cb_detect_pose_gray(det_.ctx(), image.buf, image.width, image.height, image.stride, (size_t)image.stride * image.height, 1, &g,
+                                  SIGN_FLIP_CONST, dets.data(), &count, &pose, &ok, &used));
+        const uint64_t ts = now_us - frame_time_us;
+        if (ok) {
+            cb_vision_measurement m{};
+            check(cb_pack_vision_measurements(&pose, &ok, &count, &ts, cam_id_, 1, &m));
+            const RobotPose rp{m.x, m.y, m.rot};
+            const VisionUncertainty vu{m.std_x, m.std_y, m.std_rot};
+            if (comm_.publish) comm_.publish(cam_id_, m.tag_count, ts, rp, vu);
+            return std::make_pair(rp, vu);
+        }
+        const uint64_t now_ms = now_us / 1000;
+        if (!last_time_ || now_ms - *last_time_ > 5) {                            // empty heartbeat at most every 5 ms (lib.rs:365-376)
+            if (comm_.publish) comm_.publish(cam_id_, 0, ts, RobotPose{}, VisionUncertainty{});
+            last_time_ = now_ms;
+        }
+        return std::nullopt;
+    }
+
+  private:
+    void check(int rc) { if (rc != CB_OK) throw Error(rc, cb_last_error(det_.ctx())); }
+    Detector det_;
+    uint8_t cam_id_;
+    Comm comm_;
+    std::optional<uint64_t> last_time_;
 };
 
 }  // namespace chalkydri

@@ -14,7 +14,18 @@ int main(int argc, char **argv)
         chalkydri::Image im{img.data(), 640, 480, 640};
         auto d = det.detect(im);
         std::printf("detections on a flat frame: %zu\n", d.size());
-        return d.empty() ? 0 : 2;
+        // the task mirror on the fused device call: a flat frame publishes the heartbeat once
+        int published = 0;
+        chalkydri::Comm comm;
+        comm.gyro_angle = [] { return std::optional<double>(0.25); };
+        comm.publish = [&](uint8_t, uint8_t tags, uint64_t, const chalkydri::RobotPose &, const chalkydri::VisionUncertainty &) { published += tags == 0; };
+        cb_iso3 tag{};
+        tag.q[0] = 1.0;
+        chalkydri::AprilTags task(chalkydri::DetectorBuilder::default_().add_family_bits("tag36h11", 3).capacity(640, 480, 1, 16), {{1, tag}},
+                                  {500, 500, 320, 240, 0, 0, 0, 0, 0}, std::nullopt, 7, comm);
+        const auto r = task.process(1000000, 990000, im);
+        std::printf("task on a flat frame: pose %s, heartbeats %d\n", r ? "some" : "none", published);
+        return d.empty() && !r && published == 1 ? 0 : 2;
     } catch (const chalkydri::Error &e) {
         std::printf("no usable GPU: %s\n", e.what());
         return cb_device_count() == 0 ? 0 : 3;    // loud failure is the expected behaviour on a CPU-only host
