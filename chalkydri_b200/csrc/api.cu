@@ -43,6 +43,18 @@ struct cb_ctx {
     cudaStream_t tier_stream[4]{};                 // the size tiers of the two cluster sorts run side by side
     cudaEvent_t ev_fork = nullptr, ev_tier[4]{};
     uint32_t *h_chunk_err = nullptr;              // pinned: error flag of every chunk of a pipelined call
+    // streaming form (cb_detect_gray_submit / cb_detect_gray_collect): up to two batches in flight, each with its own pinned
+    // staging, so the H2D copy of batch k+1 runs under the kernels of batch k
+    struct StreamSlot {
+        cb_detection *h_dets = nullptr;
+        int32_t *h_counts = nullptr;
+        uint32_t *h_err = nullptr;               // error flag per chunk
+        cudaEvent_t start = nullptr, done = nullptr;
+        int batch = 0, nchunks = 0, launches = 0, thr_launches = 0;
+    } ss[2];
+    int ss_head = 0, ss_pending = 0;
+    unsigned ss_chunk = 0;                       // batches submitted so far: parity picks d_in or d_in2
+    uint8_t *d_in2 = nullptr;                    // second input buffer of the streaming form (allocated on the first submit)
     std::string err;
     bool family_set = false;
     DetParams prm{};
@@ -114,6 +126,12 @@ static int fail(cb_ctx *c, int code, const char *fmt, ...)
         if (e_ != cudaSuccess) return fail(ctx, CB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// the synchronous entry points share buffers with batches still in flight on the streaming form
+#define CB_NOT_STREAMING(ctx)                                                                                                            \
+    do {                                                                                                                                 \
+        if ((ctx)->ss_pending) return fail(ctx, CB_ERR_STATE, "%d submitted batch(es) not collected yet: call cb_detect_gray_collect first", (ctx)->ss_pending); \
+    } while (0)
+
 static uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
 __global__ void table_init_kernel(ClusterSlot *t, size_t n)
@@ -151,15 +169,25 @@ void cb_destroy(cb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);      // batches submitted and never collected
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
                     ctx->d_table, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
                     ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (ctx->d_in2) cudaFree(ctx->d_in2);
     for (void *p : {(void *)ctx->d_field_ids, (void *)ctx->d_field_poses, (void *)ctx->d_cam9, (void *)ctx->d_pose_buf}) if (p) cudaFree(p);
     if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->h_chunk_err) cudaFreeHost(ctx->h_chunk_err);
+    for (auto &sl : ctx->ss) {
+        if (sl.h_dets) cudaFreeHost(sl.h_dets);
+        if (sl.h_counts) cudaFreeHost(sl.h_counts);
+        if (sl.h_err) cudaFreeHost(sl.h_err);
+        if (sl.start) cudaEventDestroy(sl.start);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->pose_stream) cudaStreamDestroy(ctx->pose_stream);
@@ -619,6 +647,7 @@ int cb_detect_gray_device(cb_ctx *ctx, const uint8_t *frames_dev, int width, int
                           int batch, cb_detection *out, int32_t *out_counts)
 {
     if (!ctx || !frames_dev || !out || !out_counts) return CB_ERR_ARG;
+    CB_NOT_STREAMING(ctx);
     CK(cudaSetDevice(ctx->device));
     cb_timing acc{};
     for (int b0 = 0; b0 < batch; b0 += ctx->max_batch) {
@@ -729,6 +758,7 @@ int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, in
                    cb_detection *out, int32_t *out_counts)
 {
     if (!ctx || !frames || !out || !out_counts) return CB_ERR_ARG;
+    CB_NOT_STREAMING(ctx);
     CK(cudaSetDevice(ctx->device));
     if ((size_t)stride * height > ctx->max_npix) return fail(ctx, CB_ERR_ARG, "stride*height exceeds the context's frame capacity");
     if (!ctx->family_set) return fail(ctx, CB_ERR_STATE, "no tag family set: call cb_set_family_tag36h11 first");
@@ -759,11 +789,100 @@ int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, in
     return CB_OK;
 }
 
+// ---- streaming form: a continuous feed of batches (the reference's camera loop hands frames over from a 4-slot host pool,
+//      crates/chalkydri/src/cameras/gst_to_cu.rs:66,72) ----
+// submit() only enqueues: the H2D copy of a batch goes to the one of two whole-batch input buffers that the batch before the
+// previous one has released, on the copy stream, so it runs under the kernels of the batch in front of it, and the kernels
+// see the batch in one piece (no chunking: 180 GB of HBM hold a second input buffer easily).  collect() waits for the oldest batch.
+int cb_detect_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch)
+{
+    if (!ctx || !frames) return CB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->family_set) return fail(ctx, CB_ERR_STATE, "no tag family set: call cb_set_family_tag36h11 first");
+    if (ctx->ss_pending >= 2) return fail(ctx, CB_ERR_STATE, "two batches are already in flight: call cb_detect_gray_collect first");
+    if (batch < 1 || batch > ctx->max_batch) return fail(ctx, CB_ERR_ARG, "submit batch %d outside 1..max_batch (%d)", batch, ctx->max_batch);
+    if ((size_t)stride * height > ctx->max_npix) return fail(ctx, CB_ERR_ARG, "stride*height exceeds the context's frame capacity");
+    {
+        Geom g;
+        int rc = make_geom(ctx, width, height, stride, frame_stride, 1, g);      // argument validation
+        if (rc) return rc;
+    }
+    const size_t D = ctx->caps.dets_per_frame;
+    cb_ctx::StreamSlot &sl = ctx->ss[(ctx->ss_head + ctx->ss_pending) & 1];
+    if (!sl.h_dets) {
+        CK(cudaMallocHost((void **)&sl.h_dets, (size_t)ctx->max_batch * D * sizeof(cb_detection)));
+        CK(cudaMallocHost((void **)&sl.h_counts, (size_t)ctx->max_batch * sizeof(int32_t)));
+        CK(cudaMallocHost((void **)&sl.h_err, 8 * sizeof(uint32_t)));
+        CK(cudaEventCreate(&sl.start));
+        CK(cudaEventCreate(&sl.done));
+    }
+    if (!ctx->d_in2) CK(cudaMalloc((void **)&ctx->d_in2, ctx->in_bytes + 64));
+    const size_t bytes = (size_t)stride * height;
+    const size_t dfs = (bytes + 15) / 16 * 16;
+    const int nbuf = 2;
+    const int half = ctx->max_batch;             // one chunk per batch
+    uint8_t *bufs[2] = {ctx->d_in, ctx->d_in2};
+    sl.batch = batch; sl.nchunks = 0; sl.launches = 0; sl.thr_launches = 0;
+    CK(cudaEventRecord(sl.start, ctx->copy_stream));
+    for (int b0 = 0; b0 < batch; b0 += half) {
+        const int n = std::min(half, batch - b0), bi = (int)(ctx->ss_chunk % nbuf), c = sl.nchunks;
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[bi], 0));
+        if (frame_stride == dfs) CK(cudaMemcpyAsync(bufs[bi], frames + (size_t)b0 * frame_stride, (size_t)n * frame_stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+        else CK(cudaMemcpy2DAsync(bufs[bi], dfs, frames + (size_t)b0 * frame_stride, frame_stride, bytes, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copied[bi], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[bi], 0));
+        Geom g;
+        int rc = make_geom(ctx, width, height, stride, dfs, n, g);
+        if (rc) return rc;
+        rc = run_pipeline(ctx, bufs[bi], g, ST_FULL);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_consumed[bi], ctx->stream));
+        CK(cudaMemcpyAsync(sl.h_dets + (size_t)b0 * D, ctx->d_dets, (size_t)n * D * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(sl.h_counts + b0, ctx->d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(sl.h_err + c, ctx->d_small + 4 * (size_t)ctx->max_batch, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        sl.launches += ctx->timing.kernel_launches;
+        sl.thr_launches += ctx->timing.threshold_launches;
+        sl.nchunks++;
+        ctx->ss_chunk++;
+    }
+    CK(cudaEventRecord(sl.done, ctx->stream));
+    ctx->ss_pending++;
+    return CB_OK;
+}
+
+int cb_detect_gray_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts)
+{
+    if (!ctx || !out || !out_counts) return CB_ERR_ARG;
+    if (ctx->ss_pending == 0) return fail(ctx, CB_ERR_STATE, "nothing to collect: no batch has been submitted");
+    CK(cudaSetDevice(ctx->device));
+    cb_ctx::StreamSlot &sl = ctx->ss[ctx->ss_head];
+    const cudaError_t e = cudaEventSynchronize(sl.done);
+    ctx->ss_head ^= 1;            // the batch leaves the queue whatever its outcome
+    ctx->ss_pending--;
+    if (e != cudaSuccess) return fail(ctx, CB_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+    for (int c = 0; c < sl.nchunks; c++)
+        if (sl.h_err[c]) { ctx->h_small[4 * (size_t)ctx->max_batch] = sl.h_err[c]; return check_errflag(ctx); }
+    const size_t D = ctx->caps.dets_per_frame;
+    for (int b = 0; b < sl.batch; b++) {
+        out_counts[b] = sl.h_counts[b];
+        memcpy(out + (size_t)b * D, sl.h_dets + (size_t)b * D, (size_t)out_counts[b] * sizeof(cb_detection));
+        for (int k = 0; k < out_counts[b]; k++) out[(size_t)b * D + k].frame = b;
+    }
+    cb_timing t{};
+    cudaEventElapsedTime(&t.total_ms, sl.start, sl.done);      // first copy queued -> lists on the host (includes waiting behind the batch in front)
+    t.kernel_launches = sl.launches; t.threshold_launches = sl.thr_launches;
+    ctx->timing = t;
+    return CB_OK;
+}
+
+int cb_detect_gray_pending(const cb_ctx *ctx) { return ctx ? ctx->ss_pending : CB_ERR_ARG; }
+
 // pre-processing front ends: convert into a gray buffer on the device, then the gray pipeline
 static int detect_converted(cb_ctx *ctx, const uint8_t *frames, int width, int height, int bytes_per_px, int batch, cb_detection *out,
                             int32_t *out_counts)
 {
     if (!ctx || !frames || !out || !out_counts) return CB_ERR_ARG;
+    CB_NOT_STREAMING(ctx);
     CK(cudaSetDevice(ctx->device));
     if (width > ctx->max_w || height > ctx->max_h) return fail(ctx, CB_ERR_ARG, "frame larger than the context's capacity");
     const size_t npix = (size_t)width * height;
@@ -820,6 +939,7 @@ int cb_detect_yuyv(cb_ctx *ctx, const uint8_t *frames_yuyv, int width, int heigh
 static int tap_common(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, int stage, Geom &g)
 {
     if (!ctx || !frames) return CB_ERR_ARG;
+    CB_NOT_STREAMING(ctx);
     CK(cudaSetDevice(ctx->device));
     if (batch > ctx->max_batch) return fail(ctx, CB_ERR_ARG, "tap batch %d exceeds max_batch %d", batch, ctx->max_batch);
     if ((size_t)stride * height > ctx->max_npix) return fail(ctx, CB_ERR_ARG, "stride*height exceeds the context's frame capacity");

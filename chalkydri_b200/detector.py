@@ -103,6 +103,7 @@ class Detector:
             raise ChalkydriError(capi.CB_ERR_CUDA, L.cb_last_error(None).decode())
         self.max_batch, self.max_dets = max_batch, max_dets
         self.device = device
+        self._inflight = []          # (frames, batch) of submitted batches: keeps the host arrays alive until collect()
         self._check(L.cb_set_family_tag36h11(self._ctx, bits_corrected))
 
     def close(self):
@@ -148,6 +149,33 @@ class Detector:
             counts = np.zeros(B, np.int32)
         self._check(self._L.cb_detect_gray(self._ctx, capi.ptr(frames), W, H, W, H * W, B, capi.ptr(out), capi.ptr(counts)))
         return out, counts
+
+    # ---- streaming form: submit batch k+1 before collecting batch k, and its H2D copy runs under batch k's kernels ----
+    def submit(self, frames: np.ndarray):
+        """Enqueue frames [B,H,W] u8 (B <= max_batch; keep the array alive and unchanged until collect())."""
+        if frames.dtype != np.uint8 or frames.ndim != 3 or not frames.flags.c_contiguous:
+            raise ValueError("frames must be a C-contiguous [B,H,W] uint8 array")
+        B, H, W = frames.shape
+        self._check(self._L.cb_detect_gray_submit(self._ctx, capi.ptr(frames), W, H, W, H * W, B))
+        self._inflight.append((frames, B))
+
+    def collect(self, out: np.ndarray | None = None, counts: np.ndarray | None = None):
+        """Wait for the oldest submitted batch -> (detections [B,max_dets], counts [B]) like detect_batch."""
+        B = self._inflight[0][1] if self._inflight else 1          # nothing in flight: the library reports CB_ERR_STATE
+        if out is None:
+            out = np.zeros((B, self.max_dets), DET_DTYPE)
+        if counts is None:
+            counts = np.zeros(B, np.int32)
+        try:
+            self._check(self._L.cb_detect_gray_collect(self._ctx, capi.ptr(out), capi.ptr(counts)))
+        finally:
+            if self._inflight:
+                self._inflight.pop(0)
+        return out, counts
+
+    @property
+    def pending(self) -> int:
+        return int(self._L.cb_detect_gray_pending(self._ctx))
 
     def detect_batch_device(self, dev_ptr: int, B: int, H: int, W: int, stride: int | None = None, frame_stride: int | None = None,
                             out: np.ndarray | None = None, counts: np.ndarray | None = None):

@@ -34,6 +34,53 @@ class VisionUncertainty:     # whacknet/src/lib.rs (x, y, rot std-devs)
     rot: float = 0.0
 
 
+MAX_DETECTIONS = 16          # crates/apriltags/src/lib.rs:42
+
+
+class AprilTagDetections:
+    """The task's detection payload (crates/apriltags/src/lib.rs:47-52): three parallel fixed-capacity lists (`CuArrayVec<_, 16>`)
+    of tag id, tag pose (`CuPose<f32>`, a 4x4 f32 transform) and decision margin.  Serialised like the reference's serde impls
+    (:69-121): a sequence of `(id, pose, decision_margin)` tuples.  Pushing beyond the capacity raises, like `ArrayVec::push`."""
+
+    def __init__(self):
+        self.ids: list[int] = []
+        self.poses: list[np.ndarray] = []
+        self.decision_margins: list[float] = []
+
+    def push(self, tag_id: int, pose, decision_margin: float):
+        if len(self.ids) >= MAX_DETECTIONS:
+            raise OverflowError(f"AprilTagDetections holds at most {MAX_DETECTIONS} detections")
+        self.ids.append(int(tag_id))
+        self.poses.append(np.asarray(pose, np.float32).reshape(4, 4))
+        self.decision_margins.append(float(np.float32(decision_margin)))
+
+    @staticmethod
+    def from_detections(dets, poses=None) -> "AprilTagDetections":
+        """From a frame's detection records (DET_DTYPE); poses: per-detection 4x4 transforms (identity when absent)."""
+        r = AprilTagDetections()
+        for i, d in enumerate(dets[:MAX_DETECTIONS]):
+            r.push(d["id"], np.eye(4) if poses is None else poses[i], d["decision_margin"])
+        return r
+
+    def filtered_by_decision_margin(self, threshold: float):
+        """lib.rs:127-141: `(id, &pose, margin)` of the detections whose margin is strictly above the threshold, in order."""
+        thr = np.float32(threshold)
+        return ((i, p, m) for i, p, m in zip(self.ids, self.poses, self.decision_margins) if np.float32(m) > thr)
+
+    def to_tuples(self):                     # impl Serialize, lib.rs:69-87
+        return [(i, p.tolist(), m) for i, p, m in zip(self.ids, self.poses, self.decision_margins)]
+
+    @staticmethod
+    def from_tuples(seq) -> "AprilTagDetections":        # impl Deserialize, lib.rs:89-121
+        r = AprilTagDetections()
+        for i, p, m in seq:
+            r.push(i, p, m)
+        return r
+
+    def __len__(self):
+        return len(self.ids)
+
+
 def calib_params(calib_json: str):
     m = json.loads(calib_json)["OpenCVModel5"]
     return np.array([m[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3")], np.float64)

@@ -86,6 +86,21 @@ int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, in
 /* same with the frames already resident in device memory (frames_dev is a device pointer) */
 int cb_detect_gray_device(cb_ctx *ctx, const uint8_t *frames_dev, int width, int height, int stride,
                           size_t frame_stride, int batch, cb_detection *out, int32_t *out_counts);
+/* Streaming form of cb_detect_gray for a continuous feed of batches: the reference's camera loop hands frames to
+ * AprilTags::process one after another from a 4-slot host pool (crates/chalkydri/src/cameras/gst_to_cu.rs:66,72;
+ * crates/apriltags/src/lib.rs:293-301), so batch k+1 is already in host memory while batch k is being detected.
+ *   cb_detect_gray_submit  enqueues one batch (1..max_batch frames, same argument meaning as cb_detect_gray) and returns
+ *                          without waiting; at most two batches may be in flight (CB_ERR_STATE beyond that).  The frames
+ *                          must stay valid and unchanged until the batch has been collected; pinned memory
+ *                          (cb_host_alloc) lets the H2D copy of batch k+1 run under the kernels of batch k.
+ *   cb_detect_gray_collect waits for the OLDEST submitted batch and writes its lists exactly like cb_detect_gray
+ *                          (CB_ERR_STATE when nothing is in flight).  A failed batch still leaves the queue.
+ *   cb_detect_gray_pending number of submitted, not yet collected batches (0..2).
+ * While batches are in flight every other detection / tap entry point of the context returns CB_ERR_STATE. */
+int cb_detect_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride,
+                          int batch);
+int cb_detect_gray_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts);
+int cb_detect_gray_pending(const cb_ctx *ctx);
 /* packed-RGB input (CAT contract, crates/chalkydri-apriltags/src/lib.rs:265-267): gray = utils.rs:43 */
 int cb_detect_rgb(cb_ctx *ctx, const uint8_t *frames_rgb, int width, int height, int batch, cb_detection *out,
                   int32_t *out_counts);

@@ -79,6 +79,14 @@ class Detector {
     {
         check(cb_detect_gray(ctx_, frames, w, h, stride, frame_stride, batch, out, counts));
     }
+    // streaming form for a continuous feed (the camera loop's 4-slot host pool, gst_to_cu.rs:66,72): submit batch k+1, then
+    // collect batch k -- its H2D copy runs under batch k's kernels.  At most two batches in flight; frames stay valid until collected.
+    void submit(const uint8_t *frames, int w, int h, int stride, size_t frame_stride, int batch)
+    {
+        check(cb_detect_gray_submit(ctx_, frames, w, h, stride, frame_stride, batch));
+    }
+    void collect(cb_detection *out, int32_t *counts) { check(cb_detect_gray_collect(ctx_, out, counts)); }
+    int pending() const { return cb_detect_gray_pending(ctx_); }
     cb_timing timing() const { cb_timing t; cb_get_timing(ctx_, &t); return t; }
     cb_ctx *ctx() { return ctx_; }
     int max_dets() const { return max_dets_; }

@@ -48,6 +48,10 @@ unsafe extern "C" {
     pub fn cb_set_family_tag36h11(ctx: *mut cb_ctx, bits_corrected: c_int) -> c_int;
     pub fn cb_detect_gray(ctx: *mut cb_ctx, frames: *const u8, width: c_int, height: c_int, stride: c_int, frame_stride: usize,
                           batch: c_int, out: *mut cb_detection, out_counts: *mut i32) -> c_int;
+    pub fn cb_detect_gray_submit(ctx: *mut cb_ctx, frames: *const u8, width: c_int, height: c_int, stride: c_int, frame_stride: usize,
+                                 batch: c_int) -> c_int;
+    pub fn cb_detect_gray_collect(ctx: *mut cb_ctx, out: *mut cb_detection, out_counts: *mut i32) -> c_int;
+    pub fn cb_detect_gray_pending(ctx: *const cb_ctx) -> c_int;
     pub fn cb_sqpnp_set(ctx: *mut cb_ctx, max_iter: c_int, tolerance: f64) -> c_int;
     pub fn cb_sqpnp_batch(ctx: *mut cb_ctx, tags: *const cb_iso3, bearings: *const f64, n_tags: *const i32, max_tags: c_int,
                           robot_to_cam: *const cb_iso3, gyro: *const f64, sign_change_error: f64, n: i64, out: *mut cb_pose,
@@ -142,6 +146,19 @@ impl Detector {
         };
         if rc != 0 { panic!("chalkydri_b200: {}", last_error(self.ctx)); } // the reference unwraps as well
         self.out[..count as usize].iter().map(|d| Detection(*d)).collect()
+    }
+    /// Streaming form: enqueue a batch of frames (`frame_stride` bytes apart) and return at once; at most two batches in
+    /// flight.  The borrow keeps the frames alive: the caller holds `frames` until the matching `collect`.
+    pub fn submit(&mut self, frames: &[u8], width: i32, height: i32, stride: i32, frame_stride: usize, batch: i32) -> Result<(), String> {
+        assert!(frames.len() >= frame_stride * (batch as usize - 1) + (stride as usize) * (height as usize));
+        let rc = unsafe { cb_detect_gray_submit(self.ctx, frames.as_ptr(), width, height, stride, frame_stride, batch) };
+        if rc != 0 { Err(last_error(self.ctx)) } else { Ok(()) }
+    }
+    /// Wait for the oldest submitted batch: `out[b * max_dets + k]`, `counts[b]`.
+    pub fn collect(&mut self, out: &mut [cb_detection], counts: &mut [i32]) -> Result<(), String> {
+        assert!(out.len() >= counts.len() * self.max_dets);
+        let rc = unsafe { cb_detect_gray_collect(self.ctx, out.as_mut_ptr(), counts.as_mut_ptr()) };
+        if rc != 0 { Err(last_error(self.ctx)) } else { Ok(()) }
     }
     pub fn raw(&self) -> *mut cb_ctx { self.ctx }
 }

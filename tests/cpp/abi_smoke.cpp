@@ -14,6 +14,15 @@ int main(int argc, char **argv)
         chalkydri::Image im{img.data(), 640, 480, 640};
         auto d = det.detect(im);
         std::printf("detections on a flat frame: %zu\n", d.size());
+        // streaming form: two batches in flight, collected oldest first
+        std::vector<cb_detection> lists(16);
+        int32_t n1 = -1, n2 = -1;
+        det.submit(img.data(), 640, 480, 640, (size_t)640 * 480, 1);
+        det.submit(img.data(), 640, 480, 640, (size_t)640 * 480, 1);
+        det.collect(lists.data(), &n1);
+        det.collect(lists.data(), &n2);
+        std::printf("streaming: %d + %d detections, %d pending\n", n1, n2, det.pending());
+        if (n1 != 0 || n2 != 0 || det.pending() != 0) return 4;
         // the task mirror on the fused device call: a flat frame publishes the heartbeat once
         int published = 0;
         chalkydri::Comm comm;

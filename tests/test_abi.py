@@ -120,3 +120,23 @@ def test_cpp_mirror_compiles_and_fails_loudly(lib, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "version chalkydri_b200" in r.stdout
+
+
+def test_apriltag_detections_payload():
+    """AprilTagDetections (crates/apriltags/src/lib.rs:47-141): capacity 16, strict margin filter, tuple round trip."""
+    from chalkydri_b200 import capi
+    from chalkydri_b200.pipeline import MAX_DETECTIONS, AprilTagDetections
+    dets = np.zeros(20, capi.DET_DTYPE)
+    dets["id"] = np.arange(20)
+    dets["decision_margin"] = np.linspace(10, 105, 20, dtype=np.float32)
+    a = AprilTagDetections.from_detections(dets)
+    assert len(a) == MAX_DETECTIONS == 16
+    with pytest.raises(OverflowError):
+        a.push(99, np.eye(4), 1.0)
+    kept = list(a.filtered_by_decision_margin(float(dets["decision_margin"][4])))
+    assert [k[0] for k in kept] == list(range(5, 16))                 # strictly greater, order kept
+    assert kept[0][1].dtype == np.float32 and kept[0][1].shape == (4, 4)
+    b = AprilTagDetections.from_tuples(a.to_tuples())
+    assert b.ids == a.ids and b.decision_margins == a.decision_margins
+    assert all((p == q).all() for p, q in zip(a.poses, b.poses))
+    assert list(AprilTagDetections().filtered_by_decision_margin(0.0)) == []

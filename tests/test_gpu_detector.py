@@ -322,3 +322,63 @@ def test_error_behaviour():
     with pytest.raises(ChalkydriError):
         det._check(det._L.cb_set_family_tag36h11(det.ctx, 4))
     det.close()
+
+
+def test_streaming_submit_collect_matches_the_synchronous_call(oracle):
+    """cb_detect_gray_submit / _collect: batches of different sizes, two in flight, results identical to cb_detect_gray
+    (bit for bit: same kernels, same chunk rule apart from the chunk sizes) and to the oracle on sampled frames."""
+    from chalkydri_b200 import capi
+    det = make_detector(640, 480, 8)
+    batches = []
+    for i, n in enumerate((8, 5, 1, 8, 3)):
+        f, _ = synth.render_batch(640, 480, n, 2, seed=20 + i, unique=min(n, 4), edge_px=(50, 110))
+        h = capi.pinned_array(f.shape, np.uint8)
+        h[...] = f
+        batches.append(h)
+    want = [tuple(a.copy() for a in det.detect_batch(b)) for b in batches]
+    got = []
+    det.submit(batches[0])
+    for k in range(len(batches)):
+        if k + 1 < len(batches):
+            det.submit(batches[k + 1])
+            assert det.pending == 2
+        got.append(det.collect())
+    assert det.pending == 0
+    for (o, c), (wo, wc), b in zip(got, want, batches):
+        assert c.tolist() == wc.tolist()
+        for i in range(len(c)):
+            assert o[i, :c[i]].tobytes() == wo[i, :c[i]].tobytes()
+        assert_same_detections(o[0, :c[0]], oracle.detect(np.asarray(b[0])))
+    det.detect_batch(batches[1])                  # the synchronous call works again once the queue is empty
+    det.close()
+    for b in batches:
+        capi.free_pinned(b)
+
+
+def test_streaming_queue_rules():
+    from chalkydri_b200.capi import ChalkydriError, CB_ERR_STATE
+    det = make_detector(640, 480, 4)
+    f = np.full((2, 480, 640), 128, np.uint8)
+    with pytest.raises(ChalkydriError) as e:
+        det.collect()                                                   # nothing submitted
+    assert e.value.code == CB_ERR_STATE
+    with pytest.raises(ChalkydriError):
+        det.submit(np.zeros((5, 480, 640), np.uint8))                   # more than max_batch
+    det.submit(f)
+    det.submit(f)
+    with pytest.raises(ChalkydriError) as e:
+        det.submit(f)                                                   # a third batch in flight
+    assert e.value.code == CB_ERR_STATE
+    with pytest.raises(ChalkydriError) as e:
+        det.detect_batch(f)                                             # synchronous call while batches are in flight
+    assert e.value.code == CB_ERR_STATE
+    with pytest.raises(ChalkydriError):
+        det.threshold(f)
+    _, c = det.collect()
+    assert c.tolist() == [0, 0]
+    det.collect()
+    assert det.pending == 0
+    det.close()
+    det2 = make_detector(640, 480, 4)              # destroying a context with a batch still in flight is safe
+    det2.submit(f)
+    det2.close()
