@@ -39,7 +39,7 @@ class Timing(C.Structure):
 EXPORTS = ["cb_create", "cb_destroy", "cb_last_error", "cb_set_family_tag36h11", "cb_set_params", "cb_detect_gray",
            "cb_detect_gray_device", "cb_detect_gray_submit", "cb_detect_gray_collect", "cb_detect_gray_pending", "cb_detect_rgb", "cb_detect_yuyv", "cb_decimated_size", "cb_threshold", "cb_labels",
            "cb_quads", "cb_get_timing", "cb_sqpnp_set", "cb_sqpnp_batch", "cb_sqpnp_batch_device",
-           "cb_create_solver_camera_transform", "cb_unproject_opencv5", "cb_set_field", "cb_set_camera", "cb_detect_pose_gray", "cb_pack_vision_measurements", "cb_cat_calc_otsu", "cb_cat_thresh",
+           "cb_create_solver_camera_transform", "cb_unproject_opencv5", "cb_set_field", "cb_set_camera", "cb_detect_pose_gray", "cb_detect_pose_gray_submit", "cb_detect_pose_gray_collect", "cb_pack_vision_measurements", "cb_cat_calc_otsu", "cb_cat_thresh",
            "cb_cat_detect_corners", "cb_cat_check_edges", "cb_cat_connected_components", "cb_host_alloc", "cb_host_free",
            "cb_device_alloc", "cb_device_free", "cb_memcpy_h2d", "cb_memcpy_d2h", "cb_device_count", "cb_version"]
 
@@ -85,6 +85,8 @@ def lib():
         L.cb_set_field.argtypes = [vp, vp, vp, i32]
         L.cb_set_camera.argtypes = [vp, vp, vp]
         L.cb_detect_pose_gray.argtypes = [vp, vp, i32, i32, i32, sz, i32, vp, f64, vp, vp, vp, vp, vp]
+        L.cb_detect_pose_gray_submit.argtypes = [vp, vp, i32, i32, i32, sz, i32, vp, f64]
+        L.cb_detect_pose_gray_collect.argtypes = [vp, vp, vp, vp, vp, vp]
         L.cb_cat_calc_otsu.argtypes = [vp, vp, i32, i32, vp]
         L.cb_cat_thresh.argtypes = [vp, vp, i32, i32, vp]
         L.cb_cat_detect_corners.argtypes = [vp, vp, i32, i32, vp, i64, vp]

@@ -51,6 +51,13 @@ struct cb_ctx {
         uint32_t *h_err = nullptr;               // error flag per chunk
         cudaEvent_t start = nullptr, done = nullptr;
         int batch = 0, nchunks = 0, launches = 0, thr_launches = 0;
+        // fused detect -> pose batches (cb_detect_pose_gray_submit): gyro staging in, poses out
+        bool has_pose = false;
+        double *h_gyro = nullptr;
+        cb_pose *h_poses = nullptr;
+        uint8_t *h_ok = nullptr;
+        int32_t *h_ntags = nullptr;
+        cudaEvent_t pose_done = nullptr;
     } ss[2];
     int ss_head = 0, ss_pending = 0;
     unsigned ss_chunk = 0;                       // batches submitted so far: parity picks d_in or d_in2
@@ -170,6 +177,7 @@ void cb_destroy(cb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);      // batches submitted and never collected
+    if (ctx->pose_stream) cudaStreamSynchronize(ctx->pose_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
                     ctx->d_table, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
@@ -187,6 +195,11 @@ void cb_destroy(cb_ctx *ctx)
         if (sl.h_err) cudaFreeHost(sl.h_err);
         if (sl.start) cudaEventDestroy(sl.start);
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.h_gyro) cudaFreeHost(sl.h_gyro);
+        if (sl.h_poses) cudaFreeHost(sl.h_poses);
+        if (sl.h_ok) cudaFreeHost(sl.h_ok);
+        if (sl.h_ntags) cudaFreeHost(sl.h_ntags);
+        if (sl.pose_done) cudaEventDestroy(sl.pose_done);
     }
     for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -794,7 +807,10 @@ int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, in
 // submit() only enqueues: the H2D copy of a batch goes to the one of two whole-batch input buffers that the batch before the
 // previous one has released, on the copy stream, so it runs under the kernels of the batch in front of it, and the kernels
 // see the batch in one piece (no chunking: 180 GB of HBM hold a second input buffer easily).  collect() waits for the oldest batch.
-int cb_detect_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch)
+}  // extern "C"
+
+static int stream_submit(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
+                         const double *gyro, double sign_change_error)
 {
     if (!ctx || !frames) return CB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -817,6 +833,30 @@ int cb_detect_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int hei
         CK(cudaEventCreate(&sl.done));
     }
     if (!ctx->d_in2) CK(cudaMalloc((void **)&ctx->d_in2, ctx->in_bytes + 64));
+    const int slot = (ctx->ss_head + ctx->ss_pending) & 1;
+    const int pose_base = slot * ctx->max_batch;          // each slot owns max_batch frames of the pose buffers
+    sl.has_pose = gyro != nullptr;
+    if (gyro) {
+        if (!ctx->camera_set) return fail(ctx, CB_ERR_STATE, "no camera set: call cb_set_camera first");
+        if (!sl.h_gyro) {
+            CK(cudaMallocHost((void **)&sl.h_gyro, (size_t)ctx->max_batch * sizeof(double)));
+            CK(cudaMallocHost((void **)&sl.h_poses, (size_t)ctx->max_batch * sizeof(cb_pose)));
+            CK(cudaMallocHost((void **)&sl.h_ok, (size_t)ctx->max_batch));
+            CK(cudaMallocHost((void **)&sl.h_ntags, (size_t)ctx->max_batch * sizeof(int32_t)));
+            CK(cudaEventCreateWithFlags(&sl.pose_done, cudaEventDisableTiming));
+        }
+        if (ctx->pose_cap < 2 * ctx->max_batch) {
+            // a pose batch in flight implies the buffer already has this size, so nothing is using the old one
+            if (ctx->d_pose_buf) { CK(cudaStreamSynchronize(ctx->pose_stream)); cudaFree(ctx->d_pose_buf); ctx->d_pose_buf = nullptr; ctx->pose_cap = 0; }
+            CK(cudaMalloc((void **)&ctx->d_pose_buf, pose_buf_bytes((size_t)2 * ctx->max_batch)));
+            ctx->pose_cap = 2 * ctx->max_batch;
+        }
+        memcpy(sl.h_gyro, gyro, (size_t)batch * sizeof(double));         // the caller's array is free again when submit returns
+        PoseBufs pb = pose_bufs(ctx);
+        CK(cudaMemcpyAsync(pb.gyro + pose_base, sl.h_gyro, (size_t)batch * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(pb.poses + pose_base, 0, (size_t)batch * sizeof(cb_pose), ctx->stream));
+        ctx->pose_sign_change_error = sign_change_error;
+    }
     const size_t bytes = (size_t)stride * height;
     const size_t dfs = (bytes + 15) / 16 * 16;
     const int nbuf = 2;
@@ -834,7 +874,10 @@ int cb_detect_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int hei
         Geom g;
         int rc = make_geom(ctx, width, height, stride, dfs, n, g);
         if (rc) return rc;
+        ctx->pose_active = gyro != nullptr;
+        ctx->pose_frame_base = pose_base + b0;
         rc = run_pipeline(ctx, bufs[bi], g, ST_FULL);
+        ctx->pose_active = false;
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_consumed[bi], ctx->stream));
         CK(cudaMemcpyAsync(sl.h_dets + (size_t)b0 * D, ctx->d_dets, (size_t)n * D * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
@@ -846,17 +889,29 @@ int cb_detect_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int hei
         ctx->ss_chunk++;
     }
     CK(cudaEventRecord(sl.done, ctx->stream));
+    if (gyro) {
+        // the batch's solve was queued on pose_stream by run_pipeline; its results are read back on the same stream, so
+        // the detection kernels of the next batch (ctx->stream) never wait for a solve
+        PoseBufs pb = pose_bufs(ctx);
+        CK(cudaMemcpyAsync(sl.h_poses, pb.poses + pose_base, (size_t)batch * sizeof(cb_pose), cudaMemcpyDeviceToHost, ctx->pose_stream));
+        CK(cudaMemcpyAsync(sl.h_ok, pb.ok + pose_base, (size_t)batch, cudaMemcpyDeviceToHost, ctx->pose_stream));
+        CK(cudaMemcpyAsync(sl.h_ntags, pb.n_tags + pose_base, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->pose_stream));
+        CK(cudaEventRecord(sl.pose_done, ctx->pose_stream));
+    }
     ctx->ss_pending++;
     return CB_OK;
 }
 
-int cb_detect_gray_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts)
+static int stream_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts, cb_pose *poses, uint8_t *pose_ok, int32_t *pose_tags, bool want_pose)
 {
-    if (!ctx || !out || !out_counts) return CB_ERR_ARG;
+
+    if (!ctx || !out || !out_counts || (want_pose && (!poses || !pose_ok))) return CB_ERR_ARG;
     if (ctx->ss_pending == 0) return fail(ctx, CB_ERR_STATE, "nothing to collect: no batch has been submitted");
     CK(cudaSetDevice(ctx->device));
     cb_ctx::StreamSlot &sl = ctx->ss[ctx->ss_head];
-    const cudaError_t e = cudaEventSynchronize(sl.done);
+    if (want_pose && !sl.has_pose) return fail(ctx, CB_ERR_STATE, "the oldest batch in flight was submitted without poses: collect it with cb_detect_gray_collect");
+    cudaError_t e = cudaEventSynchronize(sl.done);
+    if (e == cudaSuccess && sl.has_pose) e = cudaEventSynchronize(sl.pose_done);
     ctx->ss_head ^= 1;            // the batch leaves the queue whatever its outcome
     ctx->ss_pending--;
     if (e != cudaSuccess) return fail(ctx, CB_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
@@ -868,11 +923,41 @@ int cb_detect_gray_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts)
         memcpy(out + (size_t)b * D, sl.h_dets + (size_t)b * D, (size_t)out_counts[b] * sizeof(cb_detection));
         for (int k = 0; k < out_counts[b]; k++) out[(size_t)b * D + k].frame = b;
     }
+    if (want_pose) {
+        memcpy(poses, sl.h_poses, (size_t)sl.batch * sizeof(cb_pose));
+        memcpy(pose_ok, sl.h_ok, (size_t)sl.batch);
+        if (pose_tags) memcpy(pose_tags, sl.h_ntags, (size_t)sl.batch * sizeof(int32_t));
+    }
     cb_timing t{};
     cudaEventElapsedTime(&t.total_ms, sl.start, sl.done);      // first copy queued -> lists on the host (includes waiting behind the batch in front)
     t.kernel_launches = sl.launches; t.threshold_launches = sl.thr_launches;
     ctx->timing = t;
     return CB_OK;
+}
+
+extern "C" {
+
+int cb_detect_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch)
+{
+    return stream_submit(ctx, frames, width, height, stride, frame_stride, batch, nullptr, 0.0);
+}
+
+int cb_detect_gray_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts)
+{
+    return stream_collect(ctx, out, out_counts, nullptr, nullptr, nullptr, false);
+}
+
+// AprilTags::process (crates/apriltags/src/lib.rs:293-379) for a continuous feed: cb_detect_pose_gray in the streaming form
+int cb_detect_pose_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
+                               const double *gyro, double sign_change_error)
+{
+    if (!gyro) return CB_ERR_ARG;
+    return stream_submit(ctx, frames, width, height, stride, frame_stride, batch, gyro, sign_change_error);
+}
+
+int cb_detect_pose_gray_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts, cb_pose *poses, uint8_t *pose_ok, int32_t *pose_tags)
+{
+    return stream_collect(ctx, out, out_counts, poses, pose_ok, pose_tags, true);
 }
 
 int cb_detect_gray_pending(const cb_ctx *ctx) { return ctx ? ctx->ss_pending : CB_ERR_ARG; }

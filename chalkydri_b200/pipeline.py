@@ -138,27 +138,16 @@ class AprilTags:
                                              None if r2c is None else capi.ptr(r2c)))
         self._device_path_ready = True
 
-    def process_batch(self, now_us: int, frame_times_us, grays: np.ndarray, gyro=None):
-        """`process` for a batch of frames in ONE library call (cb_detect_pose_gray): detections never leave the device between
-        detect, field lookup, un-projection and the per-frame SQPnP.  gyro: per-frame yaw (None / NaN = no reading, like
-        comm.gyro_angle() == None); default: comm.gyro_angle() for every frame.  Publishes and returns per frame what `process`
-        would: (RobotPose, VisionUncertainty) or None."""
-        from . import capi
-        from .capi import DET_DTYPE, POSE_DTYPE
-        self._configure_device_path()
-        L = capi.lib()
-        grays = np.ascontiguousarray(grays)
-        B, H, W = grays.shape
+    def _gyro_array(self, gyro, B):
         if gyro is None:
             gy = self.comm.gyro_angle()
             gyro = [gy] * B
-        gy = np.array([np.nan if v is None else float(v) for v in gyro], np.float64)
-        out = np.zeros((B, 64), DET_DTYPE); counts = np.zeros(B, np.int32)
-        poses = np.zeros(B, POSE_DTYPE); ok = np.zeros(B, np.uint8); ntags = np.zeros(B, np.int32)
-        self.detector._check(L.cb_detect_pose_gray(self.detector.ctx, capi.ptr(grays), W, H, W, H * W, B, capi.ptr(gy), SIGN_FLIP_CONST,
-                                                   capi.ptr(out), capi.ptr(counts), capi.ptr(poses), capi.ptr(ok), capi.ptr(ntags)))
+        return np.array([np.nan if v is None else float(v) for v in gyro], np.float64)
+
+    def _publish_batch(self, now_us, frame_times_us, counts, poses, ok):
+        """What `process` does with each frame's result (lib.rs:340-376): publish the pose, or the >5 ms heartbeat."""
         results = []
-        for b in range(B):
+        for b in range(len(counts)):
             ts = now_us - int(frame_times_us[b])
             if ok[b]:
                 rot = poses[b]["rot"].reshape(3, 3).T          # column-major like nalgebra
@@ -173,8 +162,61 @@ class AprilTags:
                 self.comm.publish(self.cam_id, 0, ts, RobotPose(), VisionUncertainty())
                 self.last_time = now_ms
             results.append(None)
-        self.last_batch = (out, counts, poses, ok, ntags)
         return results
+
+    def process_batch(self, now_us: int, frame_times_us, grays: np.ndarray, gyro=None):
+        """`process` for a batch of frames in ONE library call (cb_detect_pose_gray): detections never leave the device between
+        detect, field lookup, un-projection and the per-frame SQPnP.  gyro: per-frame yaw (None / NaN = no reading, like
+        comm.gyro_angle() == None); default: comm.gyro_angle() for every frame.  Publishes and returns per frame what `process`
+        would: (RobotPose, VisionUncertainty) or None."""
+        from . import capi
+        from .capi import DET_DTYPE, POSE_DTYPE
+        self._configure_device_path()
+        L = capi.lib()
+        grays = np.ascontiguousarray(grays)
+        B, H, W = grays.shape
+        gy = self._gyro_array(gyro, B)
+        out = np.zeros((B, 64), DET_DTYPE); counts = np.zeros(B, np.int32)
+        poses = np.zeros(B, POSE_DTYPE); ok = np.zeros(B, np.uint8); ntags = np.zeros(B, np.int32)
+        self.detector._check(L.cb_detect_pose_gray(self.detector.ctx, capi.ptr(grays), W, H, W, H * W, B, capi.ptr(gy), SIGN_FLIP_CONST,
+                                                   capi.ptr(out), capi.ptr(counts), capi.ptr(poses), capi.ptr(ok), capi.ptr(ntags)))
+        self.last_batch = (out, counts, poses, ok, ntags)
+        return self._publish_batch(now_us, frame_times_us, counts, poses, ok)
+
+    # ---- continuous feed: submit batch k+1, then collect batch k (cb_detect_pose_gray_submit / _collect) ----
+    def submit_batch(self, frame_times_us, grays: np.ndarray, gyro=None):
+        """Enqueue a batch (at most two in flight; keep `grays` alive and unchanged until the matching collect_batch)."""
+        from . import capi
+        self._configure_device_path()
+        L = capi.lib()
+        if grays.dtype != np.uint8 or grays.ndim != 3 or not grays.flags.c_contiguous:
+            raise ValueError("grays must be a C-contiguous [B,H,W] uint8 array")
+        B, H, W = grays.shape
+        gy = self._gyro_array(gyro, B)
+        self.detector._check(L.cb_detect_pose_gray_submit(self.detector.ctx, capi.ptr(grays), W, H, W, H * W, B, capi.ptr(gy), SIGN_FLIP_CONST))
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        self._inflight.append((grays, [int(t) for t in frame_times_us]))
+
+    def collect_batch(self, now_us: int):
+        """Wait for the oldest submitted batch, publish and return per frame what `process` would."""
+        from . import capi
+        from .capi import DET_DTYPE, POSE_DTYPE
+        L = capi.lib()
+        inflight = getattr(self, "_inflight", [])
+        B = inflight[0][0].shape[0] if inflight else 1                 # nothing in flight: the library reports CB_ERR_STATE
+        out = np.zeros((B, 64), DET_DTYPE); counts = np.zeros(B, np.int32)
+        poses = np.zeros(B, POSE_DTYPE); ok = np.zeros(B, np.uint8); ntags = np.zeros(B, np.int32)
+        try:
+            self.detector._check(L.cb_detect_pose_gray_collect(self.detector.ctx, capi.ptr(out), capi.ptr(counts), capi.ptr(poses), capi.ptr(ok),
+                                                               capi.ptr(ntags)))
+        except capi.ChalkydriError as e:
+            if e.code != capi.CB_ERR_STATE and inflight:       # a failed batch has left the queue; a refused collect has not
+                inflight.pop(0)
+            raise
+        times = inflight.pop(0)[1] if inflight else []
+        self.last_batch = (out, counts, poses, ok, ntags)
+        return self._publish_batch(now_us, times, counts, poses, ok)
 
     def process(self, now_us: int, frame_time_us: int, gray: np.ndarray):
         out, counts = self.detector.detect_batch(np.ascontiguousarray(gray)[None])

@@ -150,6 +150,15 @@ int cb_detect_pose_gray(cb_ctx *ctx, const uint8_t *frames, int width, int heigh
                         const double *gyro, double sign_change_error, cb_detection *out, int32_t *out_counts, cb_pose *poses,
                         uint8_t *pose_ok, int32_t *pose_tags);
 
+/* Streaming form of cb_detect_pose_gray (same queue and rules as cb_detect_gray_submit / _collect; the two forms may be mixed,
+ * batches are collected oldest first).  gyro[batch] is copied before submit returns.  A batch's SQPnP solve and the read-back
+ * of its poses run on a side stream under the detection kernels of the next batch.  cb_detect_pose_gray_collect on a batch
+ * that was submitted without poses returns CB_ERR_STATE and leaves it queued. */
+int cb_detect_pose_gray_submit(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride,
+                               int batch, const double *gyro, double sign_change_error);
+int cb_detect_pose_gray_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts, cb_pose *poses, uint8_t *pose_ok,
+                                int32_t *pose_tags);
+
 /* ---- output contract of the task: the 64-byte record whacknet sends to the robot controller
  *      (struct VisionMeasurement, crates/whacknet/src/lib.rs:40-66; the reference's one test checks its size, :92-95) ---- */
 typedef struct {

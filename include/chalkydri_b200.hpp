@@ -205,7 +205,35 @@ class AprilTags {
         uint8_t ok = 0;
         check(cb_detect_pose_gray(det_.ctx(), image.buf, image.width, image.height, image.stride, (size_t)image.stride * image.height, 1, &g,
                                   SIGN_FLIP_CONST, dets.data(), &count, &pose, &ok, &used));
-        const uint64_t ts = now_us - frame_time_us;
+        return publish(now_us, now_us - frame_time_us, pose, ok, count);
+    }
+
+    // continuous feed: submit(frame k+1) before collect(frame k); the frame stays valid until its collect (the camera pool
+    // slot is handed back afterwards).  Same publish rules as process().
+    void submit(uint64_t frame_time_us, const Image &image)
+    {
+        constexpr double SIGN_FLIP_CONST = 600.0;
+        const std::optional<double> gyro = comm_.gyro_angle ? comm_.gyro_angle() : std::nullopt;
+        const double g = gyro ? *gyro : std::nan("");
+        check(cb_detect_pose_gray_submit(det_.ctx(), image.buf, image.width, image.height, image.stride, (size_t)image.stride * image.height, 1, &g,
+                                         SIGN_FLIP_CONST));
+        times_[(head_ + pending_++) & 1] = frame_time_us;
+    }
+    std::optional<std::pair<RobotPose, VisionUncertainty>> collect(uint64_t now_us)
+    {
+        std::vector<cb_detection> dets((size_t)det_.max_dets());
+        int32_t count = 0, used = 0;
+        cb_pose pose{};
+        uint8_t ok = 0;
+        check(cb_detect_pose_gray_collect(det_.ctx(), dets.data(), &count, &pose, &ok, &used));
+        const uint64_t ts = now_us - times_[head_];
+        head_ ^= 1; pending_--;
+        return publish(now_us, ts, pose, ok, count);
+    }
+
+  private:
+    std::optional<std::pair<RobotPose, VisionUncertainty>> publish(uint64_t now_us, uint64_t ts, const cb_pose &pose, uint8_t ok, int32_t count)
+    {
         if (ok) {
             cb_vision_measurement m{};
             check(cb_pack_vision_measurements(&pose, &ok, &count, &ts, cam_id_, 1, &m));
@@ -221,9 +249,9 @@ class AprilTags {
         }
         return std::nullopt;
     }
-
-  private:
     void check(int rc) { if (rc != CB_OK) throw Error(rc, cb_last_error(det_.ctx())); }
+    uint64_t times_[2] = {0, 0};
+    int head_ = 0, pending_ = 0;
     Detector det_;
     uint8_t cam_id_;
     Comm comm_;

@@ -52,6 +52,10 @@ unsafe extern "C" {
                                  batch: c_int) -> c_int;
     pub fn cb_detect_gray_collect(ctx: *mut cb_ctx, out: *mut cb_detection, out_counts: *mut i32) -> c_int;
     pub fn cb_detect_gray_pending(ctx: *const cb_ctx) -> c_int;
+    pub fn cb_detect_pose_gray_submit(ctx: *mut cb_ctx, frames: *const u8, width: c_int, height: c_int, stride: c_int, frame_stride: usize,
+                                      batch: c_int, gyro: *const f64, sign_change_error: f64) -> c_int;
+    pub fn cb_detect_pose_gray_collect(ctx: *mut cb_ctx, out: *mut cb_detection, out_counts: *mut i32, poses: *mut cb_pose,
+                                       pose_ok: *mut u8, pose_tags: *mut i32) -> c_int;
     pub fn cb_sqpnp_set(ctx: *mut cb_ctx, max_iter: c_int, tolerance: f64) -> c_int;
     pub fn cb_sqpnp_batch(ctx: *mut cb_ctx, tags: *const cb_iso3, bearings: *const f64, n_tags: *const i32, max_tags: c_int,
                           robot_to_cam: *const cb_iso3, gyro: *const f64, sign_change_error: f64, n: i64, out: *mut cb_pose,

@@ -34,7 +34,13 @@ int main(int argc, char **argv)
                                   {500, 500, 320, 240, 0, 0, 0, 0, 0}, std::nullopt, 7, comm);
         const auto r = task.process(1000000, 990000, im);
         std::printf("task on a flat frame: pose %s, heartbeats %d\n", r ? "some" : "none", published);
-        return d.empty() && !r && published == 1 ? 0 : 2;
+        // the task's streaming form: two frames in flight; 20 ms later the heartbeat is due again, the second one is not
+        task.submit(1010000, im);
+        task.submit(1011000, im);
+        const auto r1 = task.collect(1020000), r2 = task.collect(1021000);
+        std::printf("task, streaming: %s %s, heartbeats %d\n", r1 ? "some" : "none", r2 ? "some" : "none", published);
+        if (r1 || r2 || published != 2) return 5;
+        return d.empty() && !r ? 0 : 2;
     } catch (const chalkydri::Error &e) {
         std::printf("no usable GPU: %s\n", e.what());
         return cb_device_count() == 0 ? 0 : 3;    // loud failure is the expected behaviour on a CPU-only host

@@ -122,6 +122,12 @@ def test_cpp_mirror_compiles_and_fails_loudly(lib, tmp_path):
     assert "version chalkydri_b200" in r.stdout
 
 
+@pytest.mark.gpu
+def test_cpp_mirror_runs_on_the_gpu(lib, tmp_path):
+    """The same program on a GPU box: Detector::detect, the streaming form and the AprilTags task (process / submit / collect)."""
+    test_cpp_mirror_compiles_and_fails_loudly(lib, tmp_path)
+
+
 def test_apriltag_detections_payload():
     """AprilTagDetections (crates/apriltags/src/lib.rs:47-141): capacity 16, strict margin filter, tuple round trip."""
     from chalkydri_b200 import capi

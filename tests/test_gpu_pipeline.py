@@ -98,3 +98,53 @@ def test_fused_path_equals_single_frame_process(oracle):
         else:
             assert batch[b] is not None
             assert abs(single[0].x - batch[b][0].x) < 1e-9 and abs(single[0].y - batch[b][0].y) < 1e-9 and abs(single[0].rot - batch[b][0].rot) < 1e-9
+
+
+def test_streaming_pose_batches_equal_the_blocking_call(oracle):
+    """cb_detect_pose_gray_submit / _collect with two batches in flight (sizes 4, 2, 4): same detections, same Some/None, poses
+    bit for bit those of cb_detect_pose_gray, and the same publish sequence; mixing with gray-only batches keeps the queue order."""
+    from chalkydri_b200.capi import ChalkydriError, CB_ERR_STATE
+    W, H = 1280, 720
+    batches, gyros = [], []
+    for i, n in enumerate((4, 2, 4)):
+        f, _ = synth.render_batch(W, H, n, 1, seed=40 + i, edge_px=(90, 200))
+        if i == 0:
+            f[2] = 128                                   # heartbeat frame
+        batches.append(np.ascontiguousarray(f))
+        gyros.append([0.3, None, -0.7, 1.1][:n])         # a frame without a gyro reading in every batch
+    c1, c2 = Comm(0.3), Comm(0.3)
+    t1, _ = make_task(W, H, 4, c1)
+    t2, _ = make_task(W, H, 4, c2)
+    want, want_raw = [], []
+    for f, g in zip(batches, gyros):
+        want.append(t1.process_batch(7_000_000, [6_990_000] * len(f), f, gyro=g))
+        want_raw.append([a.copy() for a in t1.last_batch])
+    t2.submit_batch([6_990_000] * len(batches[0]), batches[0], gyro=gyros[0])
+    got, got_raw = [], []
+    for k in range(3):
+        if k + 1 < 3:
+            t2.submit_batch([6_990_000] * len(batches[k + 1]), batches[k + 1], gyro=gyros[k + 1])
+            assert t2.detector.pending == 2
+        got.append(t2.collect_batch(7_000_000))
+        got_raw.append([a.copy() for a in t2.last_batch])
+    solved = 0
+    for w, g, wr, gr in zip(want, got, want_raw, got_raw):
+        assert [r is None for r in w] == [r is None for r in g]
+        assert wr[1].tolist() == gr[1].tolist() and wr[3].tolist() == gr[3].tolist() and wr[4].tolist() == gr[4].tolist()
+        for b in range(len(wr[1])):
+            assert wr[0][b, :wr[1][b]].tobytes() == gr[0][b, :gr[1][b]].tobytes()
+            if wr[3][b]:
+                assert wr[2][b].tobytes() == gr[2][b].tobytes()
+                solved += 1
+    assert solved >= 4
+    assert [(m[0], m[1], m[2]) for m in c1.published] == [(m[0], m[1], m[2]) for m in c2.published]
+    # a gray-only batch in front of a pose batch: the pose collect refuses it and leaves it queued
+    t2.detector.submit(batches[1])
+    t2.submit_batch([0, 0, 0, 0], batches[2], gyro=gyros[2])
+    with pytest.raises(ChalkydriError) as e:
+        t2.collect_batch(1)
+    assert e.value.code == CB_ERR_STATE and t2.detector.pending == 2
+    _, c = t2.detector.collect()
+    assert c.tolist() == want_raw[1][1].tolist()
+    last = t2.collect_batch(7_000_000)
+    assert [r is None for r in last] == [r is None for r in want[2]] and t2.detector.pending == 0
