@@ -129,3 +129,102 @@ def test_batch_threads_match_single(oracle):
     out4, c4 = oracle.detect_batch(frames, nthreads=4)
     assert (c1 == c4).all() and c1.sum() >= 6
     assert out1.tobytes() == out4.tobytes()
+
+
+def threshold_np(im, min_white_black_diff=5):
+    """A1 + A2 written a second time, vectorised: point decimation by 2, 4x4 tile extrema, 3x3 tile-neighbourhood
+    dilate / erode, per-pixel binarisation, and upstream's remainder rule (last full tile, never 127)."""
+    d = im[::2, ::2].astype(np.int32)
+    h, w = d.shape
+    th, tw = h // 4, w // 4
+    t = d[:th * 4, :tw * 4].reshape(th, 4, tw, 4)
+    tmax, tmin = t.max((1, 3)), t.min((1, 3))
+    pmax = np.pad(tmax, 1, constant_values=-1)
+    pmin = np.pad(tmin, 1, constant_values=1 << 20)
+    nmax = np.max([pmax[1 + dy:1 + dy + th, 1 + dx:1 + dx + tw] for dy in (-1, 0, 1) for dx in (-1, 0, 1)], axis=0)
+    nmin = np.min([pmin[1 + dy:1 + dy + th, 1 + dx:1 + dx + tw] for dy in (-1, 0, 1) for dx in (-1, 0, 1)], axis=0)
+    ty = np.minimum(np.arange(h) // 4, th - 1)[:, None]
+    tx = np.minimum(np.arange(w) // 4, tw - 1)[None, :]
+    mx, mn = nmax[ty, tx], nmin[ty, tx]
+    out = np.where(d > mn + (mx - mn) // 2, 255, 0).astype(np.uint8)
+    full = (np.arange(h) < th * 4)[:, None] & (np.arange(w) < tw * 4)[None, :]
+    out[full & (mx - mn < min_white_black_diff)] = 127
+    return out
+
+
+@pytest.mark.parametrize("W,H,seed", [(640, 480, 1), (322, 246, 2), (100, 74, 3)])
+def test_threshold_against_numpy_restatement(oracle, W, H, seed):
+    """bit-exact stage: frames with tags (structure) and a noise frame with partial tiles on both edges"""
+    im, _ = synth.render_frame(W, H, 2, seed=seed, edge_px=(30, 60)) if W > 200 else (np.random.default_rng(seed).integers(0, 256, (H, W), dtype=np.uint8), None)
+    thr = oracle.threshold(im)
+    assert (thr == threshold_np(im)).all()
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_partition_against_scipy_graph_components(oracle, seed):
+    """A3 as a graph problem: the links upstream's scan makes (x in 1..w-2: left, up; white also up-left / up-right), handed to
+    scipy.sparse.csgraph.connected_components; the oracle's min-index labels must describe the same partition -- including
+    upstream's behaviour at the unscanned border columns."""
+    sparse = pytest.importorskip("scipy.sparse")
+    from scipy.sparse.csgraph import connected_components
+    im, _ = synth.render_frame(320, 240, 2, seed=seed, edge_px=(40, 80))
+    _, taps = oracle.detect(im, taps=True)
+    t = taps["thresh"]
+    h, w = t.shape
+    idx = np.arange(h * w).reshape(h, w)
+    src, dst = [], []
+
+    def link(a, b, cond):
+        src.append(idx[a][cond]); dst.append(idx[b][cond])
+
+    xs = slice(1, w - 1)
+    good = t != 127
+    link((slice(None), xs), (slice(None), slice(0, w - 2)), (t[:, xs] == t[:, 0:w - 2]) & good[:, xs])               # left
+    link((slice(1, None), xs), (slice(0, h - 1), xs), (t[1:, xs] == t[:-1, xs]) & good[1:, xs])                          # up
+    white = t == 255
+    link((slice(1, None), xs), (slice(0, h - 1), slice(0, w - 2)), white[1:, xs] & white[:-1, 0:w - 2])                  # up-left
+    # up-right: upstream skips it when (x, y-1) == (x+1, y-1), counting on the left-link of pixel (x+1, y-1) -- which does not
+    # exist for x+1 = w-1 (never scanned).  So this one guard is part of the semantics: last-column pixels stay on their own
+    # unless the pixel to their left differs.  (The guards on the up and up-left links are redundant everywhere.)
+    link((slice(1, None), xs), (slice(0, h - 1), slice(2, w)), white[1:, xs] & white[:-1, 2:w] & (t[:-1, xs] != t[:-1, 2:w]))
+    s, d = np.concatenate(src), np.concatenate(dst)
+    g = sparse.coo_matrix((np.ones(len(s), np.int8), (s, d)), shape=(h * w, h * w))
+    ncomp, comp = connected_components(g, directed=False)
+    first = np.full(ncomp, h * w, np.int64)
+    np.minimum.at(first, comp, np.arange(h * w))
+    want = first[comp]
+    lab = taps["labels"].ravel().astype(np.int64)
+    assert (lab[good.ravel()] == want[good.ravel()]).all()
+    assert (taps["comp_size"].ravel()[good.ravel()] == np.bincount(comp, minlength=ncomp)[comp][good.ravel()]).all()
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_gradient_cluster_points_against_numpy_count(oracle, seed):
+    """A4 counted a second way, vectorised: boundary points for the probes (1,0), (0,1), (-1,1), (1,1) between components of at
+    least 25 pixels with v0 + v1 == 255, the (-1,1) probe suppressed when the previous pixel's (1,1) probe connected
+    (`connected_last`); clusters = distinct unordered component pairs."""
+    im, _ = synth.render_frame(320, 240, 2, seed=seed, edge_px=(40, 80))
+    _, taps = oracle.detect(im, taps=True)
+    t = taps["thresh"].astype(np.int32)
+    h, w = t.shape
+    big = (taps["comp_size"] >= 25) & (t != 127)
+
+    def conn(dx, dy):
+        c = np.zeros((h, w), bool)
+        ys, xs = slice(1, h - 1), slice(1, w - 1)
+        nb = (slice(1 + dy, h - 1 + dy), slice(1 + dx, w - 1 + dx))
+        c[ys, xs] = big[ys, xs] & big[nb] & (t[ys, xs] + t[nb] == 255)
+        return c
+
+    c10, c01, cm11, c11 = conn(1, 0), conn(0, 1), conn(-1, 1), conn(1, 1)
+    last = np.zeros((h, w), bool)
+    last[:, 1:] = c11[:, :-1]
+    probes = ((c10, (1, 0)), (c01, (0, 1)), (cm11 & ~last, (-1, 1)), (c11, (1, 1)))
+    assert sum(int(c.sum()) for c, _ in probes) == int(taps["npoints"]) > 1000
+    lab = taps["labels"].astype(np.int64)
+    keys = []
+    for c, (dx, dy) in probes:
+        ys, xs = np.nonzero(c)
+        a, b = lab[ys, xs], lab[ys + dy, xs + dx]
+        keys.append(np.minimum(a, b) * (h * w) + np.maximum(a, b))
+    assert len(np.unique(np.concatenate(keys))) == int(taps["nclusters"])
