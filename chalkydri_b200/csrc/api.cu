@@ -986,10 +986,10 @@ static int detect_converted(cb_ctx *ctx, const uint8_t *frames, int width, int h
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
         CK(cudaMemcpyAsync(d_rawin, frames + (size_t)b0 * npix * bytes_per_px, (size_t)n * npix * bytes_per_px, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaEventRecord(ctx->ev[8], ctx->stream));
-        for (int i = 0; i < n; i++) {   // one launch per frame keeps every frame's gray plane 16-byte aligned
-            const unsigned blocks = (unsigned)((npix + 16 * 256 - 1) / (16 * 256));
-            if (bytes_per_px == 3) rgb_to_gray_kernel<<<blocks, 256, 0, ctx->stream>>>(d_rawin + (size_t)i * npix * 3, ctx->d_gray + (size_t)i * gfs, npix);
-            else yuyv_to_gray_kernel<<<blocks, 256, 0, ctx->stream>>>(d_rawin + (size_t)i * npix * 2, ctx->d_gray + (size_t)i * gfs, npix);
+        {   // one launch for the whole chunk: grid.y = frame; every warp converts 512 pixels
+            const dim3 grid((unsigned)((npix + PRE_PX_PER_WARP * (PRE_THREADS / 32) - 1) / (PRE_PX_PER_WARP * (PRE_THREADS / 32))), (unsigned)n);
+            if (bytes_per_px == 3) rgb_to_gray_kernel<<<grid, PRE_THREADS, 0, ctx->stream>>>(d_rawin, ctx->d_gray, npix, npix * 3, gfs);
+            else yuyv_to_gray_kernel<<<grid, PRE_THREADS, 0, ctx->stream>>>(d_rawin, ctx->d_gray, npix, npix * 2, gfs);
         }
         CK(cudaEventRecord(ctx->ev[9], ctx->stream));
         Geom g;
@@ -1000,7 +1000,7 @@ static int detect_converted(cb_ctx *ctx, const uint8_t *frames, int width, int h
         float pre = 0, h2d = 0;
         cudaEventElapsedTime(&pre, ctx->ev[8], ctx->ev[9]);
         cudaEventElapsedTime(&h2d, ctx->ev[0], ctx->ev[8]);
-        ctx->timing.preprocess_ms = pre; ctx->timing.h2d_ms = h2d; ctx->timing.kernel_launches += n;
+        ctx->timing.preprocess_ms = pre; ctx->timing.h2d_ms = h2d; ctx->timing.kernel_launches += 1;
         for (int i = 0; i < n; i++)
             for (int k = 0; k < out_counts[b0 + i]; k++) out[(size_t)(b0 + i) * ctx->caps.dets_per_frame + k].frame = b0 + i;
         accumulate_timing(acc, ctx->timing);

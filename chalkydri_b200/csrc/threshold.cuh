@@ -421,41 +421,64 @@ __device__ __forceinline__ uint8_t cat_gray(uint32_t r, uint32_t gch, uint32_t b
     return (uint8_t)min(255, max(0, (int)v));
 }
 
-// 16 pixels per thread: three 128-bit loads of packed RGB, one 128-bit store of gray
-__global__ void rgb_to_gray_kernel(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ gray, size_t npix)
+// One launch converts a whole batch: blockIdx.y = frame (frame f at rgb + f * in_stride, gray + f * out_stride).
+// A warp owns 512 consecutive pixels = 1536 B of packed RGB.  Its three 128-bit loads are fully coalesced (lane t takes
+// uint4 t, t + 32, t + 64 of the chunk: every sector fetched once, every byte of it used), the chunk is parked in the warp's
+// 1536 B of shared memory, and each lane reads back its own 16 pixels (48 B: three uint4 at a 12-word stride -- the eight
+// lanes of a quarter-warp land on banks {0,12,24,4,16,28,8,20} + 0..3, i.e. conflict-free) and stores 16 gray bytes.
+constexpr int PRE_THREADS = 256;
+constexpr int PRE_PX_PER_WARP = 512;
+__global__ void __launch_bounds__(PRE_THREADS) rgb_to_gray_kernel(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ gray, size_t npix,
+                                                                   size_t in_stride, size_t out_stride)
 {
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (i >= npix) return;
-    if (i + 16 <= npix && (((uintptr_t)rgb) & 15) == 0 && (((uintptr_t)gray) & 15) == 0) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(rgb + 3 * i);
-        uint4 a = ldg_stream(src), b2 = ldg_stream(src + 1), c = ldg_stream(src + 2);
-        uint32_t wds[12] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w, c.x, c.y, c.z, c.w};
+    __shared__ uint4 stage[PRE_THREADS / 32][96];
+    rgb += (size_t)blockIdx.y * in_stride;
+    gray += (size_t)blockIdx.y * out_stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t p0 = ((size_t)blockIdx.x * (PRE_THREADS / 32) + warp) * PRE_PX_PER_WARP;      // first pixel of the warp's chunk
+    if (p0 >= npix) return;
+    if (p0 + PRE_PX_PER_WARP <= npix && (((uintptr_t)rgb) & 15) == 0 && (((uintptr_t)gray) & 15) == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(rgb + 3 * p0);
+        stage[warp][lane] = ldg_stream(src + lane);
+        stage[warp][lane + 32] = ldg_stream(src + lane + 32);
+        stage[warp][lane + 64] = ldg_stream(src + lane + 64);
+        __syncwarp();
+        const uint4 a = stage[warp][3 * lane], b2 = stage[warp][3 * lane + 1], c = stage[warp][3 * lane + 2];
+        const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w, c.x, c.y, c.z, c.w};
         uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            uint32_t r = (wds[(3 * k) >> 2] >> (8 * ((3 * k) & 3))) & 0xff;
-            uint32_t gg = (wds[(3 * k + 1) >> 2] >> (8 * ((3 * k + 1) & 3))) & 0xff;
-            uint32_t bl = (wds[(3 * k + 2) >> 2] >> (8 * ((3 * k + 2) & 3))) & 0xff;
+            const uint32_t r = (wds[(3 * k) >> 2] >> (8 * ((3 * k) & 3))) & 0xff;
+            const uint32_t gg = (wds[(3 * k + 1) >> 2] >> (8 * ((3 * k + 1) & 3))) & 0xff;
+            const uint32_t bl = (wds[(3 * k + 2) >> 2] >> (8 * ((3 * k + 2) & 3))) & 0xff;
             o[k >> 2] |= (uint32_t)cat_gray(r, gg, bl) << (8 * (k & 3));
         }
-        *reinterpret_cast<uint4 *>(gray + i) = make_uint4(o[0], o[1], o[2], o[3]);
-    } else {
-        for (size_t k = i; k < npix && k < i + 16; k++) gray[k] = cat_gray(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]);
+        *reinterpret_cast<uint4 *>(gray + p0 + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {          // ragged tail of a frame, or a frame whose planes are not 16-byte aligned
+        const size_t end = p0 + PRE_PX_PER_WARP < npix ? p0 + PRE_PX_PER_WARP : npix;
+        for (size_t k = p0 + lane; k < end; k += 32) gray[k] = cat_gray(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]);
     }
 }
 
-// YUYV (Y0 U Y1 V): gray = Y.  32 bytes in, 16 out per thread.
-__global__ void yuyv_to_gray_kernel(const uint8_t *__restrict__ yuyv, uint8_t *__restrict__ gray, size_t npix)
+// YUYV (Y0 U Y1 V): gray = Y.  A warp owns 512 pixels = 1024 B; lane t loads uint4 t and t + 32 (coalesced) and stores the
+// eight Y bytes of each as one 64-bit word (coalesced).
+__global__ void __launch_bounds__(PRE_THREADS) yuyv_to_gray_kernel(const uint8_t *__restrict__ yuyv, uint8_t *__restrict__ gray, size_t npix,
+                                                                    size_t in_stride, size_t out_stride)
 {
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (i >= npix) return;
-    if (i + 16 <= npix && (((uintptr_t)yuyv) & 15) == 0 && (((uintptr_t)gray) & 15) == 0) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(yuyv + 2 * i);
-        uint4 a = ldg_stream(src), b2 = ldg_stream(src + 1);
-        *reinterpret_cast<uint4 *>(gray + i) = make_uint4(__byte_perm(a.x, a.y, 0x6420), __byte_perm(a.z, a.w, 0x6420),
-                                                          __byte_perm(b2.x, b2.y, 0x6420), __byte_perm(b2.z, b2.w, 0x6420));
+    yuyv += (size_t)blockIdx.y * in_stride;
+    gray += (size_t)blockIdx.y * out_stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t p0 = ((size_t)blockIdx.x * (PRE_THREADS / 32) + warp) * PRE_PX_PER_WARP;
+    if (p0 >= npix) return;
+    if (p0 + PRE_PX_PER_WARP <= npix && (((uintptr_t)yuyv) & 15) == 0 && (((uintptr_t)gray) & 7) == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(yuyv + 2 * p0);
+        const uint4 a = ldg_stream(src + lane), b2 = ldg_stream(src + lane + 32);
+        uint2 *dst = reinterpret_cast<uint2 *>(gray + p0);
+        dst[lane] = make_uint2(__byte_perm(a.x, a.y, 0x6420), __byte_perm(a.z, a.w, 0x6420));
+        dst[lane + 32] = make_uint2(__byte_perm(b2.x, b2.y, 0x6420), __byte_perm(b2.z, b2.w, 0x6420));
     } else {
-        for (size_t k = i; k < npix && k < i + 16; k++) gray[k] = yuyv[2 * k];
+        const size_t end = p0 + PRE_PX_PER_WARP < npix ? p0 + PRE_PX_PER_WARP : npix;
+        for (size_t k = p0 + lane; k < end; k += 32) gray[k] = yuyv[2 * k];
     }
 }
 

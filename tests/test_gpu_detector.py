@@ -382,3 +382,28 @@ def test_streaming_queue_rules():
     det2 = make_detector(640, 480, 4)              # destroying a context with a batch still in flight is safe
     det2.submit(f)
     det2.close()
+
+
+@pytest.mark.parametrize("W,H", [(1000, 750), (642, 486)])
+def test_rgb_and_yuyv_batches_with_ragged_and_unaligned_planes(oracle, W, H):
+    """The batched pre-processing launch: 1000x750 frames end in a partial 512-pixel chunk; 642x486 frames make the second and
+    third frame's RGB / YUYV planes start off a 16-byte boundary (scalar path).  Gray must equal utils.rs:43 bit for bit, which
+    the detections on the oracle's gray conversion of the same frames confirm."""
+    from tests.test_oracle_cat import gray_np
+    B = 3
+    grays, _ = synth.render_batch(W, H, B, 3, seed=50, edge_px=(50, 110))
+    det = make_detector(W, H, B)
+    rgb = np.stack([synth.gray_to_rgb(grays[b], seed=b) for b in range(B)])
+    out, counts = det.detect_rgb_batch(rgb)
+    g2 = gray_np(rgb)
+    assert g2[0, 0, 0] == oracle.cat_grayscale(*(int(v) for v in rgb[0, 0, 0]))
+    for b in range(B):
+        assert_same_detections(out[b, :counts[b]], oracle.detect(g2[b]))
+    assert counts.sum() >= 6
+    yuyv = np.empty((B, H, W * 2), np.uint8)
+    yuyv[:, :, 0::2] = grays
+    yuyv[:, :, 1::2] = 77
+    out, counts = det.detect_yuyv_batch(yuyv)
+    for b in range(B):
+        assert_same_detections(out[b, :counts[b]], oracle.detect(grays[b]))
+    det.close()
