@@ -988,7 +988,8 @@ static int detect_converted(cb_ctx *ctx, const uint8_t *frames, int width, int h
         CK(cudaEventRecord(ctx->ev[8], ctx->stream));
         {   // one launch for the whole chunk: grid.y = frame; every warp converts 512 pixels
             const dim3 grid((unsigned)((npix + PRE_PX_PER_WARP * (PRE_THREADS / 32) - 1) / (PRE_PX_PER_WARP * (PRE_THREADS / 32))), (unsigned)n);
-            if (bytes_per_px == 3) rgb_to_gray_kernel<<<grid, PRE_THREADS, 0, ctx->stream>>>(d_rawin, ctx->d_gray, npix, npix * 3, gfs);
+            const dim3 grid_rgb((unsigned)((npix + RGB_PX_PER_BLOCK - 1) / RGB_PX_PER_BLOCK), (unsigned)n);
+            if (bytes_per_px == 3) rgb_to_gray_kernel<<<grid_rgb, RGB_THREADS, 0, ctx->stream>>>(d_rawin, ctx->d_gray, npix, npix * 3, gfs);
             else yuyv_to_gray_kernel<<<grid, PRE_THREADS, 0, ctx->stream>>>(d_rawin, ctx->d_gray, npix, npix * 2, gfs);
         }
         CK(cudaEventRecord(ctx->ev[9], ctx->stream));
@@ -1007,6 +1008,48 @@ static int detect_converted(cb_ctx *ctx, const uint8_t *frames, int width, int h
     }
     ctx->timing = acc;
     return CB_OK;
+}
+
+// stage tap of the pre-processing kernels: host frames in, gray planes out (tests and tools/bench_preprocess.py)
+static int convert_tap(cb_ctx *ctx, const uint8_t *frames, int width, int height, int bytes_per_px, int batch, uint8_t *gray_out)
+{
+    if (!ctx || !frames || !gray_out || width < 1 || height < 1 || batch < 1 || batch > 65535) return CB_ERR_ARG;
+    CB_NOT_STREAMING(ctx);
+    CK(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)width * height;
+    uint8_t *d = nullptr;
+    CK(cudaMalloc((void **)&d, (size_t)batch * npix * (bytes_per_px + 1) + 32));
+    uint8_t *d_out = d + ((size_t)batch * npix * bytes_per_px + 15) / 16 * 16;
+    cudaError_t e = cudaMemcpyAsync(d, frames, (size_t)batch * npix * bytes_per_px, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[8], ctx->stream);
+    if (e == cudaSuccess) {
+        const dim3 grid((unsigned)((npix + PRE_PX_PER_WARP * (PRE_THREADS / 32) - 1) / (PRE_PX_PER_WARP * (PRE_THREADS / 32))), (unsigned)batch);
+        const dim3 grid_rgb((unsigned)((npix + RGB_PX_PER_BLOCK - 1) / RGB_PX_PER_BLOCK), (unsigned)batch);
+        if (bytes_per_px == 3) rgb_to_gray_kernel<<<grid_rgb, RGB_THREADS, 0, ctx->stream>>>(d, d_out, npix, npix * 3, npix);
+        else yuyv_to_gray_kernel<<<grid, PRE_THREADS, 0, ctx->stream>>>(d, d_out, npix, npix * 2, npix);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[9], ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(gray_out, d_out, (size_t)batch * npix, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) {
+        ctx->timing = cb_timing{};
+        cudaEventElapsedTime(&ctx->timing.preprocess_ms, ctx->ev[8], ctx->ev[9]);
+        ctx->timing.kernel_launches = 1;
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, CB_ERR_CUDA, "pre-processing tap: %s", cudaGetErrorString(e));
+    return CB_OK;
+}
+
+int cb_rgb_to_gray(cb_ctx *ctx, const uint8_t *frames_rgb, int width, int height, int batch, uint8_t *gray_out)
+{
+    return convert_tap(ctx, frames_rgb, width, height, 3, batch, gray_out);
+}
+
+int cb_yuyv_to_gray(cb_ctx *ctx, const uint8_t *frames_yuyv, int width, int height, int batch, uint8_t *gray_out)
+{
+    return convert_tap(ctx, frames_yuyv, width, height, 2, batch, gray_out);
 }
 
 int cb_detect_rgb(cb_ctx *ctx, const uint8_t *frames_rgb, int width, int height, int batch, cb_detection *out, int32_t *out_counts)

@@ -422,42 +422,65 @@ __device__ __forceinline__ uint8_t cat_gray(uint32_t r, uint32_t gch, uint32_t b
 }
 
 // One launch converts a whole batch: blockIdx.y = frame (frame f at rgb + f * in_stride, gray + f * out_stride).
-// A warp owns 512 consecutive pixels = 1536 B of packed RGB.  Its three 128-bit loads are fully coalesced (lane t takes
-// uint4 t, t + 32, t + 64 of the chunk: every sector fetched once, every byte of it used), the chunk is parked in the warp's
-// 1536 B of shared memory, and each lane reads back its own 16 pixels (48 B: three uint4 at a 12-word stride -- the eight
-// lanes of a quarter-warp land on banks {0,12,24,4,16,28,8,20} + 0..3, i.e. conflict-free) and stores 16 gray bytes.
-constexpr int PRE_THREADS = 256;
+// A warp owns RGB_CHUNKS consecutive chunks of 512 pixels = 1536 B of packed RGB each.  Lane 0 starts one TMA bulk copy per
+// chunk into the warp's shared memory (cp.async.bulk + mbarrier::complete_tx: no per-thread load or shared-store
+// instructions, every DRAM sector fetched once), all chunks in flight at once; then, chunk by chunk, each lane reads back its
+// own 16 pixels (48 B: three uint4 at a 12-word stride -- the eight lanes of a quarter-warp land on banks
+// {0,12,24,4,16,28,8,20} + 0..3, i.e. conflict-free) and stores 16 gray bytes.  The first version staged the chunk with
+// per-lane coalesced loads + shared stores and was bound by the shared-memory instruction queue (ncu: mio_throttle).
+constexpr int PRE_THREADS = 256;          // yuyv_to_gray_kernel
 constexpr int PRE_PX_PER_WARP = 512;
-__global__ void __launch_bounds__(PRE_THREADS) rgb_to_gray_kernel(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ gray, size_t npix,
+constexpr int RGB_THREADS = 128;
+constexpr int RGB_CHUNKS = 4;
+constexpr int RGB_PX_PER_BLOCK = (RGB_THREADS / 32) * RGB_CHUNKS * 512;
+__global__ void __launch_bounds__(RGB_THREADS) rgb_to_gray_kernel(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ gray, size_t npix,
                                                                    size_t in_stride, size_t out_stride)
 {
-    __shared__ uint4 stage[PRE_THREADS / 32][96];
+    __shared__ __align__(128) uint4 stage[RGB_THREADS / 32][RGB_CHUNKS][96];
+    __shared__ __align__(8) unsigned long long bar[RGB_THREADS / 32][RGB_CHUNKS];
     rgb += (size_t)blockIdx.y * in_stride;
     gray += (size_t)blockIdx.y * out_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t p0 = ((size_t)blockIdx.x * (PRE_THREADS / 32) + warp) * PRE_PX_PER_WARP;      // first pixel of the warp's chunk
-    if (p0 >= npix) return;
-    if (p0 + PRE_PX_PER_WARP <= npix && (((uintptr_t)rgb) & 15) == 0 && (((uintptr_t)gray) & 15) == 0) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(rgb + 3 * p0);
-        stage[warp][lane] = ldg_stream(src + lane);
-        stage[warp][lane + 32] = ldg_stream(src + lane + 32);
-        stage[warp][lane + 64] = ldg_stream(src + lane + 64);
-        __syncwarp();
-        const uint4 a = stage[warp][3 * lane], b2 = stage[warp][3 * lane + 1], c = stage[warp][3 * lane + 2];
-        const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w, c.x, c.y, c.z, c.w};
+    const size_t w0 = ((size_t)blockIdx.x * (RGB_THREADS / 32) + warp) * (RGB_CHUNKS * 512);      // first pixel of the warp
+    if (w0 >= npix) return;                       // barriers are per warp: no block-wide synchronisation in this kernel
+    const bool aligned = (((uintptr_t)rgb) & 15) == 0 && (((uintptr_t)gray) & 15) == 0;
+    const int nfull = aligned ? (int)((npix - w0) / 512 < (size_t)RGB_CHUNKS ? (npix - w0) / 512 : (size_t)RGB_CHUNKS) : 0;
+    if (lane == 0 && nfull > 0) {
+        for (int c = 0; c < nfull; c++) mbar_init(&bar[warp][c], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int c = 0; c < nfull; c++) {
+            mbar_expect_tx(&bar[warp][c], 1536);
+            tma_load_1d(&stage[warp][c][0], rgb + 3 * (w0 + (size_t)c * 512), 1536, &bar[warp][c]);
+        }
+    }
+    __syncwarp();
+    for (int c = 0; c < nfull; c++) {
+        mbar_wait(&bar[warp][c], 0);
+        const uint4 a = stage[warp][c][3 * lane], b2 = stage[warp][c][3 * lane + 1], cc = stage[warp][c][3 * lane + 2];
+        const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w, cc.x, cc.y, cc.z, cc.w};
         uint32_t o[4] = {0, 0, 0, 0};
+        // u8 -> f32 and f32 -> u8 without the quarter-rate conversion unit (the I2F / F2I form capped this kernel at 4.2 TB/s:
+        // four conversions per pixel): PRMT drops the byte into the mantissa of 2^23 and one FADD removes the bias (exact);
+        // the truncating cast is FADD.RZ with 2^23, whose low mantissa byte is floor(v) (0 <= v <= 252.45, so no clamp).
+        uint32_t q[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            const uint32_t r = (wds[(3 * k) >> 2] >> (8 * ((3 * k) & 3))) & 0xff;
-            const uint32_t gg = (wds[(3 * k + 1) >> 2] >> (8 * ((3 * k + 1) & 3))) & 0xff;
-            const uint32_t bl = (wds[(3 * k + 2) >> 2] >> (8 * ((3 * k + 2) & 3))) & 0xff;
-            o[k >> 2] |= (uint32_t)cat_gray(r, gg, bl) << (8 * (k & 3));
+            const float r = __fsub_rn(__uint_as_float(__byte_perm(wds[(3 * k) >> 2], 0x4B000000u, 0x7440 | ((3 * k) & 3))), 8388608.0f);
+            const float gg = __fsub_rn(__uint_as_float(__byte_perm(wds[(3 * k + 1) >> 2], 0x4B000000u, 0x7440 | ((3 * k + 1) & 3))), 8388608.0f);
+            const float bl = __fsub_rn(__uint_as_float(__byte_perm(wds[(3 * k + 2) >> 2], 0x4B000000u, 0x7440 | ((3 * k + 2) & 3))), 8388608.0f);
+            const float v = __fmaf_rn(r, 0.33f, __fmaf_rn(gg, 0.33f, __fmul_rn(bl, 0.33f)));          // utils.rs:43
+            q[k] = __float_as_uint(__fadd_rz(v, 8388608.0f));
         }
-        *reinterpret_cast<uint4 *>(gray + p0 + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
-    } else {          // ragged tail of a frame, or a frame whose planes are not 16-byte aligned
-        const size_t end = p0 + PRE_PX_PER_WARP < npix ? p0 + PRE_PX_PER_WARP : npix;
-        for (size_t k = p0 + lane; k < end; k += 32) gray[k] = cat_gray(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            o[k] = __byte_perm(__byte_perm(q[4 * k], q[4 * k + 1], 0x4040), __byte_perm(q[4 * k + 2], q[4 * k + 3], 0x4040), 0x5410);
+        *reinterpret_cast<uint4 *>(gray + w0 + (size_t)c * 512 + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    // ragged tail of a frame, or a frame whose planes are not 16-byte aligned
+    const size_t rest = w0 + (size_t)nfull * 512;
+    const size_t end = w0 + RGB_CHUNKS * 512 < npix ? w0 + RGB_CHUNKS * 512 : npix;
+    for (size_t k = rest + lane; k < end; k += 32) gray[k] = cat_gray(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]);
 }
 
 // YUYV (Y0 U Y1 V): gray = Y.  A warp owns 512 pixels = 1024 B; lane t loads uint4 t and t + 32 (coalesced) and stores the

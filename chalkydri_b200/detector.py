@@ -206,6 +206,21 @@ class Detector:
         return out, counts
 
     # ---- stage taps (parity tests) ----
+    def rgb_to_gray(self, frames_rgb: np.ndarray) -> np.ndarray:
+        """pre-processing tap: packed RGB [B,H,W,3] -> gray [B,H,W] (utils.rs:43)"""
+        frames_rgb = np.ascontiguousarray(frames_rgb, np.uint8)
+        B, H, W, _ = frames_rgb.shape
+        out = np.empty((B, H, W), np.uint8)
+        self._check(self._L.cb_rgb_to_gray(self._ctx, capi.ptr(frames_rgb), W, H, B, capi.ptr(out)))
+        return out
+
+    def yuyv_to_gray(self, frames_yuyv: np.ndarray) -> np.ndarray:
+        frames_yuyv = np.ascontiguousarray(frames_yuyv, np.uint8)
+        B, H, W2 = frames_yuyv.shape
+        out = np.empty((B, H, W2 // 2), np.uint8)
+        self._check(self._L.cb_yuyv_to_gray(self._ctx, capi.ptr(frames_yuyv), W2 // 2, H, B, capi.ptr(out)))
+        return out
+
     def decimated_size(self, W, H):
         w, h = C.c_int(), C.c_int()
         self._check(self._L.cb_decimated_size(self._ctx, W, H, C.byref(w), C.byref(h)))

@@ -109,6 +109,11 @@ int cb_detect_yuyv(cb_ctx *ctx, const uint8_t *frames_yuyv, int width, int heigh
                    int32_t *out_counts);
 
 /* ---- stage taps (parity tests; run the pipeline up to that stage on HOST input) ---- */
+/* pre-processing alone: packed RGB -> gray with CAT's formula (crates/chalkydri-apriltags/src/utils.rs:33-46), YUYV -> Y;
+ * gray_out[batch][height][width].  Frame b starts at frames + b*width*height*{3,2}; planes that do not start on a 16-byte
+ * boundary take a scalar path with the same results. */
+int cb_rgb_to_gray(cb_ctx *ctx, const uint8_t *frames_rgb, int width, int height, int batch, uint8_t *gray_out);
+int cb_yuyv_to_gray(cb_ctx *ctx, const uint8_t *frames_yuyv, int width, int height, int batch, uint8_t *gray_out);
 /* decimated size the detector works on */
 int cb_decimated_size(const cb_ctx *ctx, int width, int height, int *w, int *h);
 /* threshold(): out[batch][h][w] in {0,127,255} */

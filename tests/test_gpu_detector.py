@@ -407,3 +407,24 @@ def test_rgb_and_yuyv_batches_with_ragged_and_unaligned_planes(oracle, W, H):
     for b in range(B):
         assert_same_detections(out[b, :counts[b]], oracle.detect(grays[b]))
     det.close()
+
+
+def test_rgb_to_gray_every_colour_bit_exact():
+    """All 2^24 RGB triples through rgb_to_gray_kernel's vector path (TMA-staged chunks, conversion-free arithmetic) against the
+    exact-FMA numpy form of utils.rs:43 that tests/test_oracle_cat.py pins to the oracle; then ragged and unaligned planes
+    (scalar path) and YUYV."""
+    from tests.test_oracle_cat import gray_np
+    det = make_detector(640, 480, 1)
+    v = np.arange(1 << 24, dtype=np.uint32)
+    rgb = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=-1).astype(np.uint8).reshape(1, 4096, 4096, 3)
+    got = det.rgb_to_gray(rgb)
+    for lo in range(0, 4096, 512):                                    # in slabs: the float64 emulation is memory hungry
+        assert (got[0, lo:lo + 512] == gray_np(rgb[0, lo:lo + 512])).all()
+    rng = np.random.default_rng(3)
+    small = rng.integers(0, 256, (3, 486, 642, 3), dtype=np.uint8)    # plane size 936036 B: frames 1 and 2 start unaligned, ragged tails
+    assert (det.rgb_to_gray(small) == gray_np(small)).all()
+    yuyv = rng.integers(0, 256, (3, 486, 642 * 2), dtype=np.uint8)
+    assert (det.yuyv_to_gray(yuyv) == yuyv[:, :, 0::2]).all()
+    yuyv = rng.integers(0, 256, (2, 750, 2000), dtype=np.uint8)       # aligned planes with a partial last chunk
+    assert (det.yuyv_to_gray(yuyv) == yuyv[:, :, 0::2]).all()
+    det.close()
