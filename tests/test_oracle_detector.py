@@ -228,3 +228,25 @@ def test_gradient_cluster_points_against_numpy_count(oracle, seed):
         a, b = lab[ys, xs], lab[ys + dy, xs + dx]
         keys.append(np.minimum(a, b) * (h * w) + np.maximum(a, b))
     assert len(np.unique(np.concatenate(keys))) == int(taps["nclusters"])
+
+
+def test_detection_record_conventions(oracle):
+    """apriltag_detection_t as upstream fills it: p[i] = H (-1,1), (1,1), (1,-1), (-1,-1) and c = H (0,0) (homography_project on
+    the rotated homography), counter-clockwise corner winding in image coordinates (y down), hamming 0 and a positive decision
+    margin on clean renderings, records sorted by id."""
+    im, truth = synth.render_frame(1280, 720, 4, seed=1, edge_px=(60, 150))
+    dets = oracle.detect(im)
+    assert sorted(dets["id"].tolist()) == sorted(truth["ids"]) == dets["id"].tolist()
+    for d in dets:
+        H = d["H"].reshape(3, 3)
+
+        def project(x, y):
+            v = H @ np.array([x, y, 1.0])
+            return v[:2] / v[2]
+
+        pts = np.array([project(-1, 1), project(1, 1), project(1, -1), project(-1, -1)])
+        assert np.abs(pts - d["p"]).max() < 1e-9 and np.abs(project(0, 0) - d["c"]).max() < 1e-9
+        x, y = d["p"][:, 0], d["p"][:, 1]
+        area2 = float(np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y))
+        assert area2 < 0                                   # upstream's winding: negative shoelace sum with y pointing down
+        assert d["hamming"] == 0 and d["decision_margin"] > 20
