@@ -26,6 +26,32 @@ def detector_c1():
                         npoints=taps["npoints"], nquads=taps["nquads"], quads=taps["quads"]["p"])
 
 
+def sqpnp_64():
+    """64 seeded problems (half with two tags, 0.25 px corner noise): inputs and the oracle's Some/None + poses"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests import sqpnp_problems as sp
+    tags, bearings, n_tags, r2c, gyro, truth = sp.make_problems(64, seed=11, two_tag_frac=0.5, noise_px=0.25)
+    out, ok = po.sqpnp_batch(tags, bearings, n_tags, r2c, gyro)
+    np.savez_compressed(os.path.join(HERE, "sqpnp_64.npz"), tags_t=tags["t"], tags_q=tags["q"], bearings=bearings, n_tags=n_tags,
+                        r2c_t=r2c["t"], r2c_q=r2c["q"], gyro=gyro, ok=ok, rot=out["rot"], pos=out["pos"], std_devs=out["std_devs"],
+                        true_pos=truth["pos"], true_yaw=truth["yaw"])
+
+
+def cat_96x72():
+    """a 96x72 RGB frame through every CAT stage"""
+    rng = np.random.default_rng(12)
+    gray, _ = synth.render_frame(96, 72, 1, seed=12, edge_px=(40, 60))
+    rgb = np.clip(gray[..., None].astype(int) + rng.integers(-6, 7, (72, 96, 3)), 0, 255).astype(np.uint8)
+    color = po.cat_calc_otsu(rgb)
+    xy, n = po.cat_detect_corners(color)
+    lines, m = po.cat_check_edges(color, xy)
+    labels, sizes = po.cat_connected_components(color)
+    np.savez_compressed(os.path.join(HERE, "cat_96x72.npz"), rgb=rgb, otsu=color, thresh=po.cat_thresh(rgb), corners=xy, lines=lines,
+                        labels=labels, sizes=sizes)
+
+
 if __name__ == "__main__":
     detector_c1()
+    sqpnp_64()
+    cat_96x72()
     print("golden fixtures written")

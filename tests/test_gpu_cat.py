@@ -61,3 +61,22 @@ def test_grayscale_exhaustive_sample(oracle):
     want = np.where(g < 60, 0, np.where(g > 160, 1, 2))
     assert (d.buf == want).all()
     d.close()
+
+
+def test_golden_fixture_cat_on_gpu():
+    """The CUDA CAT stages against the committed vectors tests/golden/cat_96x72.npz (no oracle in the loop), bit for bit."""
+    import os
+    from chalkydri_b200.cat import CatDetector
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cat_96x72.npz"))
+    d = CatDetector(96, 72, ())
+    d.calc_otsu(g["rgb"])
+    assert (d.buf == g["otsu"]).all()
+    d.detect_corners()
+    assert len(d.points) == len(g["corners"]) and (d.points == g["corners"]).all()
+    d.check_edges()
+    assert len(d.lines) == len(g["lines"]) and (d.lines == g["lines"]).all()
+    uf = d.connected_components()
+    assert (uf.parent == g["labels"]).all() and (uf.cluster_sizes == g["sizes"]).all()
+    d.thresh(g["rgb"])
+    assert (d.buf == g["thresh"]).all()
+    d.close()

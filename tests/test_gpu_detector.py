@@ -217,6 +217,9 @@ def test_golden_fixture(oracle):
     assert np.abs(d["p"] - g["corners"]).max() < CORNER_TOL
     thr = det.threshold(g["frame"][None])[0]
     assert (np.packbits(thr == 255) == g["thresh_white_bits"]).all() and (np.packbits(thr == 0) == g["thresh_black_bits"]).all()
+    q, qc, _ = det.quads(g["frame"][None])
+    assert qc[0] == int(g["nquads"])
+    assert np.abs(np.array(canon_quads(q[0, :qc[0]])) - np.array(canon_quads(g["quads"]))).max() < 1e-4
     det.close()
 
 

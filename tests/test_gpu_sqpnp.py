@@ -91,3 +91,16 @@ def test_million_problem_properties():
     R = out["rot"][m].reshape(-1, 3, 3)
     assert np.abs(np.einsum("nij,nkj->nik", R, R) - np.eye(3)).max() < 1e-9
     s.close()
+
+
+def test_golden_fixture_sqpnp_on_gpu():
+    """The CUDA solver against the committed vectors tests/golden/sqpnp_64.npz (no oracle in the loop)."""
+    from chalkydri_b200.solver import SqPnP
+    from tests.test_oracle_sqpnp import load_golden_sqpnp
+    g, tags, r2c = load_golden_sqpnp()
+    s = SqPnP.new()
+    out, ok = s.solve_robot_pose_batch(tags, g["bearings"], g["n_tags"], r2c, g["gyro"], 600.0)
+    ref = np.zeros(len(ok), out.dtype)
+    ref["pos"], ref["rot"], ref["std_devs"] = g["pos"], g["rot"], g["std_devs"]
+    compare(out, ok, ref, g["ok"])
+    s.close()

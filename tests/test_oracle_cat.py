@@ -221,3 +221,17 @@ def test_connected_components_partition(oracle):
     lab, sizes = oracle.cat_connected_components(c)
     wl, ws = ccl_py(c)
     assert (lab == wl).all() and (sizes == ws).all()
+
+
+def test_golden_fixture_cat(oracle):
+    """Regression pin: tests/golden/cat_96x72.npz (tests/golden/make_golden.py), every stage bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cat_96x72.npz"))
+    color = oracle.cat_calc_otsu(g["rgb"])
+    assert (color == g["otsu"]).all() and (oracle.cat_thresh(g["rgb"]) == g["thresh"]).all()
+    xy, n = oracle.cat_detect_corners(color)
+    assert n == len(g["corners"]) and (xy == g["corners"]).all()
+    lines, m = oracle.cat_check_edges(color, xy)
+    assert m == len(g["lines"]) and (lines == g["lines"]).all()
+    labels, sizes = oracle.cat_connected_components(color)
+    assert (labels == g["labels"]).all() and (sizes == g["sizes"]).all()

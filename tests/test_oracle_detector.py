@@ -121,6 +121,8 @@ def test_golden_fixture_c1(oracle):
     assert (np.packbits(taps["thresh"] == 255) == g["thresh_white_bits"]).all()
     assert (np.packbits(taps["thresh"] == 0) == g["thresh_black_bits"]).all()
     assert int(taps["npoints"]) == int(g["npoints"]) and int(taps["nquads"]) == int(g["nquads"])
+    assert np.abs(taps["quads"]["p"] - g["quads"]).max() < 1e-6         # candidate quads (float, decimated coordinates)
+    assert np.allclose(dets["decision_margin"], g["margin"], rtol=1e-6) and np.allclose(dets["H"], g["H"], rtol=1e-9, atol=1e-9)
 
 
 def test_batch_threads_match_single(oracle):

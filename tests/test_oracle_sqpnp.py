@@ -113,3 +113,24 @@ def test_noisy_problems_and_none_cases(oracle):
     k = int(np.nonzero(ok)[0][0])
     one = oracle.sqpnp_solve_robot_pose(tags[k, :n_tags[k]], bearings[k, :4 * n_tags[k]], r2c, float(gyro[k]))
     assert one is not None and one.tobytes() == out[k].tobytes()
+
+
+def load_golden_sqpnp():
+    import os
+    from chalkydri_b200.capi import ISO_DTYPE
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sqpnp_64.npz"))
+    tags = np.zeros(g["tags_t"].shape[:2], ISO_DTYPE)
+    tags["t"], tags["q"] = g["tags_t"], g["tags_q"]
+    r2c = np.zeros((), ISO_DTYPE)
+    r2c["t"], r2c["q"] = g["r2c_t"], g["r2c_q"]
+    return g, tags, r2c
+
+
+def test_golden_fixture_sqpnp(oracle):
+    """Regression pin: tests/golden/sqpnp_64.npz (tests/golden/make_golden.py) -- same Some/None, same poses."""
+    g, tags, r2c = load_golden_sqpnp()
+    out, ok = oracle.sqpnp_batch(tags, g["bearings"], g["n_tags"], r2c, g["gyro"])
+    assert ok.tolist() == g["ok"].tolist() and ok.sum() >= 60
+    m = ok > 0
+    assert np.abs(out["pos"][m] - g["pos"][m]).max() < 1e-9 and np.abs(out["rot"][m] - g["rot"][m]).max() < 1e-9
+    assert np.allclose(out["std_devs"][m], g["std_devs"][m], rtol=1e-9)
