@@ -5,7 +5,7 @@
 
 #include "chalkydri_b200.hpp"
 
-int main(int argc, char **argv)
+int main()
 {
     std::printf("version %s devices %d\n", cb_version(), cb_device_count());
     try {
