@@ -20,6 +20,30 @@ def camera_to_rank(camera: int, world: int) -> int:
     return camera % world
 
 
+def stream_shard(detector, frames: np.ndarray, batch: int, out: np.ndarray | None = None, counts: np.ndarray | None = None):
+    """One rank's share of a frame stream through the streaming form of the detector call: `frames` [n,H,W] is cut into batches of
+    `batch` frames, batch k+1 is submitted before batch k is collected (two in flight), and the records come back with `frame`
+    = index inside `frames` (the library numbers frames inside a batch).  `detector` needs submit(frames) / collect(out=, counts=)
+    / max_dets -- chalkydri_b200.detector.Detector, or a stand-in in the CPU tests."""
+    from .capi import DET_DTYPE
+    n = len(frames)
+    if out is None:
+        out = np.zeros((n, detector.max_dets), DET_DTYPE)
+    if counts is None:
+        counts = np.zeros(n, np.int32)
+    starts = list(range(0, n, batch))
+    if not starts:
+        return out, counts
+    detector.submit(frames[starts[0]:starts[0] + batch])
+    for k, s in enumerate(starts):
+        if k + 1 < len(starts):
+            detector.submit(frames[starts[k + 1]:starts[k + 1] + batch])
+        detector.collect(out=out[s:s + batch], counts=counts[s:s + batch])
+        e = min(s + batch, n)
+        out["frame"][s:e] = np.arange(s, e, dtype=np.int32)[:, None]      # batch-local -> shard-local frame index (every record of the row)
+    return out, counts
+
+
 def gather_detections(local_out: np.ndarray, local_counts: np.ndarray, lo: int, n_total: int, dist=None, device=None):
     """Gather every rank's [n_local, cap] detection records + counts into rank 0's [n_total, cap] array, ordered by frame index.
 

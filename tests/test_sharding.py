@@ -61,3 +61,62 @@ def test_gather_two_ranks_gloo(tmp_path):
     for f in range(n_total):
         for k in range(counts[f]):
             assert out[f, k]["frame"] == f and out[f, k]["id"] == f * 10 + k and out[f, k]["p"][0, 0] == f + 0.5
+
+
+class _StandInDetector:
+    """submit / collect with the library's queue rules (two in flight, oldest first, frame = index inside the batch); frame f
+    "contains" pixel-value-coded detections: count = value of its first pixel, ids derived from its second."""
+    max_dets = 4
+
+    def __init__(self):
+        self.q = []
+
+    def submit(self, frames):
+        assert len(self.q) < 2, "more than two batches in flight"
+        self.q.append(frames)
+
+    def collect(self, out, counts):
+        frames = self.q.pop(0)
+        assert len(out) == len(frames) == len(counts)
+        for b, f in enumerate(frames):
+            counts[b] = int(f[0, 0])
+            for k in range(counts[b]):
+                out[b, k]["frame"] = b
+                out[b, k]["id"] = int(f[0, 1]) * 10 + k
+
+
+def _stream_worker(rank, world, port, n_total, batch, tmp):
+    import torch.distributed as dist
+    from chalkydri_b200.sharding import gather_detections, shard_range, stream_shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(n_total, rank, world)
+    frames = np.zeros((hi - lo, 2, 2), np.uint8)
+    for i in range(lo, hi):
+        frames[i - lo, 0, 0] = i % 4                     # detections in frame i
+        frames[i - lo, 0, 1] = i % 25                    # id base
+    out, counts = stream_shard(_StandInDetector(), frames, batch)
+    g_out, g_counts = gather_detections(out, counts, lo, n_total, dist)
+    if rank == 0:
+        np.save(os.path.join(tmp, "s_out.npy"), g_out)
+        np.save(os.path.join(tmp, "s_counts.npy"), g_counts)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_stream_two_ranks_gloo(tmp_path):
+    """BASELINE configs[3] on the CPU: a 23-frame stream over two ranks in batches of 5 (ragged last batches), the streaming call
+    per rank, one gather -- every record ends up under its job-wide frame index."""
+    pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    n_total = 23
+    mp.spawn(_stream_worker, args=(2, port, n_total, 5, str(tmp_path)), nprocs=2, join=True)
+    out = np.load(tmp_path / "s_out.npy")
+    counts = np.load(tmp_path / "s_counts.npy")
+    assert counts.tolist() == [f % 4 for f in range(n_total)]
+    for f in range(n_total):
+        for k in range(counts[f]):
+            assert out[f, k]["frame"] == f and out[f, k]["id"] == (f % 25) * 10 + k

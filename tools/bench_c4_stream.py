@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 from chalkydri_b200 import synth, capi
 from chalkydri_b200.detector import DetectorBuilder, DET_DTYPE
-from chalkydri_b200.sharding import shard_range, gather_detections
+from chalkydri_b200.sharding import shard_range, gather_detections, stream_shard
 
 TOTAL, W, H, BATCH, CAP, UNIQUE = 4096, 1280, 800, 256, 16, 8
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
@@ -39,16 +39,10 @@ for i in range(n):
     h[i] = uniq[(lo + i) % UNIQUE]
 out = np.zeros((n, CAP), DET_DTYPE); counts = np.zeros(n, np.int32)
 det = DetectorBuilder.default().add_family_bits("tag36h11", 3).device(local).capacity(W, H, BATCH, CAP).build()
-starts = list(range(0, n, BATCH))
 
 
 def one_pass():
-    det.submit(h[starts[0]:starts[0] + BATCH])
-    for k, s in enumerate(starts):
-        if k + 1 < len(starts):
-            det.submit(h[starts[k + 1]:starts[k + 1] + BATCH])
-        det.collect(out=out[s:s + BATCH], counts=counts[s:s + BATCH])
-        out["frame"][s:s + BATCH] += s            # batch-local -> shard-local frame index
+    stream_shard(det, h, BATCH, out=out, counts=counts)
     return gather_detections(out, counts, lo, TOTAL, dist if world > 1 else None, device=torch.device("cuda", local))
 
 
