@@ -146,3 +146,47 @@ def test_apriltag_detections_payload():
     assert b.ids == a.ids and b.decision_margins == a.decision_margins
     assert all((p == q).all() for p, q in zip(a.poses, b.poses))
     assert list(AprilTagDetections().filtered_by_decision_margin(0.0)) == []
+
+
+def test_task_publish_rules_host_logic():
+    """AprilTags::process publish rules (crates/apriltags/src/lib.rs:340-376) in the Python task mirror, without a device: a solved
+    frame publishes (x, y, euler yaw) with the saturating tag count and ts = now - frame time; an unsolved one publishes the
+    empty heartbeat only when more than 5 ms have passed since the last heartbeat."""
+    from chalkydri_b200 import capi
+    from chalkydri_b200.pipeline import AprilTags, RobotPose, VisionUncertainty
+
+    class Comm:
+        def __init__(self):
+            self.sent = []
+
+        def gyro_angle(self):
+            return 0.5
+
+        def publish(self, cam_id, tag_count, ts_us, pose, unc):
+            self.sent.append((cam_id, tag_count, ts_us, pose, unc))
+
+    task = object.__new__(AprilTags)              # the publish path needs no detector
+    task.comm, task.cam_id, task.last_time = Comm(), 9, None
+    a = 0.4
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    poses = np.zeros(4, capi.POSE_DTYPE)
+    poses["rot"][:] = R.T.reshape(-1)             # column-major like nalgebra
+    poses["pos"][:] = (2.0, -1.0, 0.1)
+    poses["std_devs"][:] = (0.1, 0.2, 0.3)
+    ok = np.array([1, 0, 0, 1], np.uint8)
+    counts = np.array([2, 0, 3, 300], np.int32)
+    res = task._publish_batch(10_000_000, [9_990_000, 9_991_000, 9_992_000, 9_993_000], counts, poses, ok)
+    assert [r is not None for r in res] == [True, False, False, True]
+    sent = task.comm.sent
+    assert [(m[0], m[1], m[2]) for m in sent] == [(9, 2, 10_000), (9, 0, 9_000), (9, 255, 7_000)]     # second unsolved frame: no heartbeat
+    assert isinstance(sent[0][3], RobotPose) and abs(sent[0][3].rot - a) < 1e-12 and (sent[0][3].x, sent[0][3].y) == (2.0, -1.0)
+    assert (sent[0][4].x, sent[0][4].y, sent[0][4].rot) == (0.1, 0.2, 0.3)
+    assert sent[1][3] == RobotPose() and sent[1][4] == VisionUncertainty()
+    # 5 ms later exactly: still quiet (the reference tests `> 5`); 6 ms later: heartbeat again
+    task._publish_batch(10_005_000, [10_000_000], counts[1:2], poses[1:2], ok[1:2])
+    assert len(sent) == 3
+    task._publish_batch(10_006_000, [10_000_000], counts[1:2], poses[1:2], ok[1:2])
+    assert len(sent) == 4 and sent[3][1] == 0
+    # gyro defaults to comm.gyro_angle() for every frame, None -> NaN (no reading, lib.rs:329)
+    assert task._gyro_array(None, 3).tolist() == [0.5, 0.5, 0.5]
+    assert np.isnan(task._gyro_array([0.1, None], 2)[1])
