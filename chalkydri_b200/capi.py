@@ -37,7 +37,7 @@ class Timing(C.Structure):
 
 # every symbol include/chalkydri_b200.h declares
 EXPORTS = ["cb_create", "cb_destroy", "cb_last_error", "cb_set_family_tag36h11", "cb_set_params", "cb_detect_gray",
-           "cb_detect_gray_device", "cb_detect_gray_submit", "cb_detect_gray_collect", "cb_detect_gray_pending", "cb_detect_rgb", "cb_detect_yuyv", "cb_rgb_to_gray", "cb_yuyv_to_gray", "cb_decimated_size", "cb_threshold", "cb_labels",
+           "cb_detect_gray_device", "cb_detect_gray_submit", "cb_detect_gray_collect", "cb_detect_gray_pending", "cb_detect_rgb", "cb_detect_yuyv", "cb_detect_yuv420", "cb_rgb_to_gray", "cb_yuyv_to_gray", "cb_decimated_size", "cb_threshold", "cb_labels",
            "cb_quads", "cb_get_timing", "cb_sqpnp_set", "cb_sqpnp_batch", "cb_sqpnp_batch_device",
            "cb_create_solver_camera_transform", "cb_unproject_opencv5", "cb_set_field", "cb_set_camera", "cb_detect_pose_gray", "cb_detect_pose_gray_submit", "cb_detect_pose_gray_collect", "cb_pack_vision_measurements", "cb_cat_calc_otsu", "cb_cat_thresh",
            "cb_cat_detect_corners", "cb_cat_check_edges", "cb_cat_connected_components", "cb_host_alloc", "cb_host_free",
@@ -71,6 +71,7 @@ def lib():
         L.cb_detect_gray_pending.argtypes = [vp]
         L.cb_detect_rgb.argtypes = [vp, vp, i32, i32, i32, vp, vp]
         L.cb_detect_yuyv.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+        L.cb_detect_yuv420.argtypes = [vp, vp, i32, i32, i32, vp, vp]
         L.cb_rgb_to_gray.argtypes = [vp, vp, i32, i32, i32, vp]
         L.cb_yuyv_to_gray.argtypes = [vp, vp, i32, i32, i32, vp]
         L.cb_decimated_size.argtypes = [vp, i32, i32, vp, vp]

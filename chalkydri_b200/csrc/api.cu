@@ -343,7 +343,10 @@ int cb_set_params(cb_ctx *ctx, float quad_decimate, float quad_sigma, int refine
 {
     if (!ctx) return CB_ERR_ARG;
     if (quad_sigma != 0.0f) return fail(ctx, CB_ERR_UNSUPPORTED, "quad_sigma %g: blur is not implemented (the reference leaves it at 0)", quad_sigma);
-    if (quad_decimate != 2.0f) return fail(ctx, CB_ERR_UNSUPPORTED, "quad_decimate %g: only 2 (the reference's setting) is implemented in this build", quad_decimate);
+    // upstream: factor 1.5 averages 3x3 blocks, every other factor f > 1 point-samples at (int)f; f <= 1 works on the frame itself
+    if (!(quad_decimate >= 1.0f && quad_decimate <= 16.0f) || (float)(int)quad_decimate != quad_decimate)
+        return fail(ctx, CB_ERR_UNSUPPORTED, "quad_decimate %g: integer factors 1..16 are implemented (2 is the reference's setting and the fused fast path; 1.5 is not offered)", quad_decimate);
+    CB_NOT_STREAMING(ctx);
     if (max_nmaxima < 4 || max_nmaxima > 10) return fail(ctx, CB_ERR_UNSUPPORTED, "max_nmaxima %d outside 4..10", max_nmaxima);
     DetParams &p = ctx->prm;
     p.quad_decimate = quad_decimate; p.refine_edges = refine_edges; p.decode_sharpening = decode_sharpening;
@@ -381,6 +384,11 @@ static int make_geom(cb_ctx *ctx, int width, int height, int stride, size_t fram
     g.W = width; g.H = height; g.stride = stride; g.frame_stride = frame_stride;
     g.f = (int)ctx->prm.quad_decimate;
     g.w = 1 + (width - 1) / g.f; g.h = 1 + (height - 1) / g.f;
+    // the per-pixel buffers hold ceil(max_w / 2) x ceil(max_h / 2) decimated pixels (cb_create): quad_decimate = 1 needs a
+    // context created with twice the frame size
+    if (g.w > (ctx->max_w + 1) / 2 || g.h > (ctx->max_h + 1) / 2)
+        return fail(ctx, CB_ERR_ARG, "quad_decimate %d: the detector's working image %dx%d exceeds the context's %dx%d (create the context with max_width / max_height of twice the frame size)",
+                    g.f, g.w, g.h, (ctx->max_w + 1) / 2, (ctx->max_h + 1) / 2);
     g.tp = (g.w + 15) / 16 * 16;
     g.tw = g.w / 4; g.th = g.h / 4;
     g.batch = batch;
@@ -647,7 +655,7 @@ static int upload_chunk(cb_ctx *ctx, const uint8_t *frames, size_t frame_stride,
     dev_frame_stride = (bytes + 15) / 16 * 16;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (frame_stride == dev_frame_stride) {
-        CK(cudaMemcpyAsync(ctx->d_in, frames, (size_t)n * frame_stride, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_in, frames, (size_t)(n - 1) * frame_stride + bytes, cudaMemcpyHostToDevice, ctx->stream));   // never past the last frame's pixels
     } else {
         CK(cudaMemcpy2DAsync(ctx->d_in, dev_frame_stride, frames, frame_stride, bytes, n, cudaMemcpyHostToDevice, ctx->stream));
     }
@@ -735,7 +743,7 @@ static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, 
             done_base = b0;
         }
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[bi], 0));
-        if (frame_stride == dfs) CK(cudaMemcpyAsync(bufs[bi], frames + (size_t)b0 * frame_stride, (size_t)n * frame_stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (frame_stride == dfs) CK(cudaMemcpyAsync(bufs[bi], frames + (size_t)b0 * frame_stride, (size_t)(n - 1) * frame_stride + bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         else CK(cudaMemcpy2DAsync(bufs[bi], dfs, frames + (size_t)b0 * frame_stride, frame_stride, bytes, n, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(ctx->ev_copied[bi], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[bi], 0));
@@ -867,7 +875,7 @@ static int stream_submit(cb_ctx *ctx, const uint8_t *frames, int width, int heig
     for (int b0 = 0; b0 < batch; b0 += half) {
         const int n = std::min(half, batch - b0), bi = (int)(ctx->ss_chunk % nbuf), c = sl.nchunks;
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[bi], 0));
-        if (frame_stride == dfs) CK(cudaMemcpyAsync(bufs[bi], frames + (size_t)b0 * frame_stride, (size_t)n * frame_stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (frame_stride == dfs) CK(cudaMemcpyAsync(bufs[bi], frames + (size_t)b0 * frame_stride, (size_t)(n - 1) * frame_stride + bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         else CK(cudaMemcpy2DAsync(bufs[bi], dfs, frames + (size_t)b0 * frame_stride, frame_stride, bytes, n, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(ctx->ev_copied[bi], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[bi], 0));
@@ -1061,6 +1069,15 @@ int cb_detect_yuyv(cb_ctx *ctx, const uint8_t *frames_yuyv, int width, int heigh
 {
     if (width % 2) return fail(ctx, CB_ERR_ARG, "YUYV needs an even width");
     return detect_converted(ctx, frames_yuyv, width, height, 2, batch, out, out_counts);
+}
+
+// NV12 / NV21 / I420 / YV12 camera buffers (crates/chalkydri/src/cameras/gst_to_cu.rs:152-188): the first width*height bytes of
+// each frame are the Y plane, which IS the gray image; the chroma planes behind it are never uploaded (a strided copy).
+int cb_detect_yuv420(cb_ctx *ctx, const uint8_t *frames, int width, int height, int batch, cb_detection *out, int32_t *out_counts)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if ((width | height) & 1) return fail(ctx, CB_ERR_ARG, "4:2:0 formats need even width and height");
+    return cb_detect_gray(ctx, frames, width, height, width, (size_t)width * height * 3 / 2, batch, out, out_counts);
 }
 
 // ---- stage taps ----

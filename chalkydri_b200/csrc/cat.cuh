@@ -74,8 +74,10 @@ constexpr int OC_BLOCK = 256;
 
 __device__ __forceinline__ int cat_corner_flag(const uint8_t *__restrict__ c, int w, int h, int x, int y)
 {
-    // x in [3, w-3], y in [3, h-3] (inclusive, lib.rs:293-294); ring samples outside the image cannot be evaluated
-    if (x + 3 >= w || y + 3 >= h) return 0;
+    // x in [3, w-3], y in [3, h-3] (inclusive, lib.rs:293-294).  px() is an unchecked linear index (utils.rs:27-29): at x = w-3
+    // the (x+3, .) samples are column 0 of the next row, which `at` reproduces; pixels whose furthest sample lies beyond the
+    // w*h buffer (undefined behaviour in the reference) are skipped
+    if ((size_t)(y + 3) * w + (size_t)(x + 3) >= (size_t)w * h) return 0;
     auto at = [&](int xx, int yy) { return c[(size_t)yy * w + xx]; };
     if (at(x, y) != 0) return 0;
     const bool ul = at(x - 1, y - 1) == 0, ur = at(x + 1, y - 1) == 0, dl = at(x - 1, y + 1) == 0, dr = at(x + 1, y + 1) == 0;

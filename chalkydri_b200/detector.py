@@ -205,6 +205,16 @@ class Detector:
         self._check(self._L.cb_detect_yuyv(self._ctx, capi.ptr(frames_yuyv), W, H, B, capi.ptr(out), capi.ptr(counts)))
         return out, counts
 
+    def detect_yuv420_batch(self, frames_yuv: np.ndarray):
+        """NV12 / NV21 / I420 / YV12 buffers [B, H*3/2, W] (gst_to_cu.rs:152-188): the Y plane is the gray image."""
+        B, H32, W = frames_yuv.shape
+        H = H32 * 2 // 3
+        assert frames_yuv.dtype == np.uint8 and frames_yuv.flags.c_contiguous and H * 3 // 2 == H32
+        out = np.zeros((B, self.max_dets), DET_DTYPE)
+        counts = np.zeros(B, np.int32)
+        self._check(self._L.cb_detect_yuv420(self._ctx, capi.ptr(frames_yuv), W, H, B, capi.ptr(out), capi.ptr(counts)))
+        return out, counts
+
     # ---- stage taps (parity tests) ----
     def rgb_to_gray(self, frames_rgb: np.ndarray) -> np.ndarray:
         """pre-processing tap: packed RGB [B,H,W,3] -> gray [B,H,W] (utils.rs:43)"""

@@ -28,11 +28,14 @@ def scaled_calib(width: int, height: int, distortion: bool = True):
     return (fx * s, fy * s, cx * sx, cy * sy, k1, k2, p1, p2, k3)
 
 
-def tag_pattern(tag_id: int) -> np.ndarray:
-    """10x10 cell image (1 = white) of a tag36h11 tag including the white quiet zone."""
+def tag_pattern(tag_id: int, flip_bits=()) -> np.ndarray:
+    """10x10 cell image (1 = white) of a tag36h11 tag including the white quiet zone.  `flip_bits`: indices (0..35, AprilTag-3
+    bit order) of data bits to invert -- a tag printed / seen with that many bit errors (hamming distance len(flip_bits))."""
     g = np.ones((10, 10), np.uint8)
     g[1:9, 1:9] = 0
     code = TAG36H11_CODES[tag_id]
+    for i in flip_bits:
+        code ^= 1 << (35 - int(i))
     for i in range(36):
         bit = (code >> (35 - i)) & 1
         g[BIT_Y[i] + 1, BIT_X[i] + 1] = bit
@@ -85,8 +88,10 @@ _CORNER_TAG = np.array([[-1, 1], [1, 1], [1, -1], [-1, -1]], np.float64)
 
 def render_frame(width: int, height: int, n_tags: int, seed: int, edge_px=(40.0, 200.0), max_tilt_deg: float = 60.0,
                  calib=None, small_tags: int = 0, small_edge_px=(12.0, 24.0), noise_sigma: float = 3.0,
-                 blur: bool = True, ss: int = 3):
-    """Render one frame. Returns (gray u8 [H,W], truth dict)."""
+                 blur: bool = True, ss: int = 3, bit_errors=0):
+    """Render one frame. Returns (gray u8 [H,W], truth dict).  `bit_errors`: number of inverted data bits per tag (an int, or a
+    sequence cycled over the tags); the flipped positions come from their own seeded stream, so frames rendered with
+    bit_errors = 0 are unchanged.  truth["hamming"] holds the number of flipped bits of every placed tag."""
     rng = np.random.default_rng(seed)
     if calib is None:
         calib = scaled_calib(width, height)
@@ -103,7 +108,7 @@ def render_frame(width: int, height: int, n_tags: int, seed: int, edge_px=(40.0,
     else:
         ids = rng.permutation(587)[:n_tags]
     placed = []   # (cx, cy, radius)
-    truth = {"ids": [], "corners": [], "R": [], "t": [], "edge_px": []}
+    truth = {"ids": [], "corners": [], "R": [], "t": [], "edge_px": [], "hamming": []}
     half = TAG_SIZE_M / 2.0
     for ti, tag_id in enumerate(ids):
         lo, hi = (small_edge_px if ti >= n_tags - small_tags else edge_px)
@@ -153,7 +158,9 @@ def render_frame(width: int, height: int, n_tags: int, seed: int, edge_px=(40.0,
         ux = np.floor(Pt[..., 0] / cell + 5.0).astype(int)
         uy = np.floor(Pt[..., 1] / cell + 5.0).astype(int)
         inside = (ux >= 0) & (ux < 10) & (uy >= 0) & (uy < 10)
-        pat = tag_pattern(int(tag_id))
+        nflip = int(bit_errors if np.isscalar(bit_errors) else bit_errors[ti % len(bit_errors)])
+        flips = np.random.default_rng([int(seed) & 0x7fffffff, 0xB17, ti]).permutation(36)[:nflip] if nflip else ()
+        pat = tag_pattern(int(tag_id), flips)
         val = np.where(inside, pat[np.clip(uy, 0, 9), np.clip(ux, 0, 9)], 0).astype(np.float32)
         hh, ww = y1 - y0, x1 - x0
         alpha = inside.astype(np.float32).reshape(hh, ss, ww, ss).mean((1, 3))
@@ -166,6 +173,7 @@ def render_frame(width: int, height: int, n_tags: int, seed: int, edge_px=(40.0,
         truth["R"].append(R)
         truth["t"].append(t)
         truth["edge_px"].append(edge)
+        truth["hamming"].append(nflip)
     if noise_sigma > 0:
         img = img + rng.normal(0.0, noise_sigma, img.shape).astype(np.float32)
     if blur:
@@ -177,6 +185,7 @@ def render_frame(width: int, height: int, n_tags: int, seed: int, edge_px=(40.0,
         img = k[0] * p[1:-1, :-2] + k[1] * p[1:-1, 1:-1] + k[2] * p[1:-1, 2:]
     out = np.clip(np.rint(img), 0, 255).astype(np.uint8)
     truth["ids"] = np.array(truth["ids"], np.int32)
+    truth["hamming"] = np.array(truth["hamming"], np.int32)
     truth["corners"] = np.array(truth["corners"], np.float64).reshape(-1, 4, 2)
     return out, truth
 

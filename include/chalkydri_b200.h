@@ -72,7 +72,9 @@ const char *cb_last_error(const cb_ctx *ctx);
 int cb_set_family_tag36h11(cb_ctx *ctx, int bits_corrected);
 
 /* apriltag_detector_t fields the reference leaves at their defaults.  quad_decimate must be an
- * integer >= 1 (2 takes the fused fast path); quad_sigma must be 0; deglitch is not offered. */
+ * integer in 1..16 (2, the reference's value, takes the fused fast path; upstream's special 1.5 is CB_ERR_UNSUPPORTED);
+ * quad_decimate = 1 needs a context created with twice the frame size (the per-pixel buffers are sized for the decimated
+ * frame).  quad_sigma must be 0; deglitch is not offered.  CB_ERR_STATE while batches are in flight. */
 int cb_set_params(cb_ctx *ctx, float quad_decimate, float quad_sigma, int refine_edges, double decode_sharpening,
                   int min_cluster_pixels, int max_nmaxima, float critical_rad, float max_line_fit_mse,
                   int min_white_black_diff);
@@ -107,6 +109,11 @@ int cb_detect_rgb(cb_ctx *ctx, const uint8_t *frames_rgb, int width, int height,
 /* YUYV (YUY2) camera buffers (crates/chalkydri/src/cameras/gst_to_cu.rs:152-188 lists the formats): gray = Y */
 int cb_detect_yuyv(cb_ctx *ctx, const uint8_t *frames_yuyv, int width, int height, int batch, cb_detection *out,
                    int32_t *out_counts);
+/* planar / semi-planar 4:2:0 camera buffers -- NV12, NV21, I420, YV12 (gst_to_cu.rs:152-188): frame b starts at
+ * frames + b*width*height*3/2 and its first width*height bytes (the Y plane) are the gray image.  Same as cb_detect_gray
+ * with stride = width and frame_stride = width*height*3/2; only the Y planes are uploaded.  width, height even. */
+int cb_detect_yuv420(cb_ctx *ctx, const uint8_t *frames, int width, int height, int batch, cb_detection *out,
+                     int32_t *out_counts);
 
 /* ---- stage taps (parity tests; run the pipeline up to that stage on HOST input) ---- */
 /* pre-processing alone: packed RGB -> gray with CAT's formula (crates/chalkydri-apriltags/src/utils.rs:33-46), YUYV -> Y;

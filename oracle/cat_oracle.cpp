@@ -119,9 +119,11 @@ int64_t orc_cat_detect_corners(const uint8_t *c, int w, int h, int32_t *xy, int6
     auto at = [&](int x, int y) { return c[(size_t)y * w + x]; };
     for (int x = 3; x <= w - 3; x++)
         for (int y = 3; y <= h - 3; y++) {
-            /* the reference reads (x+3, y+3) with x = w-3: one past the row end / image end (unchecked).  Pixels whose
-               radius-3 ring leaves the image cannot be evaluated; they are skipped here. */
-            if (x + 3 >= w || y + 3 >= h) continue;
+            /* px() is an unchecked linear index (utils.rs:27-29), so at x = w-3 the reference's (x+3, y-3) / (x+3, y+3) samples
+               are column 0 of the NEXT row -- defined behaviour, reproduced here by the same linear indexing.  Only pixels
+               whose furthest sample (x+3, y+3) lies beyond the w*h buffer (row h-3, and (w-3, h-4)) read out of bounds in
+               the reference (undefined behaviour): those cannot be evaluated and are skipped. */
+            if ((size_t)(y + 3) * w + (size_t)(x + 3) >= (size_t)w * h) continue;
             if (at(x, y) != BLACK) continue;
             bool ul = at(x - 1, y - 1) == BLACK, ur = at(x + 1, y - 1) == BLACK;
             bool dl = at(x - 1, y + 1) == BLACK, dr = at(x + 1, y + 1) == BLACK;

@@ -26,6 +26,48 @@ def detector_c1():
                         npoints=taps["npoints"], nquads=taps["nquads"], quads=taps["quads"]["p"])
 
 
+def detector_biterr():
+    """four tags with 0 / 1 / 2 / 3 inverted data bits (tests/frames.py): the oracle's lists for bits_corrected 0..3"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests import frames as fr
+    im, truth = fr.bit_error_frame()
+    rec = {"frame": im, "true_ids": truth["ids"], "true_hamming": truth["hamming"]}
+    for bits in range(4):
+        dets = po.detect(im, po.default_params(bits_corrected=bits))
+        rec[f"ids_b{bits}"], rec[f"hamming_b{bits}"], rec[f"corners_b{bits}"] = dets["id"], dets["hamming"], dets["p"]
+        rec[f"margin_b{bits}"] = dets["decision_margin"]
+    np.savez_compressed(os.path.join(HERE, "detector_biterr.npz"), **rec)
+
+
+def detector_cv2_pin():
+    """INDEPENDENT pin (not produced by the oracle): OpenCV 4.13's aruco module carries its own port of the UMich AprilTag quad
+    detector (CORNER_REFINE_APRILTAG: threshold -> union-find -> gradient clusters -> fit_quad).  Its corners on the c1 frame,
+    un-decimated, are what quad_decimate = 1 / refine_edges = 0 of this detector must reproduce (measured: <= 0.05 px), and
+    its decode with maxCorrectionBits = k is bits_corrected = k on the bit-error frame."""
+    import cv2
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests import frames as fr
+    dic = cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_APRILTAG_36h11)
+    prm = cv2.aruco.DetectorParameters()
+    prm.cornerRefinementMethod = cv2.aruco.CORNER_REFINE_APRILTAG
+    prm.aprilTagQuadDecimate = 0.0
+    rec = {"cv2_version": np.array(cv2.__version__)}
+    for name, seed in (("c1", 1), ("s2", 2), ("s3", 3)):
+        im, _ = synth.render_frame(1280, 720, 4, seed=seed, edge_px=(60, 150))
+        corners, ids, _ = cv2.aruco.ArucoDetector(dic, prm).detectMarkers(im)
+        order = np.argsort(ids.ravel())
+        rec[f"{name}_seed"] = seed
+        rec[f"{name}_ids"] = ids.ravel()[order].astype(np.int32)
+        rec[f"{name}_corners"] = np.array([corners[k].reshape(4, 2) for k in order], np.float64)      # AprilTag pixel convention
+    im, _ = fr.bit_error_frame()
+    for k in range(4):
+        dic.maxCorrectionBits = k
+        prm.errorCorrectionRate = 1.0
+        _, ids, _ = cv2.aruco.ArucoDetector(dic, prm).detectMarkers(im)
+        rec[f"biterr_ids_k{k}"] = np.sort(ids.ravel()).astype(np.int32) if ids is not None else np.zeros(0, np.int32)
+    np.savez_compressed(os.path.join(HERE, "detector_cv2_pin.npz"), **rec)
+
+
 def sqpnp_64():
     """64 seeded problems (half with two tags, 0.25 px corner noise): inputs and the oracle's Some/None + poses"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -52,6 +94,8 @@ def cat_96x72():
 
 if __name__ == "__main__":
     detector_c1()
+    detector_biterr()
+    detector_cv2_pin()
     sqpnp_64()
     cat_96x72()
     print("golden fixtures written")

@@ -80,3 +80,27 @@ def test_golden_fixture_cat_on_gpu():
     d.thresh(g["rgb"])
     assert (d.buf == g["thresh"]).all()
     d.close()
+
+
+def test_last_column_reads_wrap_to_the_next_row_on_gpu(oracle):
+    """x = w-3 (inside the reference's loop, lib.rs:293): px(x+3, y-+3) is column 0 of the next row (utils.rs:27-29)."""
+    from chalkydri_b200.cat import CatDetector
+    from tests.test_oracle_cat import corners_py
+    w, h = 40, 30
+    base = np.full((h, w), 1, np.uint8)
+    base[10:20, w - 3:] = 0
+    with_corner = base.copy()
+    with_corner[14, 0] = 0                             # px(w-3+3, 10+3) = row 14, column 0: the wrapped far sample turns black
+    ring_other = with_corner.copy()
+    ring_other[8, 0] = 2                               # px(w-3+3, 10-3) = row 8, column 0 is Other: ring not all good
+    d = CatDetector(w, h, ())
+    found = []
+    for c in (base, with_corner, ring_other):
+        d.buf[...] = c
+        d.detect_corners()
+        rxy, rn = oracle.cat_detect_corners(c)
+        got = [tuple(p) for p in d.points.tolist()]
+        assert got == [tuple(p) for p in rxy[:rn].tolist()] == corners_py(c)
+        found.append((w - 3, 10) in got)
+    assert found == [False, True, False]
+    d.close()

@@ -431,3 +431,164 @@ def test_rgb_to_gray_every_colour_bit_exact():
     yuyv = rng.integers(0, 256, (2, 750, 2000), dtype=np.uint8)       # aligned planes with a partial last chunk
     assert (det.yuyv_to_gray(yuyv) == yuyv[:, :, 0::2]).all()
     det.close()
+
+
+# ---- round 2: error-corrected decode, family bits, reconcile, decimation factors, 4:2:0 buffers ------------------------------
+
+def make_detector_bits(W, H, bits, B=1, dets=128):
+    from chalkydri_b200.detector import DetectorBuilder
+    return DetectorBuilder.default().add_family_bits("tag36h11", bits).capacity(W, H, B, dets).build()
+
+
+@pytest.mark.parametrize("bits", [0, 1, 2, 3])
+def test_hamming_decode_and_family_bits(oracle, bits):
+    """add_family_bits(family, bits) for bits 0..3 (the reference configures 3, falls back to 1: crates/apriltags/src/lib.rs:230,
+    279-282) on tags carrying 0..4 inverted data bits: ids and hamming bit-exact against the oracle, and against what the
+    rendering says must decode (k <= bits -> hamming k, otherwise nothing)."""
+    from tests import frames as fr
+    frames, truths = [], []
+    for k in range(5):
+        im, t = synth.render_frame(1280, 720, 4, seed=31, edge_px=(70, 150), bit_errors=k)
+        frames.append(im); truths.append(t)
+    im, t = fr.bit_error_frame()
+    frames.append(im); truths.append(t)
+    frames = np.stack(frames)
+    det = make_detector_bits(1280, 720, bits, B=len(frames))
+    out, counts = det.detect_batch(frames)
+    for b, t in enumerate(truths):
+        got = out[b, :counts[b]]
+        assert_same_detections(got, oracle.detect(frames[b], oracle.default_params(bits_corrected=bits)))
+        want = {int(i): int(h) for i, h in zip(t["ids"], t["hamming"]) if h <= bits}
+        assert {int(d["id"]): int(d["hamming"]) for d in got} == want
+    det.close()
+
+
+def test_bit_error_golden_fixture():
+    """tests/golden/detector_biterr.npz (hamming 0..3 in one frame) with no oracle in the loop, plus OpenCV's decode of the same
+    frame with maxCorrectionBits = k (tests/golden/detector_cv2_pin.npz): the same set of tags."""
+    g = np.load(os.path.join(GOLD, "detector_biterr.npz"))
+    pin = np.load(os.path.join(GOLD, "detector_cv2_pin.npz"))
+    for bits in range(4):
+        det = make_detector_bits(1280, 720, bits)
+        out, counts = det.detect_batch(g["frame"][None])
+        d = out[0, :counts[0]]
+        assert d["id"].tolist() == g[f"ids_b{bits}"].tolist() == pin[f"biterr_ids_k{bits}"].tolist()
+        assert d["hamming"].tolist() == g[f"hamming_b{bits}"].tolist()
+        if len(d):
+            assert np.abs(d["p"] - g[f"corners_b{bits}"]).max() < CORNER_TOL
+            assert np.allclose(d["decision_margin"], g[f"margin_b{bits}"], rtol=MARGIN_RTOL, atol=1e-3)
+        det.close()
+
+
+def test_reconcile_overlapping_duplicates(oracle):
+    """Two detections of one id with overlapping polygons (a small copy of a tag inside one of its own white cells): upstream's
+    swap-remove reconcile keeps the lower hamming, then the higher decision margin.  All five cases in one batch."""
+    from tests import frames as fr
+    frames = np.stack([fr.nested_same_id_frame(**kw) for kw, _ in fr.RECONCILE_CASES] +
+                      [fr.nested_same_id_frame(**dict(kw, small_id=9)) for kw, _ in fr.RECONCILE_CASES])
+    det = make_detector(1456, 1088, len(frames))
+    out, counts = det.detect_batch(frames)
+    n = len(fr.RECONCILE_CASES)
+    for b, (kw, want) in enumerate(fr.RECONCILE_CASES):
+        got = out[b, :counts[b]]
+        assert_same_detections(got, oracle.detect(frames[b]))
+        assert got["id"].tolist() == [7]
+        if want is not None:
+            assert (np.ptp(got[0]["p"][:, 0]) > 400) == (want == "big")
+        both = out[n + b, :counts[n + b]]
+        assert both["id"].tolist() == [7, 9]                     # distinct ids: both survive
+        assert_same_detections(both, oracle.detect(frames[n + b]))
+    det.close()
+
+
+@pytest.mark.parametrize("f,W,H", [(1.0, 640, 480), (3.0, 640, 480), (3.0, 1000, 750), (1.0, 322, 246), (4.0, 1280, 720)])
+def test_other_decimation_factors(oracle, f, W, H):
+    """quad_decimate 1, 3, 4 (cb_set_params; the reference leaves it at 2): every stage against the oracle.  Factor 1 works on
+    the frame itself (corners are not rescaled) and needs a context created with twice the frame size."""
+    frames, _ = synth.render_batch(W, H, 2, 3, seed=7, edge_px=(60, 110) if W < 1000 else (80, 200))
+    det = make_detector(2 * W, 2 * H, 2) if f == 1.0 else make_detector(W, H, 2)
+    det.set_params(quad_decimate=f)
+    prm = oracle.default_params(quad_decimate=f)
+    thr = det.threshold(frames)
+    lab, sz = det.labels(frames)
+    q, qc, _ = det.quads(frames)
+    out, counts = det.detect_batch(frames)
+    for b in range(2):
+        ref, taps = oracle.detect(frames[b], prm, taps=True)
+        assert thr[b].shape == taps["thresh"].shape and (thr[b] == taps["thresh"]).all()
+        assert (lab[b] == taps["labels"]).all() and (sz[b] == taps["comp_size"]).all()
+        assert qc[b] == taps["nquads"]
+        gq, oq = canon_quads(q[b, :qc[b]]), canon_quads(taps["quads"]["p"])
+        assert np.abs(np.array(gq) - np.array(oq)).max() < 1e-4 if gq else True
+        assert_same_detections(out[b, :counts[b]], ref)
+        assert counts[b] >= 2
+    det.close()
+
+
+def test_decimation_argument_rules():
+    from chalkydri_b200.capi import ChalkydriError, CB_ERR_UNSUPPORTED, CB_ERR_ARG
+    det = make_detector(640, 480, 1)
+    for bad in (1.5, 0.5, 0.0, 17.0):
+        with pytest.raises(ChalkydriError) as e:
+            det.set_params(quad_decimate=bad)
+        assert e.value.code == CB_ERR_UNSUPPORTED
+    det.set_params(quad_decimate=1.0)
+    with pytest.raises(ChalkydriError) as e:                          # the context's buffers hold a 320x240 working image
+        det.detect_batch(np.zeros((1, 480, 640), np.uint8))
+    assert e.value.code == CB_ERR_ARG and "twice the frame size" in str(e.value)
+    out, counts = det.detect_batch(np.full((1, 240, 320), 128, np.uint8))
+    assert counts[0] == 0
+    det.close()
+
+
+def test_quads_against_opencv_apriltag_port():
+    """INDEPENDENT PIN, no oracle in the loop: the CUDA detector at quad_decimate = 1 / refine_edges = 0 against the corners
+    OpenCV's own port of the UMich quad detector (aruco CORNER_REFINE_APRILTAG) found on the same frames, committed in
+    tests/golden/detector_cv2_pin.npz (measured <= 0.05 px, asserted < 0.08 px); and the default path within 0.3 px."""
+    pin = np.load(os.path.join(GOLD, "detector_cv2_pin.npz"))
+    det1 = make_detector(2560, 1440, 1)
+    det1.set_params(quad_decimate=1.0, refine_edges=0)
+    det2 = make_detector(1280, 720, 1)
+
+    def quad_dist(c, p):
+        return min(np.abs(np.roll(cc, s, 0) - p).max() for cc in (c, c[::-1]) for s in range(4))
+
+    for name in ("c1", "s2", "s3"):
+        im, _ = synth.render_frame(1280, 720, 4, seed=int(pin[f"{name}_seed"]), edge_px=(60, 150))
+        for det, tol in ((det1, 0.08), (det2, 0.3)):
+            out, counts = det.detect_batch(im[None])
+            d = out[0, :counts[0]]
+            assert d["id"].tolist() == pin[f"{name}_ids"].tolist()
+            for rec, c in zip(d, pin[f"{name}_corners"]):
+                assert quad_dist(c, rec["p"]) < tol
+    det1.close(); det2.close()
+
+
+def test_yuv420_buffers(oracle):
+    """NV12 / I420 camera buffers (gst_to_cu.rs:152-188): the Y plane is the gray image, frames are width*height*3/2 apart and
+    the chroma bytes behind each Y plane are never looked at.  Blocking call, chunk-pipelined call (batch >= 64) and the
+    streaming form with a frame stride."""
+    from tests import frames as fr
+    from chalkydri_b200 import capi
+    grays, _ = synth.render_batch(640, 480, 70, 2, seed=5, unique=5, edge_px=(50, 110))
+    yuv = fr.yuv420_from_gray(grays, seed=1)
+    det = make_detector(640, 480, 16)
+    out, counts = det.detect_yuv420_batch(yuv[:3])
+    for b in range(3):
+        assert_same_detections(out[b, :counts[b]], oracle.detect(grays[b]))
+    ref_out, ref_counts = det.detect_batch(grays)
+    out, counts = det.detect_yuv420_batch(yuv)                      # 70 frames through a 16-frame context: pipelined chunks
+    assert counts.tolist() == ref_counts.tolist() and counts.sum() >= 100
+    for b in range(70):
+        assert out[b, :counts[b]].tobytes() == ref_out[b, :counts[b]].tobytes()
+    # streaming form on the same buffers: frame_stride = 1.5 * W * H
+    h = capi.pinned_array(yuv[:16].shape, np.uint8)
+    h[...] = yuv[:16]
+    det._check(det._L.cb_detect_gray_submit(det.ctx, capi.ptr(h), 640, 480, 640, 640 * 480 * 3 // 2, 16))
+    o2 = np.zeros((16, det.max_dets), out.dtype); c2 = np.zeros(16, np.int32)
+    det._check(det._L.cb_detect_gray_collect(det.ctx, capi.ptr(o2), capi.ptr(c2)))
+    assert c2.tolist() == ref_counts[:16].tolist()
+    for b in range(16):
+        assert o2[b, :c2[b]].tobytes() == ref_out[b, :c2[b]].tobytes()
+    capi.free_pinned(h)
+    det.close()

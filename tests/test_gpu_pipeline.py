@@ -148,3 +148,34 @@ def test_streaming_pose_batches_equal_the_blocking_call(oracle):
     assert c.tolist() == want_raw[1][1].tolist()
     last = t2.collect_batch(7_000_000)
     assert [r is None for r in last] == [r is None for r in want[2]] and t2.detector.pending == 0
+
+
+def test_blocking_pose_call_with_a_pose_batch_in_flight_leaves_it_intact():
+    """The blocking cb_detect_pose_gray shares the pose buffers with batches queued by cb_detect_pose_gray_submit: it must refuse
+    (CB_ERR_STATE) BEFORE touching them, so the batch in flight still collects the poses it would have produced alone."""
+    from chalkydri_b200.capi import ChalkydriError, CB_ERR_STATE
+    W, H = 1280, 720
+    f, _ = synth.render_batch(W, H, 4, 1, seed=40, edge_px=(90, 200))
+    g = [0.3, 0.1, -0.7, 1.1]
+    t1, _ = make_task(W, H, 4, Comm(0.3))
+    want = t1.process_batch(7_000_000, [6_990_000] * 4, f, gyro=g)
+    want_raw = [a.copy() for a in t1.last_batch]
+    assert sum(r is not None for r in want) >= 2
+    t2, _ = make_task(W, H, 4, Comm(0.3))
+    t2.process_batch(7_000_000, [6_990_000] * 4, f, gyro=g)          # sizes the pose buffers, then the race the advisor described:
+    for _ in range(3):
+        t2.submit_batch([6_990_000] * 4, f, gyro=g)
+        with pytest.raises(ChalkydriError) as e:
+            t2.process_batch(7_000_000, [6_990_000] * 4, np.full_like(f, 128), gyro=[2.0] * 4)
+        assert e.value.code == CB_ERR_STATE
+        t2._device_path_ready = False
+        with pytest.raises(ChalkydriError):
+            t2._configure_device_path()                                 # cb_set_field / cb_set_camera are refused as well
+        t2._device_path_ready = True
+        got = t2.collect_batch(7_000_000)
+        got_raw = t2.last_batch
+        assert [r is None for r in got] == [r is None for r in want]
+        assert got_raw[3].tolist() == want_raw[3].tolist()
+        for b in range(4):
+            if want_raw[3][b]:
+                assert got_raw[2][b].tobytes() == want_raw[2][b].tobytes()

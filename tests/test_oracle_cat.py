@@ -116,22 +116,45 @@ def ternary_map(w, h, seed):
 
 
 def corners_py(c):
-    """detect_corners / process_pixel (lib.rs:291-309,345-400): x outer, y inner"""
+    """detect_corners / process_pixel (lib.rs:291-309,345-400): x outer, y inner.  px() is an unchecked LINEAR index
+    (utils.rs:27-29): in the last scanned column x = w-3 the (x+3, .) samples are column 0 of the next row; only samples beyond
+    the w*h buffer (undefined behaviour in the reference) make a pixel unevaluable."""
     h, w = c.shape
+    flat = c.reshape(-1)
+    px = lambda x, y: y * w + x                           # noqa: E731
     out = []
     for x in range(3, w - 3 + 1):
         for y in range(3, h - 3 + 1):
-            if x + 3 >= w or y + 3 >= h:
-                continue                                   # the reference reads out of bounds here; the oracle skips
-            if c[y, x] != BLACK:
+            if px(x + 3, y + 3) >= w * h:
                 continue
-            d = [c[y - 1, x - 1], c[y - 1, x + 1], c[y + 1, x - 1], c[y + 1, x + 1]]
+            if flat[px(x, y)] != BLACK:
+                continue
+            d = [flat[px(x - 1, y - 1)], flat[px(x + 1, y - 1)], flat[px(x - 1, y + 1)], flat[px(x + 1, y + 1)]]
             if not (sum(int(v == BLACK) for v in d) & 1):
                 continue
-            f = [c[y - 3, x + 3], c[y + 3, x + 3], c[y + 3, x - 3], c[y - 3, x - 3]]
+            f = [flat[px(x + 3, y - 3)], flat[px(x + 3, y + 3)], flat[px(x - 3, y + 3)], flat[px(x - 3, y - 3)]]
             if all(v != OTHER for v in f) and (sum(int(v == BLACK) for v in f) & 1):
                 out.append((x, y))
     return out
+
+
+def test_last_column_reads_wrap_to_the_next_row(oracle):
+    """x = w-3 is inside the reference's loop (3..=width-3): its right-hand ring samples are px(x+3, y-+3) = column 0 of rows
+    y-2 / y+4.  A corner there is found exactly when those wrapped samples say so."""
+    w, h = 40, 30
+    c = np.full((h, w), WHITE, np.uint8)
+    c[10:20, w - 3:] = BLACK                               # a black block whose top-left corner is pixel (w-3, 10)
+    x, y = w - 3, 10
+    as_list = lambda r: [tuple(p) for p in r[0][:r[1]].tolist()]      # noqa: E731
+    # the four far samples are White, White (wrapped: c[y-2, 0], c[y+4, 0]), White, White: even parity, no corner
+    assert (x, y) not in corners_py(c) and as_list(oracle.cat_detect_corners(c)) == corners_py(c)
+    c2 = c.copy()
+    c2[y + 4, 0] = BLACK                                   # the wrapped "bottom right" sample px(x+3, y+3) turns black: a corner
+    assert (x, y) in corners_py(c2)
+    assert as_list(oracle.cat_detect_corners(c2)) == corners_py(c2)
+    c3 = c2.copy()
+    c3[y - 2, 0] = OTHER                                   # the wrapped "top right" sample px(x+3, y-3) is Other: ring not all good
+    assert (x, y) not in corners_py(c3) and as_list(oracle.cat_detect_corners(c3)) == corners_py(c3)
 
 
 def test_detect_corners_order_and_predicate(oracle):

@@ -68,16 +68,17 @@ def test_c1_against_cv2_aruco(oracle):
     im, truth = synth.render_frame(1280, 720, 4, seed=1, edge_px=(60, 150))
     dets = oracle.detect(im)
     prm = cv2.aruco.DetectorParameters()
-    prm.cornerRefinementMethod = cv2.aruco.CORNER_REFINE_SUBPIX
+    prm.cornerRefinementMethod = cv2.aruco.CORNER_REFINE_APRILTAG       # OpenCV's own port of the UMich quad detector
     det = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_APRILTAG_36h11), prm)
     corners, ids, _ = det.detectMarkers(im)
     assert sorted(ids.ravel().tolist()) == sorted(dets["id"].tolist())
     for c, i in zip(corners, ids.ravel()):
         d = dets[dets["id"].tolist().index(int(i))]
-        c = c.reshape(4, 2) + 0.5          # OpenCV reports pixel-centre coordinates
-        # same quadrilateral up to cyclic order / direction
+        c = c.reshape(4, 2)                # the AprilTag path reports AprilTag's pixel convention (no half-pixel shift)
+        # same quadrilateral up to cyclic order / direction; 0.3 px covers refine_edges, which OpenCV's port does not run
+        # (test_quads_against_opencv_apriltag_port compares like with like at 0.08 px)
         best = min(np.abs(np.roll(cc, s, 0) - d["p"]).max() for cc in (c, c[::-1]) for s in range(4))
-        assert best < 1.0, (int(i), best)
+        assert best < 0.3, (int(i), best)
 
 
 def test_threshold_values_and_remainder(oracle):
@@ -252,3 +253,110 @@ def test_detection_record_conventions(oracle):
         area2 = float(np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y))
         assert area2 < 0                                   # upstream's winding: negative shoelace sum with y pointing down
         assert d["hamming"] == 0 and d["decision_margin"] > 20
+
+
+# ---- round 2: error-corrected decode, family bits, reconcile, decimation factors, and an independent quad pin ----------
+
+@pytest.mark.parametrize("bits", [0, 1, 2, 3])
+def test_hamming_decode_and_family_bits(oracle, bits):
+    """quick_decode with add_family_bits(family, bits) (crates/apriltags/src/lib.rs:229-230 bits 3, :279-282 bits 1): a tag with k
+    inverted data bits decodes with hamming k when k <= bits and is rejected otherwise (tag36h11's minimum distance 11 keeps the
+    radius-3 balls of all 587 x 4 rotated codes disjoint, so the answer is unique)."""
+    from tests import frames as fr
+    for k in range(5):
+        im, truth = synth.render_frame(1280, 720, 4, seed=31, edge_px=(70, 150), bit_errors=k)
+        dets = oracle.detect(im, oracle.default_params(bits_corrected=bits))
+        if k <= bits:
+            assert sorted(dets["id"].tolist()) == sorted(truth["ids"].tolist()) and (dets["hamming"] == k).all()
+            match_truth(dets, truth, 0.5)
+        else:
+            assert len(dets) == 0
+    im, truth = fr.bit_error_frame()
+    dets = oracle.detect(im, oracle.default_params(bits_corrected=bits))
+    want = {int(i): int(h) for i, h in zip(truth["ids"], truth["hamming"]) if h <= bits}
+    assert {int(d["id"]): int(d["hamming"]) for d in dets} == want
+
+
+def test_family_bits_out_of_range(oracle):
+    im = np.full((64, 64), 128, np.uint8)
+    for bits in (-1, 4):
+        with pytest.raises(RuntimeError):
+            oracle.detect(im, oracle.default_params(bits_corrected=bits))
+
+
+def test_bit_error_golden_fixture_and_cv2_decode(oracle):
+    """tests/golden/detector_biterr.npz (regression pin) and detector_cv2_pin.npz (OpenCV's decoder with maxCorrectionBits = k
+    accepts exactly the tags bits_corrected = k accepts)."""
+    g = np.load(os.path.join(GOLD, "detector_biterr.npz"))
+    pin = np.load(os.path.join(GOLD, "detector_cv2_pin.npz"))
+    from tests import frames as fr
+    im, _ = fr.bit_error_frame()
+    assert (im == g["frame"]).all(), "generator drifted"
+    for bits in range(4):
+        dets = oracle.detect(im, oracle.default_params(bits_corrected=bits))
+        assert dets["id"].tolist() == g[f"ids_b{bits}"].tolist() and dets["hamming"].tolist() == g[f"hamming_b{bits}"].tolist()
+        assert np.abs(dets["p"] - g[f"corners_b{bits}"]).max() < 1e-9 if len(dets) else True
+        assert sorted(dets["id"].tolist()) == pin[f"biterr_ids_k{bits}"].tolist()
+    assert g["hamming_b3"].max() == 3
+
+
+def test_reconcile_overlapping_duplicates(oracle):
+    """Two detections of one id with overlapping polygons: upstream keeps the lower hamming, then the higher decision margin."""
+    from tests import frames as fr
+    for kw, want in fr.RECONCILE_CASES:
+        both = oracle.detect(fr.nested_same_id_frame(**dict(kw, small_id=9)))          # distinct ids: nothing to reconcile
+        assert both["id"].tolist() == [7, 9]
+        big, small = both[0], both[1]
+        dets = oracle.detect(fr.nested_same_id_frame(**kw))
+        assert dets["id"].tolist() == [7], kw
+        width = float(np.ptp(dets[0]["p"][:, 0]))
+        if want is None:              # equal hamming, margins of the same order: whichever survives must be one of the two, intact
+            want = "big" if width > 400 else "small"
+        assert (width > 400) == (want == "big"), (kw, width)
+        ref = big if want == "big" else small
+        assert dets[0]["hamming"] == ref["hamming"] and np.abs(dets[0]["p"] - ref["p"]).max() < 1e-9
+        if want == "big":
+            assert dets[0]["decision_margin"] == big["decision_margin"]
+
+
+@pytest.mark.parametrize("f", [1.0, 3.0])
+def test_other_decimation_factors(oracle, f):
+    """quad_decimate 1 (detector works on the frame itself, corners not rescaled) and 3 (point sampling every third pixel,
+    min_tag_width = max(3, 8 / f))."""
+    im, truth = synth.render_frame(640, 480, 3, seed=7, edge_px=(60, 110))
+    dets, taps = oracle.detect(im, oracle.default_params(quad_decimate=f), taps=True)
+    assert taps["thresh"].shape == ((480, 640) if f == 1.0 else (160, 214))
+    match_truth(dets, truth, 0.5)
+    with pytest.raises(RuntimeError):
+        oracle.detect(im, oracle.default_params(quad_decimate=1.5))
+
+
+@pytest.mark.parametrize("name", ["c1", "s2", "s3"])
+def test_quads_against_opencv_apriltag_port(oracle, name):
+    """INDEPENDENT PIN of rows A2-A5 + A7.  OpenCV's aruco module contains its own port of the UMich quad detector
+    (CORNER_REFINE_APRILTAG); on the same frame, un-decimated and without refine_edges, this restatement must find the same
+    quadrilaterals: measured <= 0.05 px, asserted < 0.08 px (the previous round compared with CORNER_REFINE_SUBPIX at 1 px).
+    Checked against the committed OpenCV output, and against OpenCV itself when it is importable."""
+    pin = np.load(os.path.join(GOLD, "detector_cv2_pin.npz"))
+    im, _ = synth.render_frame(1280, 720, 4, seed=int(pin[f"{name}_seed"]), edge_px=(60, 150))
+    dets = oracle.detect(im, oracle.default_params(quad_decimate=1.0, refine_edges=0))
+    assert dets["id"].tolist() == pin[f"{name}_ids"].tolist()
+
+    def quad_dist(c, p):
+        return min(np.abs(np.roll(cc, s, 0) - p).max() for cc in (c, c[::-1]) for s in range(4))
+
+    for d, c in zip(dets, pin[f"{name}_corners"]):
+        assert quad_dist(c, d["p"]) < 0.08
+    # the full default path (decimate 2 + refine_edges on the full-resolution frame) lands within 0.3 px of the same corners
+    full = oracle.detect(im)
+    for d, c in zip(full, pin[f"{name}_corners"]):
+        assert quad_dist(c, d["p"]) < 0.3
+    try:
+        import cv2
+    except ImportError:
+        return
+    prm = cv2.aruco.DetectorParameters()
+    prm.cornerRefinementMethod = cv2.aruco.CORNER_REFINE_APRILTAG
+    corners, ids, _ = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_APRILTAG_36h11), prm).detectMarkers(im)
+    for c, i in zip(corners, ids.ravel()):
+        assert quad_dist(c.reshape(4, 2), dets[dets["id"].tolist().index(int(i))]["p"]) < 0.08
