@@ -2,15 +2,19 @@
 """bench.py -- frames/s of the AprilTag detection hot path on N B200 GPUs (BASELINE.json metric).
 
 A "step" is one pass of the whole detector (decimate+threshold -> union-find -> gradient clusters -> quad fit ->
-refine/decode/reconcile) over one batch of synthetic frames of the configuration BASELINE.json quotes for one GPU
-(configs[1]: 256 frames of 1456x1088 with 8 tags each).  Frames are independent, so N GPUs each process their own
-batch (weak scaling, no collective on the data path; rank 0 gathers per-rank detection counts).
+refine/decode/reconcile) over one batch of 256 synthetic frames at the resolution the metric names (1280x720, 4 tag36h11 tags
+per frame: the scene of BASELINE.json configs[0] at the batch size of configs[1]).  Frames are independent, so N GPUs each process
+their own batch (weak scaling, no collective on the data path).
 
-  value  : device-resident frames/s (frames already in HBM; CUDA events on the library's stream, max over ranks)
-  e2e    : frames/s through the public API with HOST (pinned) frames, H2D and D2H inside the timed region; the headline uses
-           the streaming form of the call (submit batch k+1, collect batch k), e2e.sync_call the blocking call
-  roofline: the HBM-bound kernel the north star names (fused decimate+threshold), algorithmic bytes 0.75*W*H per frame
+  value        : device-resident frames/s (frames already in HBM; CUDA events on the library's stream, max over ranks)
+  e2e          : frames/s through the public API with HOST (pinned) frames, H2D and D2H inside the timed region (streaming form of
+                 the call: submit batch k+1, collect batch k); e2e.sync_call = the blocking call
+  roofline     : the HBM-bound kernel the north star names (fused decimate+threshold), algorithmic bytes 0.75*W*H per frame
   cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/), timed on this box's cores
+  also_c2      : the same arms on BASELINE.json configs[1] (256 x 1456x1088, 8 tags), with the per-stage times
+  c4_stream    : BASELINE.json configs[3] (4096 x 1280x800 frames sharded over the N GPUs, lists gathered to one host array)
+  sqpnp_1M     : BASELINE.json configs[4] (1 M pose problems), N = 1 only
+  p50_frame_latency_ms : one 1280x720 frame through the reference-shaped call (host frame in, list out)
 
 Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
@@ -29,26 +33,40 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, TAGS, BATCH = 1456, 1088, 8, 256        # BASELINE.json configs[1]
-WORKLOAD = "c2: 256 x 1456x1088 gray frames, 8 tag36h11 tags each (BASELINE.json configs[1])"
-# BASELINE.json's metric string, verbatim (it names the reference's own 1280x720 CPU case, configs[0]); the workload this
-# bench measures is configs[1] -- the single-GPU configuration the metric is quoted on -- and is named in config.workload.
-METRIC = "frames/sec at 1/2/4/8 B200 (1280\u00d7720 tag36h11); p50 per-frame latency"
+BATCH = 256
+WORKLOADS = {
+    # the workload `value` / `e2e` are quoted on: the metric string's resolution
+    "c1": dict(W=1280, H=720, tags=4, unique=8, seed=0x5EED + 1, edge=(60.0, 150.0),
+               name="256 x 1280x720 gray frames, 4 tag36h11 tags each (the metric's resolution: the scene of BASELINE.json "
+                    "configs[0] in batches of configs[1]'s size)"),
+    "c2": dict(W=1456, H=1088, tags=8, unique=16, seed=0x5EED + 2, edge=(40.0, 200.0),
+               name="c2: 256 x 1456x1088 gray frames, 8 tag36h11 tags each (BASELINE.json configs[1])"),
+}
+METRIC = "frames/sec at 1/2/4/8 B200 (1280×720 tag36h11); p50 per-frame latency"
 try:
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "BASELINE.json")) as _f:
+    with open(os.path.join(ROOT, "BASELINE.json")) as _f:
         METRIC = json.load(_f)["metric"]
 except (OSError, KeyError, ValueError):
     pass
 UNIT = "frames/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of threshold_f2_tma_kernel over a 128-frame launch (ncu --set full), per frame;
-# the ternary map (0.25*W*H per frame) is only partly written back to DRAM inside the kernel (it stays in the 126 MB L2)
-NCU_TRAFFIC_BYTES_PER_FRAME = (110.668032e6 + 20.104960e6) / 128
+# dram__bytes_read.sum + dram__bytes_write.sum of the threshold kernel per frame from one `ncu --set full` capture of a
+# 256-frame launch of each workload (profiles/); None = not captured for that workload
+NCU_TRAFFIC_BYTES_PER_FRAME = {"c2": (110.668032e6 + 20.104960e6) / 128, "c1": None}
+NCU_TRAFFIC_SOURCE = {"c2": "ncu --set full, profiles/r01_ncu_threshold_tma.txt: (dram read + write) / 128 frames", "c1": None}
+try:                                                            # refreshed by tools/ncu_summary.py when a new capture is summarised
+    with open(os.path.join(ROOT, "profiles", "threshold_traffic.json")) as _f:
+        for _k, _v in json.load(_f).items():
+            NCU_TRAFFIC_BYTES_PER_FRAME[_k] = _v["bytes_per_frame"]
+            NCU_TRAFFIC_SOURCE[_k] = _v["source"]
+except (OSError, KeyError, ValueError):
+    pass
 
 
-def make_frames(rank: int, batch: int = BATCH, unique: int = 16):
+def make_frames(wl: str, rank: int, batch: int = BATCH):
     from chalkydri_b200 import synth
-    frames, truths = synth.render_batch(W, H, batch, TAGS, seed=0x5EED + 2 + 1000 * rank, unique=unique, edge_px=(40.0, 200.0))
-    return frames, truths
+    w = WORKLOADS[wl]
+    return synth.render_batch(w["W"], w["H"], batch, w["tags"], seed=w["seed"] + 1000 * rank, unique=min(w["unique"], batch),
+                              edge_px=w["edge"])
 
 
 class ClockSampler(threading.Thread):
@@ -62,7 +80,7 @@ class ClockSampler(threading.Thread):
     def _run_nvml(self):
         import pynvml as nv
         nv.nvmlInit()
-        # CUDA_VISIBLE_DEVICES remaps ordinals: resolve the physical device through its UUID / PCI bus id when torch knows it
+        # CUDA_VISIBLE_DEVICES remaps ordinals: resolve the physical device through its PCI bus id when torch knows it
         try:
             import torch
             h = nv.nvmlDeviceGetHandleByPciBusId(torch.cuda.get_device_properties(self.gpu).pci_bus_id.encode()) \
@@ -110,51 +128,182 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
-def cpu_baseline(frames: np.ndarray, seconds_target: float = 12.0):
-    """oracle detector on a bounded sample of the same workload, all host threads (one frame per thread)."""
+def cpu_baseline(frames: np.ndarray, wl: str, seconds_target: float = 10.0):
+    """The oracle detector on a bounded sample of the same workload: on ONE thread (the reference's effective setting -- upstream's
+    nthreads defaults to 1 and crates/apriltags/src/lib.rs:258-261 never changes it) and on all host threads, one frame per thread."""
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     po.detect_batch(frames[:1], cap=64, nthreads=1)
     t1 = time.perf_counter() - t0
-    n = int(max(cores, min(len(frames), seconds_target / max(t1, 1e-3) * cores)))
+    n1 = int(max(2, min(len(frames), 0.3 * seconds_target / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    po.detect_batch(frames[:n1], cap=64, nthreads=1)
+    dt1 = time.perf_counter() - t0
+    n = int(max(cores, min(len(frames), 0.7 * seconds_target / max(t1, 1e-3) * cores)))
     n = min(n, len(frames))
     t0 = time.perf_counter()
     _, counts = po.detect_batch(frames[:n], cap=64, nthreads=cores)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} frames of the c2 workload, one frame per thread on {cores} threads "
-                      f"(single-thread first frame: {1.0 / t1:.1f} frames/s); CPU restatement of the reference path (oracle/), "
-                      f"{int(counts.sum())} detections"}
+            "sample": f"{n} frames of the {wl} workload, one frame per thread on {cores} threads; CPU restatement of the reference "
+                      f"path (oracle/; the Rust reference and its un-vendored C detector cannot be built here), {int(counts.sum())} detections",
+            "single_thread": {"value": n1 / dt1, "unit": UNIT, "cores": 1,
+                              "sample": f"{n1} frames on one thread (upstream's nthreads = 1, which the reference never changes)"}}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; the Rust reference cannot be built here) on host cores."""
+    """--impl reference: the reference's CPU path (oracle port; the Rust reference cannot be built here) on all host cores, on the
+    SAME configuration as our arm: every step is the full 256-frame batch of the headline workload."""
     if rank != 0:
         return
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
-    sample = max(2 * cores, 32)
-    frames, _ = make_frames(0, batch=sample, unique=min(sample, 16))
+    frames, _ = make_frames("c1", 0)
     for _ in range(args.warmup):
-        po.detect_batch(frames[:cores], cap=64, nthreads=cores)
+        po.detect_batch(frames[:2 * cores], cap=64, nthreads=cores)
     t0 = time.perf_counter()
     ndet = 0
     for _ in range(args.steps):
         _, counts = po.detect_batch(frames, cap=64, nthreads=cores)
         ndet += int(counts.sum())
     dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
+    value = BATCH * args.steps / dt
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "frames_per_step": sample, "note": "bounded sample of the c2 workload per step"},
+            "config": {"workload": WORKLOADS["c1"]["name"], "frames_per_step_per_gpu": BATCH,
+                       "parallelism": f"one frame per host thread on {cores} threads (rank 0 only)",
+                       "l2": "n/a (CPU arm)", "unique_frames": WORKLOADS["c1"]["unique"]},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} frames per step x {args.steps} steps, one frame per thread on {cores} threads; "
+                             "sample": f"{BATCH} frames per step x {args.steps} steps, one frame per thread on {cores} threads; "
                                        f"the Rust reference (un-vendored git deps, no cargo) cannot be built here, so this is oracle/"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "detections": ndet}
     print(json.dumps(line), flush=True)
+
+
+class Arms:
+    """The three arms (device-resident, blocking host call, streaming host call) of one workload on this rank's GPU."""
+
+    def __init__(self, wl, rank, local_rank, barrier):
+        from chalkydri_b200 import capi
+        from chalkydri_b200.detector import DetectorBuilder, DET_DTYPE
+        self.wl, self.w, self.barrier, self.capi = wl, WORKLOADS[wl], barrier, capi
+        self.frames, self.truths = make_frames(wl, rank)
+        W, H = self.w["W"], self.w["H"]
+        self.det = DetectorBuilder.default().add_family_bits("tag36h11", 3).device(local_rank).capacity(W, H, BATCH, 64).build()
+        self.L = capi.lib()
+        self.h_frames = capi.pinned_array(self.frames.shape, np.uint8)
+        self.h_frames[...] = self.frames
+        self.out = capi.pinned_array((BATCH, 64), DET_DTYPE)
+        self.counts = capi.pinned_array((BATCH,), np.int32)
+        self.d_frames = self.L.cb_device_alloc(self.det.ctx, self.frames.nbytes)
+        assert self.d_frames, "device allocation failed"
+        assert self.L.cb_memcpy_h2d(self.det.ctx, self.d_frames, capi.ptr(self.h_frames), self.frames.nbytes) == 0
+
+    def device_arm(self, steps, warmup):
+        det, W, H = self.det, self.w["W"], self.w["H"]
+        for _ in range(max(warmup, 3)):
+            det.detect_batch_device(self.d_frames, BATCH, H, W, out=self.out, counts=self.counts)
+        self.barrier()
+        stage = {k: 0.0 for k in ("threshold_ms", "ccl_ms", "cluster_ms", "quad_ms", "decode_ms", "d2h_ms", "total_ms")}
+        launches = thr_launches = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            det.detect_batch_device(self.d_frames, BATCH, H, W, out=self.out, counts=self.counts)
+            t = det.timing()
+            for k in stage:
+                stage[k] += t[k]
+            launches += t["kernel_launches"]
+            thr_launches += t["threshold_launches"]
+        self.barrier()
+        return {"stage": stage, "launches": launches, "thr_launches": thr_launches, "wall": time.perf_counter() - t0,
+                "ndet": int(self.counts.sum())}
+
+    def sync_arm(self, steps):
+        for _ in range(2):
+            self.det.detect_batch(self.h_frames, out=self.out, counts=self.counts)
+        self.barrier()
+        t0 = time.perf_counter()
+        dev_ms = 0.0
+        for _ in range(steps):
+            self.det.detect_batch(self.h_frames, out=self.out, counts=self.counts)
+            dev_ms += self.det.timing()["total_ms"]
+        self.barrier()
+        return {"wall": time.perf_counter() - t0, "dev_ms": dev_ms}
+
+    def _stream_steps(self, n):
+        d, hf = self.det, self.h_frames
+        d.submit(hf)
+        for s_ in range(n):
+            if s_ + 1 < n:
+                d.submit(hf)
+            d.collect(out=self.out, counts=self.counts)
+
+    def stream_arm(self, steps):
+        self._stream_steps(2)
+        self.barrier()
+        t0 = time.perf_counter()
+        self._stream_steps(steps)
+        self.barrier()
+        return {"wall": time.perf_counter() - t0, "ndet": int(self.counts.sum())}
+
+    def latency(self, iters):
+        lat = []
+        one = self.h_frames[:1]
+        for i in range(iters + 5):
+            t0 = time.perf_counter()
+            self.det.detect_batch(one, out=self.out[:1], counts=self.counts[:1])
+            if i >= 5:
+                lat.append((time.perf_counter() - t0) * 1e3)
+        return float(np.median(lat)) if lat else None
+
+    def close(self):
+        self.L.cb_device_free(self.det.ctx, self.d_frames)
+        self.det.close()
+        for a in (self.h_frames, self.out, self.counts):
+            self.capi.free_pinned(a)
+
+
+def sqpnp_1m(n=1_000_000):
+    """BASELINE.json configs[4]: 1 M pose problems through cb_sqpnp_batch (kernel events and the whole host call), the CPU
+    restatement of chalkydri_sqpnp on a bounded sample beside it."""
+    from chalkydri_b200.solver import SqPnP
+    from tests.sqpnp_problems import make_problems
+    from oracle import pyoracle as po
+    tags, bearings, n_tags, r2c, gyro, _ = make_problems(n, 0x5EED + 5, 0.1, 0.25)
+    s = SqPnP.new()
+    for _ in range(2):
+        out, ok = s.solve_robot_pose_batch(tags, bearings, n_tags, r2c, gyro, 600.0)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        out, ok = s.solve_robot_pose_batch(tags, bearings, n_tags, r2c, gyro, 600.0)
+        wall = time.perf_counter() - t0
+        t = s.timing()
+        ts.append((t["decode_ms"], t["total_ms"], wall * 1e3))
+    k_ms, tot_ms, wall_ms = np.median(np.array(ts), 0)
+    s.close()
+    m, cores = min(n, 20000), os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ref, rok = po.sqpnp_batch(tags[:m], bearings[:m], n_tags[:m], r2c, gyro[:m], 600.0, nthreads=1)
+    t1 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    po.sqpnp_batch(tags[:m], bearings[:m], n_tags[:m], r2c, gyro[:m], 600.0, nthreads=cores)
+    tn = time.perf_counter() - t0
+    both = ok[:m].astype(bool) & rok.astype(bool)
+    scale = np.maximum(1.0, np.abs(ref["pos"][both]).max(1))
+    return {"workload": f"c5: {n} SQPnP problems (90% one tag, 10% two tags, 0.25 px corner noise, gyro sigma 2 deg)",
+            "value": n / (k_ms * 1e-3), "unit": "problems/s", "kernel_ms": float(k_ms),
+            "e2e": {"value": n / (wall_ms * 1e-3), "unit": "problems/s", "wall_ms": float(wall_ms), "h2d_kernel_d2h_ms": float(tot_ms),
+                    "api": "cb_sqpnp_batch: host arrays in, poses out"},
+            "ok_fraction": float(ok.mean()),
+            "cpu_baseline": {"kind": "port", "sample": f"{m} problems", "value": m / tn, "unit": "problems/s", "cores": cores,
+                             "single_thread": m / t1},
+            "parity_on_sample": {"ok_equal": bool((ok[:m] == rok).all()),
+                                 "max_rel_pos_diff": float((np.abs(out["pos"][:m][both] - ref["pos"][both]).max(1) / scale).max()),
+                                 "max_rot_diff": float(np.abs(out["rot"][:m][both] - ref["rot"][both]).max())}}
 
 
 def main():
@@ -164,7 +313,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-c1", action="store_true", help="skip the secondary 1280x720 measurement")
+    ap.add_argument("--no-c2", action="store_true", help="skip the configs[1] measurement")
+    ap.add_argument("--no-c4", action="store_true", help="skip the configs[3] stream")
+    ap.add_argument("--no-sqpnp", action="store_true", help="skip the configs[4] measurement")
     ap.add_argument("--latency-iters", type=int, default=50)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -180,6 +331,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    # host threads and pinned buffers of this rank next to its GPU (NUMA): the end-to-end arm moves 236 MB per step per rank
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByPciBusId(torch.cuda.get_device_properties(local_rank).pci_bus_id.encode()))
+        affinity = f"nvml ideal CPUs of GPU {local_rank}: {len(os.sched_getaffinity(0))} cpus"
+    except Exception as e:                                # noqa: BLE001 -- affinity is an optimisation, never a requirement
+        affinity = f"not set ({type(e).__name__})"
     if world > 1:
         # NCCL prints its version banner (NCCL_DEBUG=VERSION and up) with printf when the communicator comes up; stdout must
         # carry exactly one JSON line, so fd 1 points at stderr until the first collective has run.
@@ -196,128 +355,11 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    from chalkydri_b200 import capi
-    from chalkydri_b200.detector import DetectorBuilder, DET_DTYPE
-
-    frames, truths = make_frames(rank)
-    det = DetectorBuilder.default().add_family_bits("tag36h11", 3).device(local_rank).capacity(W, H, BATCH, 64).build()
-    L = capi.lib()
-    # pinned host copies (e2e arm) and a device-resident copy (value arm)
-    h_frames = capi.pinned_array(frames.shape, np.uint8)
-    h_frames[...] = frames
-    out = capi.pinned_array((BATCH, 64), DET_DTYPE)
-    counts = capi.pinned_array((BATCH,), np.int32)
-    d_frames = L.cb_device_alloc(det.ctx, frames.nbytes)
-    assert d_frames, "device allocation failed"
-    assert L.cb_memcpy_h2d(det.ctx, d_frames, capi.ptr(h_frames), frames.nbytes) == 0
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ----
-    for _ in range(max(args.warmup, 3)):
-        det.detect_batch_device(d_frames, BATCH, H, W, out=out, counts=counts)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    stage = {k: 0.0 for k in ("threshold_ms", "ccl_ms", "cluster_ms", "quad_ms", "decode_ms", "d2h_ms", "total_ms")}
-    launches = thr_launches = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        det.detect_batch_device(d_frames, BATCH, H, W, out=out, counts=counts)
-        t = det.timing()
-        for k in stage:
-            stage[k] += t[k]
-        launches += t["kernel_launches"]
-        thr_launches += t["threshold_launches"]
-    barrier()
-    wall_dev = time.perf_counter() - t0
-    dev_ms = stage["total_ms"]                       # CUDA events on the library's stream (kernels + list D2H)
-    ndet = int(counts.sum())
-    want = sum(len(t["ids"]) for t in truths)
-
-    # ---- end-to-end arm: pinned host frames in, detection lists out ----
-    for _ in range(2):
-        det.detect_batch(h_frames, out=out, counts=counts)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_dev_ms = 0.0
-    for _ in range(args.steps):
-        det.detect_batch(h_frames, out=out, counts=counts)
-        e2e_dev_ms += det.timing()["total_ms"]
-    barrier()
-    wall_e2e_sync = time.perf_counter() - t0
-
-    # ---- the same arm through the streaming form of the call (cb_detect_gray_submit / _collect): batch k+1 is submitted
-    #      before batch k is collected, as in a camera loop; every step's H2D and D2H are inside the timed region ----
-    def stream_steps(d, hf, n):
-        d.submit(hf)
-        for s_ in range(n):
-            if s_ + 1 < n:
-                d.submit(hf)
-            d.collect(out=out, counts=counts)
-
-    stream_steps(det, h_frames, 2)
-    barrier()
-    t0 = time.perf_counter()
-    stream_steps(det, h_frames, args.steps)
-    barrier()
-    wall_e2e = time.perf_counter() - t0
-    ndet_stream = int(counts.sum())
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-
-    # ---- p50 single-frame latency through the public API (host frame in, list out) ----
-    lat = []
-    one = h_frames[:1]
-    for i in range(args.latency_iters + 5):
-        t0 = time.perf_counter()
-        det.detect_batch(one, out=out[:1], counts=counts[:1])
-        if i >= 5:
-            lat.append((time.perf_counter() - t0) * 1e3)
-    p50 = float(np.median(lat)) if lat else None
-
-    # ---- the metric string names 1280x720: the same two arms on a 256-frame batch of the c1 resolution (N = 1 only) ----
-    also = None
-    if world == 1 and not args.no_c1:
-        from chalkydri_b200 import synth
-        W1, H1 = 1280, 720
-        f1, _ = synth.render_batch(W1, H1, BATCH, 4, seed=0x5EED + 1, unique=8, edge_px=(60.0, 150.0))
-        det1 = DetectorBuilder.default().add_family_bits("tag36h11", 3).device(local_rank).capacity(W1, H1, BATCH, 64).build()
-        h1 = capi.pinned_array(f1.shape, np.uint8)
-        h1[...] = f1
-        d1 = L.cb_device_alloc(det1.ctx, f1.nbytes)
-        assert d1 and L.cb_memcpy_h2d(det1.ctx, d1, capi.ptr(h1), f1.nbytes) == 0
-        for _ in range(3):
-            det1.detect_batch_device(d1, BATCH, H1, W1, out=out, counts=counts)
-        ms = 0.0
-        for _ in range(args.steps):
-            det1.detect_batch_device(d1, BATCH, H1, W1, out=out, counts=counts)
-            ms += det1.timing()["total_ms"]
-        nd1 = int(counts.sum())
-        for _ in range(2):
-            det1.detect_batch(h1, out=out, counts=counts)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            det1.detect_batch(h1, out=out, counts=counts)
-        torch.cuda.synchronize()
-        w1 = time.perf_counter() - t0
-        stream_steps(det1, h1, 2)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        stream_steps(det1, h1, args.steps)
-        torch.cuda.synchronize()
-        w1s = time.perf_counter() - t0
-        also = {"workload": "256 x 1280x720 gray frames, 4 tag36h11 tags each (the resolution the metric string names)",
-                "value": BATCH * args.steps / (ms / 1e3), "e2e": BATCH * args.steps / w1s, "e2e_sync_call": BATCH * args.steps / w1,
-                "unit": UNIT, "detections_per_step": nd1}
-        L.cb_device_free(det1.ctx, d1)
-        det1.close()
-
-    # max over ranks
     def rmax(x):
         if world == 1:
             return x
@@ -332,14 +374,64 @@ def main():
         dist.all_reduce(t_, op=dist.ReduceOp.SUM)
         return float(t_.item())
 
-    dev_s = rmax(dev_ms / 1e3)
-    wall_dev = rmax(wall_dev)
-    wall_e2e = rmax(wall_e2e)
-    wall_e2e_sync = rmax(wall_e2e_sync)
-    total_det = rsum(ndet)
     frames_total = BATCH * args.steps * world
-    value = frames_total / dev_s
-    e2e_value = frames_total / wall_e2e
+
+    def measure(wl, sampler=None):
+        a = Arms(wl, rank, local_rank, barrier)
+        if sampler:
+            sampler.start()
+        dev = a.device_arm(args.steps, args.warmup)
+        sync = a.sync_arm(args.steps)
+        stream = a.stream_arm(args.steps)
+        if sampler:
+            sampler.stop_flag = True
+            sampler.join(timeout=2)
+        dev_s = rmax(dev["stage"]["total_ms"] / 1e3)
+        r = {"arms": a, "dev": dev, "dev_s": dev_s, "value": frames_total / dev_s, "e2e": frames_total / rmax(stream["wall"]),
+             "e2e_wall": rmax(stream["wall"]), "e2e_sync": frames_total / rmax(sync["wall"]), "e2e_sync_wall": rmax(sync["wall"]),
+             "e2e_sync_dev_ms": sync["dev_ms"], "wall_dev": rmax(dev["wall"]), "ndet": rsum(dev["ndet"]), "ndet_stream": stream["ndet"],
+             "want": sum(len(t["ids"]) for t in a.truths) * world}
+        return r
+
+    sampler = ClockSampler(local_rank)
+    m1 = measure("c1", sampler)
+    a1 = m1["arms"]
+    p50 = a1.latency(args.latency_iters)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(a1.frames, "c1")
+    frames_nbytes, out_nbytes = int(a1.frames.nbytes), int(a1.out.nbytes + a1.counts.nbytes)
+    a1.close()
+
+    also_c2 = None
+    if not args.no_c2:
+        m2 = measure("c2")
+        a2 = m2["arms"]
+        w2 = WORKLOADS["c2"]
+        thr_ms2 = m2["dev"]["stage"]["threshold_ms"] / max(m2["dev"]["thr_launches"], 1)
+        also_c2 = {"workload": w2["name"], "value": m2["value"], "ms_per_step": m2["dev_s"] / args.steps * 1e3, "e2e": m2["e2e"],
+                   "e2e_sync_call": m2["e2e_sync"], "unit": UNIT, "h2d_bytes_per_step": int(a2.frames.nbytes),
+                   "stage_ms_per_step": {k: v / args.steps for k, v in m2["dev"]["stage"].items()},
+                   "threshold_gbs": 0.75 * w2["W"] * w2["H"] * BATCH / (thr_ms2 * 1e-3) / 1e9,
+                   "detections_per_step": m2["ndet"], "expected_tags_per_step": m2["want"]}
+        if rank == 0 and not args.no_cpu_baseline:
+            also_c2["cpu_baseline"] = cpu_baseline(a2.frames, "c2", seconds_target=8.0)
+        a2.close()
+
+    c4 = None
+    if not args.no_c4:
+        try:
+            from tools import bench_c4_stream
+            c4 = bench_c4_stream.run(rank, local_rank, world, dist if world > 1 else None)
+        except Exception as e:                            # noqa: BLE001 -- an extra key must never take the headline down
+            c4 = {"error": f"{type(e).__name__}: {e}"}
+
+    sq = None
+    if rank == 0 and world == 1 and not args.no_sqpnp:
+        try:
+            sq = sqpnp_1m()
+        except Exception as e:                            # noqa: BLE001
+            sq = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peaks = {}
@@ -348,41 +440,44 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        thr_bytes = 0.75 * W * H * BATCH                       # algorithmic bytes of one launch
-        thr_ms = stage["threshold_ms"] / max(thr_launches, 1)
+        w1 = WORKLOADS["c1"]
+        stage = m1["dev"]["stage"]
+        thr_bytes = 0.75 * w1["W"] * w1["H"] * BATCH                       # algorithmic bytes of one launch
+        thr_ms = stage["threshold_ms"] / max(m1["dev"]["thr_launches"], 1)
         achieved = thr_bytes / (thr_ms * 1e-3) / 1e9
+        traffic = NCU_TRAFFIC_BYTES_PER_FRAME.get("c1")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": m1["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": m1["dev_s"] / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": BATCH, "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                       "l2": "inputs (405 MB per step) exceed the 126 MB L2", "unique_frames": 16},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
-                    "d2h_bytes_per_step": int(out.nbytes + counts.nbytes), "ms_per_step_wall": wall_e2e / args.steps * 1e3,
+            "config": {"workload": w1["name"], "frames_per_step_per_gpu": BATCH,
+                       "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                       "l2": f"inputs ({frames_nbytes / 1e6:.0f} MB per step) exceed the 126 MB L2", "unique_frames": w1["unique"],
+                       "host_affinity": affinity},
+            "e2e": {"value": m1["e2e"], "unit": UNIT, "h2d_bytes_per_step": frames_nbytes, "d2h_bytes_per_step": out_nbytes,
+                    "ms_per_step_wall": m1["e2e_wall"] / args.steps * 1e3,
                     "api": "cb_detect_gray_submit / cb_detect_gray_collect: pinned host frames in, detection lists out, batch k+1 "
                            "submitted before batch k is collected (two in flight); every step's copies are inside the timed region",
-                    "detections_per_step": ndet_stream,
-                    "sync_call": {"api": "cb_detect_gray (one blocking call per step)", "value": frames_total / wall_e2e_sync,
-                                  "ms_per_step_wall": wall_e2e_sync / args.steps * 1e3,
-                                  "ms_per_step_device_events": e2e_dev_ms / args.steps}},
-            "also_1280x720": also,
-            "gpu_launches": int(launches),
+                    "detections_per_step": m1["ndet_stream"],
+                    "sync_call": {"api": "cb_detect_gray (one blocking call per step)", "value": m1["e2e_sync"],
+                                  "ms_per_step_wall": m1["e2e_sync_wall"] / args.steps * 1e3,
+                                  "ms_per_step_device_events": m1["e2e_sync_dev_ms"] / args.steps}},
+            "gpu_launches": int(m1["dev"]["launches"]),
             "clocks": sampler.result(),
-            "roofline": {"kernel": "threshold_f2_tma_kernel (fused decimate + tile min/max + 3x3 dilate + binarise, TMA-staged)", "bound": "hbm", "achieved": achieved,
-                         "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_FRAME * BATCH,
-                         "traffic_source": "ncu --set full, profiles/r01_ncu_threshold_tma.txt: (dram read + write) / 128 frames", "ms_per_launch": thr_ms,
-                         "algorithmic_bytes_per_launch": thr_bytes},
+            "roofline": {"kernel": "threshold kernel (fused decimate + tile min/max + 3x3 dilate + binarise, TMA-staged)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic * BATCH if traffic else None,
+                         "traffic_source": NCU_TRAFFIC_SOURCE.get("c1"), "ms_per_launch": thr_ms, "algorithmic_bytes_per_launch": thr_bytes},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-            "wall_ms_per_step_device_arm": wall_dev / args.steps * 1e3,
+            "wall_ms_per_step_device_arm": m1["wall_dev"] / args.steps * 1e3,
             "p50_frame_latency_ms": p50,
-            "detections_per_step": total_det, "expected_tags_per_step": want * world,
+            "detections_per_step": m1["ndet"], "expected_tags_per_step": m1["want"],
+            "also_c2": also_c2, "c4_stream": c4, "sqpnp_1M": sq,
         }
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(frames)
+        if cpu:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    L.cb_device_free(det.ctx, d_frames)
-    det.close()
     if world > 1:
         dist.destroy_process_group()
 

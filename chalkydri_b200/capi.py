@@ -35,13 +35,19 @@ class Timing(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class PoolTiming(C.Structure):
+    _fields_ = [("wall_ms", C.c_float), ("max_device_ms", C.c_float), ("min_device_ms", C.c_float), ("n_devices", C.c_int32)]
+
+
 # every symbol include/chalkydri_b200.h declares
 EXPORTS = ["cb_create", "cb_destroy", "cb_last_error", "cb_set_family_tag36h11", "cb_set_params", "cb_detect_gray",
            "cb_detect_gray_device", "cb_detect_gray_submit", "cb_detect_gray_collect", "cb_detect_gray_pending", "cb_detect_rgb", "cb_detect_yuyv", "cb_detect_yuv420", "cb_rgb_to_gray", "cb_yuyv_to_gray", "cb_decimated_size", "cb_threshold", "cb_labels",
            "cb_quads", "cb_get_timing", "cb_sqpnp_set", "cb_sqpnp_batch", "cb_sqpnp_batch_device",
            "cb_create_solver_camera_transform", "cb_unproject_opencv5", "cb_set_field", "cb_set_camera", "cb_detect_pose_gray", "cb_detect_pose_gray_submit", "cb_detect_pose_gray_collect", "cb_pack_vision_measurements", "cb_cat_calc_otsu", "cb_cat_thresh",
            "cb_cat_detect_corners", "cb_cat_check_edges", "cb_cat_connected_components", "cb_host_alloc", "cb_host_free",
-           "cb_device_alloc", "cb_device_free", "cb_memcpy_h2d", "cb_memcpy_d2h", "cb_device_count", "cb_version"]
+           "cb_device_alloc", "cb_device_free", "cb_memcpy_h2d", "cb_memcpy_d2h", "cb_device_count", "cb_version",
+           "cb_pool_create", "cb_pool_destroy", "cb_pool_last_error", "cb_pool_size", "cb_pool_context", "cb_pool_set_family_tag36h11",
+           "cb_pool_detect_gray", "cb_pool_get_timing"]
 
 _lib = None
 
@@ -101,6 +107,14 @@ def lib():
         L.cb_device_free.restype = None; L.cb_device_free.argtypes = [vp, vp]
         L.cb_memcpy_h2d.argtypes = [vp, vp, vp, sz]
         L.cb_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+        L.cb_pool_create.restype = vp; L.cb_pool_create.argtypes = [vp, i32, i32, i32, i32, i32]
+        L.cb_pool_destroy.restype = None; L.cb_pool_destroy.argtypes = [vp]
+        L.cb_pool_last_error.restype = C.c_char_p; L.cb_pool_last_error.argtypes = [vp]
+        L.cb_pool_size.argtypes = [vp]
+        L.cb_pool_context.restype = vp; L.cb_pool_context.argtypes = [vp, i32]
+        L.cb_pool_set_family_tag36h11.argtypes = [vp, i32]
+        L.cb_pool_detect_gray.argtypes = [vp, vp, i32, i32, i32, sz, i32, vp, vp]
+        L.cb_pool_get_timing.argtypes = [vp, vp]
         L.cb_device_count.restype = i32
         L.cb_version.restype = C.c_char_p
         _lib = L

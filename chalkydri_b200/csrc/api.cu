@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1190,3 +1191,4 @@ int cb_memcpy_d2h(cb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes
 
 #include "api_solver.inc"
 #include "api_cat.inc"
+#include "api_pool.inc"

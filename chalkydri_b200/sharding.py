@@ -44,8 +44,50 @@ def stream_shard(detector, frames: np.ndarray, batch: int, out: np.ndarray | Non
     return out, counts
 
 
+class SharedDetections:
+    """ONE host array for the whole job that every rank of the box maps (POSIX shared memory): `out` [n_total, cap] records and
+    `counts` [n_total].  Rank r's streaming calls write its lists straight into out[lo:hi] / counts[lo:hi] -- "each GPU's D2H
+    into its slice of one host array"  for the one-process-per-GPU launch: no collective, no re-upload of records,
+    no padding.  The creating rank calls unlink() after everyone closed."""
+
+    def __init__(self, name: str, n_total: int, cap: int, create: bool):
+        from multiprocessing import shared_memory
+        from .capi import DET_DTYPE
+        rec = DET_DTYPE.itemsize
+        self.nbytes = n_total * cap * rec + n_total * 4
+        if create:
+            try:
+                shared_memory.SharedMemory(name=name).unlink()           # a stale segment of a crashed run
+            except FileNotFoundError:
+                pass
+            self._shm = shared_memory.SharedMemory(name=name, create=True, size=self.nbytes)
+        else:
+            self._shm = shared_memory.SharedMemory(name=name)
+        self._owner = create
+        self.out = np.ndarray((n_total, cap), DET_DTYPE, buffer=self._shm.buf, offset=0)
+        self.counts = np.ndarray((n_total,), np.int32, buffer=self._shm.buf, offset=n_total * cap * rec)
+
+    def close(self):
+        self.out = self.counts = None
+        self._shm.close()
+
+    def unlink(self):
+        if self._owner:
+            self._shm.unlink()
+
+
+def stream_shard_into(detector, frames: np.ndarray, batch: int, shared: SharedDetections, lo: int):
+    """stream_shard for rank-local `frames` = job frames [lo, lo + len(frames)): lists go straight into the shared array's slice,
+    `frame` becomes the job-wide index."""
+    hi = lo + len(frames)
+    stream_shard(detector, frames, batch, out=shared.out[lo:hi], counts=shared.counts[lo:hi])
+    shared.out["frame"][lo:hi] += lo
+
+
 def gather_detections(local_out: np.ndarray, local_counts: np.ndarray, lo: int, n_total: int, dist=None, device=None):
-    """Gather every rank's [n_local, cap] detection records + counts into rank 0's [n_total, cap] array, ordered by frame index.
+    """Gather every rank's [n_local, cap] detection records + counts into rank 0's [n_total, cap] array, ordered by frame index,
+    through torch.distributed (any backend).  This is the generic route -- across nodes, or when the ranks do not share a host;
+    on one box the ranks write into a SharedDetections array instead and nothing is gathered at all.
 
     Returns (out, counts) on rank 0 and (None, None) elsewhere.  With dist=None (single process) it is the identity."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:

@@ -207,6 +207,32 @@ int cb_cat_check_edges(cb_ctx *ctx, const uint8_t *color, int width, int height,
 /* Detector::connected_components (lib.rs:501-549): min-index labels and component sizes */
 int cb_cat_connected_components(cb_ctx *ctx, const uint8_t *color, int width, int height, uint32_t *labels, uint32_t *sizes);
 
+/* ---- several GPUs of one box, one process: frames are independent, so a batch is sharded over the GPUs with no
+ *      collective -- one context and one host thread per GPU, each GPU's lists written straight into its slice of the caller's
+ *      one output array.  This is the batched form of running one AprilTags task per camera (crates/apriltags/src/lib.rs:166-182,
+ *      three of them in chalkydri.ron:2-105) with camera streams spread over GPUs. ---- */
+typedef struct cb_pool cb_pool;
+typedef struct {
+    float wall_ms;                /* host wall time of the last cb_pool_detect_gray call */
+    float max_device_ms;          /* busiest / least busy worker thread (submit of its first batch .. collect of its last) */
+    float min_device_ms;
+    int32_t n_devices;
+} cb_pool_timing;
+/* devices[n_devices]: CUDA ordinals (one context each; an ordinal may repeat); devices == NULL or n_devices <= 0: every visible
+ * GPU.  The other arguments are cb_create's, per GPU.  NULL on failure (cb_pool_last_error(NULL) has the text). */
+cb_pool *cb_pool_create(const int *devices, int n_devices, int max_width, int max_height, int max_batch, int max_dets_per_frame);
+void cb_pool_destroy(cb_pool *pool);
+const char *cb_pool_last_error(const cb_pool *pool);
+int cb_pool_size(const cb_pool *pool);
+cb_ctx *cb_pool_context(cb_pool *pool, int i);       /* the i-th GPU's context, e.g. for cb_set_params; owned by the pool */
+int cb_pool_set_family_tag36h11(cb_pool *pool, int bits_corrected);
+/* cb_detect_gray over every GPU of the pool: GPU g takes the contiguous frames [g*n/N, (g+1)*n/N) in batches of at most
+ * max_batch through the streaming form (two batches in flight per GPU); out / out_counts are indexed by the frame's position in
+ * `frames` exactly like cb_detect_gray, and cb_detection.frame is that position.  Use pinned frames (cb_host_alloc). */
+int cb_pool_detect_gray(cb_pool *pool, const uint8_t *frames, int width, int height, int stride, size_t frame_stride,
+                        int n_frames, cb_detection *out, int32_t *out_counts);
+int cb_pool_get_timing(const cb_pool *pool, cb_pool_timing *t);
+
 /* ---- plumbing ---- */
 void *cb_host_alloc(size_t bytes);        /* pinned host memory for frames / outputs */
 void cb_host_free(void *p);

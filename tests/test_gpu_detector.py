@@ -521,7 +521,7 @@ def test_other_decimation_factors(oracle, f, W, H):
         gq, oq = canon_quads(q[b, :qc[b]]), canon_quads(taps["quads"]["p"])
         assert np.abs(np.array(gq) - np.array(oq)).max() < 1e-4 if gq else True
         assert_same_detections(out[b, :counts[b]], ref)
-        assert counts[b] >= 2
+        assert counts[b] >= (2 if W >= 640 else 1)
     det.close()
 
 
@@ -592,3 +592,45 @@ def test_yuv420_buffers(oracle):
         assert o2[b, :c2[b]].tobytes() == ref_out[b, :c2[b]].tobytes()
     capi.free_pinned(h)
     det.close()
+
+
+def test_pool_shards_frames_over_contexts_without_a_collective(oracle):
+    """cb_pool_detect_gray (single process): one context + one host thread per GPU, contiguous shares, every share's
+    lists written into its slice of the caller's one array.  A box with one GPU lists it twice -- two contexts, two threads, the
+    same code path as two GPUs.  37 frames in batches of 8: ragged shares (19 + 18) and ragged last batches."""
+    from chalkydri_b200 import capi
+    from chalkydri_b200.pool import DetectorPool
+    frames, _ = synth.render_batch(640, 480, 37, 2, seed=61, unique=6, edge_px=(50, 110))
+    h = capi.pinned_array(frames.shape, np.uint8)
+    h[...] = frames
+    det = make_detector(640, 480, 8, 16)
+    want, wc = det.detect_batch(frames)
+    det.close()
+    for devices in ([0], [0, 0], [0, 0, 0]):
+        pool = DetectorPool(devices, 640, 480, 8, 16)
+        assert len(pool) == len(devices)
+        for _ in range(2):                                     # a second call reuses the contexts
+            out, counts = pool.detect_batch(h)
+            assert counts.tolist() == wc.tolist() and counts.sum() >= 37
+            for b in range(37):
+                assert out[b, :counts[b]].tobytes() == want[b, :wc[b]].tobytes()
+                assert (out[b, :counts[b]]["frame"] == b).all()
+        t = pool.timing()
+        assert t["n_devices"] == len(devices) and t["wall_ms"] > 0
+        pool.close()
+    assert_same_detections(want[5, :wc[5]], oracle.detect(frames[5]))
+    capi.free_pinned(h)
+
+
+def test_pool_reports_errors_per_gpu():
+    from chalkydri_b200.capi import ChalkydriError
+    from chalkydri_b200.pool import DetectorPool
+    pool = DetectorPool([0, 0], 640, 480, 4, 16)
+    with pytest.raises(ChalkydriError) as e:
+        pool.detect_batch(np.zeros((6, 600, 800), np.uint8))      # larger than the contexts
+    assert "GPU 0" in str(e.value)
+    out, counts = pool.detect_batch(np.full((6, 480, 640), 128, np.uint8))      # the queues were drained: the pool still works
+    assert counts.tolist() == [0] * 6
+    pool.close()
+    with pytest.raises(ChalkydriError):
+        DetectorPool([99], 640, 480, 4, 16)

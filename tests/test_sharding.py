@@ -120,3 +120,49 @@ def test_sharded_stream_two_ranks_gloo(tmp_path):
     for f in range(n_total):
         for k in range(counts[f]):
             assert out[f, k]["frame"] == f and out[f, k]["id"] == (f % 25) * 10 + k
+
+
+def _shared_worker(rank, world, port, n_total, batch, name, tmp):
+    import torch.distributed as dist
+    from chalkydri_b200.sharding import SharedDetections, shard_range, stream_shard_into
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    shared = SharedDetections(name, n_total, _StandInDetector.max_dets, create=True) if rank == 0 else None
+    if rank == 0:
+        shared.counts[:] = -1
+    dist.barrier()
+    if rank != 0:
+        shared = SharedDetections(name, n_total, _StandInDetector.max_dets, create=False)
+    lo, hi = shard_range(n_total, rank, world)
+    frames = np.zeros((hi - lo, 2, 2), np.uint8)
+    for i in range(lo, hi):
+        frames[i - lo, 0, 0] = i % 4
+        frames[i - lo, 0, 1] = i % 25
+    stream_shard_into(_StandInDetector(), frames, batch, shared, lo)
+    dist.barrier()                                        # the only synchronisation: every slice is in the array
+    if rank == 0:
+        np.save(os.path.join(tmp, "sh_out.npy"), shared.out.copy())
+        np.save(os.path.join(tmp, "sh_counts.npy"), shared.counts.copy())
+    shared.close()
+    dist.barrier()
+    if rank == 0:
+        shared.unlink()
+    dist.destroy_process_group()
+
+
+def test_sharded_stream_into_one_shared_host_array(tmp_path):
+    """The one-box form of BASELINE configs[3]: two ranks write their lists straight into their slices of ONE host array (POSIX
+    shared memory); no gather, no collective on the data path (the barriers only order create / fill / read)."""
+    pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    n_total = 23
+    mp.spawn(_shared_worker, args=(2, port, n_total, 5, f"cb_test_{os.getpid()}", str(tmp_path)), nprocs=2, join=True)
+    out = np.load(tmp_path / "sh_out.npy")
+    counts = np.load(tmp_path / "sh_counts.npy")
+    assert counts.tolist() == [f % 4 for f in range(n_total)]
+    for f in range(n_total):
+        for k in range(counts[f]):
+            assert out[f, k]["frame"] == f and out[f, k]["id"] == (f % 25) * 10 + k

@@ -1,78 +1,151 @@
 """BASELINE.json configs[3]: a multi-camera stream of 4096 1280x800 frames sharded over N B200 GPUs, detection lists gathered to
-the host of rank 0.  Strong scaling: the 4096 frames are fixed, rank r takes the contiguous chunk shard_range(4096, r, N)
-(no collective on the data path), feeds it in batches of 256 through the streaming form of the detector call (pinned host
-frames, batch k+1 submitted before batch k is collected) and the fixed-size detection records are gathered once at the end.
-The timed region covers every H2D copy, every kernel, every list read-back and the gather; time = max over ranks.
+one host array.  Strong scaling: the 4096 frames are fixed.  No NCCL / no collective on the data path, no re-upload, no padding:
+
+  multi_process      (how bench.py is launched: one process per GPU) rank r takes the contiguous chunk shard_range(4096, r, N),
+                     feeds it in batches of 256 through the streaming form of the detector call (pinned host frames, batch k+1
+                     submitted before batch k is collected) and its lists are written straight into rank r's slice of ONE host
+                     array that all ranks map (POSIX shared memory); rank 0 owns the array.  Time = barrier .. barrier, max over ranks.
+  single_process_pool (rank 0 alone, the other ranks idle) the same stream through cb_pool_detect_gray: one process, one host
+                     thread + one context per GPU inside the library, every GPU's lists land in its slice of the caller's array.
 
   python tools/bench_c4_stream.py                       (1 GPU)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/bench_c4_stream.py
 """
-import json, os, sys, time
+import json
+import os
+import sys
+import time
+
 import numpy as np
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
-import torch.distributed as dist
-from chalkydri_b200 import synth, capi
-from chalkydri_b200.detector import DetectorBuilder, DET_DTYPE
-from chalkydri_b200.sharding import shard_range, gather_detections, stream_shard
 
 TOTAL, W, H, BATCH, CAP, UNIQUE = 4096, 1280, 800, 256, 16, 8
-rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
-reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-torch.cuda.set_device(local)
-if world > 1:
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    saved = os.dup(1); os.dup2(2, 1)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dist.barrier(); torch.cuda.synchronize()
-    sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
-
-# frame i of the stream is unique frame i % UNIQUE ("cameras" take turns); 0..6 tags per frame
-uniq, truths = [], []
-for u in range(UNIQUE):
-    f, t = synth.render_frame(W, H, u % 7, seed=0x5EED + 4 + 31 * u, edge_px=(40.0, 160.0))
-    uniq.append(f); truths.append(len(t["ids"]))
-lo, hi = shard_range(TOTAL, rank, world)
-n = hi - lo
-h = capi.pinned_array((n, H, W), np.uint8)
-for i in range(n):
-    h[i] = uniq[(lo + i) % UNIQUE]
-out = np.zeros((n, CAP), DET_DTYPE); counts = np.zeros(n, np.int32)
-det = DetectorBuilder.default().add_family_bits("tag36h11", 3).device(local).capacity(W, H, BATCH, CAP).build()
 
 
-def one_pass():
-    stream_shard(det, h, BATCH, out=out, counts=counts)
-    return gather_detections(out, counts, lo, TOTAL, dist if world > 1 else None, device=torch.device("cuda", local))
+def unique_frames():
+    """frame i of the stream is unique frame i % UNIQUE ("cameras" take turns); 0..6 tags per frame"""
+    from chalkydri_b200 import synth
+    uniq, ntags = [], []
+    for u in range(UNIQUE):
+        f, t = synth.render_frame(W, H, u % 7, seed=0x5EED + 4 + 31 * u, edge_px=(40.0, 160.0))
+        uniq.append(f)
+        ntags.append(len(t["ids"]))
+    return uniq, ntags
 
 
-def barrier():
+def run(rank, local, world, dist, reps=3, total=TOTAL):
+    import torch
+    from chalkydri_b200 import capi
+    from chalkydri_b200.detector import DetectorBuilder, DET_DTYPE
+    from chalkydri_b200.sharding import SharedDetections, shard_range, stream_shard_into
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rmax(x):
+        if dist is None:
+            return x
+        t_ = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    uniq, ntags = unique_frames()
+    want = sum(ntags[i % UNIQUE] for i in range(total))
+    lo, hi = shard_range(total, rank, world)
+    n = hi - lo
+    h = capi.pinned_array((n, H, W), np.uint8)
+    for i in range(n):
+        h[i] = uniq[(lo + i) % UNIQUE]
+    # ONE host array for the whole job; every rank maps it and fills its own slice
+    name = f"cb_c4_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if dist is not None else os.getpid()}"
+    shared = SharedDetections(name, total, CAP, create=True) if rank == 0 else None
+    barrier()
+    if rank != 0:
+        shared = SharedDetections(name, total, CAP, create=False)
+    g_out, g_counts = shared.out, shared.counts
+    det = DetectorBuilder.default().add_family_bits("tag36h11", 3).device(local).capacity(W, H, BATCH, CAP).build()
+
+    def one_pass():
+        stream_shard_into(det, h, BATCH, shared, lo)
+
+    one_pass()
+    walls = []
+    for _ in range(reps):
+        if rank == 0:
+            g_counts[:] = -1
+        barrier()
+        t0 = time.perf_counter()
+        one_pass()
+        barrier()                                       # every slice is in the array
+        walls.append(time.perf_counter() - t0)
+    wall = rmax(float(np.median(walls)))
+    res = None
+    if rank == 0:
+        have = g_counts > 0
+        res = {"workload": f"c4: {total} x {W}x{H} frames, 0-6 tags each, sharded over {world} GPU(s), lists gathered into one host array",
+               "scaling": "strong", "n_gpus": world, "unit": "frames/s",
+               "multi_process": {"value": total / wall, "ms_per_pass": wall * 1e3, "passes": reps, "detections": int(g_counts.sum()),
+                                 "ground_truth_tags": int(want), "all_slices_filled": bool((g_counts >= 0).all()),
+                                 "gathered_in_frame_order": bool((g_out["frame"][have, 0] == np.nonzero(have)[0]).all()),
+                                 "h2d_bytes_per_pass": total * W * H, "gathered_bytes_per_pass": int(shared.nbytes),
+                                 "api": "cb_detect_gray_submit / cb_detect_gray_collect per rank, lists written into the rank's slice "
+                                        "of one shared host array; no NCCL, no re-upload, no padding"}}
+        ref_counts = g_counts.copy()
+    det.close()
+    capi.free_pinned(h)
+    del g_out, g_counts
+    shared.close()
+    barrier()
+    if rank == 0:
+        shared.unlink()
+        # single process, one thread + context per GPU (cb_pool_detect_gray); the other ranks wait at the barrier below
+        from chalkydri_b200.pool import DetectorPool
+        ngpu = world if dist is not None else 1
+        try:
+            hp = capi.pinned_array((total, H, W), np.uint8)
+            for i in range(total):
+                hp[i] = uniq[i % UNIQUE]
+            out = np.zeros((total, CAP), DET_DTYPE)
+            counts = np.zeros(total, np.int32)
+            pool = DetectorPool(list(range(ngpu)), W, H, BATCH, CAP)
+            pool.detect_batch(hp, out=out, counts=counts)
+            pw = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                pool.detect_batch(hp, out=out, counts=counts)
+                pw.append(time.perf_counter() - t0)
+            pwall = float(np.median(pw))
+            have = counts > 0
+            res["single_process_pool"] = {"value": total / pwall, "ms_per_pass": pwall * 1e3, "passes": reps, "detections": int(counts.sum()),
+                                          "same_lists_as_multi_process": bool((counts == ref_counts).all()),
+                                          "gathered_in_frame_order": bool((out["frame"][have, 0] == np.nonzero(have)[0]).all()),
+                                          "timing": pool.timing(),
+                                          "api": "cb_pool_detect_gray: one process, one host thread + one context per GPU, every GPU's "
+                                                 "lists land in its slice of the caller's array"}
+            pool.close()
+            capi.free_pinned(hp)
+        except Exception as e:                           # noqa: BLE001
+            res["single_process_pool"] = {"error": f"{type(e).__name__}: {e}"}
+    barrier()
+    return res
+
+
+if __name__ == "__main__":
+    import torch
+    import torch.distributed as dist
+    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    torch.cuda.set_device(local)
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-
-
-one_pass()
-walls = []
-for _ in range(reps):
-    barrier()
-    t0 = time.perf_counter()
-    g_out, g_counts = one_pass()
-    barrier()
-    walls.append(time.perf_counter() - t0)
-wall = float(np.median(walls))
-if world > 1:
-    t_ = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-    wall = float(t_.item())
-if rank == 0:
-    want = sum(truths[i % UNIQUE] for i in range(TOTAL))
-    frames_in_order = bool((g_out["frame"][g_counts > 0, 0] == np.nonzero(g_counts > 0)[0]).all())
-    print(json.dumps({"config": "c4", "workload": f"{TOTAL} x {W}x{H} frames, 0-6 tags each, sharded over {world} GPU(s), lists gathered to rank 0",
-                      "scaling": "strong", "n_gpus": world, "value": TOTAL / wall, "unit": "frames/s", "ms_per_pass": wall * 1e3,
-                      "passes": reps, "detections": int(g_counts.sum()), "ground_truth_tags": int(want), "gathered_in_frame_order": frames_in_order,
-                      "h2d_bytes_per_pass": TOTAL * W * H, "gathered_bytes_per_pass": int(g_out.nbytes + g_counts.nbytes),
-                      "api": "cb_detect_gray_submit / cb_detect_gray_collect per rank + one dist.gather of the records"}), flush=True)
-det.close()
-if world > 1:
-    dist.destroy_process_group()
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        saved = os.dup(1); os.dup2(2, 1)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier(); torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    r = run(rank, local, world, dist if world > 1 else None, reps=int(sys.argv[1]) if len(sys.argv) > 1 else 3)
+    if rank == 0:
+        print(json.dumps(r), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
