@@ -128,6 +128,29 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
+def set_gpu_local_affinity(gpu_index: int) -> str:
+    """Bind this process to the CPUs NVML reports as local to the GPU (same socket / NUMA node as its PCIe root); pinned buffers
+    allocated afterwards are first-touched there.  An optimisation, never a requirement: every failure is reported, not raised."""
+    try:
+        import pynvml as nv
+        import torch
+        nv.nvmlInit()
+        try:
+            h = nv.nvmlDeviceGetHandleByPciBusId(torch.cuda.get_device_properties(gpu_index).pci_bus_id.encode())
+        except Exception:                                 # noqa: BLE001 -- older torch: no pci_bus_id; ordinals match unless CUDA_VISIBLE_DEVICES remaps
+            h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {c for c in range(ncpu) if (int(words[c // 64]) >> (c % 64)) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "nvml reports no local cpus inside this process' cpu set"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to the {len(cpus)} cpus local to GPU {gpu_index} (of {ncpu})"
+    except Exception as e:                                # noqa: BLE001
+        return f"not set ({type(e).__name__}: {e})"
+
+
 def cpu_baseline(frames: np.ndarray, wl: str, seconds_target: float = 10.0):
     """The oracle detector on a bounded sample of the same workload: on ONE thread (the reference's effective setting -- upstream's
     nthreads defaults to 1 and crates/apriltags/src/lib.rs:258-261 never changes it) and on all host threads, one frame per thread."""
@@ -332,13 +355,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     # host threads and pinned buffers of this rank next to its GPU (NUMA): the end-to-end arm moves 236 MB per step per rank
-    try:
-        import pynvml as nv
-        nv.nvmlInit()
-        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByPciBusId(torch.cuda.get_device_properties(local_rank).pci_bus_id.encode()))
-        affinity = f"nvml ideal CPUs of GPU {local_rank}: {len(os.sched_getaffinity(0))} cpus"
-    except Exception as e:                                # noqa: BLE001 -- affinity is an optimisation, never a requirement
-        affinity = f"not set ({type(e).__name__})"
+    affinity = set_gpu_local_affinity(local_rank)
     if world > 1:
         # NCCL prints its version banner (NCCL_DEBUG=VERSION and up) with printf when the communicator comes up; stdout must
         # carry exactly one JSON line, so fd 1 points at stderr until the first collective has run.

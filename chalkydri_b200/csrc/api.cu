@@ -92,7 +92,11 @@ struct cb_ctx {
     uint8_t *d_tmin = nullptr, *d_tmax = nullptr;    size_t tile_bytes = 0;
     uint32_t *d_labels = nullptr, *d_sizes = nullptr; size_t label_bytes = 0;
     ClusterSlot *d_table = nullptr;
-    uint4 *d_ent = nullptr;                    // per-point words of the cluster count pass, 16 B per decimated pixel
+    int cluster_mode = 0;                      // 0: band-ordered count / scatter (round 2), 1: tile passes + scan-order sort (round 1; CB_CLUSTERS=tiles)
+    ClbArea *d_areas = nullptr;                // band tables of the count pass (first areas, then the pool of chained sub-band areas)
+    uint32_t areas_first_cap = 0, areas_pool_cap = 0;
+    uint32_t *d_cursors = nullptr;             // prefix-pass cursors when clusters_per_frame does not fit shared memory
+    uint4 *d_ent = nullptr;                    // tiles: per-point words of the count pass, 16 B per decimated pixel; bands: the staging lists (same size)
     unsigned long long *d_tile_keys = nullptr;  // per-tile tables of the count pass
     uint32_t *d_tile_cnt = nullptr;
     ClusterRec *d_clusters = nullptr;
@@ -181,7 +185,7 @@ void cb_destroy(cb_ctx *ctx)
     if (ctx->pose_stream) cudaStreamSynchronize(ctx->pose_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
-                    ctx->d_table, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
+                    ctx->d_table, ctx->d_areas, ctx->d_cursors, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
                     ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->d_in2) cudaFree(ctx->d_in2);
@@ -284,9 +288,19 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     {
         const size_t dw = (size_t)ctx->max_w / 2 + 1, dh = (size_t)ctx->max_h / 2 + 1;      // decimated size bound (quad_decimate = 2)
         const size_t tiles = ((dw + CL_TW - 1) / CL_TW) * ((dh + CL_TH - 1) / CL_TH);
+        if (const char *e = getenv("CB_CLUSTERS")) ctx->cluster_mode = strcmp(e, "tiles") == 0 ? 1 : 0;      // A/B hook
         ok = ok && alloc((void **)&ctx->d_ent, B * dw * dh * sizeof(uint4));
-        ok = ok && alloc((void **)&ctx->d_tile_keys, B * tiles * CL_CAP * sizeof(unsigned long long));
-        ok = ok && alloc((void **)&ctx->d_tile_cnt, B * tiles * CL_CAP * sizeof(uint32_t));
+        if (ctx->cluster_mode == 1) {
+            ok = ok && alloc((void **)&ctx->d_tile_keys, B * tiles * CL_CAP * sizeof(unsigned long long));
+            ok = ok && alloc((void **)&ctx->d_tile_cnt, B * tiles * CL_CAP * sizeof(uint32_t));
+        } else {
+            // bands: at most ~num_sms * 128 first areas when bands are short, B * ceil(h / 4) when they have 4 rows; as many
+            // again for chained sub-bands (a band whose private table fills up)
+            const size_t first = std::max<size_t>((size_t)ctx->num_sms * 128 + 2 * B, B * (dh / 4 + 2));
+            ctx->areas_first_cap = (uint32_t)first; ctx->areas_pool_cap = (uint32_t)first;
+            ok = ok && alloc((void **)&ctx->d_areas, 2 * first * sizeof(ClbArea));
+            if ((size_t)c.clusters_per_frame * sizeof(uint32_t) > 160 * 1024) ok = ok && alloc((void **)&ctx->d_cursors, B * c.clusters_per_frame * sizeof(uint32_t));
+        }
     }
     ok = ok && alloc((void **)&ctx->d_clusters, B * c.clusters_per_frame * sizeof(ClusterRec));
     ok = ok && alloc((void **)&ctx->d_worklist, 4 * B * c.clusters_per_frame * sizeof(uint32_t));
@@ -307,9 +321,13 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, thr_tma_warp_bytes(THR_TMA_ROWB) * THR_TMA_WARPS) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(threshold_tm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<6>::SMEM) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(threshold_tm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<4>::SMEM) == cudaSuccess;
 #define CB_SORT_ATTR(CFG) ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::BYTES) == cudaSuccess;
         CB_SORT_ATTR(SortS8<1>) CB_SORT_ATTR(SortS16<1>) CB_SORT_ATTR(SortM<1>) CB_SORT_ATTR(SortL1<1>) CB_SORT_ATTR(SortL2<1>)
         CB_SORT_ATTR(SortS8<2>) CB_SORT_ATTR(SortS16<2>) CB_SORT_ATTR(SortM<2>) CB_SORT_ATTR(SortL1<2>) CB_SORT_ATTR(SortL2<2>)
+        CB_SORT_ATTR(SortS8<3>) CB_SORT_ATTR(SortS16<3>) CB_SORT_ATTR(SortM<3>) CB_SORT_ATTR(SortL1<3>) CB_SORT_ATTR(SortL2<3>)
+        if (!ctx->d_cursors) ok = ok && cudaFuncSetAttribute(cluster_band_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c.clusters_per_frame * sizeof(uint32_t))) == cudaSuccess;
 #undef CB_SORT_ATTR
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
             uint16_t combos[210];
@@ -424,6 +442,63 @@ static size_t pose_buf_bytes(size_t n)
            up(n * sizeof(cb_pose)) + up(n);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (libcuda is not linked)
+typedef CUresult (*cb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cb_encode_tiled_fn tensor_map_encoder()
+{
+    static cb_encode_tiled_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (cb_encode_tiled_fn)p;
+    }();
+    return fn;
+}
+
+// Launch of the tensor-map threshold kernel.  Returns false when the tensor map cannot be built (the caller then takes the 1-D TMA kernel).
+template <int T>
+static bool launch_threshold_tm(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int min_diff, cudaStream_t st)
+{
+    typedef TmCfg<T> C;
+    cb_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return false;
+    // 3-D tensor of 8-byte elements: x = tile column (8 input bytes = 4 decimated pixels), y = EVEN input row (row stride doubled),
+    // z = frame.  Box = the 32 T tiles of a warp x the 4 rows of a tile row.
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)(g.stride / 8), (cuuint64_t)g.h, (cuuint64_t)g.batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)2 * g.stride, (cuuint64_t)g.frame_stride};
+    const cuuint32_t box[3] = {32u * T, 4u, 1u}, estr[3] = {1u, 1u, 1u};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t *>(d_frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    TmPlan plan;
+    plan.strips = (g.tw + C::MAX_IW - 1) / C::MAX_IW;
+    plan.iw = ((g.tw + plan.strips - 1) / plan.strips + 1) / 2 * 2;
+    {   // equal waves: every warp does seg_rows + 2 tile rows plus the fill of its ring
+        const int ctas_per_sm = std::max(1, (int)((227 * 1024) / (C::SMEM + 1024)));
+        const long long resident = (long long)ctx->num_sms * ctas_per_sm * TM_WARPS;
+        const int max_segs = std::max(1, g.th / 6);
+        long long best_cost = -1;
+        int best = 1;
+        for (int ys = 1; ys <= max_segs; ys++) {
+            const int rows = (g.th + ys - 1) / ys, segs = (g.th + rows - 1) / rows;
+            if (segs != ys) continue;
+            const long long warps = (long long)plan.strips * segs * g.batch;
+            const long long cost = ((warps + resident - 1) / resident) * (rows + 2 + TM_STAGES);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ys; }
+        }
+        if (const char *e = getenv("CB_THR_YSEGS")) best = std::max(1, std::min(max_segs, atoi(e)));      // experiment hook
+        plan.seg_rows = (g.th + best - 1) / best;
+        plan.ysegs = (g.th + plan.seg_rows - 1) / plan.seg_rows;
+    }
+    const long long warps = (long long)plan.strips * plan.ysegs * g.batch;
+    const int wt = (g.w % 4 || g.h % 4) ? 1 : 0;
+    threshold_tm_kernel<T><<<(unsigned)((warps + TM_WARPS - 1) / TM_WARPS), TM_WARPS * 32, C::SMEM, st>>>(map, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g,
+                                                                                                     std::max(-1000, std::min(1000, min_diff)), plan, wt);
+    return true;
+}
+
 static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int stage)
 {
     cudaStream_t st = ctx->stream;
@@ -440,10 +515,20 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     // ---- A1+A2 threshold ----
     const bool fast = g.f == 2 && (g.stride % 16 == 0) && (g.frame_stride % 16 == 0) && ((uintptr_t)d_frames % 16 == 0) && g.tw > 0 && g.th > 0;
     if (fast) {
-        // variant switch for A/B profiling: CB_THRESHOLD = tma (default) | tiled
+        // variant switch for A/B profiling: CB_THRESHOLD = tmap (default: tensor-map TMA, 6 or 4 tiles per lane) | tma (round 1: four
+        // 1-D bulk copies per tile row) | tiled (first version, CTA tiles with block barriers)
         static const char *variant_env = getenv("CB_THRESHOLD");
-        static const int variant = variant_env == nullptr ? 0 : (strcmp(variant_env, "tiled") == 0 ? 2 : 0);
-        if (variant == 2) {
+        static const int variant = variant_env == nullptr ? 0 : (strcmp(variant_env, "tiled") == 0 ? 2 : (strcmp(variant_env, "tma") == 0 ? 1 : 0));
+        bool done = false;
+        if (variant == 0) {
+            // tiles per lane: the choice that keeps most lanes busy (one strip of T = 6 spans up to 188 tiles = 1504 input pixels)
+            const int s6 = (g.tw + TmCfg<6>::MAX_IW - 1) / TmCfg<6>::MAX_IW, s4 = (g.tw + TmCfg<4>::MAX_IW - 1) / TmCfg<4>::MAX_IW;
+            int use6 = (double)g.tw / (s6 * 32 * 6) >= (double)g.tw / (s4 * 32 * 4);
+            if (const char *e = getenv("CB_THR_T")) use6 = atoi(e) == 6;
+            done = use6 ? launch_threshold_tm<6>(ctx, d_frames, g, prm.min_white_black_diff, st) : launch_threshold_tm<4>(ctx, d_frames, g, prm.min_white_black_diff, st);
+        }
+        if (done) {
+        } else if (variant == 2) {
             dim3 grid((g.tw + THR_IW - 1) / THR_IW, (g.th + THR_IH - 1) / THR_IH, B), block(THR_TX, THR_TY);
             threshold_f2_kernel<<<grid, block, 0, st>>>(d_frames, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g, prm.min_white_black_diff);
         } else {
@@ -522,7 +607,28 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         const size_t nslots = (size_t)B * caps.slots_per_frame;
         table_init_kernel<<<(unsigned)((nslots + 255) / 256), 256, 0, st>>>(ctx->d_table, nslots);
         launches += 1;
-        if (g.h > 2 && g.w > 2) {
+        if (g.h > 2 && g.w > 2 && ctx->cluster_mode == 0) {
+            // band-ordered passes (clusters.cuh): rows per band so that the launch has ~128 warps per SM to balance
+            BandPlan bp;
+            bp.rows = (int)std::max<long long>(1, std::min<long long>(4, ((long long)B * (g.h - 2)) / ((long long)ctx->num_sms * 128)));
+            bp.nbands = (g.h - 2 + bp.rows - 1) / bp.rows;
+            if ((uint32_t)B * bp.nbands > ctx->areas_first_cap) return fail(ctx, CB_ERR_ARG, "internal: band tables too small (%d bands)", B * bp.nbands);
+            bp.pool_cap = ctx->areas_pool_cap;
+            const uint32_t nfirst = (uint32_t)B * bp.nbands, nall = nfirst + bp.pool_cap;
+            uint32_t *d_pool = d_misc + 6;
+            uint32_t *d_stage = reinterpret_cast<uint32_t *>(ctx->d_ent);
+            cluster_band_count_kernel<<<(nfirst + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, d_misc, d_stage,
+                                                                                                   ctx->d_areas, d_pool, g, caps, bp);
+            cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, wl_stride,
+                                                                                            d_misc + 8, 2, (uint32_t)QT0, (uint32_t)QT1,
+                                                                                            (uint32_t)QT2, d_misc, g, caps, prm.min_cluster_pixels);
+            cluster_band_resolve_kernel<<<(nall + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(ctx->d_table, ctx->d_areas, d_pool, g, caps, bp);
+            cluster_band_prefix_kernel<<<B, CLB_CAP, ctx->d_cursors ? 0 : caps.clusters_per_frame * sizeof(uint32_t), st>>>(ctx->d_areas, ctx->d_clusters, d_ncl,
+                                                                                                                      ctx->d_cursors, caps, bp);
+            cluster_band_scatter_kernel<<<(nall + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(d_stage, ctx->d_areas, d_pool, ctx->d_scankey, g, caps, bp);
+            launches += 5;
+        }
+        if (g.h > 2 && g.w > 2 && ctx->cluster_mode == 1) {
             dim3 gc((g.w + CL_TW - 1) / CL_TW, (g.h - 2 + CL_TH - 1) / CL_TH, B);
             cluster_count_kernel<<<gc, CL_THREADS, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, d_misc, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, g, caps);
             // misc: [0] error flags, [3] quads total, [4] decode counter, [8 + 2t] items of tier t, [9 + 2t] its work counter
@@ -544,6 +650,15 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
                                                                                              d_misc + (CNT), ctx->d_scratch, g, caps, prm);
         CK(cudaEventRecord(ctx->ev_fork, st));
         for (int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(ctx->tier_stream[i], ctx->ev_fork, 0));
+        if (ctx->cluster_mode == 0) {
+            // the points arrive in scan order: one sort (by slope) per tier, with sort #1's box / polarity tests in front
+            CB_LAUNCH_SORT1(SortL2<3>, 1, 25, st)
+            CB_LAUNCH_SORT1(SortL1<3>, 3, 24, ctx->tier_stream[0])
+            CB_LAUNCH_SORT1(SortM<3>, 6, 23, ctx->tier_stream[1])
+            CB_LAUNCH_SORT1(SortS16<3>, 3, 22, ctx->tier_stream[2])
+            CB_LAUNCH_SORT1(SortS8<3>, 4, 21, ctx->tier_stream[3])
+            launches -= 5;
+        } else {
         CB_LAUNCH_SORT1(SortL2<1>, 1, 20, st)
         CB_LAUNCH_SORT1(SortL2<2>, 1, 25, st)
         CB_LAUNCH_SORT1(SortL1<1>, 3, 19, ctx->tier_stream[0])
@@ -554,6 +669,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         CB_LAUNCH_SORT1(SortS16<2>, 3, 22, ctx->tier_stream[2])
         CB_LAUNCH_SORT1(SortS8<1>, 4, 16, ctx->tier_stream[3])
         CB_LAUNCH_SORT1(SortS8<2>, 4, 21, ctx->tier_stream[3])
+        }
 #undef CB_LAUNCH_SORT1
         for (int i = 0; i < 4; i++) {
             CK(cudaEventRecord(ctx->ev_tier[i], ctx->tier_stream[i]));

@@ -240,9 +240,12 @@ __device__ __forceinline__ void sort_scan_cluster(uint32_t *__restrict__ K, int 
 
 // ---- sort #2: slopes in scan order, ptsort() ------------------------------------------------------------------------
 // K holds the scan-ordered keys on entry and the sorted points (px | py << 16) on return.
-template <int NT, int E, bool PAD>
-__device__ __forceinline__ void sort_slope_cluster(uint32_t *__restrict__ K, int n, unsigned long long *A, unsigned long long *B,
-                                                   SortScratch &S, const Geom &g)
+// CHECK: K arrives in scan order straight from the band scatter pass (clusters.cuh), and the two tests sort #1 used to make --
+// bounding box against min_tag_width, border polarity -- happen here before any sorting; a rejected cluster gets
+// cursor = 0xffffffff.  Returns false for a rejected cluster.
+template <int NT, int E, bool PAD, bool CHECK>
+__device__ __forceinline__ bool sort_slope_cluster(uint32_t *__restrict__ K, int n, unsigned long long *A, unsigned long long *B,
+                                                   SortScratch &S, const Geom &g, ClusterRec *__restrict__ rec_global, const DetParams &prm)
 {
     typedef Grp<NT> G;
     const int tid = G::tid();
@@ -258,6 +261,39 @@ __device__ __forceinline__ void sort_slope_cluster(uint32_t *__restrict__ K, int
     ymax = G::reduce(ymax, [](int a, int c) { return max(a, c); }, S.red_i);
     const float cx = (float)((xmin + xmax) * 0.5 + 0.05118);
     const float cy = (float)((ymin + ymax) * 0.5 + -0.028581);
+    if (CHECK) {
+        if ((xmax - xmin) * (ymax - ymin) < prm.min_tag_width) { if (tid == 0) rec_global->cursor = 0xffffffffu; return false; }
+        // border polarity: see sort_scan_cluster -- the sign of upstream's float chain is known from the exact sum unless the
+        // terms nearly cancel; then the chain is replayed, and the points already are in the order upstream adds them in
+        double sum = 0, sum_abs = 0;
+        for (int i = tid; i < n; i += NT) {
+            int px, py, gx, gy;
+            decode_point(K[i], g.w, px, py, gx, gy);
+            const float dx = (float)px - cx, dy = (float)py - cy;
+            const float t = dx * (float)gx + dy * (float)gy;
+            sum += (double)t; sum_abs += fabs((double)t);
+        }
+        sum = G::reduce(sum, [](double a, double c) { return a + c; }, S.red_d);
+        sum_abs = G::reduce(sum_abs, [](double a, double c) { return a + c; }, S.red_d);
+        const bool certain = fabs(sum) > 2.0 * (double)n * 5.9604644775390625e-8 * sum_abs;
+        if (certain && sum < 0) { if (tid == 0) rec_global->cursor = 0xffffffffu; return false; }
+        if (!certain) {
+            G::sync();
+            if (tid == 0) {
+                float dot = 0.f;
+                for (int i = 0; i < n; i++) {
+                    int px, py, gx, gy;
+                    decode_point(K[i], g.w, px, py, gx, gy);
+                    const float dx = (float)px - cx, dy = (float)py - cy;
+                    dot += dx * (float)gx + dy * (float)gy;
+                }
+                S.work = dot < 0.f ? 1 : 0;
+                if (dot < 0.f) rec_global->cursor = 0xffffffffu;
+            }
+            G::sync();
+            if (S.work) return false;
+        }
+    }
     // slopes in scan order (upstream fit_quad step 1)
     for (int j = tid; j < n; j += NT) {
         int px, py, gx, gy;
@@ -301,6 +337,7 @@ __device__ __forceinline__ void sort_slope_cluster(uint32_t *__restrict__ K, int
     }
     G::sync();
     for (int j = tid; j < n; j += NT) K[j] = stage[j];
+    return true;
 }
 
 // ---- kernels: persistent groups pulling (frame, cluster) items from a range of the tier work lists ----------------------
@@ -320,7 +357,8 @@ __device__ __forceinline__ bool tier_item(uint32_t wi, const uint32_t *__restric
 
 template <int E> constexpr int sort_padded(int n) { return n + n / E + 1; }
 
-// Configuration of one sort kernel.  WHICH = 1: sort_scan_cluster on u32, WHICH = 2: sort_slope_cluster on u64.
+// Configuration of one sort kernel.  WHICH = 1: sort_scan_cluster on u32, WHICH = 2: sort_slope_cluster on u64, WHICH = 3:
+// sort_slope_cluster with sort #1's box / polarity tests in front (points arrive in scan order, no sort #1 ran).
 // NT = 32: SORT_WARPS clusters per CTA, one per warp; otherwise one cluster per CTA of NT threads.  The kernel pulls from
 // work lists T_LO..T_HI and processes the clusters of NMIN..NMAX points (several kernels can share one list); above MAXN
 // points the work arrays live in the global scratch area.
@@ -368,6 +406,7 @@ sort_clusters_kernel(uint32_t *__restrict__ scankey, ClusterRec *__restrict__ cl
         const int n = (int)rec.count;
         if (n < 24 || n < NMIN || n > NMAX) continue;
         if (WHICH == 2 && rec.cursor == 0xffffffffu) continue;
+        constexpr bool CHECK = WHICH == 3;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
         // NMAX <= MAXN: the global-memory variant is never needed (and not compiled into the kernel).
         // (A half-E variant for the small clusters of the one-warp tiers measured slower: twice the code in the kernel.)
@@ -383,11 +422,11 @@ sort_clusters_kernel(uint32_t *__restrict__ scankey, ClusterRec *__restrict__ cl
             }
         } else {
             unsigned long long *A = reinterpret_cast<unsigned long long *>(base), *B = reinterpret_cast<unsigned long long *>(base + SH::ARRAY_BYTES);
-            if (EH != E && n <= MAXN / 2) sort_slope_cluster<NT, EH, true>(scankey + pbase, n, A, B, S, g);
-            else if (NEVER_GLOBAL || n <= MAXN) sort_slope_cluster<NT, E, true>(scankey + pbase, n, A, B, S, g);
+            if (EH != E && n <= MAXN / 2) sort_slope_cluster<NT, EH, true, CHECK>(scankey + pbase, n, A, B, S, g, clusters + item, prm);
+            else if (NEVER_GLOBAL || n <= MAXN) sort_slope_cluster<NT, E, true, CHECK>(scankey + pbase, n, A, B, S, g, clusters + item, prm);
             else {
                 unsigned long long *GA = scratch + pbase * 2;
-                sort_slope_cluster<NT, E, false>(scankey + pbase, n, GA, GA + n, S, g);
+                sort_slope_cluster<NT, E, false, CHECK>(scankey + pbase, n, GA, GA + n, S, g, clusters + item, prm);
             }
         }
         if (NT == 32) __syncwarp();

@@ -10,6 +10,8 @@
 // instructions, exchanges them through 4 KB of shared memory, dilates in shared memory and writes the
 // ternary map with 64-bit coalesced stores.  Algorithmic traffic: W*H/2 read + W*H/4 written.
 #pragma once
+#include <cuda.h>      // CUtensorMap (the type only: cuTensorMapEncodeTiled is looked up at run time, libcuda is not linked)
+
 #include "common.cuh"
 
 namespace cb {
@@ -357,6 +359,195 @@ threshold_f2_tma_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ ou
         }
         mn_a = mn_b; mn_b = mn_c; mx_a = mx_b; mx_b = mx_c;
     }
+}
+
+// ---- tensor-map variant (default since round 2) ---------------------------------------------------------------------
+// Same warp-per-strip streaming structure as above, rebuilt around what ncu said about it (issue bound at 58 %, a third of
+// the lanes idle at 1280 px, 100+ instructions per step spent on issuing four 1-D bulk copies from an elected lane):
+//   * ONE tensor-map TMA per tile row.  The frames are described as a 3-D tensor of 8-byte elements (one element = the 8
+//     input bytes of one tile row) with the row stride DOUBLED, so the map addresses the even input rows only; a box of
+//     {32 T tiles, 4 rows, 1 frame} is one cp.async.bulk.tensor (SASS UTMALDG), out-of-range tiles / rows are zero-filled
+//     by the engine (no edge cases in the issue code);
+//   * T tiles per lane, T = 6 or 4 chosen per frame width so that one warp spans the frame (1280 px: 27 of 32 lanes busy with
+//     T = 6 against 21 with two strips of T = 4);
+//   * every reduction on native 16-bit SIMD (VIMNMX3.U16x2): tile min/max, the vertical and -- after a PRMT that shifts
+//     the pairs by one tile -- the horizontal 3-tap of the dilation; the binarisation is an add that carries "px > thresh"
+//     into bit 15 of each 16-bit lane and one PRMT in sign-replicate mode that turns four such bits into four 0x00 / 0xff
+//     bytes (the byte-SIMD compare is emulated on sm_100);
+//   * the pixel registers of the previous tile row ping-pong (loop unrolled twice) instead of being moved;
+//   * neighbouring row segments run in opposite directions, so the halo rows two warps share are read at the same time
+//     (second read hits L2).
+constexpr int TM_WARPS = 4, TM_STAGES = 4;
+struct TmPlan { int strips, iw, ysegs, seg_rows; };      // iw: interior tiles per strip (even)
+template <int T> struct TmCfg {
+    static constexpr int P = T / 2, ROWB = 32 * T * 8, STAGEB = 4 * ROWB;
+    static constexpr int SMEM = TM_WARPS * TM_STAGES * STAGEB + TM_WARPS * TM_STAGES * 8;
+    static constexpr int MAX_IW = 32 * T - 4;
+};
+
+__device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *map, int x, int y, int z, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));     // selector bit 3 of a nibble: replicate the byte's sign
+    return d;
+}
+
+template <int T>
+__global__ void __launch_bounds__(TM_WARPS * 32)
+threshold_tm_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ out, uint8_t *__restrict__ tmin, uint8_t *__restrict__ tmax,
+                    Geom g, int min_diff, TmPlan plan, int write_tiles)
+{
+    typedef TmCfg<T> C;
+    constexpr int P = C::P;
+    extern __shared__ __align__(128) unsigned char tm_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *ring = tm_smem + (size_t)wid * (TM_STAGES * C::STAGEB);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(tm_smem + (size_t)TM_WARPS * TM_STAGES * C::STAGEB) + wid * TM_STAGES;
+    const long long widx = (long long)blockIdx.x * TM_WARPS + wid;
+    const long long per_frame = (long long)plan.strips * plan.ysegs;
+    if (widx >= per_frame * g.batch) return;                 // (no block-wide barrier in this kernel)
+    const int b = (int)(widx / per_frame);
+    const int rem = (int)(widx % per_frame);
+    const int seg = rem / plan.strips, strip = rem % plan.strips;
+    const int s0 = strip * plan.iw, s1 = min(s0 + plan.iw, g.tw);
+    const int y0 = seg * plan.seg_rows, y1 = min(y0 + plan.seg_rows, g.th);
+    if (y0 >= y1 || s0 >= s1) return;
+    const int tbase = s0 - 2;                                 // first tile of lane 0 (even: outputs are stored as 8-byte tile pairs)
+    const int t0 = tbase + T * lane;                          // first tile of this lane
+    const int dir = (seg & 1) ? -1 : 1;                       // neighbouring segments meet at their shared halo rows at the same time
+    const int nsteps = y1 - y0 + 2;
+    const int rstart = dir > 0 ? y0 - 1 : y1;
+    const uint32_t full = 0xffffffffu;
+    uint8_t *o = out + (size_t)b * g.h * g.tp;
+
+    if (lane == 0) {
+        for (int s = 0; s < TM_STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < TM_STAGES && s < nsteps; s++) {
+            mbar_expect_tx(&bars[s], (uint32_t)C::STAGEB);
+            tma_load_3d(ring + (size_t)s * C::STAGEB, &tmap, tbase, 4 * (rstart + dir * s), b, &bars[s]);
+        }
+    }
+    __syncwarp();
+
+    // lane constants: validity of the lane's tile pairs (16-bit lane = one tile), which pairs are written
+    uint32_t mn_or[P], mx_and[P];
+    int pair_st[P];                                          // 0: nothing of the pair is written, 1: its first tile, 2: both
+    bool any_in = false;
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        const int ta = t0 + 2 * j, tb = ta + 1;
+        const bool va = ta >= 0 && ta < g.tw, vb = tb >= 0 && tb < g.tw;
+        mn_or[j] = (va ? 0u : 0x000000ffu) | (vb ? 0u : 0x00ff0000u);
+        mx_and[j] = (va ? 0x0000ffffu : 0u) | (vb ? 0xffff0000u : 0u);
+        pair_st[j] = (ta >= s0 && ta < s1) ? (tb < s1 ? 2 : 1) : 0;
+        any_in |= pair_st[j] != 0;
+    }
+    const uint32_t fconst = (uint32_t)((0x8000 - min_diff) & 0xffff) * 0x00010001u;     // D + fconst has bit 15 set iff D >= min_diff
+    uint32_t pxa[4][2 * T], pxb[4][2 * T];          // per tile and row: pixels (0, 1) and (2, 3) in 16-bit lanes, as the compare wants them
+    uint32_t mnA[P], mnB[P], mxA[P], mxB[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) { mnA[j] = mnB[j] = 0x00ff00ffu; mxA[j] = mxB[j] = 0u; }
+#pragma unroll
+    for (int dy = 0; dy < 4; dy++)
+#pragma unroll
+        for (int k = 0; k < 2 * T; k++) { pxa[dy][k] = 0; pxb[dy][k] = 0; }
+    uint8_t *ocol = o + (ptrdiff_t)t0 * 4;
+    const ptrdiff_t tp_ = g.tp;
+
+    // one tile row: CUR receives its pixels, the row before it (pixels in PREV, min/max in *B) is written out
+#define CB_TM_STEP(CUR, PREV, IT)                                                                                                     \
+    {                                                                                                                                 \
+        const int it_ = (IT), stage_ = it_ % TM_STAGES, r_ = rstart + dir * it_;                                                      \
+        mbar_wait(&bars[stage_], (uint32_t)((it_ / TM_STAGES) & 1));                                                                  \
+        const unsigned char *sp_ = ring + (size_t)stage_ * C::STAGEB + lane * (8 * T);                                                \
+        uint32_t mnp_[T], mxp_[T];                                                                                                    \
+        _Pragma("unroll") for (int dy = 0; dy < 4; dy++) {                                                                            \
+            uint32_t w_[2 * T];                                                                                                       \
+            _Pragma("unroll") for (int q = 0; q < T / 2; q++) {                                                                       \
+                const uint4 v_ = *reinterpret_cast<const uint4 *>(sp_ + dy * C::ROWB + 16 * q);                                       \
+                w_[4 * q] = v_.x; w_[4 * q + 1] = v_.y; w_[4 * q + 2] = v_.z; w_[4 * q + 3] = v_.w;                                   \
+            }                                                                                                                         \
+            _Pragma("unroll") for (int k = 0; k < T; k++) {                                                                           \
+                const uint32_t e0_ = w_[2 * k] & 0x00ff00ffu, e1_ = w_[2 * k + 1] & 0x00ff00ffu;                                      \
+                if (dy == 0) { mnp_[k] = __vminu2(e0_, e1_); mxp_[k] = __vmaxu2(e0_, e1_); }                                          \
+                else { mnp_[k] = __vimin3_u16x2(mnp_[k], e0_, e1_); mxp_[k] = __vimax3_u16x2(mxp_[k], e0_, e1_); }                    \
+                CUR[dy][2 * k] = e0_; CUR[dy][2 * k + 1] = e1_;                                                                       \
+            }                                                                                                                         \
+        }                                                                                                                             \
+        __syncwarp();                                                                                                                 \
+        if (lane == 0 && it_ + TM_STAGES < nsteps) {                                                                                  \
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                                              \
+            mbar_expect_tx(&bars[stage_], (uint32_t)C::STAGEB);                                                                       \
+            tma_load_3d(ring + (size_t)stage_ * C::STAGEB, &tmap, tbase, 4 * (r_ + dir * TM_STAGES), b, &bars[stage_]);               \
+        }                                                                                                                             \
+        const bool rvalid_ = r_ >= 0 && r_ < g.th;                                                                                    \
+        uint32_t mnC_[P], mxC_[P], vmn_[P + 2], vmx_[P + 2];                                                                          \
+        _Pragma("unroll") for (int j = 0; j < P; j++) {                                                                               \
+            const uint32_t a_ = __vminu2(prmt(mnp_[2 * j], mnp_[2 * j + 1], 0x5410u), prmt(mnp_[2 * j], mnp_[2 * j + 1], 0x7632u));   \
+            const uint32_t c_ = __vmaxu2(prmt(mxp_[2 * j], mxp_[2 * j + 1], 0x5410u), prmt(mxp_[2 * j], mxp_[2 * j + 1], 0x7632u));   \
+            mnC_[j] = rvalid_ ? (a_ | mn_or[j]) : 0x00ff00ffu;                                                                        \
+            mxC_[j] = rvalid_ ? (c_ & mx_and[j]) : 0u;                                                                                \
+            vmn_[j + 1] = __vimin3_u16x2(mnA[j], mnB[j], mnC_[j]);                                                                    \
+            vmx_[j + 1] = __vimax3_u16x2(mxA[j], mxB[j], mxC_[j]);                                                                    \
+        }                                                                                                                             \
+        vmn_[0] = __shfl_up_sync(full, vmn_[P], 1); vmx_[0] = __shfl_up_sync(full, vmx_[P], 1);                                       \
+        vmn_[P + 1] = __shfl_down_sync(full, vmn_[1], 1); vmx_[P + 1] = __shfl_down_sync(full, vmx_[1], 1);                           \
+        if (lane == 0) { vmn_[0] = 0x00ff00ffu; vmx_[0] = 0u; }                                                                       \
+        if (lane == 31) { vmn_[P + 1] = 0x00ff00ffu; vmx_[P + 1] = 0u; }                                                              \
+        const int ro_ = r_ - dir;                                                                                                     \
+        if (it_ >= 2 && any_in) {                                                                                                     \
+            uint8_t *const p0_ = ocol + (ptrdiff_t)(ro_ * 4) * tp_, *const p1_ = p0_ + tp_, *const p2_ = p1_ + tp_, *const p3_ = p2_ + tp_; \
+            uint32_t sh_mn_ = prmt(vmn_[0], vmn_[1], 0x5432u), sh_mx_ = prmt(vmx_[0], vmx_[1], 0x5432u);                              \
+            _Pragma("unroll") for (int j = 0; j < P; j++) {                                                                           \
+                const uint32_t nx_mn_ = prmt(vmn_[j + 1], vmn_[j + 2], 0x5432u), nx_mx_ = prmt(vmx_[j + 1], vmx_[j + 2], 0x5432u);    \
+                const uint32_t dmn_ = __vimin3_u16x2(vmn_[j + 1], sh_mn_, nx_mn_), dmx_ = __vimax3_u16x2(vmx_[j + 1], sh_mx_, nx_mx_); \
+                sh_mn_ = nx_mn_; sh_mx_ = nx_mx_;                                                                                     \
+                const uint32_t D_ = dmx_ - dmn_;                                                                                      \
+                const uint32_t cc_ = 0x7fff7fffu - (dmn_ + ((D_ >> 1) & 0x7fff7fffu));                                                \
+                const uint32_t F_ = D_ + fconst;                                                                                      \
+                const uint32_t c0_ = prmt(cc_, 0u, 0x1010u), c1_ = prmt(cc_, 0u, 0x3232u);                                            \
+                const uint32_t nf0_ = prmt(F_, 0u, 0x9999u), nf1_ = prmt(F_, 0u, 0xbbbbu);                                            \
+                const uint32_t fl0_ = 0x7f7f7f7fu & ~nf0_, fl1_ = 0x7f7f7f7fu & ~nf1_;                                                \
+                uint32_t ra_[4], rb_[4];                                                                                              \
+                _Pragma("unroll") for (int dy = 0; dy < 4; dy++) {                                                                    \
+                    ra_[dy] = (prmt(PREV[dy][4 * j] + c0_, PREV[dy][4 * j + 1] + c0_, 0xfdb9u) & nf0_) | fl0_;                        \
+                    rb_[dy] = (prmt(PREV[dy][4 * j + 2] + c1_, PREV[dy][4 * j + 3] + c1_, 0xfdb9u) & nf1_) | fl1_;                    \
+                }                                                                                                                     \
+                if (pair_st[j] == 2) {                                                                                                \
+                    *reinterpret_cast<uint2 *>(p0_ + 8 * j) = make_uint2(ra_[0], rb_[0]);                                             \
+                    *reinterpret_cast<uint2 *>(p1_ + 8 * j) = make_uint2(ra_[1], rb_[1]);                                             \
+                    *reinterpret_cast<uint2 *>(p2_ + 8 * j) = make_uint2(ra_[2], rb_[2]);                                             \
+                    *reinterpret_cast<uint2 *>(p3_ + 8 * j) = make_uint2(ra_[3], rb_[3]);                                             \
+                } else if (pair_st[j] == 1) {                                                                                         \
+                    *reinterpret_cast<uint32_t *>(p0_ + 8 * j) = ra_[0]; *reinterpret_cast<uint32_t *>(p1_ + 8 * j) = ra_[1];         \
+                    *reinterpret_cast<uint32_t *>(p2_ + 8 * j) = ra_[2]; *reinterpret_cast<uint32_t *>(p3_ + 8 * j) = ra_[3];         \
+                }                                                                                                                     \
+                if (write_tiles && pair_st[j]) {                                                                                      \
+                    const size_t ti_ = ((size_t)b * g.th + ro_) * g.tw + t0 + 2 * j;                                                  \
+                    tmin[ti_] = (uint8_t)mnB[j]; tmax[ti_] = (uint8_t)mxB[j];                                                         \
+                    if (pair_st[j] == 2) { tmin[ti_ + 1] = (uint8_t)(mnB[j] >> 16); tmax[ti_ + 1] = (uint8_t)(mxB[j] >> 16); }        \
+                }                                                                                                                     \
+            }                                                                                                                         \
+        }                                                                                                                             \
+        _Pragma("unroll") for (int j = 0; j < P; j++) { mnA[j] = mnB[j]; mnB[j] = mnC_[j]; mxA[j] = mxB[j]; mxB[j] = mxC_[j]; }       \
+    }
+
+    int it = 0;
+    for (; it + 1 < nsteps; it += 2) {
+        CB_TM_STEP(pxa, pxb, it)
+        CB_TM_STEP(pxb, pxa, it + 1)
+    }
+    if (it < nsteps) CB_TM_STEP(pxa, pxb, it)
+#undef CB_TM_STEP
 }
 
 // ---- generic path (any integer decimation factor, any alignment): three simple kernels ----
