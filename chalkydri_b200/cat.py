@@ -83,13 +83,30 @@ class CatDetector:
             raise ChalkydriError(capi.CB_ERR_OVERFLOW, f"{n.value} lines exceed the capacity {cap}")
         self.lines = lines[:n.value].copy()
 
-    def process_frame(self, input_):
-        """lib.rs:265-287: calc_otsu -> reset points / lines -> detect_corners -> check_edges."""
+    def process_frame(self, input_, cap: int = 1 << 20, want_color: bool = True):
+        """lib.rs:265-287: calc_otsu -> reset points / lines -> detect_corners -> check_edges, in ONE library call
+        (cb_cat_process_frame): the frame goes up once and the intermediate maps stay on the device."""
+        rgb = self._rgb(input_)
+        if getattr(self, "_xy_buf", None) is None or len(self._xy_buf) < cap:
+            self._xy_buf, self._lines_buf = np.zeros((cap, 2), np.int32), np.zeros((cap, 4), np.int32)
+        n, m = C.c_int64(), C.c_int64()
+        self._check(self._L.cb_cat_process_frame(self._ctx, capi.ptr(rgb), self.width, self.height, capi.ptr(self.buf) if want_color else None,
+                                                 capi.ptr(self._xy_buf), cap, C.byref(n), capi.ptr(self._lines_buf), cap, C.byref(m)))
+        self.points = self._xy_buf[:n.value].copy()
+        self.lines = self._lines_buf[:m.value].copy()
+
+    def process_frame_stagewise(self, input_):
+        """the same through the per-stage entry points (host buffers between the stages); kept for the parity tests"""
         self.calc_otsu(input_)
         self.points = np.zeros((0, 2), np.int32)
         self.lines = np.zeros((0, 4), np.int32)
         self.detect_corners()
         self.check_edges()
+
+    def timing(self) -> dict:
+        t = capi.Timing()
+        self._check(self._L.cb_get_timing(self._ctx, C.byref(t)))
+        return t.as_dict()
 
     def connected_components(self) -> UnionFind:
         lab = np.empty((self.height, self.width), np.uint32)

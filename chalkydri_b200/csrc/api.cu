@@ -92,6 +92,8 @@ struct cb_ctx {
     uint8_t *d_tmin = nullptr, *d_tmax = nullptr;    size_t tile_bytes = 0;
     uint32_t *d_labels = nullptr, *d_sizes = nullptr; size_t label_bytes = 0;
     ClusterSlot *d_table = nullptr;
+    uint8_t *d_cat = nullptr, *d_cat_tot = nullptr;   // CAT process_frame scratch (grow-only)
+    size_t cat_bytes = 0, cat_tot_bytes = 0;
     int cluster_mode = 0;                      // 0: band-ordered count / scatter (round 2), 1: tile passes + scan-order sort (round 1; CB_CLUSTERS=tiles)
     ClbArea *d_areas = nullptr;                // band tables of the count pass (first areas, then the pool of chained sub-band areas)
     uint32_t areas_first_cap = 0, areas_pool_cap = 0;
@@ -185,7 +187,7 @@ void cb_destroy(cb_ctx *ctx)
     if (ctx->pose_stream) cudaStreamSynchronize(ctx->pose_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
-                    ctx->d_table, ctx->d_areas, ctx->d_cursors, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
+                    ctx->d_table, ctx->d_areas, ctx->d_cursors, ctx->d_cat, ctx->d_cat_tot, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
                     ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->d_in2) cudaFree(ctx->d_in2);
@@ -327,7 +329,8 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         CB_SORT_ATTR(SortS8<1>) CB_SORT_ATTR(SortS16<1>) CB_SORT_ATTR(SortM<1>) CB_SORT_ATTR(SortL1<1>) CB_SORT_ATTR(SortL2<1>)
         CB_SORT_ATTR(SortS8<2>) CB_SORT_ATTR(SortS16<2>) CB_SORT_ATTR(SortM<2>) CB_SORT_ATTR(SortL1<2>) CB_SORT_ATTR(SortL2<2>)
         CB_SORT_ATTR(SortS8<3>) CB_SORT_ATTR(SortS16<3>) CB_SORT_ATTR(SortM<3>) CB_SORT_ATTR(SortL1<3>) CB_SORT_ATTR(SortL2<3>)
-        if (!ctx->d_cursors) ok = ok && cudaFuncSetAttribute(cluster_band_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c.clusters_per_frame * sizeof(uint32_t))) == cudaSuccess;
+        // (function attributes are shared by every context of the device: always the same value, the most a context may ask for)
+        ok = ok && cudaFuncSetAttribute(cluster_band_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
 #undef CB_SORT_ATTR
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
             uint16_t combos[210];
@@ -610,14 +613,15 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         if (g.h > 2 && g.w > 2 && ctx->cluster_mode == 0) {
             // band-ordered passes (clusters.cuh): rows per band so that the launch has ~128 warps per SM to balance
             BandPlan bp;
-            bp.rows = (int)std::max<long long>(1, std::min<long long>(4, ((long long)B * (g.h - 2)) / ((long long)ctx->num_sms * 128)));
+            const long long target = (long long)ctx->num_sms * 128;
+            bp.rows = (int)std::max<long long>(1, std::min<long long>(4, ((long long)B * (g.h - 2) + target - 1) / target));      // <= target + B bands when rows < 4
             bp.nbands = (g.h - 2 + bp.rows - 1) / bp.rows;
             if ((uint32_t)B * bp.nbands > ctx->areas_first_cap) return fail(ctx, CB_ERR_ARG, "internal: band tables too small (%d bands)", B * bp.nbands);
             bp.pool_cap = ctx->areas_pool_cap;
             const uint32_t nfirst = (uint32_t)B * bp.nbands, nall = nfirst + bp.pool_cap;
             uint32_t *d_pool = d_misc + 6;
             uint32_t *d_stage = reinterpret_cast<uint32_t *>(ctx->d_ent);
-            cluster_band_count_kernel<<<(nfirst + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, d_misc, d_stage,
+            cluster_band_count_kernel<<<nfirst, 32, 0, st>>>(ctx->d_mark, ctx->d_labels, ctx->d_table, d_misc, d_stage,
                                                                                                    ctx->d_areas, d_pool, g, caps, bp);
             cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, wl_stride,
                                                                                             d_misc + 8, 2, (uint32_t)QT0, (uint32_t)QT1,
@@ -625,7 +629,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             cluster_band_resolve_kernel<<<(nall + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(ctx->d_table, ctx->d_areas, d_pool, g, caps, bp);
             cluster_band_prefix_kernel<<<B, CLB_CAP, ctx->d_cursors ? 0 : caps.clusters_per_frame * sizeof(uint32_t), st>>>(ctx->d_areas, ctx->d_clusters, d_ncl,
                                                                                                                       ctx->d_cursors, caps, bp);
-            cluster_band_scatter_kernel<<<(nall + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(d_stage, ctx->d_areas, d_pool, ctx->d_scankey, g, caps, bp);
+            cluster_band_scatter_kernel<<<nall, 32, 0, st>>>(d_stage, ctx->d_areas, d_pool, ctx->d_scankey, g, caps, bp);
             launches += 5;
         }
         if (g.h > 2 && g.w > 2 && ctx->cluster_mode == 1) {

@@ -289,30 +289,53 @@ struct BandPlan { int rows, nbands; uint32_t pool_cap; };    // rows per band, b
 // staging word: slot << 24 | row in band << 21 | probe << 19 | sign << 18 | x
 __device__ __forceinline__ size_t band_stage_base(const Geom &g, int b, int y0) { return ((size_t)b * g.npix + (size_t)(y0 - 1) * g.w) * 4; }
 
-__global__ void __launch_bounds__(CLB_WARPS * 32)
+// find-or-insert in a warp's private 256-slot table (power-of-two mask; the table is closed long before it is full, so the
+// probe sequence always ends); *fresh = the key was not there before
+__device__ __forceinline__ int band_insert(unsigned long long *keys, unsigned long long key, uint32_t h, bool *fresh)
+{
+    uint32_t s = h & (CLB_CAP - 1);
+    for (;;) {
+        const unsigned long long cur = *((volatile unsigned long long *)&keys[s]);
+        if (cur == key) { *fresh = false; return (int)s; }
+        if (cur == EMPTY_KEY) {
+            const unsigned long long old = atomicCAS(&keys[s], EMPTY_KEY, key);
+            if (old == EMPTY_KEY) { *fresh = true; return (int)s; }
+            if (old == key) { *fresh = false; return (int)s; }
+        }
+        s = (s + 1) & (CLB_CAP - 1);
+    }
+}
+
+// (One warp per CTA: the band, its row range and every loop bound then depend on blockIdx alone, which the compiler knows to be
+// warp-uniform.)  The walk has a producer and a consumer half.  Producer, per 32-pixel step: pixel values (loaded three steps
+// ahead) -> which probes emit -> component labels (loaded one step ahead) -> pair keys, appended in scan order to a small
+// queue in shared memory.  Consumer, whenever 32 points are queued: ONE match.any on the keys, one table probe per distinct
+// key, one coalesced 128-byte store of staging words -- every lane busy, where probing the four directions one after the
+// other kept about a quarter of the lanes busy and cost four match rounds per step.
+__global__ void __launch_bounds__(32, 24)
 cluster_band_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, ClusterSlot *__restrict__ table,
                           uint32_t *__restrict__ errflag, uint32_t *__restrict__ stage, ClbArea *__restrict__ areas,
                           uint32_t *__restrict__ pool_counter, Geom g, Caps caps, BandPlan bp)
 {
-    __shared__ unsigned long long s_key[CLB_WARPS][CLB_CAP];
-    __shared__ uint32_t s_cnt[CLB_WARPS][CLB_CAP];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ unsigned long long K[CLB_CAP];       // the band's table: pair key -> slot
+    __shared__ uint32_t Cn[CLB_CAP];                //                   points per slot
+    __shared__ unsigned long long Qk[256];          // queue of points waiting for a full round: key
+    __shared__ uint32_t Qm[256];                    //                                           staging word without the slot
+    const int lane = threadIdx.x;
     const uint32_t full = 0xffffffffu, lt = (1u << lane) - 1u;
-    const uint32_t job = blockIdx.x * CLB_WARPS + wid;
+    const uint32_t job = blockIdx.x;
     const uint32_t nfirst = (uint32_t)g.batch * bp.nbands;
-    if (job >= nfirst) return;                                  // (no block-wide barrier in this kernel)
     const int b = job / bp.nbands, band = job % bp.nbands;
     const int y0 = 1 + band * bp.rows, y1 = min(y0 + bp.rows, g.h - 1);       // rows y0 .. y1 - 1 (upstream scans y = 1 .. h - 2)
-    unsigned long long *K = s_key[wid];
-    uint32_t *Cn = s_cnt[wid];
     for (int e = lane; e < CLB_CAP; e += 32) { K[e] = EMPTY_KEY; Cn[e] = 0; }
     __syncwarp();
     const uint8_t *m = mark + (size_t)b * g.h * g.tp;
     const uint32_t *lab = labels + (size_t)b * g.npix;
     ClusterSlot *tab = table + (size_t)b * caps.slots_per_frame;
     uint32_t *st = stage + band_stage_base(g, b, y0);
-    uint32_t npts = 0, sub_start = 0, area_idx = job;
-    bool dead = false;
+    uint32_t npts = 0, sub_start = 0, area_idx = job, n_slots = 0, q_head = 0, q_tail = 0;
+    // a sub-band is closed before its table is half full (CB_TILE_PROBES lowers the limit so that tests reach the chained areas)
+    const uint32_t slot_limit = caps.tile_probes >= CL_PROBES ? 120u : caps.tile_probes * 48u;
 
     // close the current (sub-)band: records out, frame table updated, private table cleared; `more`: another sub-band follows
     auto flush = [&](bool more) {
@@ -323,7 +346,7 @@ cluster_band_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__re
             const int s = s0 + lane;
             const unsigned long long key = K[s];
             const uint32_t cnt = Cn[s];
-            const bool used = key != EMPTY_KEY && cnt > 0;
+            const bool used = key != EMPTY_KEY;
             const uint32_t bu = __ballot_sync(full, used);
             if (used) {
                 ClbRec r;
@@ -332,102 +355,119 @@ cluster_band_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__re
                 const uint32_t gs = slot_insert(tab, caps.slots_per_frame, key);
                 if (gs == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
                 else atomicAdd(&tab[gs].count, cnt);
+                K[s] = EMPTY_KEY; Cn[s] = 0;
             }
             n_used += __popc(bu);
-            if (key != EMPTY_KEY) { K[s] = EMPTY_KEY; Cn[s] = 0; }
         }
         uint32_t next = CLB_NONE;
         if (more) {
             if (lane == 0) next = atomicAdd(pool_counter, 1u);
             next = __shfl_sync(full, next, 0);
-            if (next >= bp.pool_cap) { if (lane == 0) atomicOr(errflag, ERR_HASH_FULL); next = CLB_NONE; dead = true; }
+            // no chained area left: the call fails with ERR_HASH_FULL; this area is simply reused so that the walk stays in bounds
+            if (next >= bp.pool_cap) { if (lane == 0) atomicOr(errflag, ERR_HASH_FULL); next = CLB_NONE; }
             else next += nfirst;
         }
         if (lane == 0) { A->n_used = n_used; A->st_start = sub_start; A->st_end = npts; A->next = next; A->band = job; }
-        sub_start = npts;
+        sub_start = npts; n_slots = 0;
         if (next != CLB_NONE) area_idx = next;
         __syncwarp();
     };
 
-    const int nseg = (g.w + 31) / 32;
-    for (int y = y0; y < y1 && !dead; y++) {
-        const uint8_t *r0 = m + (size_t)y * g.tp, *r1 = r0 + g.tp;
-        const uint32_t *l0 = lab + (size_t)y * g.w, *l1 = l0 + g.w;
-        uint32_t p0 = 127, p1 = 127;                        // values left of lane 0: the previous segment's last pixels
-        uint32_t c0 = lane < g.w ? r0[lane] : 127u, c1 = lane < g.w ? r1[lane] : 127u;
-        for (int seg = 0; seg < nseg && !dead; seg++) {
-            const int x = seg * 32 + lane, xn = x + 32;
-            uint32_t n0 = 127, n1 = 127;                    // the next segment's pixels are in flight while this one is processed
-            if (xn < g.w) { n0 = r0[xn]; n1 = r1[xn]; }
-            uint32_t vl = __shfl_up_sync(full, c0, 1), vr = __shfl_down_sync(full, c0, 1);
-            uint32_t bl = __shfl_up_sync(full, c1, 1), br = __shfl_down_sync(full, c1, 1);
-            const uint32_t nf0 = __shfl_sync(full, n0, 0), nf1 = __shfl_sync(full, n1, 0);
-            if (lane == 0) { vl = p0; bl = p1; }
-            if (lane == 31) { vr = nf0; br = nf1; }
-            const uint32_t v0 = c0, b0 = c1;
-            p0 = __shfl_sync(full, c0, 31); p1 = __shfl_sync(full, c1, 31);
-            c0 = n0; c1 = n1;
-            uint32_t em = 0;
-            if (x >= 1 && x <= g.w - 2 && v0 != 127u) {
-                const bool connected_last = (x - 1 >= 1) && vl != 127u && (vl + b0 == 255u);
-                em = (v0 + vr == 255u ? 1u : 0u) | (v0 + b0 == 255u ? 2u : 0u) | ((v0 + bl == 255u && !connected_last) ? 4u : 0u) | (v0 + br == 255u ? 8u : 0u);
-            }
-            const uint32_t bal0 = __ballot_sync(full, em & 1u), bal1 = __ballot_sync(full, em & 2u), bal2 = __ballot_sync(full, em & 4u),
-                           bal3 = __ballot_sync(full, em & 8u);
-            if ((bal0 | bal1 | bal2 | bal3) == 0) continue;
-            const uint32_t bals[4] = {bal0, bal1, bal2, bal3};
-            unsigned long long key[4];
-            uint32_t sgn = 0;
-            {
-                const uint32_t rep0 = em ? l0[x] : 0u;
-                const uint32_t vn[4] = {vr, b0, bl, br};
-#pragma unroll
-                for (int d = 0; d < 4; d++) {
-                    key[d] = EMPTY_KEY;
-                    if ((em >> d) & 1u) {
-                        const uint32_t rep1 = d == 0 ? l0[x + 1] : (d == 1 ? l1[x] : (d == 2 ? l1[x - 1] : l1[x + 1]));
-                        key[d] = rep0 < rep1 ? ((unsigned long long)rep1 << 32) | rep0 : ((unsigned long long)rep0 << 32) | rep1;
-                        sgn |= (vn[d] > v0 ? 1u : 0u) << d;
-                    }
-                }
-            }
-            // phase 1: every key gets a slot of the warp's table; a full table closes the sub-band first (the retry probes the
-            // whole, now empty, table: a step has at most 128 distinct keys)
-            int e[4];
-            uint32_t peers[4];
-            for (int attempt = 0; attempt < 2; attempt++) {
-                bool ovf = false;
-                const int probes = attempt ? CLB_CAP : (int)caps.tile_probes;
-#pragma unroll
-                for (int d = 0; d < 4; d++) {
-                    e[d] = -1; peers[d] = 0;
-                    if (bals[d] == 0) continue;                                   // warp-uniform
-                    peers[d] = __match_any_sync(full, key[d]);
-                    if (!((em >> d) & 1u)) continue;
-                    const int leader = __ffs(peers[d]) - 1;
-                    int ee = -1;
-                    if (lane == leader) ee = tile_insert_n(K, key[d], hash_key(key[d]), probes);
-                    ee = __shfl_sync(peers[d], ee, leader);
-                    e[d] = ee;
-                    ovf |= ee < 0;
-                }
-                if (!__any_sync(full, ovf)) break;
-                flush(true);
-                if (dead) break;
-            }
-            if (dead) break;
-            // phase 2: counts, and the points themselves at their scan-order position (lane-major, then probe)
-            uint32_t off = npts + __popc(bal0 & lt) + __popc(bal1 & lt) + __popc(bal2 & lt) + __popc(bal3 & lt);
+    // consumer: the n (<= 32) oldest queued points get their slot, are counted and leave for the staging list
+    auto consume = [&](uint32_t n) {
+        if (n_slots > 0 && n_slots + n > slot_limit) flush(true);
+        const bool active = (uint32_t)lane < n;
+        const uint32_t qi = (q_head + lane) & 255u;
+        const unsigned long long key = active ? Qk[qi] : EMPTY_KEY;
+        const uint32_t meta = Qm[qi];
+        const uint32_t peers = __match_any_sync(full, key);
+        const int leader = __ffs(peers) - 1;
+        bool fresh = false;
+        int e = 0;
+        if (active && lane == leader) {
+            // (two multiplies and a fold: the table has 256 slots and at most half of them are ever used)
+            const uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u);
+            e = band_insert(K, key, h >> 24, &fresh);
+            atomicAdd(&Cn[e], (uint32_t)__popc(peers));
+        }
+        n_slots += __popc(__ballot_sync(full, fresh));
+        e = __shfl_sync(full, e, leader);
+        if (active) st[npts + lane] = ((uint32_t)e << 24) | meta;
+        npts += n; q_head += n;
+        __syncwarp();
+    };
+
+    // The band is walked as one sequence of 32-pixel steps (row-major).
+    const int nseg = (g.w + 31) / 32, nrows = y1 - y0, nsteps = nrows * nseg;
+    struct Pos { int seg, y; };                                  // a step's segment and row, advanced without divisions
+    auto advance = [&](Pos &q) { if (++q.seg == nseg) { q.seg = 0; q.y++; } };
+    auto load_px = [&](const Pos &q, uint32_t &a0, uint32_t &a1) {
+        a0 = 127u; a1 = 127u;
+        const int x = q.seg * 32 + lane;
+        if (q.y < y1 && x < g.w) { const uint8_t *r0 = m + (size_t)q.y * g.tp; a0 = r0[x]; a1 = r0[g.tp + x]; }
+    };
+    // emit mask and labels of a step whose pixel values are (c0, c1), left neighbours (p0, p1), next segment (n0, n1)
+    struct Pending { uint32_t em, sgn, rep0, rep[4], meta; };
+    auto prepare = [&](const Pos &q, uint32_t c0, uint32_t c1, uint32_t p0, uint32_t p1, uint32_t n0, uint32_t n1, Pending &P) {
+        const int seg = q.seg, x = seg * 32 + lane;
+        P.meta = ((uint32_t)(q.y - y0) << 21) | (uint32_t)x;
+        uint32_t vl = __shfl_up_sync(full, c0, 1), vr = __shfl_down_sync(full, c0, 1);
+        uint32_t bl = __shfl_up_sync(full, c1, 1), br = __shfl_down_sync(full, c1, 1);
+        const uint32_t nf0 = __shfl_sync(full, n0, 0), nf1 = __shfl_sync(full, n1, 0);
+        if (lane == 0) { vl = seg == 0 ? 127u : p0; bl = seg == 0 ? 127u : p1; }
+        if (lane == 31) { vr = seg + 1 < nseg ? nf0 : 127u; br = seg + 1 < nseg ? nf1 : 127u; }
+        P.em = 0; P.sgn = 0; P.rep0 = 0;
+        if (x >= 1 && x <= g.w - 2 && c0 != 127u) {
+            const bool connected_last = (x - 1 >= 1) && vl != 127u && (vl + c1 == 255u);
+            P.em = (c0 + vr == 255u ? 1u : 0u) | (c0 + c1 == 255u ? 2u : 0u) | ((c0 + bl == 255u && !connected_last) ? 4u : 0u) | (c0 + br == 255u ? 8u : 0u);
+            P.sgn = (vr > c0 ? 1u : 0u) | (c1 > c0 ? 2u : 0u) | (bl > c0 ? 4u : 0u) | (br > c0 ? 8u : 0u);
+        }
+        if (P.em) {
+            const uint32_t *l0 = lab + (size_t)q.y * g.w + x, *l1 = l0 + g.w;
+            P.rep0 = l0[0];
+            if (P.em & 1u) P.rep[0] = l0[1];
+            if (P.em & 2u) P.rep[1] = l1[0];
+            if (P.em & 4u) P.rep[2] = l1[-1];
+            if (P.em & 8u) P.rep[3] = l1[1];
+        }
+    };
+
+    uint32_t c0, c1, n0, n1, nn0, nn1, p0 = 127u, p1 = 127u;
+    Pos q_prep{0, y0}, q_load{0, y0};
+    load_px(q_load, c0, c1); advance(q_load);
+    load_px(q_load, n0, n1); advance(q_load);
+    load_px(q_load, nn0, nn1); advance(q_load);
+    Pending cur, nxt;
+    prepare(q_prep, c0, c1, p0, p1, n0, n1, cur); advance(q_prep);
+    for (int step = 0; step < nsteps; step++) {
+        // producer, stage A for step + 1 (its labels fly while this step is queued), pixel values for step + 3
+        p0 = __shfl_sync(full, c0, 31); p1 = __shfl_sync(full, c1, 31);
+        c0 = n0; c1 = n1; n0 = nn0; n1 = nn1;
+        load_px(q_load, nn0, nn1); advance(q_load);
+        nxt.em = 0;
+        if (step + 1 < nsteps) { prepare(q_prep, c0, c1, p0, p1, n0, n1, nxt); advance(q_prep); }
+        // producer, stage B for this step: keys into the queue in scan order (lane-major, then probe)
+        const uint32_t em = cur.em;
+        const uint32_t bal0 = __ballot_sync(full, em & 1u), bal1 = __ballot_sync(full, em & 2u), bal2 = __ballot_sync(full, em & 4u),
+                       bal3 = __ballot_sync(full, em & 8u);
+        if ((bal0 | bal1 | bal2 | bal3) != 0) {
+            uint32_t off = q_tail + __popc(bal0 & lt) + __popc(bal1 & lt) + __popc(bal2 & lt) + __popc(bal3 & lt);
 #pragma unroll
             for (int d = 0; d < 4; d++) {
                 if (!((em >> d) & 1u)) continue;
-                if (lane == __ffs(peers[d]) - 1) atomicAdd(&Cn[e[d]], (uint32_t)__popc(peers[d]));
-                st[off++] = ((uint32_t)e[d] << 24) | ((uint32_t)(y - y0) << 21) | ((uint32_t)d << 19) | (((sgn >> d) & 1u) << 18) | (uint32_t)x;
+                const uint32_t r0 = cur.rep0, r1 = cur.rep[d];
+                Qk[off & 255u] = r0 < r1 ? ((unsigned long long)r1 << 32) | r0 : ((unsigned long long)r0 << 32) | r1;
+                Qm[off & 255u] = cur.meta | ((uint32_t)d << 19) | (((cur.sgn >> d) & 1u) << 18);
+                off++;
             }
-            npts += __popc(bal0) + __popc(bal1) + __popc(bal2) + __popc(bal3);
+            q_tail += __popc(bal0) + __popc(bal1) + __popc(bal2) + __popc(bal3);
+            __syncwarp();
+            while (q_tail - q_head >= 32u) consume(32u);
         }
+        cur = nxt;
     }
-    if (!dead) flush(false);
+    if (q_tail != q_head) consume(q_tail - q_head);
+    flush(false);
 }
 
 // resolve: every record learns its cluster (index into the frame's selected-cluster list, CLB_NONE = not selected).  One warp per area.
@@ -461,48 +501,56 @@ cluster_band_prefix_kernel(ClbArea *__restrict__ areas, const ClusterRec *__rest
     const uint32_t ncl = min(nclusters[b], caps.clusters_per_frame);
     for (uint32_t c = t; c < ncl; c += CLB_CAP) cur[c] = clusters[(size_t)b * caps.clusters_per_frame + c].offset;
     __syncthreads();
-    // the first area of band i + 1 is loaded while band i is processed (its address does not depend on anything)
-    uint32_t a = (uint32_t)b * bp.nbands;
-    uint32_t n_used = areas[a].n_used, next = areas[a].next;
-    ClbRec r = areas[a].rec[t];
-    for (int band = 0; band < bp.nbands; band++) {
-        uint32_t pn_used = 0, pnext = CLB_NONE;
-        ClbRec pr;
-        pr.key = 0; pr.cnt = 0; pr.slot = 0;
-        const uint32_t a_next_band = (uint32_t)b * bp.nbands + band + 1;
-        if (band + 1 < bp.nbands) { pn_used = areas[a_next_band].n_used; pnext = areas[a_next_band].next; pr = areas[a_next_band].rec[t]; }
-        for (;;) {
-            if ((uint32_t)t < n_used) {
-                const uint32_t c = (uint32_t)r.key;
-                uint32_t base = CLB_NONE;
-                if (c < ncl) { base = cur[c]; cur[c] = base + r.cnt; }      // the records of one area name distinct clusters
-                areas[a].rec[t].cnt = base;
+    // The first areas of the next PF bands are loaded together (their addresses do not depend on anything), so the walk pays one
+    // memory round trip per PF bands instead of one per band; chained sub-bands (rare) are loaded on demand.
+    constexpr int PF = 8;
+    for (int band0 = 0; band0 < bp.nbands; band0 += PF) {
+        uint32_t n_used[PF], next[PF];
+        ClbRec r[PF];
+#pragma unroll
+        for (int k = 0; k < PF; k++) {
+            n_used[k] = 0; next[k] = CLB_NONE; r[k].key = CLB_NONE; r[k].cnt = 0; r[k].slot = 0;
+            if (band0 + k < bp.nbands) {
+                const ClbArea *A = areas + (size_t)b * bp.nbands + band0 + k;
+                n_used[k] = A->n_used; next[k] = A->next; r[k] = A->rec[t];
             }
-            __syncthreads();
-            if (next == CLB_NONE) break;
-            a = next;                                                       // chained sub-band (rare): loaded on demand
-            n_used = areas[a].n_used; next = areas[a].next; r = areas[a].rec[t];
         }
-        a = a_next_band; n_used = pn_used; next = pnext; r = pr;
+#pragma unroll
+        for (int k = 0; k < PF; k++) {
+            if (band0 + k >= bp.nbands) break;
+            uint32_t a = (uint32_t)b * bp.nbands + band0 + k, nu = n_used[k], nx = next[k];
+            ClbRec rr = r[k];
+            for (;;) {
+                if ((uint32_t)t < nu) {
+                    const uint32_t c = (uint32_t)rr.key;
+                    uint32_t base = CLB_NONE;
+                    if (c < ncl) { base = cur[c]; cur[c] = base + rr.cnt; }      // the records of one area name distinct clusters
+                    areas[a].rec[t].cnt = base;
+                }
+                __syncthreads();
+                if (nx == CLB_NONE) break;
+                a = nx;
+                nu = areas[a].n_used; nx = areas[a].next; rr = areas[a].rec[t];
+            }
+        }
     }
 }
 
 // scatter: one warp per (sub-)band
-__global__ void __launch_bounds__(CLB_WARPS * 32)
+__global__ void __launch_bounds__(32)
 cluster_band_scatter_kernel(const uint32_t *__restrict__ stage, const ClbArea *__restrict__ areas, const uint32_t *__restrict__ pool_counter,
                             uint32_t *__restrict__ scankey, Geom g, Caps caps, BandPlan bp)
 {
-    __shared__ uint32_t s_cur[CLB_WARPS][CLB_CAP];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ uint32_t cur[CLB_CAP];
+    const int lane = threadIdx.x;
     const uint32_t full = 0xffffffffu, lt = (1u << lane) - 1u;
-    const uint32_t a = blockIdx.x * CLB_WARPS + wid;
+    const uint32_t a = blockIdx.x;
     const uint32_t nfirst = (uint32_t)g.batch * bp.nbands;
     if (a >= nfirst + min(*pool_counter, bp.pool_cap)) return;
     const ClbArea *A = areas + a;
     const uint32_t n_used = A->n_used, st_start = A->st_start, st_end = A->st_end, job = A->band;
     if (st_end <= st_start) return;
     const int b = job / bp.nbands, band = job % bp.nbands, y0 = 1 + band * bp.rows;
-    uint32_t *cur = s_cur[wid];
     for (int s = lane; s < CLB_CAP; s += 32) cur[s] = CLB_NONE;
     __syncwarp();
     bool any = false;
@@ -515,17 +563,18 @@ cluster_band_scatter_kernel(const uint32_t *__restrict__ stage, const ClbArea *_
     __syncwarp();
     const uint32_t *st = stage + band_stage_base(g, b, y0);
     uint32_t *out = scankey + (size_t)b * caps.points_per_frame;
-    uint32_t word = st_start + lane < st_end ? st[st_start + lane] : 0xffffffffu;
+    uint32_t word = st_start + lane < st_end ? st[st_start + lane] : 0u;
     for (uint32_t i0 = st_start; i0 < st_end; i0 += 32) {
         const uint32_t w = word;
-        if (i0 + 32 + lane < st_end) word = st[i0 + 32 + lane]; else word = 0xffffffffu;
-        const uint32_t slot = w >> 24;                          // idle lanes: slot 255, which is never used
+        const bool active = i0 + lane < st_end;
+        word = i0 + 32 + lane < st_end ? st[i0 + 32 + lane] : 0u;
+        const uint32_t slot = active ? (w >> 24) : 256u + (uint32_t)lane;          // idle lanes: a group of their own
         const uint32_t peers = __match_any_sync(full, slot);
         const int leader = __ffs(peers) - 1;
         uint32_t base = CLB_NONE;
-        if (lane == leader) { base = cur[slot]; if (base != CLB_NONE) cur[slot] = base + __popc(peers); }
+        if (active && lane == leader) { base = cur[slot]; if (base != CLB_NONE) cur[slot] = base + __popc(peers); }
         base = __shfl_sync(full, base, leader);
-        if (base != CLB_NONE) {
+        if (active && base != CLB_NONE) {
             const uint32_t x = w & 0x3ffffu, row = (w >> 21) & 7u, ds = (w >> 18) & 7u;      // ds = probe << 1 | sign
             out[base + __popc(peers & lt)] = (((uint32_t)(y0 + row) * (uint32_t)g.w + x) << 3) | ds;
         }

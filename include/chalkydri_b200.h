@@ -204,6 +204,13 @@ int cb_cat_detect_corners(cb_ctx *ctx, const uint8_t *color, int width, int heig
 /* Detector::check_edges (lib.rs:409-499): (x1,y1,x2,y2) in the reference's order */
 int cb_cat_check_edges(cb_ctx *ctx, const uint8_t *color, int width, int height, const int32_t *xy, int64_t npts,
                        int32_t *lines, int64_t cap, int64_t *n);
+/* Detector::process_frame (lib.rs:265-287) in ONE call: calc_otsu -> reset -> detect_corners -> check_edges.  The frame is uploaded
+ * once; gray plane, colour map and corner list stay on the device between the stages (the reference's only benchmark times exactly
+ * this call on a 703x905 frame, crates/chalkydri-apriltags/bench.rs:8-26).  xy / lines as above; color (optional, may be NULL)
+ * receives the Color map.  CB_ERR_OVERFLOW when a list does not fit its capacity (n_points / n_lines still report the need).
+ * cb_get_timing: h2d_ms, preprocess_ms (all CAT kernels), d2h_ms, total_ms. */
+int cb_cat_process_frame(cb_ctx *ctx, const uint8_t *rgb, int width, int height, uint8_t *color, int32_t *xy, int64_t xy_cap,
+                         int64_t *n_points, int32_t *lines, int64_t lines_cap, int64_t *n_lines);
 /* Detector::connected_components (lib.rs:501-549): min-index labels and component sizes */
 int cb_cat_connected_components(cb_ctx *ctx, const uint8_t *color, int width, int height, uint32_t *labels, uint32_t *sizes);
 

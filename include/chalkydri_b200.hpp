@@ -5,6 +5,7 @@
 //   apriltag::{DetectorBuilder, Detector, Detection}   /root/reference/crates/apriltags/src/lib.rs:19,258-261,301-314
 //   chalkydri_sqpnp::SqPnP                              /root/reference/crates/chalkydri_sqpnp/src/lib.rs:183-304,430-461
 //   the Copper task AprilTags (new / process)           /root/reference/crates/apriltags/src/lib.rs:166-379
+//   chalkydri-apriltags ("CAT") Detector                 /root/reference/crates/chalkydri-apriltags/src/lib.rs:142-181,265-287,501-549
 // Config errors throw (the reference unwrap()s / panics), the solver returns std::optional (the reference: Option).
 #pragma once
 #include <array>
@@ -97,15 +98,24 @@ class Detector {
     int max_dets_, max_batch_;
 };
 
+// apriltag::Family (the reference parses its `family` config string with Family::from_str and unwraps, lib.rs:229)
+enum class Family { Tag36h11 };
+inline Family family_from_str(const std::string &name)
+{
+    if (name == "tag36h11") return Family::Tag36h11;
+    throw Error(CB_ERR_UNSUPPORTED, "unknown family " + name + " (this build carries tag36h11, the reference's FAMILY)");
+}
+
 class DetectorBuilder {
   public:
     static DetectorBuilder default_() { return DetectorBuilder(); }
-    DetectorBuilder &add_family_bits(const std::string &family, size_t bits_corrected)
+    // DetectorBuilder::add_family_bits(family, bits) (lib.rs:259, 280)
+    DetectorBuilder &add_family_bits(Family, size_t bits_corrected)
     {
-        if (family != "tag36h11") throw Error(CB_ERR_UNSUPPORTED, "unknown family " + family + " (this build carries tag36h11, the reference's FAMILY)");
         bits_ = (int)bits_corrected;
         return *this;
     }
+    DetectorBuilder &add_family_bits(const std::string &family, size_t bits_corrected) { return add_family_bits(family_from_str(family), bits_corrected); }
     DetectorBuilder &device(int d) { device_ = d; return *this; }
     DetectorBuilder &capacity(int max_w, int max_h, int max_batch = 1, int max_dets = 64) { w_ = max_w; h_ = max_h; batch_ = max_batch; dets_ = max_dets; return *this; }
     Detector build() const
@@ -130,7 +140,9 @@ class SqPnP {
         ctx_ = cb_create(device, 8, 8, 1, 1);
         if (!ctx_) throw Error(CB_ERR_CUDA, cb_last_error(nullptr));
     }
-    SqPnP(const SqPnP &) = delete;
+    // Clone (lib.rs:182: #[derive(Clone, Debug, Default)]): a fresh solver with the same settings -- the scratch is per instance
+    SqPnP(const SqPnP &o) : SqPnP() { max_iter_ = o.max_iter_; tol_ = o.tol_; cb_sqpnp_set(ctx_, max_iter_, tol_); }
+    SqPnP &operator=(const SqPnP &o) { max_iter_ = o.max_iter_; tol_ = o.tol_; cb_sqpnp_set(ctx_, max_iter_, tol_); return *this; }
     ~SqPnP() { cb_destroy(ctx_); }
     SqPnP &max_iter(size_t n) { max_iter_ = (int)n; cb_sqpnp_set(ctx_, max_iter_, tol_); return *this; }      // lib.rs:214-217
     SqPnP &tolerance(double t) { tol_ = t; cb_sqpnp_set(ctx_, max_iter_, tol_); return *this; }               // lib.rs:219-222
@@ -256,6 +268,109 @@ class AprilTags {
     uint8_t cam_id_;
     Comm comm_;
     std::optional<uint64_t> last_time_;
+};
+
+// ---- the in-house CAT detector (crates/chalkydri-apriltags/src/lib.rs) ----
+namespace cat {
+
+enum Color : uint8_t { Black = 0, White = 1, Other = 2 };                        // utils.rs:1-6
+
+// the UnionFind connected_components() returns (lib.rs:42-113): parent[] = smallest pixel index of the component
+struct UnionFind {
+    std::vector<uint32_t> parent, cluster_sizes;
+    size_t find(size_t idx) const { return parent[idx]; }
+    size_t get_size(size_t idx) const { return cluster_sizes[idx]; }
+};
+
+class Detector {
+  public:
+    // Detector::new(width, height, valid_tags) (lib.rs:158-181)
+    Detector(size_t width, size_t height, std::vector<size_t> valid_tags = {}, int device = 0)
+        : width_(width), height_(height), valid_tags_(std::move(valid_tags)), buf(width * height, (uint8_t)Black)
+    {
+        ctx_ = cb_create(device, 8, 8, 1, 1);
+        if (!ctx_) throw Error(CB_ERR_CUDA, cb_last_error(nullptr));
+    }
+    Detector(const Detector &o) : Detector(o.width_, o.height_, o.valid_tags_) {}          // Clone = a fresh, empty detector (lib.rs:663-667)
+    Detector &operator=(const Detector &) = delete;
+    ~Detector() { cb_destroy(ctx_); }
+
+    // process_frame(&mut self, input: &[u8]) (lib.rs:265-287); panics on a wrong length (lib.rs:267)
+    void process_frame(const uint8_t *input, size_t len)
+    {
+        if (len != width_ * height_ * 3) throw std::invalid_argument("process_frame: input must be width * height * 3 bytes of packed RGB");
+        points_.resize(cap_ * 2);
+        lines_.resize(cap_ * 4);
+        int64_t n = 0, m = 0;
+        check(cb_cat_process_frame(ctx_, input, (int)width_, (int)height_, buf.data(), points_.data(), (int64_t)cap_, &n, lines_.data(), (int64_t)cap_, &m));
+        points_.resize((size_t)n * 2);
+        lines_.resize((size_t)m * 4);
+    }
+    void calc_otsu(const uint8_t *input) { check(cb_cat_calc_otsu(ctx_, input, (int)width_, (int)height_, buf.data())); }       // lib.rs:191
+    void thresh(const uint8_t *input) { check(cb_cat_thresh(ctx_, input, (int)width_, (int)height_, buf.data())); }             // lib.rs:319
+    void detect_corners()                                                                                                        // lib.rs:291
+    {
+        points_.resize(cap_ * 2);
+        int64_t n = 0;
+        check(cb_cat_detect_corners(ctx_, buf.data(), (int)width_, (int)height_, points_.data(), (int64_t)cap_, &n));
+        if ((size_t)n > cap_) throw Error(CB_ERR_OVERFLOW, "corner list capacity");
+        points_.resize((size_t)n * 2);
+    }
+    void check_edges()                                                                                                           // lib.rs:480
+    {
+        lines_.resize(cap_ * 4);
+        int64_t n = 0;
+        check(cb_cat_check_edges(ctx_, buf.data(), (int)width_, (int)height_, points_.data(), (int64_t)(points_.size() / 2), lines_.data(), (int64_t)cap_, &n));
+        if ((size_t)n > cap_) throw Error(CB_ERR_OVERFLOW, "line list capacity");
+        lines_.resize((size_t)n * 4);
+    }
+    UnionFind connected_components() const                                                                                        // lib.rs:501
+    {
+        UnionFind uf;
+        uf.parent.resize(width_ * height_);
+        uf.cluster_sizes.resize(width_ * height_);
+        const int rc = cb_cat_connected_components(ctx_, buf.data(), (int)width_, (int)height_, uf.parent.data(), uf.cluster_sizes.data());
+        if (rc != CB_OK) throw Error(rc, cb_last_error(ctx_));
+        return uf;
+    }
+    const std::vector<int32_t> &points() const { return points_; }      // (x, y) pairs, the reference's scan order
+    const std::vector<int32_t> &lines() const { return lines_; }        // (x1, y1, x2, y2)
+    cb_timing timing() const { cb_timing t; cb_get_timing(ctx_, &t); return t; }
+    std::vector<uint8_t> buf;                                           // the Color map (bufs.buf)
+
+  private:
+    void check(int rc) { if (rc != CB_OK) throw Error(rc, cb_last_error(ctx_)); }
+    cb_ctx *ctx_ = nullptr;
+    size_t width_, height_, cap_ = (size_t)1 << 20;
+    std::vector<size_t> valid_tags_;
+    std::vector<int32_t> points_, lines_;
+};
+
+}  // namespace cat
+
+// ---- several GPUs, one process (cb_pool_*): one context + host thread per GPU, lists into slices of one array ----
+class DetectorPool {
+  public:
+    DetectorPool(const std::vector<int> &devices, int max_w, int max_h, int max_batch, int max_dets, int bits_corrected = 3) : max_dets_(max_dets)
+    {
+        pool_ = cb_pool_create(devices.empty() ? nullptr : devices.data(), (int)devices.size(), max_w, max_h, max_batch, max_dets);
+        if (!pool_) throw Error(CB_ERR_CUDA, cb_pool_last_error(nullptr));
+        check(cb_pool_set_family_tag36h11(pool_, bits_corrected));
+    }
+    DetectorPool(const DetectorPool &) = delete;
+    ~DetectorPool() { cb_pool_destroy(pool_); }
+    int size() const { return cb_pool_size(pool_); }
+    // out[f * max_dets + k], counts[f] for frame f of `frames`
+    void detect(const uint8_t *frames, int w, int h, int stride, size_t frame_stride, int n_frames, cb_detection *out, int32_t *counts)
+    {
+        check(cb_pool_detect_gray(pool_, frames, w, h, stride, frame_stride, n_frames, out, counts));
+    }
+    cb_pool_timing timing() const { cb_pool_timing t; cb_pool_get_timing(pool_, &t); return t; }
+
+  private:
+    void check(int rc) { if (rc != CB_OK) throw Error(rc, cb_pool_last_error(pool_)); }
+    cb_pool *pool_ = nullptr;
+    int max_dets_;
 };
 
 }  // namespace chalkydri

@@ -190,3 +190,33 @@ def test_task_publish_rules_host_logic():
     # gyro defaults to comm.gyro_angle() for every frame, None -> NaN (no reading, lib.rs:329)
     assert task._gyro_array(None, 3).tolist() == [0.5, 0.5, 0.5]
     assert np.isnan(task._gyro_array([0.1, None], 2)[1])
+
+
+def test_rust_extern_block_lists_the_header():
+    """rust/chalkydri-b200-sys/src/ffi.rs declares exactly the symbols of include/chalkydri_b200.h (text comparison: the image has
+    no rustc), and the wrapper crate uses every one of them."""
+    ffi = open(os.path.join(ROOT, "rust", "chalkydri-b200-sys", "src", "ffi.rs")).read()
+    block = ffi[ffi.index('unsafe extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    declared = re.findall(r"pub fn (cb_[a-z0-9_]+)\s*\(", block)
+    assert len(declared) == len(set(declared))
+    assert sorted(declared) == header_symbols()
+    wrappers = open(os.path.join(ROOT, "rust", "chalkydri-b200-sys", "src", "lib.rs")).read()
+    unused = [s for s in declared if not re.search(r"\b" + s + r"\b", wrappers)]
+    assert unused == [], f"declared but never called from the wrapper crate: {unused}"
+    # the seams the reference's task code needs (crates/apriltags/src/lib.rs:19,229,259; crates/chalkydri_sqpnp/src/lib.rs:182,194)
+    for needle in ("impl FromStr for Family", "pub fn add_family_bits(mut self, family: Family, bits_corrected: usize)",
+                   "impl Default for SqPnP", "impl Clone for SqPnP", "#[derive(Debug)]\npub struct SqPnP",
+                   "pub fn new(width: usize, height: usize, valid_tags: &'static [usize])", "pub fn process_frame(&mut self, input: &[u8])",
+                   "pub fn connected_components(&self) -> UnionFind"):
+        assert needle in wrappers, needle
+
+
+def test_cpp_header_covers_the_abi():
+    """include/chalkydri_b200.hpp (the host mirror that IS compiled and run) calls every entry point a host needs; the ones it
+    leaves to the raw header are stage taps and plumbing."""
+    hpp = open(os.path.join(ROOT, "include", "chalkydri_b200.hpp")).read()
+    used = {s for s in header_symbols() if re.search(r"\b" + s + r"\b", hpp)}
+    for s in ("cb_detect_gray", "cb_detect_gray_submit", "cb_detect_gray_collect", "cb_detect_pose_gray", "cb_sqpnp_batch",
+              "cb_cat_process_frame", "cb_cat_connected_components", "cb_pool_detect_gray", "cb_pack_vision_measurements"):
+        assert s in used
