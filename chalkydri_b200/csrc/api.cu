@@ -94,6 +94,7 @@ struct cb_ctx {
     ClusterSlot *d_table = nullptr;
     uint8_t *d_cat = nullptr, *d_cat_tot = nullptr;   // CAT process_frame scratch (grow-only)
     size_t cat_bytes = 0, cat_tot_bytes = 0;
+    int sort_bucket_form = 1;                  // slope sort: bucket form (round 2) or merge sort only (CB_SORT=merge, A/B hook)
     int cluster_mode = 0;                      // 0: band-ordered count / scatter (round 2), 1: tile passes + scan-order sort (round 1; CB_CLUSTERS=tiles)
     ClbArea *d_areas = nullptr;                // band tables of the count pass (first areas, then the pool of chained sub-band areas)
     uint32_t areas_first_cap = 0, areas_pool_cap = 0;
@@ -291,6 +292,7 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         const size_t dw = (size_t)ctx->max_w / 2 + 1, dh = (size_t)ctx->max_h / 2 + 1;      // decimated size bound (quad_decimate = 2)
         const size_t tiles = ((dw + CL_TW - 1) / CL_TW) * ((dh + CL_TH - 1) / CL_TH);
         if (const char *e = getenv("CB_CLUSTERS")) ctx->cluster_mode = strcmp(e, "tiles") == 0 ? 1 : 0;      // A/B hook
+        if (const char *e = getenv("CB_SORT")) ctx->sort_bucket_form = strcmp(e, "merge") == 0 ? 0 : 1;
         ok = ok && alloc((void **)&ctx->d_ent, B * dw * dh * sizeof(uint4));
         if (ctx->cluster_mode == 1) {
             ok = ok && alloc((void **)&ctx->d_tile_keys, B * tiles * CL_CAP * sizeof(unsigned long long));
@@ -651,7 +653,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         // main stream plus four side streams): a tier with few, large CTAs no longer leaves the rest of the SMs idle.
 #define CB_LAUNCH_SORT1(CFG, GRID, CNT, STREAM)                                                                                                  \
         sort_clusters_kernel<CFG><<<ctx->num_sms * (GRID), CFG::THREADS, CFG::BYTES, STREAM>>>(ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, \
-                                                                                             d_misc + (CNT), ctx->d_scratch, g, caps, prm);
+                                                                                             d_misc + (CNT), ctx->d_scratch, g, caps, prm, ctx->sort_bucket_form);
         CK(cudaEventRecord(ctx->ev_fork, st));
         for (int i = 0; i < 4; i++) CK(cudaStreamWaitEvent(ctx->tier_stream[i], ctx->ev_fork, 0));
         if (ctx->cluster_mode == 0) {

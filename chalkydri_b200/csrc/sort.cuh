@@ -238,6 +238,62 @@ __device__ __forceinline__ void sort_scan_cluster(uint32_t *__restrict__ K, int 
     for (int j = tid; j < n; j += NT) K[j] = src[sidx<E, PAD>(j)];
 }
 
+// ---- bucket form of the slope sort -------------------------------------------------------------------------------------------
+// The composite keys are unique, so ANY correct sort gives upstream's order -- and the slope is an angle, spread roughly evenly
+// over a closed boundary.  So instead of O(n log n) merge passes: a monotone map from the float slope to one of ~n/4 buckets
+// (same order as the keys: every step of it is a monotone function evaluated without contraction), a shared-memory histogram,
+// a prefix sum, a scatter, and the exact position of a point inside its bucket by counting the smaller keys among the handful
+// of points that share it.  ~100 instructions per point where the merge sort spent well over a thousand.  Clusters whose
+// points crowd into a few directions (a bucket above SORT_BUCKET_LIMIT: long thin shapes seen from inside) take the merge sort.
+constexpr int SORT_BUCKET_LIMIT = 96;
+
+// monotone non-decreasing in the float `slope` (= quadrant + dy/dx, quadrant in {-65536, 0, 65536, 131072}, dy/dx >= 0)
+__device__ __forceinline__ int slope_bucket(uint32_t orderable, int nb4, float scale)
+{
+    const uint32_t bits = (orderable & 0x80000000u) ? (orderable & 0x7fffffffu) : ~orderable;     // inverse of float_orderable
+    const float s = __uint_as_float(bits);
+    int q;
+    float t;
+    if (s >= 131072.f) { q = 3; t = s - 131072.f; }
+    else if (s >= 65536.f) { q = 2; t = s - 65536.f; }
+    else if (s >= 0.f) { q = 1; t = s; }
+    else { q = 0; t = s + 65536.f; }                        // (the differences are exact: Sterbenz)
+    const float u = t < 1.f ? 0.5f * t : 1.f - 0.5f / t;    // [0, 1): tan -> something close to the angle; each branch monotone, equal at 1
+    int k = (int)(u * scale);
+    k = max(0, min(k, nb4 - 1));
+    return q * nb4 + k;
+}
+
+// exclusive prefix sum of cnt[0 .. nb) into base[0 .. nb) by a group of NT threads (nb a power of two >= 32); returns the largest count
+template <int NT>
+__device__ __forceinline__ uint32_t bucket_scan(const uint32_t *cnt, uint32_t *base, int nb, int tid, SortScratch &S)
+{
+    typedef Grp<NT> G;
+    const int per = nb >= NT ? nb / NT : 1;
+    const bool on = tid * per < nb;
+    uint32_t sum = 0, mx = 0;
+    if (on)
+        for (int k = 0; k < per; k++) { const uint32_t c = cnt[tid * per + k]; sum += c; mx = max(mx, c); }
+    // inclusive scan of `sum` across the group
+    const int lane = tid & 31;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    uint32_t warp_off = 0;
+    if (NT > 32) {
+        const int wid = tid >> 5;
+        __syncthreads();
+        if (lane == 31) S.red_i[wid] = (int)incl;
+        __syncthreads();
+        for (int k = 0; k < wid; k++) warp_off += (uint32_t)S.red_i[k];
+    }
+    uint32_t run = warp_off + incl - sum;
+    if (on)
+        for (int k = 0; k < per; k++) { const uint32_t c = cnt[tid * per + k]; base[tid * per + k] = run; run += c; }
+    mx = G::reduce(mx, [](uint32_t a, uint32_t c) { return max(a, c); }, reinterpret_cast<uint32_t *>(S.red_f));
+    return mx;
+}
+
 // ---- sort #2: slopes in scan order, ptsort() ------------------------------------------------------------------------
 // K holds the scan-ordered keys on entry and the sorted points (px | py << 16) on return.
 // CHECK: K arrives in scan order straight from the band scatter pass (clusters.cuh), and the two tests sort #1 used to make --
@@ -245,7 +301,8 @@ __device__ __forceinline__ void sort_scan_cluster(uint32_t *__restrict__ K, int 
 // cursor = 0xffffffff.  Returns false for a rejected cluster.
 template <int NT, int E, bool PAD, bool CHECK>
 __device__ __forceinline__ bool sort_slope_cluster(uint32_t *__restrict__ K, int n, unsigned long long *A, unsigned long long *B,
-                                                   SortScratch &S, const Geom &g, ClusterRec *__restrict__ rec_global, const DetParams &prm)
+                                                   SortScratch &S, const Geom &g, ClusterRec *__restrict__ rec_global, const DetParams &prm,
+                                                   uint32_t *hist, int hist_buckets)
 {
     typedef Grp<NT> G;
     const int tid = G::tid();
@@ -328,6 +385,42 @@ __device__ __forceinline__ bool sort_slope_cluster(uint32_t *__restrict__ K, int
         }
     }
     G::sync();
+    if (hist != nullptr) {
+        // bucket form: histogram -> prefix -> scatter -> exact rank inside the bucket
+        int nb = 32;
+        while (nb < hist_buckets && nb * 4 < n) nb <<= 1;
+        const int nb4 = nb >> 2;
+        const float scale = (float)nb4;
+        uint32_t *cnt = hist, *base = hist + hist_buckets;
+        for (int k = tid; k < nb; k += NT) cnt[k] = 0;
+        G::sync();
+        for (int i = tid; i < n; i += NT) atomicAdd(&cnt[slope_bucket((uint32_t)(A[sidx<E, PAD>(i)] >> 32), nb4, scale)], 1u);
+        G::sync();
+        const uint32_t biggest = bucket_scan<NT>(cnt, base, nb, tid, S);
+        G::sync();
+        if (biggest <= (uint32_t)SORT_BUCKET_LIMIT) {
+            for (int k = tid; k < nb; k += NT) cnt[k] = base[k];                   // cursors
+            G::sync();
+            for (int i = tid; i < n; i += NT) {
+                const unsigned long long key = A[sidx<E, PAD>(i)];
+                B[atomicAdd(&cnt[slope_bucket((uint32_t)(key >> 32), nb4, scale)], 1u)] = key;
+            }
+            G::sync();
+            uint32_t *stage = reinterpret_cast<uint32_t *>(A);               // the keys now live in B
+            for (int p = tid; p < n; p += NT) {
+                const unsigned long long key = B[p];
+                const int bk = slope_bucket((uint32_t)(key >> 32), nb4, scale);
+                const uint32_t s0 = base[bk], s1 = cnt[bk];                     // the cursor ended at the bucket's end
+                uint32_t r = s0;
+                for (uint32_t q = s0; q < s1; q++) r += B[q] < key ? 1u : 0u;
+                const uint32_t tie = (uint32_t)key;
+                stage[r] = K[(0xffffffu - (tie >> 3)) + (tie & 7u)];
+            }
+            G::sync();
+            for (int j = tid; j < n; j += NT) K[j] = stage[j];
+            return true;
+        }
+    }
     unsigned long long *src = A, *dst = B;
     block_sort<NT, E, PAD>(src, dst, n, tid);
     uint32_t *stage = reinterpret_cast<uint32_t *>(dst);
@@ -370,7 +463,9 @@ struct SortCfg {
     static constexpr int THREADS = NT * GROUPS;
     static constexpr int ELEM = WHICH == 1 ? 4 : 8;
     static constexpr size_t ARRAY_BYTES = ((size_t)sort_padded<E>(MAXN) * ELEM + 15) / 16 * 16;
-    static constexpr size_t GROUP_BYTES = 2 * ARRAY_BYTES + (sizeof(SortScratch) + 15) / 16 * 16;
+    static constexpr int HIST_BUCKETS = WHICH == 1 ? 0 : MAXN / 4;               // bucket form of the slope sort: counts + starts
+    static constexpr size_t SCRATCH_BYTES = (sizeof(SortScratch) + 15) / 16 * 16;
+    static constexpr size_t GROUP_BYTES = 2 * ARRAY_BYTES + SCRATCH_BYTES + (size_t)2 * HIST_BUCKETS * sizeof(uint32_t);
     static constexpr size_t BYTES = GROUPS * GROUP_BYTES;
 };
 
@@ -378,7 +473,7 @@ template <typename C>
 __global__ void __launch_bounds__(C::THREADS)
 sort_clusters_kernel(uint32_t *__restrict__ scankey, ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ worklists,
                      size_t wl_stride, const uint32_t *__restrict__ nwork, uint32_t *__restrict__ work_counter,
-                     unsigned long long *__restrict__ scratch, Geom g, Caps caps, DetParams prm)
+                     unsigned long long *__restrict__ scratch, Geom g, Caps caps, DetParams prm, int bucket_form)
 {
     typedef C SH;
     constexpr int NT = C::NT, E = C::E, MAXN = C::MAXN, WHICH = C::WHICH, T_LO = C::T_LO, T_HI = C::T_HI, NMIN = C::NMIN, NMAX = C::NMAX;
@@ -422,11 +517,12 @@ sort_clusters_kernel(uint32_t *__restrict__ scankey, ClusterRec *__restrict__ cl
             }
         } else {
             unsigned long long *A = reinterpret_cast<unsigned long long *>(base), *B = reinterpret_cast<unsigned long long *>(base + SH::ARRAY_BYTES);
-            if (EH != E && n <= MAXN / 2) sort_slope_cluster<NT, EH, true, CHECK>(scankey + pbase, n, A, B, S, g, clusters + item, prm);
-            else if (NEVER_GLOBAL || n <= MAXN) sort_slope_cluster<NT, E, true, CHECK>(scankey + pbase, n, A, B, S, g, clusters + item, prm);
+            uint32_t *hist = bucket_form ? reinterpret_cast<uint32_t *>(base + 2 * SH::ARRAY_BYTES + SH::SCRATCH_BYTES) : nullptr;
+            if (EH != E && n <= MAXN / 2) sort_slope_cluster<NT, EH, true, CHECK>(scankey + pbase, n, A, B, S, g, clusters + item, prm, hist, SH::HIST_BUCKETS);
+            else if (NEVER_GLOBAL || n <= MAXN) sort_slope_cluster<NT, E, true, CHECK>(scankey + pbase, n, A, B, S, g, clusters + item, prm, hist, SH::HIST_BUCKETS);
             else {
                 unsigned long long *GA = scratch + pbase * 2;
-                sort_slope_cluster<NT, E, false, CHECK>(scankey + pbase, n, GA, GA + n, S, g, clusters + item, prm);
+                sort_slope_cluster<NT, E, false, CHECK>(scankey + pbase, n, GA, GA + n, S, g, clusters + item, prm, nullptr, 0);      // above the shared-memory tiers: merge sort in global memory
             }
         }
         if (NT == 32) __syncwarp();
