@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -32,6 +34,9 @@ static const int kHostBitX[36] = {1,2,3,4,5,2,3,4,3, 6,6,6,6,6,5,5,5,4, 6,5,4,3,
 static const int kHostBitY[36] = {1,1,1,1,1,2,2,2,3, 1,2,3,4,5,2,3,4,3, 6,6,6,6,6,5,5,5,4, 6,5,4,3,2,5,4,3,4};
 
 static thread_local std::string g_create_error;
+
+struct ThrChoice { int variant, ysegs; };
+typedef std::tuple<int, int, int, int> ThrKey;      // W, H, stride, batch
 
 enum Stage { ST_THRESH = 1, ST_LABELS = 2, ST_QUADS = 3, ST_FULL = 4 };
 
@@ -122,6 +127,7 @@ struct cb_ctx {
 
     cudaEvent_t ev[10]{};
     cb_timing timing{};
+    std::map<ThrKey, ThrChoice> thr_plans;          // threshold kernel shape per frame geometry (threshold_plan)
 };
 
 static int fail(cb_ctx *c, int code, const char *fmt, ...)
@@ -325,8 +331,6 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_y, kHostBitY, sizeof(kHostBitY)) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(threshold_f2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, thr_tma_warp_bytes(THR_TMA_ROWB) * THR_TMA_WARPS) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(threshold_tm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<6>::SMEM) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(threshold_tm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmCfg<4>::SMEM) == cudaSuccess;
 #define CB_SORT_ATTR(CFG) ok = ok && cudaFuncSetAttribute(sort_clusters_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::BYTES) == cudaSuccess;
         CB_SORT_ATTR(SortS8<1>) CB_SORT_ATTR(SortS16<1>) CB_SORT_ATTR(SortM<1>) CB_SORT_ATTR(SortL1<1>) CB_SORT_ATTR(SortL2<1>)
         CB_SORT_ATTR(SortS8<2>) CB_SORT_ATTR(SortS16<2>) CB_SORT_ATTR(SortM<2>) CB_SORT_ATTR(SortL1<2>) CB_SORT_ATTR(SortL2<2>)
@@ -461,11 +465,13 @@ static cb_encode_tiled_fn tensor_map_encoder()
     return fn;
 }
 
-// Launch of the tensor-map threshold kernel.  Returns false when the tensor map cannot be built (the caller then takes the 1-D TMA kernel).
-template <int T>
-static bool launch_threshold_tm(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int min_diff, cudaStream_t st)
+// Launch of the tensor-map threshold kernel with `ysegs` row segments per frame (<= 0: the wave-count model below).
+// Returns false when the tensor map cannot be built (the caller then takes the 1-D TMA kernel).
+template <class C>
+static bool launch_threshold_tm(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int min_diff, cudaStream_t st, int ysegs)
 {
-    typedef TmCfg<T> C;
+    constexpr int T = 2 * C::P, TM_WARPS = C::WARPS, TM_STAGES = C::STAGES;
+    if (C::SMEM > 48 * 1024 && cudaFuncSetAttribute(threshold_tm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return false;
     cb_encode_tiled_fn enc = tensor_map_encoder();
     if (!enc) return false;
     // 3-D tensor of 8-byte elements: x = tile column (8 input bytes = 4 decimated pixels), y = EVEN input row (row stride doubled),
@@ -479,29 +485,87 @@ static bool launch_threshold_tm(cb_ctx *ctx, const uint8_t *d_frames, const Geom
         return false;
     TmPlan plan;
     plan.strips = (g.tw + C::MAX_IW - 1) / C::MAX_IW;
-    plan.iw = ((g.tw + plan.strips - 1) / plan.strips + 1) / 2 * 2;
-    {   // equal waves: every warp does seg_rows + 2 tile rows plus the fill of its ring
-        const int ctas_per_sm = std::max(1, (int)((227 * 1024) / (C::SMEM + 1024)));
+    plan.iw = ((g.tw + plan.strips - 1) / plan.strips + 3) / 4 * 4;      // multiple of 4 tiles: 16-byte aligned strip starts (bulk stores)
+    if (ysegs <= 0) {   // equal waves: every warp does seg_rows + 2 tile rows plus the fill of its ring
+        const int ctas_per_sm = std::max(1, std::min((int)C::MIN_CTAS, (int)((227 * 1024) / (C::SMEM + 1024))));
         const long long resident = (long long)ctx->num_sms * ctas_per_sm * TM_WARPS;
         const int max_segs = std::max(1, g.th / 6);
         long long best_cost = -1;
-        int best = 1;
+        ysegs = 1;
         for (int ys = 1; ys <= max_segs; ys++) {
             const int rows = (g.th + ys - 1) / ys, segs = (g.th + rows - 1) / rows;
             if (segs != ys) continue;
             const long long warps = (long long)plan.strips * segs * g.batch;
             const long long cost = ((warps + resident - 1) / resident) * (rows + 2 + TM_STAGES);
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ys; }
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; ysegs = ys; }
         }
-        if (const char *e = getenv("CB_THR_YSEGS")) best = std::max(1, std::min(max_segs, atoi(e)));      // experiment hook
-        plan.seg_rows = (g.th + best - 1) / best;
-        plan.ysegs = (g.th + plan.seg_rows - 1) / plan.seg_rows;
     }
+    plan.seg_rows = (g.th + ysegs - 1) / ysegs;
+    plan.ysegs = (g.th + plan.seg_rows - 1) / plan.seg_rows;
     const long long warps = (long long)plan.strips * plan.ysegs * g.batch;
     const int wt = (g.w % 4 || g.h % 4) ? 1 : 0;
-    threshold_tm_kernel<T><<<(unsigned)((warps + TM_WARPS - 1) / TM_WARPS), TM_WARPS * 32, C::SMEM, st>>>(map, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g,
+    threshold_tm_kernel<C><<<(unsigned)((warps + TM_WARPS - 1) / TM_WARPS), TM_WARPS * 32, C::SMEM, st>>>(map, ctx->d_thresh, ctx->d_tmin, ctx->d_tmax, g,
                                                                                                      std::max(-1000, std::min(1000, min_diff)), plan, wt);
     return true;
+}
+
+// The shapes of the tensor-map kernel: tiles per lane x ring depth x CTAs per SM x store form.  One warp per CTA throughout (a CTA
+// that ends frees its slot at once; 4-warp CTAs waited for their slowest warp).  Which one is fastest depends on the frame width
+// (lanes busy with T = 6 or 4), on how the segments fill the SMs' slots and on the L2 state the stores meet, none of which a
+// static model predicted (measured spread 0.59 .. 0.71 of the HBM peak on 256 x 1280x720, tools/cuda/thr_bench.cu); large
+// batches therefore time the shapes once per geometry (threshold_plan) and keep the fastest.
+typedef bool (*thr_launch_fn)(cb_ctx *, const uint8_t *, const Geom &, int, cudaStream_t, int);
+static const thr_launch_fn kThrVariants[] = {
+    launch_threshold_tm<TmCfg<6, 3, 1, 9, 1>>,      // 0: bulk stores, 3-deep ring
+    launch_threshold_tm<TmCfg<6, 2, 1, 12, 1>>,     // 1: bulk stores, 2-deep ring, 12 warps per SM
+    launch_threshold_tm<TmCfg<6, 3, 1, 12, 0>>,     // 2: direct row-major stores
+    launch_threshold_tm<TmCfg<4, 3, 1, 12, 1>>,     // 3: T = 4, bulk stores
+    launch_threshold_tm<TmCfg<4, 3, 1, 16, 0>>,     // 4: T = 4, direct stores
+};
+static const int kThrMaxIw[] = {TmCfg<6>::MAX_IW, TmCfg<6>::MAX_IW, TmCfg<6>::MAX_IW, TmCfg<4>::MAX_IW, TmCfg<4>::MAX_IW};
+constexpr int kNumThrVariants = 5;
+
+static ThrChoice threshold_plan(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int min_diff, cudaStream_t st)
+{
+    const ThrKey key{g.W, g.H, g.stride, g.batch};
+    auto it = ctx->thr_plans.find(key);
+    if (it != ctx->thr_plans.end()) return it->second;
+    // static choice: the tiles per lane that keep most lanes busy (one strip of T = 6 spans up to 188 tiles = 1504 input pixels)
+    const int s6 = (g.tw + kThrMaxIw[0] - 1) / kThrMaxIw[0], s4 = (g.tw + kThrMaxIw[3] - 1) / kThrMaxIw[3];
+    ThrChoice best{(double)g.tw / (s6 * 32 * 6) >= (double)g.tw / (s4 * 32 * 4) ? 0 : 3, 0};
+    if (const char *e = getenv("CB_THR_T")) best.variant = atoi(e) == 6 ? 0 : 3;                      // experiment hooks
+    if (const char *e = getenv("CB_THR_CFG")) best.variant = std::max(0, std::min(kNumThrVariants - 1, atoi(e)));
+    if (const char *e = getenv("CB_THR_YSEGS")) best.ysegs = std::max(1, std::min(std::max(1, g.th / 6), atoi(e)));
+    const char *tune_env = getenv("CB_THR_TUNE");
+    const bool tune = tune_env ? atoi(tune_env) != 0 : (!getenv("CB_THR_CFG") && !getenv("CB_THR_YSEGS") && !getenv("CB_THR_T"));
+    if (tune && (size_t)g.batch * g.W * g.H >= ((size_t)32 << 20)) {
+        // time every shape x a ladder of segment heights on this batch (about 20 ms, once per geometry and context)
+        cudaEvent_t e0, e1;
+        if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+            float best_ms = 1e30f;
+            const int rows_ladder[] = {5, 6, 7, 8, 9, 10, 11, 12, 14, 16, 18, 20, 23, 26, 30, 36, 45, 60, 90};
+            for (int v = 0; v < kNumThrVariants; v++) {
+                int last_ys = -1;
+                for (int rows : rows_ladder) {
+                    if (rows > g.th) break;
+                    const int ys = (g.th + rows - 1) / rows;
+                    if (ys == last_ys || ys > std::max(1, g.th / 5)) continue;
+                    last_ys = ys;
+                    if (!kThrVariants[v](ctx, d_frames, g, min_diff, st, ys)) break;
+                    cudaEventRecord(e0, st);
+                    for (int r = 0; r < 3; r++) kThrVariants[v](ctx, d_frames, g, min_diff, st, ys);
+                    cudaEventRecord(e1, st);
+                    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (ms < best_ms) { best_ms = ms; best = ThrChoice{v, ys}; }
+                }
+            }
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+    }
+    ctx->thr_plans[key] = best;
+    return best;
 }
 
 static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int stage)
@@ -526,11 +590,8 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         static const int variant = variant_env == nullptr ? 0 : (strcmp(variant_env, "tiled") == 0 ? 2 : (strcmp(variant_env, "tma") == 0 ? 1 : 0));
         bool done = false;
         if (variant == 0) {
-            // tiles per lane: the choice that keeps most lanes busy (one strip of T = 6 spans up to 188 tiles = 1504 input pixels)
-            const int s6 = (g.tw + TmCfg<6>::MAX_IW - 1) / TmCfg<6>::MAX_IW, s4 = (g.tw + TmCfg<4>::MAX_IW - 1) / TmCfg<4>::MAX_IW;
-            int use6 = (double)g.tw / (s6 * 32 * 6) >= (double)g.tw / (s4 * 32 * 4);
-            if (const char *e = getenv("CB_THR_T")) use6 = atoi(e) == 6;
-            done = use6 ? launch_threshold_tm<6>(ctx, d_frames, g, prm.min_white_black_diff, st) : launch_threshold_tm<4>(ctx, d_frames, g, prm.min_white_black_diff, st);
+            const ThrChoice ch = threshold_plan(ctx, d_frames, g, prm.min_white_black_diff, st);
+            done = kThrVariants[ch.variant](ctx, d_frames, g, prm.min_white_black_diff, st, ch.ysegs);
         }
         if (done) {
         } else if (variant == 2) {

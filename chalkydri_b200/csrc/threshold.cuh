@@ -376,12 +376,21 @@ threshold_f2_tma_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ ou
 //     bytes (the byte-SIMD compare is emulated on sm_100);
 //   * the pixel registers of the previous tile row ping-pong (loop unrolled twice) instead of being moved;
 //   * neighbouring row segments run in opposite directions, so the halo rows two warps share are read at the same time
-//     (second read hits L2).
-constexpr int TM_WARPS = 4, TM_STAGES = 4;
-struct TmPlan { int strips, iw, ysegs, seg_rows; };      // iw: interior tiles per strip (even)
-template <int T> struct TmCfg {
-    static constexpr int P = T / 2, ROWB = 32 * T * 8, STAGEB = 4 * ROWB;
-    static constexpr int SMEM = TM_WARPS * TM_STAGES * STAGEB + TM_WARPS * TM_STAGES * 8;
+//     (second read hits L2);
+//   * the STORES decide the rest (tools/cuda/thr_bench.cu: with the stores removed the kernel runs at the speed of its loads,
+//     27 us per 256 x 1280x720 frames; with the first version's stores -- pair by pair, each pair's four rows -- 45 us, and
+//     removing all the binarisation arithmetic changed nothing).  A lane owns 24 bytes of every output row, so a 32-byte
+//     sector is completed by several 8-byte stores; issued pair-major those pieces reached the L2 far apart.  Two forms now:
+//     BULK = 1 stages the four output rows of a tile row in shared memory (conflict-free 8-byte stores at a 24-byte lane
+//     stride) and one lane writes each row with a TMA bulk store (cp.async.bulk.global.shared::cta, full lines; two staging
+//     buffers, wait_group.read before reuse); BULK = 0 stores directly but row by row.  One warp per CTA.
+struct TmPlan { int strips, iw, ysegs, seg_rows; };      // iw: interior tiles per strip (multiple of 4)
+// T tiles per lane, S ring stages per warp, NW warps per CTA, MINB CTAs per SM the register allocation is held to
+template <int T, int S = 3, int NW = 1, int MINB = 9, int BULK_STORE = 1> struct TmCfg {
+    static constexpr int P = T / 2, ROWB = 32 * T * 8, STAGEB = 4 * ROWB, STAGES = S, WARPS = NW, MIN_CTAS = MINB;
+    static constexpr int BULK = BULK_STORE;     // 1: output rows staged in shared memory and written by TMA bulk stores (full lines); 0: direct stores
+    static constexpr int ROWOUT = 32 * T * 4, OUTB = BULK ? 2 * 4 * ROWOUT : 0;      // two staging buffers of 4 output rows per warp
+    static constexpr int SMEM = NW * S * STAGEB + NW * OUTB + NW * S * 8;
     static constexpr int MAX_IW = 32 * T - 4;
 };
 
@@ -399,17 +408,17 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     return d;
 }
 
-template <int T>
-__global__ void __launch_bounds__(TM_WARPS * 32)
+template <class C>
+__global__ void __launch_bounds__(C::WARPS * 32, C::MIN_CTAS)
 threshold_tm_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ out, uint8_t *__restrict__ tmin, uint8_t *__restrict__ tmax,
                     Geom g, int min_diff, TmPlan plan, int write_tiles)
 {
-    typedef TmCfg<T> C;
-    constexpr int P = C::P;
+    constexpr int P = C::P, T = 2 * C::P, TM_STAGES = C::STAGES, TM_WARPS = C::WARPS;
     extern __shared__ __align__(128) unsigned char tm_smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *ring = tm_smem + (size_t)wid * (TM_STAGES * C::STAGEB);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(tm_smem + (size_t)TM_WARPS * TM_STAGES * C::STAGEB) + wid * TM_STAGES;
+    unsigned char *obuf = tm_smem + (size_t)TM_WARPS * TM_STAGES * C::STAGEB + (size_t)wid * C::OUTB;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(tm_smem + (size_t)TM_WARPS * (TM_STAGES * C::STAGEB + C::OUTB)) + wid * TM_STAGES;
     const long long widx = (long long)blockIdx.x * TM_WARPS + wid;
     const long long per_frame = (long long)plan.strips * plan.ysegs;
     if (widx >= per_frame * g.batch) return;                 // (no block-wide barrier in this kernel)
@@ -462,6 +471,10 @@ threshold_tm_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restric
         for (int k = 0; k < 2 * T; k++) { pxa[dy][k] = 0; pxb[dy][k] = 0; }
     uint8_t *ocol = o + (ptrdiff_t)t0 * 4;
     const ptrdiff_t tp_ = g.tp;
+    // bulk-store form: the leading nb16 bytes of each output row of the strip leave through shared memory (s0 is a multiple of 4
+    // tiles and the map pitch a multiple of 16, so source and destination are 16-byte aligned); the last <= 3 tiles are stored directly
+    const int nb16 = ((s1 - s0) * 4) & ~15;
+    const int lane_off = (t0 - s0) * 4;                       // byte offset of the lane's first tile in a staged row (negative: halo)
 
     // one tile row: CUR receives its pixels, the row before it (pixels in PREV, min/max in *B) is written out
 #define CB_TM_STEP(CUR, PREV, IT)                                                                                                     \
@@ -504,9 +517,15 @@ threshold_tm_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restric
         if (lane == 0) { vmn_[0] = 0x00ff00ffu; vmx_[0] = 0u; }                                                                       \
         if (lane == 31) { vmn_[P + 1] = 0x00ff00ffu; vmx_[P + 1] = 0u; }                                                              \
         const int ro_ = r_ - dir;                                                                                                     \
+        if (C::BULK && it_ >= 2) {      /* (warp-uniform) the bulk stores issued two steps ago have finished reading this staging buffer */ \
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");                                             \
+            __syncwarp();                                                                                                             \
+        }                                                                                                                             \
         if (it_ >= 2 && any_in) {                                                                                                     \
-            uint8_t *const p0_ = ocol + (ptrdiff_t)(ro_ * 4) * tp_, *const p1_ = p0_ + tp_, *const p2_ = p1_ + tp_, *const p3_ = p2_ + tp_; \
+            uint8_t *const p0_ = ocol + (ptrdiff_t)(ro_ * 4) * tp_;                                                                   \
+            unsigned char *const sb0_ = obuf + (it_ & 1) * (4 * C::ROWOUT) + lane_off;                                                \
             uint32_t sh_mn_ = prmt(vmn_[0], vmn_[1], 0x5432u), sh_mx_ = prmt(vmx_[0], vmx_[1], 0x5432u);                              \
+            uint32_t oa_[P][4], ob_[P][4];                                                                                            \
             _Pragma("unroll") for (int j = 0; j < P; j++) {                                                                           \
                 const uint32_t nx_mn_ = prmt(vmn_[j + 1], vmn_[j + 2], 0x5432u), nx_mx_ = prmt(vmx_[j + 1], vmx_[j + 2], 0x5432u);    \
                 const uint32_t dmn_ = __vimin3_u16x2(vmn_[j + 1], sh_mn_, nx_mn_), dmx_ = __vimax3_u16x2(vmx_[j + 1], sh_mx_, nx_mx_); \
@@ -517,25 +536,40 @@ threshold_tm_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restric
                 const uint32_t c0_ = prmt(cc_, 0u, 0x1010u), c1_ = prmt(cc_, 0u, 0x3232u);                                            \
                 const uint32_t nf0_ = prmt(F_, 0u, 0x9999u), nf1_ = prmt(F_, 0u, 0xbbbbu);                                            \
                 const uint32_t fl0_ = 0x7f7f7f7fu & ~nf0_, fl1_ = 0x7f7f7f7fu & ~nf1_;                                                \
-                uint32_t ra_[4], rb_[4];                                                                                              \
                 _Pragma("unroll") for (int dy = 0; dy < 4; dy++) {                                                                    \
-                    ra_[dy] = (prmt(PREV[dy][4 * j] + c0_, PREV[dy][4 * j + 1] + c0_, 0xfdb9u) & nf0_) | fl0_;                        \
-                    rb_[dy] = (prmt(PREV[dy][4 * j + 2] + c1_, PREV[dy][4 * j + 3] + c1_, 0xfdb9u) & nf1_) | fl1_;                    \
+                    oa_[j][dy] = (prmt(PREV[dy][4 * j] + c0_, PREV[dy][4 * j + 1] + c0_, 0xfdb9u) & nf0_) | fl0_;                     \
+                    ob_[j][dy] = (prmt(PREV[dy][4 * j + 2] + c1_, PREV[dy][4 * j + 3] + c1_, 0xfdb9u) & nf1_) | fl1_;                 \
                 }                                                                                                                     \
-                if (pair_st[j] == 2) {                                                                                                \
-                    *reinterpret_cast<uint2 *>(p0_ + 8 * j) = make_uint2(ra_[0], rb_[0]);                                             \
-                    *reinterpret_cast<uint2 *>(p1_ + 8 * j) = make_uint2(ra_[1], rb_[1]);                                             \
-                    *reinterpret_cast<uint2 *>(p2_ + 8 * j) = make_uint2(ra_[2], rb_[2]);                                             \
-                    *reinterpret_cast<uint2 *>(p3_ + 8 * j) = make_uint2(ra_[3], rb_[3]);                                             \
-                } else if (pair_st[j] == 1) {                                                                                         \
-                    *reinterpret_cast<uint32_t *>(p0_ + 8 * j) = ra_[0]; *reinterpret_cast<uint32_t *>(p1_ + 8 * j) = ra_[1];         \
-                    *reinterpret_cast<uint32_t *>(p2_ + 8 * j) = ra_[2]; *reinterpret_cast<uint32_t *>(p3_ + 8 * j) = ra_[3];         \
+                if (C::BULK && pair_st[j] && lane_off + 8 * j < nb16) {        /* (a pair never straddles nb16: both multiples of 8) */ \
+                    _Pragma("unroll") for (int dy = 0; dy < 4; dy++)                                                                  \
+                        *reinterpret_cast<uint2 *>(sb0_ + dy * C::ROWOUT + 8 * j) = make_uint2(oa_[j][dy], ob_[j][dy]);               \
                 }                                                                                                                     \
                 if (write_tiles && pair_st[j]) {                                                                                      \
                     const size_t ti_ = ((size_t)b * g.th + ro_) * g.tw + t0 + 2 * j;                                                  \
                     tmin[ti_] = (uint8_t)mnB[j]; tmax[ti_] = (uint8_t)mxB[j];                                                         \
                     if (pair_st[j] == 2) { tmin[ti_ + 1] = (uint8_t)(mnB[j] >> 16); tmax[ti_ + 1] = (uint8_t)(mxB[j] >> 16); }        \
                 }                                                                                                                     \
+            }                                                                                                                         \
+            /* direct stores, ROW BY ROW: the three 8-byte pieces a lane adds to a 32-byte sector reach the L2 back to back (the */   \
+            /* pair-major order of the first version cost 10 % of the kernel); in the bulk form only the strip's last <= 3 tiles */   \
+            _Pragma("unroll") for (int dy = 0; dy < 4; dy++)                                                                          \
+                _Pragma("unroll") for (int j = 0; j < P; j++) {                                                                       \
+                    if (C::BULK && lane_off + 8 * j < nb16) continue;                                                                 \
+                    uint8_t *const q_ = p0_ + dy * tp_ + 8 * j;                                                                       \
+                    if (pair_st[j] == 2) *reinterpret_cast<uint2 *>(q_) = make_uint2(oa_[j][dy], ob_[j][dy]);                         \
+                    else if (pair_st[j] == 1) *reinterpret_cast<uint32_t *>(q_) = oa_[j][dy];                                         \
+                }                                                                                                                     \
+        }                                                                                                                             \
+        if (C::BULK && it_ >= 2) {                                                                                                    \
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                                              \
+            __syncwarp();                                                                                                             \
+            if (lane == 0 && nb16 > 0) {                                                                                              \
+                const unsigned char *src_ = obuf + (it_ & 1) * (4 * C::ROWOUT);                                                       \
+                uint8_t *dst_ = o + (ptrdiff_t)(ro_ * 4) * tp_ + s0 * 4;                                                              \
+                _Pragma("unroll") for (int dy = 0; dy < 4; dy++)                                                                      \
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_ + dy * tp_),                \
+                                 "r"(smem_u32(src_ + dy * C::ROWOUT)), "r"(nb16) : "memory");                                         \
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");                                                             \
             }                                                                                                                         \
         }                                                                                                                             \
         _Pragma("unroll") for (int j = 0; j < P; j++) { mnA[j] = mnB[j]; mnB[j] = mnC_[j]; mxA[j] = mxB[j]; mxB[j] = mxC_[j]; }       \
@@ -548,6 +582,7 @@ threshold_tm_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restric
     }
     if (it < nsteps) CB_TM_STEP(pxa, pxb, it)
 #undef CB_TM_STEP
+    if (C::BULK && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the staging buffers live until they are read
 }
 
 // ---- generic path (any integer decimation factor, any alignment): three simple kernels ----
