@@ -74,6 +74,8 @@ struct cb_ctx {
     DecodeConst dc{};
     int sq_max_iter = 15;
     bool sq_attr_set = false;
+    double *d_sq_scratch = nullptr;      // intermediates of the three-phase solver (api_solver.inc)
+    size_t sq_scratch_cap = 0;
     double sq_tol_sq = 1e-16;
     // fused detect -> pose (cb_detect_pose_gray): field layout, camera, per-frame SQPnP problems
     int32_t *d_field_ids = nullptr;
@@ -198,6 +200,7 @@ void cb_destroy(cb_ctx *ctx)
                     ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->d_in2) cudaFree(ctx->d_in2);
+    if (ctx->d_sq_scratch) cudaFree(ctx->d_sq_scratch);
     for (void *p : {(void *)ctx->d_field_ids, (void *)ctx->d_field_poses, (void *)ctx->d_cam9, (void *)ctx->d_pose_buf}) if (p) cudaFree(p);
     if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);

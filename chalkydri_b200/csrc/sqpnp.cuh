@@ -648,6 +648,435 @@ sqpnp_kernel(const cb_iso3 *__restrict__ tags, const double *__restrict__ bearin
     }
 }
 
+// ---- three-phase form (default since round 2) ----------------------------------------------------------------------------
+// ncu of the one-kernel form above: 185 k warp instructions per problem, 70 % of them in the 15x15 LU and the two triangular
+// solves of the Newton refinement, which a half-warp executes with one row per lane -- pivot search by shuffles, two
+// __syncwarp per pivot step, a division on one lane while fifteen wait -- and everything that follows the refinement runs on
+// lane 0 alone.  The arithmetic is a few hundred flops per system; the rest is the price of spreading ONE small dense
+// system over lanes.  So the solve is split where the parallel shape changes, with the intermediates (1.4 KB per problem) in
+// global memory:
+//   sq_prepare_kernel   one WARP per problem (as before): corner points, Omega with lane-owned entries accumulated in point
+//                       order, cyclic Jacobi, eigen order; the six nearest_so3 starts on six lanes at once;
+//   sq_newton_kernel    one THREAD per (problem, start): the 15x15 KKT system of the thread lives in shared memory in
+//                       [element][lane] layout (bank = lane: conflict-free whatever row a thread's pivoting visits), the
+//                       pivot row of a step is cached in registers, no shuffles, no barriers, a division costs one warp
+//                       instruction for 32 systems.  Every element sees the operations of the reference's LU
+//                       (lib.rs:98-115 on nalgebra's partial-pivot LU) in the same order, so the results are bit for bit
+//                       those of the one-kernel form;
+//   sq_finish_kernel    one THREAD per problem: gyro penalty, candidate order, cheirality test, pose and std-devs.
+constexpr int SQ_NEWTON_SMEM = 240 * 32 * (int)sizeof(double);      // 225 matrix entries + 15 right-hand side, 32 systems
+struct SqScratch {          // per problem, structure of arrays; r: the six starts in, the six refined rotations out
+    double *omega, *q_rt, *q_tt_inv, *centroid, *r, *energy;
+    uint8_t *valid;
+};
+
+__global__ void __launch_bounds__(SQ_WARPS * 32)
+sq_prepare_kernel(const cb_iso3 *__restrict__ tags, const double *__restrict__ bearings, const int32_t *__restrict__ n_tags, int max_tags,
+                  long long nprob, SqScratch sc)
+{
+    extern __shared__ __align__(16) unsigned char sq_smem[];
+    SqWarpShared &S = reinterpret_cast<SqWarpShared *>(sq_smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const uint32_t full = 0xffffffffu;
+    const long long warps_total = (long long)gridDim.x * SQ_WARPS;
+    const double TAG_SIZE = 0.1651, CORNER_DISTANCE = TAG_SIZE / 2.0;
+    for (long long prob = (long long)blockIdx.x * SQ_WARPS + (threadIdx.x >> 5); prob < nprob; prob += warps_total) {
+        __syncwarp();
+        const int nt = n_tags[prob];
+        const int n = nt * 4;
+        if (nt < 1 || nt > max_tags || nt > SQ_MAX_TAGS) { if (lane == 0) sc.valid[prob] = 0; continue; }   // <3 points -> None
+        const cb_iso3 *ptags = tags + prob * max_tags;
+        const double *pbear = bearings + prob * max_tags * 12;
+        // ---- corner_points_from_center (lib.rs:379-394) ----
+        for (int i = lane; i < n; i += 32) {
+            const cb_iso3 iso = ptags[i >> 2];
+            Quat q; q.w = iso.q[0]; q.x = iso.q[1]; q.y = iso.q[2]; q.z = iso.q[3];
+            const int c = i & 3;
+            const double Sx = CORNER_DISTANCE;
+            const V3 corner = v3(0.0, (c == 0 || c == 3) ? -Sx : Sx, (c < 2) ? -Sx : Sx);
+            const V3 p = vadd(quat_rotate(q, corner), v3(iso.t[0], iso.t[1], iso.t[2]));
+            S.pw[i][0] = p.x; S.pw[i][1] = p.y; S.pw[i][2] = p.z;
+            S.pb[i][0] = pbear[i * 3]; S.pb[i][1] = pbear[i * 3 + 1]; S.pb[i][2] = pbear[i * 3 + 2];
+        }
+        __syncwarp();
+        V3 centroid = v3(0, 0, 0);
+        for (int i = 0; i < n; i++) centroid = vadd(centroid, v3(S.pw[i][0], S.pw[i][1], S.pw[i][2]));
+        centroid = v3(centroid.x / (double)n, centroid.y / (double)n, centroid.z / (double)n);
+        // ---- build_linear_system (lib.rs:124-180): one accumulator per lane-owned entry, points in order ----
+        for (int e = lane; e < 117; e += 32) {
+            int kind, r_, c_, a_ = 0, b_ = 0;
+            if (e < 9) { kind = 0; r_ = e % 3; c_ = e / 3; }
+            else if (e < 36) { kind = 1; const int k = e - 9; const int col = k / 9, row = k % 9; a_ = row / 3; r_ = row % 3; c_ = col; }
+            else { kind = 2; const int k = e - 36; const int col = k / 9, row = k % 9; a_ = row / 3; r_ = row % 3; b_ = col / 3; c_ = col % 3; }
+            double acc = 0;
+            for (int i = 0; i < n; i++) {
+                const double vx = S.pb[i][0], vy = S.pb[i][1], vz = S.pb[i][2];
+                const double sq_norm = vx * vx + vy * vy + vz * vz;
+                const double inv_norm = 1.0 / sq_norm;
+                const double vr = r_ == 0 ? vx : (r_ == 1 ? vy : vz), vc = c_ == 0 ? vx : (c_ == 1 ? vy : vz);
+                const double P = (r_ == c_ ? 1.0 : 0.0) - (vr * vc) * inv_norm;
+                const double X0 = S.pw[i][0] - centroid.x, X1 = S.pw[i][1] - centroid.y, X2 = S.pw[i][2] - centroid.z;
+                double add;
+                if (kind == 0) add = P;
+                else if (kind == 1) add = P * (a_ == 0 ? X0 : (a_ == 1 ? X1 : X2));
+                else {
+                    const int lo = a_ < b_ ? a_ : b_, hi = a_ < b_ ? b_ : a_;
+                    const double Xlo = lo == 0 ? X0 : (lo == 1 ? X1 : X2), Xhi = hi == 0 ? X0 : (hi == 1 ? X1 : X2);
+                    add = (P * Xlo) * Xhi;
+                }
+                acc += add;
+            }
+            if (kind == 0) S.q_tt[e] = acc;
+            else if (kind == 1) S.q_rt[e - 9] = acc;
+            else S.q_rr[e - 36] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (!mat3_try_inverse(S.q_tt, S.q_tt_inv)) for (int k = 0; k < 9; k++) S.q_tt_inv[k] = 0;
+        }
+        __syncwarp();
+        if (lane < 27) {
+            const int c = lane / 9, r_ = lane % 9;
+            double acc = 0;
+            for (int k = 0; k < 3; k++) acc += S.q_rt[k * 9 + r_] * SQM(S.q_tt_inv, k, c);
+            S.temp[c * 9 + r_] = acc;
+        }
+        __syncwarp();
+        for (int e = lane; e < 81; e += 32) {
+            const int c = e / 9, r_ = e % 9;
+            double acc = 0;
+            for (int k = 0; k < 3; k++) acc += S.temp[k * 9 + r_] * S.q_rt[k * 9 + c];
+            S.omega[e] = S.q_rr[e] - acc;
+        }
+        __syncwarp();
+        // what the later phases read
+        for (int e = lane; e < 81; e += 32) sc.omega[prob * 81 + e] = S.omega[e];
+        if (lane < 27) sc.q_rt[prob * 27 + lane] = S.q_rt[lane];
+        if (lane < 9) sc.q_tt_inv[prob * 9 + lane] = S.q_tt_inv[lane];
+        if (lane < 3) sc.centroid[prob * 3 + lane] = lane == 0 ? centroid.x : (lane == 1 ? centroid.y : centroid.z);
+        if (lane == 0) sc.valid[prob] = 1;
+        // ---- symmetric eigen: cyclic Jacobi on omega / max|omega| ----
+        double amax = 0;
+        for (int e = lane; e < 81; e += 32) amax = fmax(amax, fabs(S.omega[e]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(full, amax, o));
+        for (int e = lane; e < 81; e += 32) { S.a[e] = amax == 0 ? 0.0 : S.omega[e] / amax; S.v[e] = (e % 10 == 0) ? 1.0 : 0.0; }
+        __syncwarp();
+        if (amax != 0) {
+            for (int sweep = 0; sweep < 40; sweep++) {
+                double off = 0;
+                for (int q = 1; q < 9; q++)
+                    for (int p = 0; p < q; p++) off += S.a[q * 9 + p] * S.a[q * 9 + p];
+                if (off <= 1e-34) break;
+                for (int p = 0; p < 8; p++)
+                    for (int q = p + 1; q < 9; q++) {
+                        const double apq = S.a[q * 9 + p];
+                        if (apq == 0) continue;
+                        const double app = S.a[p * 9 + p], aqq = S.a[q * 9 + q];
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        if (theta < 0) t = -t;
+                        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                        __syncwarp();
+                        if (lane < 9) {            // columns p,q of A
+                            const double akp = S.a[p * 9 + lane], akq = S.a[q * 9 + lane];
+                            S.a[p * 9 + lane] = c * akp - s * akq;
+                            S.a[q * 9 + lane] = s * akp + c * akq;
+                        } else if (lane < 18) {    // V <- V J
+                            const int k = lane - 9;
+                            const double vkp = S.v[p * 9 + k], vkq = S.v[q * 9 + k];
+                            S.v[p * 9 + k] = c * vkp - s * vkq;
+                            S.v[q * 9 + k] = s * vkp + c * vkq;
+                        }
+                        __syncwarp();
+                        if (lane < 9) {            // rows p,q of A
+                            const double apk = S.a[lane * 9 + p], aqk = S.a[lane * 9 + q];
+                            S.a[lane * 9 + p] = c * apk - s * aqk;
+                            S.a[lane * 9 + q] = s * apk + c * aqk;
+                        }
+                        __syncwarp();
+                        if (lane == 0) { S.a[q * 9 + p] = 0; S.a[p * 9 + q] = 0; }
+                        __syncwarp();
+                    }
+            }
+        }
+        // eigenvalue order: stable sort by f64::total_cmp (lib.rs:400-401)
+        int idx[9];
+        {
+            double ev[9];
+            for (int i = 0; i < 9; i++) { ev[i] = S.a[i * 9 + i] * amax; idx[i] = i; }
+            for (int i = 1; i < 9; i++)
+                for (int j = i; j > 0 && total_key(ev[idx[j]]) < total_key(ev[idx[j - 1]]); j--) { const int t = idx[j - 1]; idx[j - 1] = idx[j]; idx[j] = t; }
+        }
+        // ---- six starts nearest_so3(+-e_t), t = 0..2 (lib.rs:402-428): candidate ci = 2 t + (sign > 0) on lane ci ----
+        if (lane < 6) {
+            const int t = lane >> 1;
+            const double sign = (lane & 1) == 0 ? -1.0 : 1.0;
+            const int col = t == 0 ? idx[0] : (t == 1 ? idx[1] : idx[2]);
+            double guess[9], r0[9];
+            for (int k = 0; k < 9; k++) guess[k] = S.v[col * 9 + k] * sign;
+            nearest_so3(guess, r0);
+            for (int k = 0; k < 9; k++) sc.r[(prob * 6 + lane) * 9 + k] = r0[k];
+        }
+    }
+}
+
+#define SQK(r, c) kkt[((r) * 15 + (c)) * 32]
+#define SQB(r) kkt[(225 + (r)) * 32]
+// one pivot step of the LU, I a compile-time constant so that the cached pivot row is indexed statically
+template <int I>
+__device__ __forceinline__ void sq_lu_step(double *kkt)
+{
+    // partial pivoting: first maximum of |M[r][I]|, r >= I, in row order
+    double best = fabs(SQK(I, I));
+    int piv = I;
+#pragma unroll
+    for (int r = I + 1; r < 15; r++) {
+        const double v = fabs(SQK(r, I));
+        if (v > best) { best = v; piv = r; }
+    }
+    const double diag = SQK(piv, I);
+    if (diag == 0) return;
+    if (piv != I) {
+#pragma unroll
+        for (int c = 0; c < 15; c++) { const double t = SQK(I, c); SQK(I, c) = SQK(piv, c); SQK(piv, c) = t; }
+        const double t = SQB(I); SQB(I) = SQB(piv); SQB(piv) = t;
+    }
+    const double inv_diag = 1.0 / diag;
+    double prow[15];
+#pragma unroll
+    for (int c = I + 1; c < 15; c++) prow[c] = SQK(I, c);
+#pragma unroll 2
+    for (int r = I + 1; r < 15; r++) {
+        const double coeff = SQK(r, I) * inv_diag;
+        SQK(r, I) = coeff;
+#pragma unroll
+        for (int c = I + 1; c < 15; c++) SQK(r, c) -= coeff * prow[c];
+    }
+}
+
+__global__ void __launch_bounds__(32)
+sq_newton_kernel(SqScratch sc, long long nsys, SqParams prm)
+{
+    extern __shared__ __align__(16) unsigned char sq_smem[];
+    double *kkt = reinterpret_cast<double *>(sq_smem) + threadIdx.x;
+    const long long sys = (long long)blockIdx.x * 32 + threadIdx.x;
+    if (sys >= nsys) return;
+    const long long prob = sys / 6;
+    if (!sc.valid[prob]) return;
+    const double *__restrict__ om = sc.omega + prob * 81;
+    double r[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) r[k] = sc.r[sys * 9 + k];
+    for (int it = 0; it < prm.max_iter; it++) {
+        // ---- the KKT system [Omega J^T; J 0] [delta; lambda] = [-Omega r; -h] (lib.rs:62-115) ----
+#pragma unroll
+        for (int row = 0; row < 9; row++) {
+            double acc = 0;
+#pragma unroll
+            for (int j = 0; j < 9; j++) { const double o = __ldg(om + j * 9 + row); SQK(row, j) = o; acc += o * r[j]; }
+            SQB(row) = -acc;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            // constraint k: |c1|^2 - 1, |c2|^2 - 1, |c3|^2 - 1, c1.c2, c1.c3, c2.c3 and its gradient row
+            const int ca = k < 3 ? k : (k == 5 ? 1 : 0), cb_ = k < 3 ? k : (k == 3 ? 1 : 2);
+            double jr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            double hval;
+            if (k < 3) {
+                hval = (r[3 * ca] * r[3 * ca] + r[3 * ca + 1] * r[3 * ca + 1] + r[3 * ca + 2] * r[3 * ca + 2]) - 1.0;
+#pragma unroll
+                for (int m = 0; m < 3; m++) jr[3 * ca + m] = 2.0 * r[3 * ca + m];
+            } else {
+                hval = r[3 * ca] * r[3 * cb_] + r[3 * ca + 1] * r[3 * cb_ + 1] + r[3 * ca + 2] * r[3 * cb_ + 2];
+#pragma unroll
+                for (int m = 0; m < 3; m++) { jr[3 * ca + m] = r[3 * cb_ + m]; jr[3 * cb_ + m] = r[3 * ca + m]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 9; j++) { SQK(9 + k, j) = jr[j]; SQK(j, 9 + k) = jr[j]; }
+#pragma unroll
+            for (int j = 9; j < 15; j++) SQK(9 + k, j) = 0;
+            SQB(9 + k) = -hval;
+        }
+        // ---- LU with partial pivoting, reciprocal-pivot multipliers ----
+        sq_lu_step<0>(kkt); sq_lu_step<1>(kkt); sq_lu_step<2>(kkt); sq_lu_step<3>(kkt); sq_lu_step<4>(kkt);
+        sq_lu_step<5>(kkt); sq_lu_step<6>(kkt); sq_lu_step<7>(kkt); sq_lu_step<8>(kkt); sq_lu_step<9>(kkt);
+        sq_lu_step<10>(kkt); sq_lu_step<11>(kkt); sq_lu_step<12>(kkt); sq_lu_step<13>(kkt); sq_lu_step<14>(kkt);
+        // forward substitution L y = b (unit diagonal), then back substitution U x = y
+        double b[15];
+#pragma unroll
+        for (int i = 0; i < 15; i++) b[i] = SQB(i);
+#pragma unroll
+        for (int i = 0; i < 15; i++)
+#pragma unroll
+            for (int rr = i + 1; rr < 15; rr++) b[rr] -= SQK(rr, i) * b[i];
+        bool singular = false;
+#pragma unroll
+        for (int i = 14; i >= 0; i--) {
+            if (!singular) {
+                const double diag = SQK(i, i);
+                if (diag == 0) singular = true;
+                else {
+                    b[i] = b[i] / diag;
+#pragma unroll
+                    for (int rr = 0; rr < i; rr++) b[rr] -= SQK(rr, i) * b[i];
+                }
+            }
+        }
+        if (singular) break;
+        double nsq = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) nsq += b[k] * b[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) r[k] += b[k];
+        if (nsq < prm.tol_sq) break;
+    }
+    // energy = r . (Omega r)
+    double e = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        double acc = 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) acc += __ldg(om + j * 9 + i) * r[j];
+        e += r[i] * acc;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) sc.r[sys * 9 + k] = r[k];
+    sc.energy[sys] = e;
+}
+#undef SQK
+#undef SQB
+
+__global__ void __launch_bounds__(128)
+sq_finish_kernel(const cb_iso3 *__restrict__ tags, const int32_t *__restrict__ n_tags, int max_tags, const cb_iso3 *__restrict__ robot_to_cam_p,
+                 const double *__restrict__ gyro_arr, long long nprob, SqScratch sc, cb_pose *__restrict__ out, uint8_t *__restrict__ ok, SqParams prm)
+{
+    const long long prob = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (prob >= nprob) return;
+    if (!sc.valid[prob]) { ok[prob] = 0; return; }
+    const double XY_STD_DEV_SCALAR = 5.0, THETA_STD_DEV_SCALAR = 2.0, MAX_TRUSTABLE_RMS = 0.1, MAX_GYRO_DELTA = 30.0;
+    const double TAG_SIZE = 0.1651, CORNER_DISTANCE = TAG_SIZE / 2.0, PI = 3.14159265358979323846;
+    const cb_iso3 r2c_in = *robot_to_cam_p;
+    Quat r2c_q; r2c_q.w = r2c_in.q[0]; r2c_q.x = r2c_in.q[1]; r2c_q.y = r2c_in.q[2]; r2c_q.z = r2c_in.q[3];
+    const V3 r2c_t = v3(r2c_in.t[0], r2c_in.t[1], r2c_in.t[2]);
+    double r2c_m[9];
+    quat_to_mat(r2c_q, r2c_m);
+    const V3 fwd_in_cam = v3(r2c_m[0], r2c_m[1], r2c_m[2]);
+    const int nt = n_tags[prob];
+    const double gyro = gyro_arr[prob];
+    const cb_iso3 *ptags = tags + prob * max_tags;
+    const double *q_rt = sc.q_rt + prob * 27, *q_tt_inv = sc.q_tt_inv + prob * 9, *om = sc.omega + prob * 81;
+    const V3 centroid = v3(sc.centroid[prob * 3], sc.centroid[prob * 3 + 1], sc.centroid[prob * 3 + 2]);
+    const double gyro_cos = cos(gyro), gyro_sin = sin(gyro);
+    // energies with the gyro penalty (lib.rs:414-424), candidates.sort_by(total_cmp) (stable), selection loop of solve() (lib.rs:267-294)
+    double cand_e[6];
+    int cord[6] = {0, 1, 2, 3, 4, 5};
+    for (int ci = 0; ci < 6; ci++) {
+        const double *r = sc.r + (prob * 6 + ci) * 9;
+        double energy = sc.energy[prob * 6 + ci];
+        const double fx = r[0] * fwd_in_cam.x + r[1] * fwd_in_cam.y + r[2] * fwd_in_cam.z;
+        const double fy = r[3] * fwd_in_cam.x + r[4] * fwd_in_cam.y + r[5] * fwd_in_cam.z;
+        const double dt = (fx * gyro_cos) + (fy * gyro_sin);
+        const double angle_error = fmax(1.0 - dt, 0.0);
+        energy += prm.sign_change_error * angle_error;
+        cand_e[ci] = energy;
+    }
+    for (int i = 1; i < 6; i++)
+        for (int j = i; j > 0 && total_key(cand_e[cord[j]]) < total_key(cand_e[cord[j - 1]]); j--) { const int t = cord[j - 1]; cord[j - 1] = cord[j]; cord[j] = t; }
+    int chosen = -1;
+    V3 t_sel = v3(0, 0, 0);
+    double rsel[9];
+    for (int k = 0; k < 6 && chosen < 0; k++) {
+        double r[9];
+        for (int j = 0; j < 9; j++) r[j] = sc.r[(prob * 6 + cord[k]) * 9 + j];
+        double qr[3];
+        for (int c = 0; c < 3; c++) {
+            double acc = 0;
+            for (int j = 0; j < 9; j++) acc += q_rt[c * 9 + j] * r[j];
+            qr[c] = acc;
+        }
+        V3 tl = mat3_mulv(q_tt_inv, v3(qr[0], qr[1], qr[2]));
+        tl = vscale(tl, -1.0);
+        const V3 tt = vsub(tl, mat3_mulv(r, centroid));
+        bool front = true;
+        for (int i = 0; i < nt * 4 && front; i++) {
+            const cb_iso3 iso = ptags[i >> 2];
+            Quat q; q.w = iso.q[0]; q.x = iso.q[1]; q.y = iso.q[2]; q.z = iso.q[3];
+            const int c = i & 3;
+            const double Sx = CORNER_DISTANCE;
+            const V3 corner = v3(0.0, (c == 0 || c == 3) ? -Sx : Sx, (c < 2) ? -Sx : Sx);
+            const V3 pw = vadd(quat_rotate(q, corner), v3(iso.t[0], iso.t[1], iso.t[2]));
+            const V3 pc = vadd(mat3_mulv(r, pw), tt);
+            if (!(pc.z > 0.0)) front = false;
+        }
+        if (front && cand_e[cord[k]] < 1.7976931348623157e308) {
+            chosen = cord[k]; t_sel = tt;
+            for (int j = 0; j < 9; j++) rsel[j] = r[j];
+        }
+    }
+    if (chosen < 0) { ok[prob] = 0; return; }
+    {
+        const double *r = rsel;
+        const double pure_energy = quad_form9(om, r);
+        double rot_w2c[9];
+        rot3_from_matrix(r, rot_w2c);
+        cb_pose o;
+        // compute_std_devs (lib.rs:224-246)
+        {
+            const double distance = sqrt(vdot(t_sel, t_sel));
+            const double n_points = (double)(nt * 4);
+            const double rms_error = sqrt(pure_energy / n_points);
+            if (rms_error > MAX_TRUSTABLE_RMS) { o.std_devs[0] = o.std_devs[1] = o.std_devs[2] = 1.7976931348623157e308; }
+            else {
+                const double distance_multiplier = 1.0 + (distance / TAG_SIZE);
+                const double base_xy_std = rms_error * distance_multiplier;
+                double xy_std = (base_xy_std / sqrt((double)nt)) * XY_STD_DEV_SCALAR;
+                xy_std = fmin(fmax(xy_std, 0.01), 10.0);
+                const double base_theta_std = rms_error / TAG_SIZE;
+                const double val = (base_theta_std * distance_multiplier / sqrt((double)nt)) * THETA_STD_DEV_SCALAR;
+                const double theta_std = fmin(fmax(val, 0.05), PI);
+                o.std_devs[0] = xy_std; o.std_devs[1] = xy_std; o.std_devs[2] = theta_std;
+            }
+        }
+        // world_to_cam^-1 * robot_to_cam (lib.rs:328-337)
+        const Quat qw = quat_from_mat(rot_w2c);
+        Quat qi; qi.w = qw.w; qi.x = -qw.x; qi.y = -qw.y; qi.z = -qw.z;
+        const V3 ti = vscale(quat_rotate(qi, t_sel), -1.0);
+        const V3 robot_pos = vadd(quat_rotate(qi, r2c_t), ti);
+        const Quat qr_ = quat_mul(qi, r2c_q);
+        double robot_rot[9];
+        quat_to_mat(qr_, robot_rot);
+        V3 tag_centroid = v3(0, 0, 0);
+        for (int i = 0; i < nt; i++) tag_centroid = vadd(tag_centroid, v3(ptags[i].t[0], ptags[i].t[1], ptags[i].t[2]));
+        tag_centroid = v3(tag_centroid.x / (double)nt, tag_centroid.y / (double)nt, tag_centroid.z / (double)nt);
+        const double vision_yaw = atan2(SQM(robot_rot, 1, 0), SQM(robot_rot, 0, 0));
+        double delta_yaw = gyro - vision_yaw;
+        {
+            const double a = delta_yaw + PI, bb = 2.0 * PI;
+            double rr = fmod(a, bb);
+            if (rr < 0.0) rr += bb;
+            delta_yaw = rr - PI;
+        }
+        const double delta_deg = fabs(delta_yaw) * (180.0 / PI);
+        double weight = fmin(fmax(delta_deg / MAX_GYRO_DELTA, 0.0), 1.0);
+        weight = weight * weight * (3.0 - 2.0 * weight);
+        const double applied = delta_yaw * weight;
+        const double cos_dt = cos(applied), sin_dt = sin(applied);
+        double rot_z[9];
+        SQM(rot_z, 0, 0) = cos_dt; SQM(rot_z, 0, 1) = -sin_dt; SQM(rot_z, 0, 2) = 0;
+        SQM(rot_z, 1, 0) = sin_dt; SQM(rot_z, 1, 1) = cos_dt;  SQM(rot_z, 1, 2) = 0;
+        SQM(rot_z, 2, 0) = 0;      SQM(rot_z, 2, 1) = 0;       SQM(rot_z, 2, 2) = 1;
+        double rot_z_rot3[9];
+        rot3_from_matrix(rot_z, rot_z_rot3);
+        const V3 rel = vsub(robot_pos, tag_centroid);
+        const V3 piv = vadd(tag_centroid, mat3_mulv(rot_z, rel));
+        mat3_mul(rot_z_rot3, robot_rot, o.rot);
+        o.pos[0] = piv.x; o.pos[1] = piv.y; o.pos[2] = piv.z;
+        out[prob] = o;
+        ok[prob] = 1;
+    }
+}
+
 // OpenCV-5 un-projection (crates/apriltags/src/lib.rs:316-321): pixel -> bearing (x, y, 1) by fixed-point undistortion
 __device__ __forceinline__ bool unproject_opencv5(const double *__restrict__ params, double u, double v, double out[3])
 {

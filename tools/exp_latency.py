@@ -1,11 +1,13 @@
-"""Single-frame latency breakdown (c2 frame) through the host-buffer entry point."""
+"""Single-frame latency breakdown (c2 or c1 frame) through the host-buffer entry point."""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from chalkydri_b200 import synth, capi
 from chalkydri_b200.detector import DetectorBuilder
-frames, _ = synth.render_batch(1456, 1088, 4, 8, seed=0x5EED + 2, edge_px=(40.0, 200.0))
-det = DetectorBuilder.default().add_family_bits("tag36h11", 3).capacity(1456, 1088, 1, 64).build()
+wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
+W, H, TAGS, SEED, EDGE = (1456, 1088, 8, 0x5EED + 2, (40.0, 200.0)) if wl == "c2" else (1280, 720, 4, 0x5EED + 1, (60.0, 150.0))
+frames, _ = synth.render_batch(W, H, 4, TAGS, seed=SEED, edge_px=EDGE)
+det = DetectorBuilder.default().add_family_bits("tag36h11", 3).capacity(W, H, 1, 64).build()
 pin = capi.pinned_array(frames[:1].shape, np.uint8); pin[:] = frames[:1]
 for _ in range(20): det.detect_batch(pin)
 ts = []
