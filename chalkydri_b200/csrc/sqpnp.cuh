@@ -824,7 +824,7 @@ sq_prepare_kernel(const cb_iso3 *__restrict__ tags, const double *__restrict__ b
 #define SQK(r, c) kkt[((r) * 15 + (c)) * 32]
 #define SQB(r) kkt[(225 + (r)) * 32]
 // one pivot step of the LU, I a compile-time constant so that the cached pivot row is indexed statically
-template <int I>
+template <int I, int U>
 __device__ __forceinline__ void sq_lu_step(double *kkt)
 {
     // partial pivoting: first maximum of |M[r][I]|, r >= I, in row order
@@ -846,7 +846,7 @@ __device__ __forceinline__ void sq_lu_step(double *kkt)
     double prow[15];
 #pragma unroll
     for (int c = I + 1; c < 15; c++) prow[c] = SQK(I, c);
-#pragma unroll 2
+#pragma unroll U
     for (int r = I + 1; r < 15; r++) {
         const double coeff = SQK(r, I) * inv_diag;
         SQK(r, I) = coeff;
@@ -855,6 +855,7 @@ __device__ __forceinline__ void sq_lu_step(double *kkt)
     }
 }
 
+template <int U>
 __global__ void __launch_bounds__(32)
 sq_newton_kernel(SqScratch sc, long long nsys, SqParams prm)
 {
@@ -899,9 +900,9 @@ sq_newton_kernel(SqScratch sc, long long nsys, SqParams prm)
             SQB(9 + k) = -hval;
         }
         // ---- LU with partial pivoting, reciprocal-pivot multipliers ----
-        sq_lu_step<0>(kkt); sq_lu_step<1>(kkt); sq_lu_step<2>(kkt); sq_lu_step<3>(kkt); sq_lu_step<4>(kkt);
-        sq_lu_step<5>(kkt); sq_lu_step<6>(kkt); sq_lu_step<7>(kkt); sq_lu_step<8>(kkt); sq_lu_step<9>(kkt);
-        sq_lu_step<10>(kkt); sq_lu_step<11>(kkt); sq_lu_step<12>(kkt); sq_lu_step<13>(kkt); sq_lu_step<14>(kkt);
+        sq_lu_step<0, U>(kkt); sq_lu_step<1, U>(kkt); sq_lu_step<2, U>(kkt); sq_lu_step<3, U>(kkt); sq_lu_step<4, U>(kkt);
+        sq_lu_step<5, U>(kkt); sq_lu_step<6, U>(kkt); sq_lu_step<7, U>(kkt); sq_lu_step<8, U>(kkt); sq_lu_step<9, U>(kkt);
+        sq_lu_step<10, U>(kkt); sq_lu_step<11, U>(kkt); sq_lu_step<12, U>(kkt); sq_lu_step<13, U>(kkt); sq_lu_step<14, U>(kkt);
         // forward substitution L y = b (unit diagonal), then back substitution U x = y
         double b[15];
 #pragma unroll
