@@ -1,0 +1,20 @@
+#!/bin/bash
+# round 2 evidence run: GPU tests, smoke, bench (both arms), ncu launch list of bench.py, ncu --set full of the threshold launch the
+# pipeline really uses (after the per-geometry shape timing), SQPnP and other configs.  Everything lands in gpurun_out/r02_*.
+set -x
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
+timeout 900 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo rc=$?
+timeout 600 python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_ref.err; echo rc=$?
+# launch list of bench.py itself (short form of the same command), only after it exited 0 without ncu
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-c2 --no-c4 --no-sqpnp --latency-iters 0 > gpurun_out/r02_bench_short.json 2> gpurun_out/r02_bench_short.err || exit 1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launch_list_bench_py.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-c2 --no-c4 --no-sqpnp --latency-iters 0 > gpurun_out/r02_ncu_bench.log 2>&1
+python tools/launch_table.py gpurun_out/r02_launch_list_bench_py.csv 24 > gpurun_out/r02_launch_list_bench_py.txt 2>&1; tail -28 gpurun_out/r02_launch_list_bench_py.txt
+# the threshold launch of the pipeline: count the launches (shape timing first), then capture the last one with --set full
+timeout 300 python tools/profile_run.py 256 2 c1 > gpurun_out/p.log 2>&1 || exit 1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:threshold_tm" --csv --log-file gpurun_out/r02_thr_launches.csv python tools/profile_run.py 256 2 c1 > gpurun_out/ncu.log 2>&1
+N=$(grep -c "threshold_tm" gpurun_out/r02_thr_launches.csv); echo "threshold launches: $N"
+timeout 600 ncu --set full --import-source on --clock-control none -k "regex:threshold_tm" --launch-skip $((N - 1)) -c 1 -o gpurun_out/r02_thr -f python tools/profile_run.py 256 2 c1 > gpurun_out/ncu.log 2>&1
+python tools/ncu_summary.py gpurun_out/r02_thr.ncu-rep threshold --traffic c1 256 "ncu --set full of the pipeline's threshold launch on 256 x 1280x720 (profiles/r02_ncu_threshold.txt): (dram read + write) / 256 frames" > gpurun_out/r02_ncu_threshold.txt 2>&1; cat gpurun_out/r02_ncu_threshold.txt
+cp profiles/threshold_traffic.json gpurun_out/r02_threshold_traffic.json
