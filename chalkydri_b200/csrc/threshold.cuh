@@ -709,6 +709,70 @@ __global__ void __launch_bounds__(RGB_THREADS) rgb_to_gray_kernel(const uint8_t 
     for (size_t k = rest + lane; k < end; k += 32) gray[k] = cat_gray(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2]);
 }
 
+// Persistent form of the conversion (default for aligned frames since round 2): the kernel above refills an SM block by block
+// (a CTA loads its 16 chunks, converts them and exits; ncu: long_scoreboard, 45 % of the warps active, 0.69 of the HBM peak).  Here
+// a warp keeps a ring of RGB_RING chunks in flight for as long as the launch lasts -- the structure of the threshold kernel: lane 0
+// re-arms a stage with the chunk RGB_RING turns ahead as soon as the warp has read it, so the loads never drain; chunk g of the
+// flattened (frame, chunk) space goes to warp g mod nwarps, i.e. at any moment the warps read one contiguous window of memory.
+// Only whole 512-pixel chunks of 16-byte aligned frames; the tails (npix mod 512 pixels per frame) are converted by the first
+// warps after their loop.
+constexpr int RGB_RING = 4, RGB_RING_WARPS = 4;
+__global__ void __launch_bounds__(RGB_RING_WARPS * 32) rgb_to_gray_ring_kernel(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ gray, size_t npix,
+                                                                               size_t in_stride, size_t out_stride, int nframes)
+{
+    __shared__ __align__(128) uint4 stage[RGB_RING_WARPS][RGB_RING][96];
+    __shared__ __align__(8) unsigned long long bar[RGB_RING_WARPS][RGB_RING];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long nwarps = (long long)gridDim.x * RGB_RING_WARPS, w = (long long)blockIdx.x * RGB_RING_WARPS + warp;
+    const long long cpf = (long long)(npix / 512), total = cpf * nframes;
+    auto src_of = [&](long long gidx) { return rgb + (size_t)(gidx / cpf) * in_stride + (size_t)(gidx % cpf) * 1536; };
+    if (lane == 0) {
+        for (int s = 0; s < RGB_RING; s++) mbar_init(&bar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < RGB_RING; s++) {
+            const long long gi = w + (long long)s * nwarps;
+            if (gi < total) { mbar_expect_tx(&bar[warp][s], 1536); tma_load_1d(&stage[warp][s][0], src_of(gi), 1536, &bar[warp][s]); }
+        }
+    }
+    __syncwarp();
+    int it = 0;
+    for (long long gi = w; gi < total; gi += nwarps, it++) {
+        const int s = it % RGB_RING;
+        mbar_wait(&bar[warp][s], (uint32_t)((it / RGB_RING) & 1));
+        const uint4 a = stage[warp][s][3 * lane], b2 = stage[warp][s][3 * lane + 1], cc = stage[warp][s][3 * lane + 2];
+        __syncwarp();
+        if (lane == 0) {
+            const long long gn = gi + (long long)RGB_RING * nwarps;
+            if (gn < total) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bar[warp][s], 1536);
+                tma_load_1d(&stage[warp][s][0], src_of(gn), 1536, &bar[warp][s]);
+            }
+        }
+        const uint32_t wds[12] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w, cc.x, cc.y, cc.z, cc.w};
+        uint32_t q[16], o[4];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {      // (the conversion-free u8 <-> f32 arithmetic of rgb_to_gray_kernel)
+            const float r = __fsub_rn(__uint_as_float(__byte_perm(wds[(3 * k) >> 2], 0x4B000000u, 0x7440 | ((3 * k) & 3))), 8388608.0f);
+            const float gg = __fsub_rn(__uint_as_float(__byte_perm(wds[(3 * k + 1) >> 2], 0x4B000000u, 0x7440 | ((3 * k + 1) & 3))), 8388608.0f);
+            const float bl = __fsub_rn(__uint_as_float(__byte_perm(wds[(3 * k + 2) >> 2], 0x4B000000u, 0x7440 | ((3 * k + 2) & 3))), 8388608.0f);
+            const float v = __fmaf_rn(r, 0.33f, __fmaf_rn(gg, 0.33f, __fmul_rn(bl, 0.33f)));          // utils.rs:43
+            q[k] = __float_as_uint(__fadd_rz(v, 8388608.0f));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            o[k] = __byte_perm(__byte_perm(q[4 * k], q[4 * k + 1], 0x4040), __byte_perm(q[4 * k + 2], q[4 * k + 3], 0x4040), 0x5410);
+        *reinterpret_cast<uint4 *>(gray + (size_t)(gi / cpf) * out_stride + (size_t)(gi % cpf) * 512 + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    // ragged tails: frame f by warp f
+    const size_t rest = (size_t)cpf * 512;
+    if (rest < npix)
+        for (long long f = w; f < nframes; f += nwarps)
+            for (size_t k = rest + lane; k < npix; k += 32)
+                gray[(size_t)f * out_stride + k] = cat_gray(rgb[(size_t)f * in_stride + 3 * k], rgb[(size_t)f * in_stride + 3 * k + 1], rgb[(size_t)f * in_stride + 3 * k + 2]);
+}
+
 // YUYV (Y0 U Y1 V): gray = Y.  A warp owns 512 pixels = 1024 B; lane t loads uint4 t and t + 32 (coalesced) and stores the
 // eight Y bytes of each as one 64-bit word (coalesced).
 __global__ void __launch_bounds__(PRE_THREADS) yuyv_to_gray_kernel(const uint8_t *__restrict__ yuyv, uint8_t *__restrict__ gray, size_t npix,
