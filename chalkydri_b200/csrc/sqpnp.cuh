@@ -17,7 +17,7 @@
 
 namespace cb {
 
-constexpr int SQ_MAX_TAGS = 16;
+constexpr int SQ_MAX_TAGS = 32;          // tags per problem (the reference solves with every visible field tag; an FRC field has 22)
 constexpr int SQ_MAX_PTS = SQ_MAX_TAGS * 4;
 constexpr int SQ_WARPS = 4;
 constexpr int SQ_KP = 17;          // row pitch (doubles) of the 15x15 KKT system: odd, so that column accesses by 16 lanes are bank-conflict free
@@ -37,6 +37,14 @@ struct SqWarpShared {
     double cand_e[6];
     double pw[SQ_MAX_PTS][3];   // world corner points
     double pb[SQ_MAX_PTS][3];   // bearings
+};
+
+// what sq_prepare_kernel needs of the above (no KKT systems, no candidates): 9.3 KB per warp
+struct SqPrepShared {
+    double omega[81], a[81], v[81], q_rr[81];
+    double q_rt[27], temp[27];
+    double q_tt[9], q_tt_inv[9];
+    double pw[SQ_MAX_PTS][3], pb[SQ_MAX_PTS][3];
 };
 
 struct SqParams {
@@ -675,7 +683,7 @@ sq_prepare_kernel(const cb_iso3 *__restrict__ tags, const double *__restrict__ b
                   long long nprob, SqScratch sc)
 {
     extern __shared__ __align__(16) unsigned char sq_smem[];
-    SqWarpShared &S = reinterpret_cast<SqWarpShared *>(sq_smem)[threadIdx.x >> 5];
+    SqPrepShared &S = reinterpret_cast<SqPrepShared *>(sq_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t full = 0xffffffffu;
     const long long warps_total = (long long)gridDim.x * SQ_WARPS;

@@ -14,7 +14,7 @@ from . import capi
 from .capi import ISO_DTYPE, POSE_DTYPE, ChalkydriError
 
 SIGN_FLIP_CONST = 600.0    # crates/apriltags/src/lib.rs:6
-MAX_TAGS = 16
+MAX_TAGS = 32            # csrc/sqpnp.cuh SQ_MAX_TAGS
 
 
 def iso(t, q) -> np.ndarray:
@@ -78,7 +78,9 @@ class SqPnP:
         tags = np.ascontiguousarray(points_isometry, ISO_DTYPE).reshape(-1)
         p2 = np.ascontiguousarray(points_2d, np.float64).reshape(-1, 3)
         n = len(tags)
-        if n * 4 < 3 or n * 4 != len(p2) or n > MAX_TAGS:     # lib.rs:255-257
+        if n > MAX_TAGS:        # the reference has no cap; silently answering None would read as "no pose"
+            raise ValueError(f"{n} tags: the solver kernels hold at most {MAX_TAGS} tags per problem")
+        if n * 4 < 3 or n * 4 != len(p2):     # lib.rs:255-257
             return None
         out, ok = self.solve_robot_pose_batch(tags[None, :], p2[None, :, :], np.array([n], np.int32), robot_to_cam,
                                               np.array([gyro], np.float64), sign_change_error)

@@ -155,7 +155,7 @@ int cb_sqpnp_batch_device(cb_ctx *ctx, const cb_iso3 *tags, const double *bearin
  *  cb_detect_pose_gray: host frames in; detection lists like cb_detect_gray, plus per frame the Some((rot, pos, std_devs)) of
  *      solve_robot_pose in poses[b] with pose_ok[b] = 1, or pose_ok[b] = 0 for None (no detections, no usable tag, solver
  *      None) and for gyro[b] = NaN (comm.gyro_angle() == None, lib.rs:329).  pose_tags (optional): tags used per frame.
- *      At most 16 tags per frame enter the solver. ---- */
+ *      At most 32 tags per frame enter the solver (the first 32 of the list, which is ordered by id). ---- */
 int cb_set_field(cb_ctx *ctx, const int32_t *ids, const cb_iso3 *poses, int n);
 int cb_set_camera(cb_ctx *ctx, const double *params9, const cb_iso3 *robot_to_cam);
 int cb_detect_pose_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,

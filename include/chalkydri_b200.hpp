@@ -152,7 +152,8 @@ class SqPnP {
                                                     const cb_iso3 &robot_to_cam, double gyro, double sign_change_error)
     {
         const size_t n = points_isometry.size();
-        if (n * 4 < 3 || n * 4 != points_2d.size() || n > 16) return std::nullopt;      // lib.rs:255-257
+        if (n > 32) throw std::invalid_argument("SqPnP: at most 32 tags per problem (csrc/sqpnp.cuh SQ_MAX_TAGS)");   // the reference has no cap: do not answer "no pose"
+        if (n * 4 < 3 || n * 4 != points_2d.size()) return std::nullopt;      // lib.rs:255-257
         const int32_t nt = (int32_t)n;
         cb_pose out;
         uint8_t ok = 0;

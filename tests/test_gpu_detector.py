@@ -198,6 +198,43 @@ def test_strided_frame_with_partial_tiles(oracle):
     det.close()
 
 
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+def test_every_threshold_kernel_shape_bit_exact(oracle, monkeypatch, cfg):
+    """The five shapes of the tensor-map threshold kernel (tiles per lane x ring depth x store form, api.cu kThrVariants) and a
+    few segment heights, on widths that give one strip, several strips, an odd number of tiles (strip tail stored directly next to the
+    bulk stores) and partial tiles: identical to the oracle's threshold map byte for byte."""
+    monkeypatch.setenv("CB_THR_CFG", str(cfg))
+    for (W, H), ysegs in (((1280, 720), 7), ((1456, 1088), 0), ((3024, 808), 3), ((1448, 240), 2), ((1450, 1084), 5)):
+        monkeypatch.setenv("CB_THR_YSEGS", str(ysegs)) if ysegs else monkeypatch.delenv("CB_THR_YSEGS", raising=False)
+        stride = (W + 15) // 16 * 16
+        rng = np.random.default_rng(W + cfg)
+        frames = np.zeros((2, H, stride), np.uint8)
+        base, _ = synth.render_batch(stride, H, 2, 3, seed=W, edge_px=(40, 120))
+        frames[:] = base
+        frames[1, :, : stride // 2] = rng.integers(0, 256, (H, stride // 2), dtype=np.uint8)      # noise: every tile a different threshold
+        det = make_detector(stride, H, 2)           # a fresh context: the plan cache is per context, the hooks are read per plan
+        w, h = (W + 1) // 2, (H + 1) // 2
+        out = np.empty((2, h, w), np.uint8)
+        from chalkydri_b200 import capi
+        rc = det._L.cb_threshold(det.ctx, capi.ptr(frames), W, H, stride, stride * H, 2, capi.ptr(out))
+        assert rc == 0, det._L.cb_last_error(det.ctx)
+        for b in range(2):
+            assert (out[b] == oracle.threshold(np.ascontiguousarray(frames[b, :, :W]))).all(), (cfg, W, H, ysegs, b)
+        det.close()
+
+
+def test_threshold_shape_timing_keeps_the_map(oracle, monkeypatch):
+    """Large batches time the kernel shapes once per geometry (threshold_plan): whatever shape wins, the map is the oracle's."""
+    monkeypatch.delenv("CB_THR_CFG", raising=False)
+    monkeypatch.delenv("CB_THR_YSEGS", raising=False)
+    frames, _ = synth.render_batch(1280, 720, 48, 4, seed=77, unique=3, edge_px=(60, 150))        # 44 MB: above the timing threshold
+    det = make_detector(1280, 720, 48)
+    thr = det.threshold(frames)
+    for b in (0, 1, 2, 47):
+        assert (thr[b] == oracle.threshold(frames[b])).all()
+    det.close()
+
+
 def test_c3_full_resolution_small_tags(oracle):
     frame, truth = synth.render_frame(4608, 2592, 40, seed=4, edge_px=(40, 300), small_tags=10)
     det = make_detector(4608, 2592, 1, 256)

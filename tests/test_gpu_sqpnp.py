@@ -104,3 +104,42 @@ def test_golden_fixture_sqpnp_on_gpu():
     ref["pos"], ref["rot"], ref["std_devs"] = g["pos"], g["rot"], g["std_devs"]
     compare(out, ok, ref, g["ok"])
     s.close()
+
+
+def test_every_visible_field_tag_enters_the_solve(oracle):
+    """The reference solves with every detection that is on the field (crates/apriltags/src/lib.rs:303-327, no cap): problems with up
+    to all 22 field tags in view (more than the 16 of round 1) against the oracle; beyond the kernels' 32 the host mirror raises."""
+    from chalkydri_b200.solver import SqPnP, MAX_TAGS
+    from tests.sqpnp_problems import CORNERS, camera_iso, qmat
+    rng = np.random.default_rng(11)
+    layout = field.load()
+    ids = sorted(layout)
+    T = np.array([layout[i]["t"] for i in ids]); Q = np.array([layout[i]["q"] for i in ids]); Rm = qmat(Q)
+    r2c = camera_iso()
+    R_r2c, t_r2c = qmat(r2c["q"]), r2c["t"]
+    n, max_tags = 300, 24
+    tags = np.zeros((n, max_tags), ISO_DTYPE); bearings = np.zeros((n, max_tags * 4, 3)); n_tags = np.zeros(n, np.int32)
+    gyro = np.zeros(n)
+    pw_all = np.einsum("kij,cj->kci", Rm, CORNERS) + T[:, None, :]
+    for i in range(n):
+        pos = np.array([rng.uniform(2, 14), rng.uniform(1, 7), 0.0]); yaw = rng.uniform(-np.pi, np.pi)
+        cy, sy = np.cos(yaw), np.sin(yaw)
+        Rr = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1.0]])
+        pc = (pw_all - pos) @ Rr @ R_r2c.T + t_r2c                    # world -> robot -> camera
+        # "in view" here: in front of the camera; a wide synthetic field of view keeps many tags (a real lens would see fewer)
+        vis = np.where((pc[:, :, 2] > 0.3).all(1))[0][:max_tags]
+        k = len(vis)
+        tags["t"][i, :k] = T[vis]; tags["q"][i, :k] = Q[vis]
+        b = pc[vis] / pc[vis][:, :, 2:3]
+        b[:, :, :2] += rng.normal(0, 0.25 / 900.0, (k, 4, 2))
+        bearings[i, :4 * k] = b.reshape(-1, 3)
+        n_tags[i] = k; gyro[i] = yaw + rng.normal(0, np.deg2rad(2.0))
+    assert n_tags.max() > 16 and n_tags.max() <= max_tags
+    s = SqPnP.new()
+    out, ok = s.solve_robot_pose_batch(tags, bearings, n_tags, r2c, gyro, 600.0)
+    ref, rok = oracle.sqpnp_batch(tags, bearings, n_tags, r2c, gyro, 600.0, nthreads=8)
+    compare(out, ok, ref, rok)
+    assert ok.mean() > 0.9
+    with pytest.raises(ValueError):
+        s.solve_robot_pose(np.zeros(MAX_TAGS + 1, ISO_DTYPE), np.zeros((4 * (MAX_TAGS + 1), 3)), r2c, 0.0, 600.0)
+    s.close()
