@@ -178,8 +178,11 @@ class AprilTags:
         gy = self._gyro_array(gyro, B)
         out = np.zeros((B, 64), DET_DTYPE); counts = np.zeros(B, np.int32)
         poses = np.zeros(B, POSE_DTYPE); ok = np.zeros(B, np.uint8); ntags = np.zeros(B, np.int32)
-        self.detector._check(L.cb_detect_pose_gray(self.detector.ctx, capi.ptr(grays), W, H, W, H * W, B, capi.ptr(gy), SIGN_FLIP_CONST,
-                                                   capi.ptr(out), capi.ptr(counts), capi.ptr(poses), capi.ptr(ok), capi.ptr(ntags)))
+        try:
+            self.detector._check(L.cb_detect_pose_gray(self.detector.ctx, capi.ptr(grays), W, H, W, H * W, B, capi.ptr(gy), SIGN_FLIP_CONST,
+                                                       capi.ptr(out), capi.ptr(counts), capi.ptr(poses), capi.ptr(ok), capi.ptr(ntags)))
+        except capi.ChalkydriError as e:
+            self._overflow_to_heartbeat(e, counts, ok)
         self.last_batch = (out, counts, poses, ok, ntags)
         return self._publish_batch(now_us, frame_times_us, counts, poses, ok)
 
@@ -211,16 +214,37 @@ class AprilTags:
             self.detector._check(L.cb_detect_pose_gray_collect(self.detector.ctx, capi.ptr(out), capi.ptr(counts), capi.ptr(poses), capi.ptr(ok),
                                                                capi.ptr(ntags)))
         except capi.ChalkydriError as e:
-            if e.code != capi.CB_ERR_STATE and inflight:       # a failed batch has left the queue; a refused collect has not
-                inflight.pop(0)
-            raise
+            if e.code == capi.CB_ERR_OVERFLOW and inflight:
+                self._overflow_to_heartbeat(e, counts, ok)     # the batch has left the queue; its frames publish heartbeats
+            else:
+                if e.code != capi.CB_ERR_STATE and inflight:       # a failed batch has left the queue; a refused collect has not
+                    inflight.pop(0)
+                raise
         times = inflight.pop(0)[1] if inflight else []
         self.last_batch = (out, counts, poses, ok, ntags)
         return self._publish_batch(now_us, times, counts, poses, ok)
 
+    def _overflow_to_heartbeat(self, e, counts, ok):
+        """A frame so cluttered that a fixed-size device table overflowed (CB_ERR_OVERFLOW) must not take the task down -- upstream's
+        detector has no such limit.  The batch is treated as "nothing detected" (heartbeats go out) and counted; every other error
+        propagates."""
+        from . import capi
+        if e.code != capi.CB_ERR_OVERFLOW:
+            raise e
+        self.overflow_batches = getattr(self, "overflow_batches", 0) + 1
+        counts[:] = 0
+        ok[:] = 0
+
     def process(self, now_us: int, frame_time_us: int, gray: np.ndarray):
-        out, counts = self.detector.detect_batch(np.ascontiguousarray(gray)[None])
-        dets = out[0, :counts[0]]
+        from . import capi
+        try:
+            out, counts = self.detector.detect_batch(np.ascontiguousarray(gray)[None])
+            dets = out[0, :counts[0]]
+        except capi.ChalkydriError as e:
+            if e.code != capi.CB_ERR_OVERFLOW:
+                raise
+            self.overflow_batches = getattr(self, "overflow_batches", 0) + 1
+            dets = []
         if len(dets) > 0:
             world, cam = self._correspondences(dets)
             gyro = self.comm.gyro_angle()

@@ -216,8 +216,10 @@ class AprilTags {
         int32_t count = 0, used = 0;
         cb_pose pose{};
         uint8_t ok = 0;
-        check(cb_detect_pose_gray(det_.ctx(), image.buf, image.width, image.height, image.stride, (size_t)image.stride * image.height, 1, &g,
-                                  SIGN_FLIP_CONST, dets.data(), &count, &pose, &ok, &used));
+        // a frame so cluttered that a fixed-size device table overflows must not take the task down (upstream has no such limit):
+        // it counts as "nothing detected" and the heartbeat goes out
+        if (!check_or_overflow(cb_detect_pose_gray(det_.ctx(), image.buf, image.width, image.height, image.stride, (size_t)image.stride * image.height, 1,
+                                                   &g, SIGN_FLIP_CONST, dets.data(), &count, &pose, &ok, &used))) { count = 0; ok = 0; }
         return publish(now_us, now_us - frame_time_us, pose, ok, count);
     }
 
@@ -238,7 +240,7 @@ class AprilTags {
         int32_t count = 0, used = 0;
         cb_pose pose{};
         uint8_t ok = 0;
-        check(cb_detect_pose_gray_collect(det_.ctx(), dets.data(), &count, &pose, &ok, &used));
+        if (!check_or_overflow(cb_detect_pose_gray_collect(det_.ctx(), dets.data(), &count, &pose, &ok, &used))) { count = 0; ok = 0; }
         const uint64_t ts = now_us - times_[head_];
         head_ ^= 1; pending_--;
         return publish(now_us, ts, pose, ok, count);
@@ -263,6 +265,8 @@ class AprilTags {
         return std::nullopt;
     }
     void check(int rc) { if (rc != CB_OK) throw Error(rc, cb_last_error(det_.ctx())); }
+    bool check_or_overflow(int rc) { if (rc == CB_ERR_OVERFLOW) { overflowed_++; return false; } check(rc); return true; }
+    uint64_t overflowed_ = 0;                  // frames answered with a heartbeat because a device table overflowed
     uint64_t times_[2] = {0, 0};
     int head_ = 0, pending_ = 0;
     Detector det_;

@@ -113,6 +113,8 @@ impl Detector {
             cb_detect_gray(self.ctx, image.buf.as_ptr(), image.width, image.height, image.stride,
                            (image.stride as usize) * (image.height as usize), 1, self.out.as_mut_ptr(), &mut count)
         };
+        // a frame so cluttered that a fixed-size device table overflowed is "nothing detected" (upstream has no such limit)
+        if rc == CB_ERR_OVERFLOW { return Vec::new(); }
         if rc != CB_OK { panic!("chalkydri_b200: {}", last_error(self.ctx)); }
         self.out[..count as usize].iter().map(|d| Detection(*d)).collect()
     }
@@ -273,9 +275,11 @@ impl PoseDetector {
         let (mut count, mut used, mut ok) = (0i32, 0i32, 0u8);
         let mut pose: cb_pose = unsafe { std::mem::zeroed() };
         let g = gyro.unwrap_or(f64::NAN);
-        check(d.ctx, unsafe { cb_detect_pose_gray(d.ctx, image.buf.as_ptr(), image.width, image.height, image.stride,
-                                                  (image.stride as usize) * (image.height as usize), 1, &g, sign_change_error,
-                                                  d.out.as_mut_ptr(), &mut count, &mut pose, &mut ok, &mut used) })?;
+        let rc = unsafe { cb_detect_pose_gray(d.ctx, image.buf.as_ptr(), image.width, image.height, image.stride,
+                                              (image.stride as usize) * (image.height as usize), 1, &g, sign_change_error,
+                                              d.out.as_mut_ptr(), &mut count, &mut pose, &mut ok, &mut used) };
+        if rc == CB_ERR_OVERFLOW { return Ok((Vec::new(), None)); }      // cluttered frame: the caller publishes its heartbeat
+        check(d.ctx, rc)?;
         let dets = d.out[..count as usize].iter().map(|x| Detection(*x)).collect();
         let res = (ok != 0).then(|| (Rotation3::from_matrix_unchecked(Matrix3::from_column_slice(&pose.rot)), Vector3::from(pose.pos), Vector3::from(pose.std_devs)));
         Ok((dets, res))

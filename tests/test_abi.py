@@ -192,6 +192,36 @@ def test_task_publish_rules_host_logic():
     assert np.isnan(task._gyro_array([0.1, None], 2)[1])
 
 
+def test_cluttered_frame_overflow_becomes_a_heartbeat():
+    """A device-table overflow (CB_ERR_OVERFLOW) on one frame must not take the task down (upstream's detector has no fixed
+    tables): `process` treats it as "nothing detected" and publishes the heartbeat; any other library error still propagates."""
+    from chalkydri_b200 import capi
+    from chalkydri_b200.pipeline import AprilTags
+
+    class Comm:
+        sent = []
+
+        def gyro_angle(self):
+            return 0.0
+
+        def publish(self, *a):
+            self.sent.append(a)
+
+    class Det:
+        code = capi.CB_ERR_OVERFLOW
+
+        def detect_batch(self, frames):
+            raise capi.ChalkydriError(self.code, "device table overflow")
+
+    task = object.__new__(AprilTags)
+    task.comm, task.cam_id, task.last_time, task.detector = Comm(), 3, None, Det()
+    assert task.process(1_000_000, 990_000, np.zeros((8, 8), np.uint8)) is None
+    assert len(task.comm.sent) == 1 and task.comm.sent[0][1] == 0 and task.overflow_batches == 1
+    task.detector.code = capi.CB_ERR_CUDA
+    with pytest.raises(capi.ChalkydriError):
+        task.process(2_000_000, 1_990_000, np.zeros((8, 8), np.uint8))
+
+
 def test_rust_extern_block_lists_the_header():
     """rust/chalkydri-b200-sys/src/ffi.rs declares exactly the symbols of include/chalkydri_b200.h (text comparison: the image has
     no rustc), and the wrapper crate uses every one of them."""
