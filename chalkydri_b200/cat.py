@@ -44,6 +44,9 @@ class CatDetector:
         if getattr(self, "_ctx", None):
             self._L.cb_destroy(self._ctx)
             self._ctx = None
+        if getattr(self, "_det_ctx", None):
+            self._L.cb_destroy(self._det_ctx)
+            self._det_ctx = None
 
     def __del__(self):
         try:
@@ -94,6 +97,29 @@ class CatDetector:
                                                  capi.ptr(self._xy_buf), cap, C.byref(n), capi.ptr(self._lines_buf), cap, C.byref(m)))
         self.points = self._xy_buf[:n.value].copy()
         self.lines = self._lines_buf[:m.value].copy()
+
+    def detect_tags(self, input_, use_otsu: bool = False, max_dets: int = 64):
+        """The decode the reference intends for CAT (book/src/maintenance/apriltags.md:58-60, lib.rs:551-613): CAT's own ternary map
+        (`thresh`, or `calc_otsu`), then the C library's stages on it -- in one library call (cb_cat_detect_tags).  Returns the
+        detection records; with `valid_tags` given to the constructor only those ids."""
+        rgb = self._rgb(input_)
+        if getattr(self, "_det_ctx", None) is None:           # the decode stages run undecimated: capacity of twice the frame size
+            self._det_ctx = self._L.cb_create(0, 2 * self.width, 2 * self.height, 1, max_dets)
+            if not self._det_ctx:
+                raise ChalkydriError(capi.CB_ERR_CUDA, self._L.cb_last_error(None).decode())
+            self._det_cap = max_dets
+            rc = self._L.cb_set_family_tag36h11(self._det_ctx, 3)
+            if rc:
+                raise ChalkydriError(rc, self._L.cb_last_error(self._det_ctx).decode())
+        out = np.zeros(self._det_cap, capi.DET_DTYPE)
+        n = C.c_int32()
+        rc = self._L.cb_cat_detect_tags(self._det_ctx, capi.ptr(rgb), self.width, self.height, 1 if use_otsu else 0, capi.ptr(out), C.byref(n))
+        if rc:
+            raise ChalkydriError(rc, self._L.cb_last_error(self._det_ctx).decode())
+        dets = out[:n.value]
+        if self.valid_tags:
+            dets = dets[np.isin(dets["id"], self.valid_tags)]
+        return dets
 
     def process_frame_stagewise(self, input_):
         """the same through the per-stage entry points (host buffers between the stages); kept for the parity tests"""

@@ -85,6 +85,7 @@ struct cb_ctx {
     bool camera_set = false;
     uint8_t *d_pose_buf = nullptr;       // [tags | bearings | n_tags | gyro | poses | ok] for pose_cap frames
     int pose_cap = 0;
+    bool external_map = false;           // cb_cat_detect_tags: d_thresh was filled from CAT's colour map, run_pipeline skips A1+A2
     bool pose_active = false;            // run_pipeline appends the chunk's problems at frame pose_frame_base ...
     int pose_frame_base = 0;
     double pose_sign_change_error = 0;   // ... and solves them on pose_stream, under the kernels of the next chunk
@@ -599,7 +600,9 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     CK(cudaEventRecord(ctx->ev[1], st));
     // ---- A1+A2 threshold ----
     const bool fast = g.f == 2 && (g.stride % 16 == 0) && (g.frame_stride % 16 == 0) && ((uintptr_t)d_frames % 16 == 0) && g.tw > 0 && g.th > 0;
-    if (fast) {
+    if (ctx->external_map) {
+        // the ternary map is already in d_thresh
+    } else if (fast) {
         // variant switch for A/B profiling: CB_THRESHOLD = tmap (default: tensor-map TMA, 6 or 4 tiles per lane) | tma (round 1: four
         // 1-D bulk copies per tile row) | tiled (first version, CTA tiles with block barriers)
         static const char *variant_env = getenv("CB_THRESHOLD");

@@ -206,4 +206,13 @@ __global__ void cat_sizes_kernel(const uint32_t *__restrict__ labels, const uint
     if (i < n) out[i] = sizes[labels[i]];
 }
 
+// Colour map (0 Black, 1 White, 2 Other; pitch = width) -> upstream's ternary map (0 / 255 / 127; pitch tp) for the decode path
+__global__ void cat_color_to_map_kernel(const uint8_t *__restrict__ color, uint8_t *__restrict__ map, int w, int h, int tp)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t c = color[(size_t)y * w + x];
+    map[(size_t)y * tp + x] = c == 0 ? 0 : (c == 1 ? 255 : 127);
+}
+
 }  // namespace cb

@@ -211,6 +211,13 @@ int cb_cat_check_edges(cb_ctx *ctx, const uint8_t *color, int width, int height,
  * cb_get_timing: h2d_ms, preprocess_ms (all CAT kernels), d2h_ms, total_ms. */
 int cb_cat_process_frame(cb_ctx *ctx, const uint8_t *rgb, int width, int height, uint8_t *color, int32_t *xy, int64_t xy_cap,
                          int64_t *n_points, int32_t *lines, int64_t lines_cap, int64_t *n_lines);
+/* CAT's decode intent -- book/src/maintenance/apriltags.md:58-60 ("Decoding tags is done pretty much the same way the C library does
+ * it") and the commented-out cluster() over connected_components(), lib.rs:551-613: the frame is thresholded the CAT way
+ * (use_otsu != 0: calc_otsu, lib.rs:191-259; 0: thresh, lib.rs:319-334) at full resolution, and from that map on the stages are the
+ * detector's (connected components, gradient clusters, quad fit, refine, decode, reconcile) sampling CAT's gray plane
+ * (utils.rs:33-46).  out[0 .. max_dets) / *out_count like cb_detect_gray with batch 1.  The context needs a tag family and, because
+ * the stages run undecimated, a capacity of twice the frame size (cb_create(.., 2*width, 2*height, ..)). */
+int cb_cat_detect_tags(cb_ctx *ctx, const uint8_t *rgb, int width, int height, int use_otsu, cb_detection *out, int32_t *out_count);
 /* Detector::connected_components (lib.rs:501-549): min-index labels and component sizes */
 int cb_cat_connected_components(cb_ctx *ctx, const uint8_t *color, int width, int height, uint32_t *labels, uint32_t *sizes);
 

@@ -8,6 +8,7 @@
 //   chalkydri-apriltags ("CAT") Detector                 /root/reference/crates/chalkydri-apriltags/src/lib.rs:142-181,265-287,501-549
 // Config errors throw (the reference unwrap()s / panics), the solver returns std::optional (the reference: Option).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -298,7 +299,7 @@ class Detector {
     }
     Detector(const Detector &o) : Detector(o.width_, o.height_, o.valid_tags_) {}          // Clone = a fresh, empty detector (lib.rs:663-667)
     Detector &operator=(const Detector &) = delete;
-    ~Detector() { cb_destroy(ctx_); }
+    ~Detector() { cb_destroy(ctx_); if (det_ctx_) cb_destroy(det_ctx_); }
 
     // process_frame(&mut self, input: &[u8]) (lib.rs:265-287); panics on a wrong length (lib.rs:267)
     void process_frame(const uint8_t *input, size_t len)
@@ -329,6 +330,28 @@ class Detector {
         if ((size_t)n > cap_) throw Error(CB_ERR_OVERFLOW, "line list capacity");
         lines_.resize((size_t)n * 4);
     }
+    // The decode the reference intends for CAT (book/src/maintenance/apriltags.md:58-60, lib.rs:551-613): CAT's own ternary map (thresh, or
+    // calc_otsu), then the C library's stages on it, in one library call.  With valid_tags given to the constructor only those ids.
+    std::vector<cb_detection> detect_tags(const uint8_t *input, size_t len, bool use_otsu = false, int max_dets = 64)
+    {
+        if (len != width_ * height_ * 3) throw std::invalid_argument("detect_tags: input must be width * height * 3 bytes of packed RGB");
+        if (!det_ctx_) {                                       // the decode stages run undecimated: capacity of twice the frame size
+            det_ctx_ = cb_create(0, 2 * (int)width_, 2 * (int)height_, 1, max_dets);
+            if (!det_ctx_) throw Error(CB_ERR_CUDA, cb_last_error(nullptr));
+            det_cap_ = max_dets;
+            const int rc = cb_set_family_tag36h11(det_ctx_, 3);
+            if (rc != CB_OK) throw Error(rc, cb_last_error(det_ctx_));
+        }
+        std::vector<cb_detection> out((size_t)det_cap_);
+        int32_t n = 0;
+        const int rc = cb_cat_detect_tags(det_ctx_, input, (int)width_, (int)height_, use_otsu ? 1 : 0, out.data(), &n);
+        if (rc != CB_OK) throw Error(rc, cb_last_error(det_ctx_));
+        out.resize((size_t)n);
+        if (!valid_tags_.empty())
+            out.erase(std::remove_if(out.begin(), out.end(), [&](const cb_detection &d) {
+                          return std::find(valid_tags_.begin(), valid_tags_.end(), (size_t)d.id) == valid_tags_.end(); }), out.end());
+        return out;
+    }
     UnionFind connected_components() const                                                                                        // lib.rs:501
     {
         UnionFind uf;
@@ -346,6 +369,8 @@ class Detector {
   private:
     void check(int rc) { if (rc != CB_OK) throw Error(rc, cb_last_error(ctx_)); }
     cb_ctx *ctx_ = nullptr;
+    cb_ctx *det_ctx_ = nullptr;                 // detect_tags(): a second context sized for the undecimated decode stages
+    int det_cap_ = 0;
     size_t width_, height_, cap_ = (size_t)1 << 20;
     std::vector<size_t> valid_tags_;
     std::vector<int32_t> points_, lines_;

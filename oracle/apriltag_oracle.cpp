@@ -843,7 +843,10 @@ inline int prefer_smaller(int pref, double q0, double q1)
     return 0;
 }
 
-int detect_impl(const uint8_t *buf, int W, int H, int stride, const orc_params &prm, orc_detection *out, int cap, orc_taps *taps)
+/* ext_map: an externally supplied ternary map (0 / 127 / 255, pitch = decimated width) used in place of threshold()'s -- the
+   CAT path (orc_detect_with_map): CAT's own colour map, then upstream's stages from connected_components() on */
+int detect_impl(const uint8_t *buf, int W, int H, int stride, const orc_params &prm, orc_detection *out, int cap, orc_taps *taps,
+                const uint8_t *ext_map = nullptr)
 {
     if (!buf || W <= 0 || H <= 0 || stride < W) return -1;
     if (prm.bits_corrected < 0 || prm.bits_corrected > 3) return -2;
@@ -859,7 +862,8 @@ int detect_impl(const uint8_t *buf, int W, int H, int stride, const orc_params &
     }
     const int w = quad_im.w, h = quad_im.h;
     std::vector<uint8_t> thr((size_t)w * h);
-    threshold(quad_im, prm.min_white_black_diff, thr.data());
+    if (ext_map) std::memcpy(thr.data(), ext_map, thr.size());
+    else threshold(quad_im, prm.min_white_black_diff, thr.data());
     UnionFind uf((uint32_t)((size_t)w * h));
     connected_components(thr.data(), w, h, uf);
     std::vector<Cluster> clusters;
@@ -1053,6 +1057,14 @@ int orc_threshold(const uint8_t *im, int W, int H, int stride, const orc_params 
 int orc_detect(const uint8_t *im, int W, int H, int stride, const orc_params *prm, orc_detection *out, int cap, orc_taps *taps)
 {
     return detect_impl(im, W, H, stride, *prm, out, cap, taps);
+}
+
+/* book/src/maintenance/apriltags.md:58-60 ("Decoding tags is done pretty much the same way the C library does it") with
+   crates/chalkydri-apriltags/src/lib.rs:551-613 (the commented-out cluster() over connected_components()): the ternary map comes
+   from CAT's own thresholding, everything after it is upstream's pipeline */
+int orc_detect_with_map(const uint8_t *im, int W, int H, int stride, const uint8_t *map, const orc_params *prm, orc_detection *out, int cap)
+{
+    return detect_impl(im, W, H, stride, *prm, out, cap, nullptr, map);
 }
 
 int orc_detect_batch(const uint8_t *frames, int W, int H, int stride, int64_t frame_stride, int batch,

@@ -88,6 +88,9 @@ int orc_threshold(const uint8_t *im, int W, int H, int stride, const orc_params 
 /* whole detector on one gray frame; returns number of detections written (<= cap), <0 on error */
 int orc_detect(const uint8_t *im, int W, int H, int stride, const orc_params *prm,
                orc_detection *out, int cap, orc_taps *taps);
+/* CAT decode intent (book/src/maintenance/apriltags.md:58-60): `map` = ternary map 0 / 127 / 255 of the (decimated) frame, pitch =
+   its width, used in place of upstream's threshold(); all later stages are upstream's */
+int orc_detect_with_map(const uint8_t *im, int W, int H, int stride, const uint8_t *map, const orc_params *prm, orc_detection *out, int cap);
 
 /* one frame per worker thread; counts[b] detections written at out[b*cap ...] */
 int orc_detect_batch(const uint8_t *frames, int W, int H, int stride, int64_t frame_stride, int batch,

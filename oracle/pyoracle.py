@@ -147,6 +147,23 @@ def detect(gray: np.ndarray, prm: Params | None = None, cap: int = 256, taps: bo
     return out[:n], d
 
 
+def detect_with_map(gray: np.ndarray, tmap: np.ndarray, prm: Params | None = None, cap: int = 256):
+    """Upstream's pipeline from connected_components() on, fed with an external ternary map (0 / 127 / 255) of the decimated frame."""
+    prm = prm or default_params()
+    gray = np.ascontiguousarray(gray, np.uint8)
+    tmap = np.ascontiguousarray(tmap, np.uint8)
+    H, W = gray.shape
+    w, h = decimated_size(W, H, prm.quad_decimate)
+    assert tmap.shape == (h, w)
+    out = np.zeros(cap, DET_DTYPE)
+    L = lib()
+    L.orc_detect_with_map.restype = C.c_int
+    n = L.orc_detect_with_map(_ptr(gray), W, H, W, _ptr(tmap), C.byref(prm), _ptr(out), cap)
+    if n < 0:
+        raise RuntimeError(f"orc_detect_with_map error {n}")
+    return out[:n]
+
+
 def detect_batch(frames: np.ndarray, prm: Params | None = None, cap: int = 64, nthreads: int = 1):
     prm = prm or default_params()
     frames = np.ascontiguousarray(frames, np.uint8)

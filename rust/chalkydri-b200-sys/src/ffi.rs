@@ -160,6 +160,8 @@ unsafe extern "C" {
                               cap: i64, n: *mut i64) -> c_int;
     pub fn cb_cat_process_frame(ctx: *mut cb_ctx, rgb: *const u8, width: c_int, height: c_int, color: *mut u8, xy: *mut i32, xy_cap: i64,
                                 n_points: *mut i64, lines: *mut i32, lines_cap: i64, n_lines: *mut i64) -> c_int;
+    pub fn cb_cat_detect_tags(ctx: *mut cb_ctx, rgb: *const u8, width: c_int, height: c_int, use_otsu: c_int, out: *mut cb_detection,
+                              out_count: *mut i32) -> c_int;
     pub fn cb_cat_connected_components(ctx: *mut cb_ctx, color: *const u8, width: c_int, height: c_int, labels: *mut u32,
                                        sizes: *mut u32) -> c_int;
     // ---- several GPUs, one process ----

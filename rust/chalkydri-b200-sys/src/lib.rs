@@ -320,6 +320,7 @@ pub mod cat {
 
     pub struct Detector {
         ctx: *mut cb_ctx,
+        det_ctx: *mut cb_ctx,                  // detect_tags(): a second context sized for the undecimated decode stages
         width: usize,
         height: usize,
         valid_tags: &'static [usize],
@@ -333,7 +334,7 @@ pub mod cat {
         pub fn new(width: usize, height: usize, valid_tags: &'static [usize]) -> Self {
             let ctx = unsafe { cb_create(0, 8, 8, 1, 1) };
             assert!(!ctx.is_null(), "chalkydri_b200: {}", last_error(std::ptr::null()));
-            Self { ctx, width, height, valid_tags, buf: vec![0; width * height], points: Vec::new(), lines: Vec::new() }
+            Self { ctx, det_ctx: std::ptr::null_mut(), width, height, valid_tags, buf: vec![0; width * height], points: Vec::new(), lines: Vec::new() }
         }
         /// `process_frame(&mut self, input: &[u8])` (lib.rs:265-287): packed RGB; asserts the length like lib.rs:267.  One library
         /// call: the frame is uploaded once, the intermediate maps stay on the device.
@@ -375,6 +376,26 @@ pub mod cat {
             if rc != CB_OK { panic!("chalkydri_b200: {}", last_error(self.ctx)); }
             self.lines = (0..(m as usize).min(CAP)).map(|i| (ln[4 * i] as usize, ln[4 * i + 1] as usize, ln[4 * i + 2] as usize, ln[4 * i + 3] as usize)).collect();
         }
+        /// The decode the reference intends for CAT (book/src/maintenance/apriltags.md:58-60, lib.rs:551-613): CAT's own ternary map
+        /// (`thresh`, or `calc_otsu`), then the C library's stages on it, in one library call.  Only `valid_tags` when that list is not empty.
+        pub fn detect_tags(&mut self, input: &[u8], use_otsu: bool) -> Vec<cb_detection> {
+            assert_eq!(input.len(), self.width * self.height * 3);
+            const MAX_DETS: usize = 64;
+            if self.det_ctx.is_null() {                       // the decode stages run undecimated: capacity of twice the frame size
+                self.det_ctx = unsafe { cb_create(0, 2 * self.width as c_int, 2 * self.height as c_int, 1, MAX_DETS as c_int) };
+                assert!(!self.det_ctx.is_null(), "chalkydri_b200: {}", last_error(std::ptr::null()));
+                let rc = unsafe { cb_set_family_tag36h11(self.det_ctx, 3) };
+                if rc != CB_OK { panic!("chalkydri_b200: {}", last_error(self.det_ctx)); }
+            }
+            let mut out: Vec<cb_detection> = vec![unsafe { std::mem::zeroed() }; MAX_DETS];
+            let mut n = 0i32;
+            let rc = unsafe { cb_cat_detect_tags(self.det_ctx, input.as_ptr(), self.width as c_int, self.height as c_int, use_otsu as c_int,
+                                                 out.as_mut_ptr(), &mut n) };
+            if rc != CB_OK { panic!("chalkydri_b200: {}", last_error(self.det_ctx)); }
+            out.truncate(n as usize);
+            if !self.valid_tags.is_empty() { out.retain(|d| self.valid_tags.contains(&(d.id as usize))); }
+            out
+        }
         /// `connected_components(&self) -> UnionFind` (lib.rs:501).
         pub fn connected_components(&self) -> UnionFind {
             let n = self.width * self.height;
@@ -389,7 +410,7 @@ pub mod cat {
         /// lib.rs:663-667: cloning makes a fresh, empty detector of the same size.
         fn clone(&self) -> Self { Self::new(self.width, self.height, self.valid_tags) }
     }
-    impl Drop for Detector { fn drop(&mut self) { unsafe { cb_destroy(self.ctx) } } }
+    impl Drop for Detector { fn drop(&mut self) { unsafe { cb_destroy(self.ctx); if !self.det_ctx.is_null() { cb_destroy(self.det_ctx) } } } }
 }
 
 /// Several GPUs of one box from one process: one context + one host thread per GPU inside the library, every GPU's lists land in

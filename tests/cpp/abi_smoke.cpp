@@ -63,6 +63,10 @@ int main()
             bool threw = false;
             try { cat.process_frame(rgb.data(), rgb.size() - 3); } catch (const std::invalid_argument &) { threw = true; }
             if (!threw) return 7;
+            // the decode path on the same (tag-free) frame: runs every stage, finds nothing
+            const auto tags = cat.detect_tags(rgb.data(), rgb.size());
+            std::printf("CAT decode: %zu tags on a checkerboard\n", tags.size());
+            if (!tags.empty()) return 12;
         }
         // Family::from_str, SqPnP: Clone
         if (chalkydri::family_from_str("tag36h11") != chalkydri::Family::Tag36h11) return 8;

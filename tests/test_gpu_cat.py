@@ -104,3 +104,43 @@ def test_last_column_reads_wrap_to_the_next_row_on_gpu(oracle):
         found.append((w - 3, 10) in got)
     assert found == [False, True, False]
     d.close()
+
+
+def high_contrast_rgb(w, h, seed, tags):
+    """tags whose black cells fall below CAT's fixed 60 and whose white cells above its 160 (lib.rs:319-334)"""
+    gray, truth = synth.render_frame(w, h, tags, seed=seed, edge_px=(60, 140))
+    g = np.clip((gray.astype(np.float32) - 128.0) * 3.0 + 128.0, 0, 255).astype(np.uint8)
+    return synth.gray_to_rgb(g, seed=seed), truth
+
+
+@pytest.mark.parametrize("w,h,seed,use_otsu", [(640, 480, 7, False), (960, 540, 3, False), (703, 905, 5, False), (640, 480, 7, True)])
+def test_cat_decode_matches_the_oracle(oracle, w, h, seed, use_otsu):
+    """CAT's decode intent (book/src/maintenance/apriltags.md:58-60, lib.rs:551-613) in one call, cb_cat_detect_tags: CAT's own ternary
+    map, then the C library's stages.  Oracle: CAT gray (utils.rs:43) and colour map from the CAT restatement, mapped to 0 / 255 /
+    127 and handed to upstream's pipeline in place of its threshold() (orc_detect_with_map, quad_decimate = 1)."""
+    from chalkydri_b200.cat import CatDetector
+    rgb, truth = high_contrast_rgb(w, h, seed, 4)
+    d = CatDetector(w, h, ())
+    got = d.detect_tags(rgb, use_otsu=use_otsu)
+    col = oracle.cat_calc_otsu(rgb) if use_otsu else oracle.cat_thresh(rgb)
+    # CAT's gray plane (utils.rs:43: two fused multiply-adds in f32, truncating cast) vectorised; a sample of it is checked against
+    # the oracle's scalar restatement (the device plane itself is covered by test_rgb_to_gray_every_colour_bit_exact)
+    flat = rgb.reshape(-1, 3).astype(np.float32)
+    v = np.float32(0.33)
+    cgray = np.floor((flat[:, 0].astype(np.float64) * float(v) + (flat[:, 1].astype(np.float64) * float(v) + (flat[:, 2] * v).astype(np.float64))).astype(np.float32)).astype(np.uint8)
+    step = max(1, w * h // 4000)
+    assert (cgray[::step] == np.array([oracle.cat_grayscale(int(r), int(g), int(b)) for r, g, b in rgb.reshape(-1, 3)[::step]], np.uint8)).all()
+    tmap = np.array([0, 255, 127], np.uint8)[col]
+    ref = oracle.detect_with_map(cgray.reshape(h, w), tmap, oracle.default_params(quad_decimate=1.0))
+    assert got["id"].tolist() == ref["id"].tolist() and got["hamming"].tolist() == ref["hamming"].tolist()
+    if len(ref):
+        assert np.abs(got["p"] - ref["p"]).max() < 1e-3
+    if not use_otsu:
+        assert len(ref) >= 2 and set(ref["id"].tolist()) <= set(int(i) for i in truth["ids"])     # the path does decode the rendered tags
+    # valid_tags filters the list like the constructor argument says
+    if len(ref):
+        keep = (int(ref["id"][0]),)
+        d2 = CatDetector(w, h, keep)
+        assert set(d2.detect_tags(rgb, use_otsu=use_otsu)["id"].tolist()) == set(keep)
+        d2.close()
+    d.close()

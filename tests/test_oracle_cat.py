@@ -258,3 +258,15 @@ def test_golden_fixture_cat(oracle):
     assert m == len(g["lines"]) and (lines == g["lines"]).all()
     labels, sizes = oracle.cat_connected_components(color)
     assert (labels == g["labels"]).all() and (sizes == g["sizes"]).all()
+
+
+def test_external_map_entry_is_upstreams_pipeline_after_threshold(oracle):
+    """orc_detect_with_map (the CAT decode oracle) fed with upstream's own threshold map is orc_detect: the entry changes where
+    the ternary map comes from and nothing else."""
+    from chalkydri_b200 import synth
+    gray, _ = synth.render_frame(640, 480, 3, seed=7, edge_px=(50, 110))
+    for f in (1.0, 2.0):
+        prm = oracle.default_params(quad_decimate=f)
+        ref = oracle.detect(gray, prm)
+        got = oracle.detect_with_map(gray, oracle.threshold(gray, prm), prm)
+        assert len(ref) >= 2 and got.tobytes() == ref.tobytes()
