@@ -106,6 +106,8 @@ struct cb_ctx {
     int cluster_mode = 0;                      // 0: band-ordered count / scatter (round 2), 1: tile passes + scan-order sort (round 1; CB_CLUSTERS=tiles)
     ClbArea *d_areas = nullptr;                // band tables of the count pass (first areas, then the pool of chained sub-band areas)
     uint32_t areas_first_cap = 0, areas_pool_cap = 0;
+    uint32_t *d_band_dense = nullptr;          // (band x cluster) matrix of the dense prefix form (small batches; allocated on first use)
+    size_t band_dense_cells = 0;
     uint32_t *d_cursors = nullptr;             // prefix-pass cursors when clusters_per_frame does not fit shared memory
     uint4 *d_ent = nullptr;                    // tiles: per-point words of the count pass, 16 B per decimated pixel; bands: the staging lists (same size)
     unsigned long long *d_tile_keys = nullptr;  // per-tile tables of the count pass
@@ -202,6 +204,7 @@ void cb_destroy(cb_ctx *ctx)
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->d_in2) cudaFree(ctx->d_in2);
     if (ctx->d_sq_scratch) cudaFree(ctx->d_sq_scratch);
+    if (ctx->d_band_dense) cudaFree(ctx->d_band_dense);
     for (void *p : {(void *)ctx->d_field_ids, (void *)ctx->d_field_poses, (void *)ctx->d_cam9, (void *)ctx->d_pose_buf}) if (p) cudaFree(p);
     if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -708,10 +711,29 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             cluster_select_kernel<<<dim3((caps.slots_per_frame + 255) / 256, B), 256, 0, st>>>(ctx->d_table, ctx->d_clusters, d_ncl, d_npt, ctx->d_worklist, wl_stride,
                                                                                             d_misc + 8, 2, (uint32_t)QT0, (uint32_t)QT1,
                                                                                             (uint32_t)QT2, d_misc, g, caps, prm.min_cluster_pixels);
-            cluster_band_resolve_kernel<<<(nall + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(ctx->d_table, ctx->d_areas, d_pool, g, caps, bp);
+            // dense form of the prefix for small batches (clusters.cuh): (band x cluster) matrix within a fixed budget
+            uint32_t *d_dense = nullptr;
+            {
+                const size_t cells = (size_t)nfirst * caps.clusters_per_frame;
+                static const bool dense_off = getenv("CB_BAND_PREFIX") && strcmp(getenv("CB_BAND_PREFIX"), "walk") == 0;      // A/B hook
+                if (!dense_off && cells * sizeof(uint32_t) <= ((size_t)48 << 20)) {
+                    if (ctx->band_dense_cells < cells) {
+                        if (ctx->d_band_dense) { CK(cudaStreamSynchronize(st)); cudaFree(ctx->d_band_dense); ctx->d_band_dense = nullptr; ctx->band_dense_cells = 0; }
+                        CK(cudaMalloc((void **)&ctx->d_band_dense, cells * sizeof(uint32_t)));
+                        ctx->band_dense_cells = cells;
+                    }
+                    d_dense = ctx->d_band_dense;
+                    CK(cudaMemsetAsync(d_dense, 0, cells * sizeof(uint32_t), st));
+                }
+            }
+            cluster_band_resolve_kernel<<<(nall + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(ctx->d_table, ctx->d_areas, d_pool, g, caps, bp, d_dense);
+            if (d_dense) {
+                cluster_band_prefix_dense_kernel<<<dim3((caps.clusters_per_frame + 127) / 128, B), 128, 0, st>>>(d_dense, ctx->d_clusters, d_ncl, d_pool, caps, bp);
+                launches++;
+            }
             cluster_band_prefix_kernel<<<B, CLB_CAP, ctx->d_cursors ? 0 : caps.clusters_per_frame * sizeof(uint32_t), st>>>(ctx->d_areas, ctx->d_clusters, d_ncl,
-                                                                                                                      ctx->d_cursors, caps, bp);
-            cluster_band_scatter_kernel<<<nall, 32, 0, st>>>(d_stage, ctx->d_areas, d_pool, ctx->d_scankey, g, caps, bp);
+                                                                                                                      ctx->d_cursors, caps, bp, d_dense ? d_pool : nullptr);
+            cluster_band_scatter_kernel<<<nall, 32, 0, st>>>(d_stage, ctx->d_areas, d_pool, ctx->d_scankey, g, caps, bp, d_dense);
             launches += 5;
         }
         if (g.h > 2 && g.w > 2 && ctx->cluster_mode == 1) {

@@ -473,7 +473,7 @@ cluster_band_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__re
 // resolve: every record learns its cluster (index into the frame's selected-cluster list, CLB_NONE = not selected).  One warp per area.
 __global__ void __launch_bounds__(CLB_WARPS * 32)
 cluster_band_resolve_kernel(const ClusterSlot *__restrict__ table, ClbArea *__restrict__ areas, const uint32_t *__restrict__ pool_counter,
-                            Geom g, Caps caps, BandPlan bp)
+                            Geom g, Caps caps, BandPlan bp, uint32_t *__restrict__ dense)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t a = blockIdx.x * CLB_WARPS + (threadIdx.x >> 5);
@@ -483,9 +483,40 @@ cluster_band_resolve_kernel(const ClusterSlot *__restrict__ table, ClbArea *__re
     const uint32_t n_used = A->n_used;
     const int b = A->band / bp.nbands;
     const ClusterSlot *tab = table + (size_t)b * caps.slots_per_frame;
+    // dense form of the prefix (small batches, no chained sub-band anywhere): the record's count goes to cell (band, cluster)
+    const bool dense_on = dense != nullptr && *pool_counter == 0;
     for (uint32_t i = lane; i < n_used; i += 32) {
         const uint32_t s = slot_find(tab, caps.slots_per_frame, A->rec[i].key);
-        A->rec[i].key = s == 0xffffffffu ? CLB_NONE : tab[s].cluster;
+        const uint32_t ci = s == 0xffffffffu ? CLB_NONE : tab[s].cluster;
+        A->rec[i].key = ci;
+        if (dense_on && ci < caps.clusters_per_frame) dense[(size_t)A->band * caps.clusters_per_frame + ci] = A->rec[i].cnt;
+    }
+}
+
+// Dense form of the prefix pass, for small batches: walking a frame's bands one after the other (the kernel below) is a chain of
+// `nbands` dependent steps -- 107 us for the 358 one-row bands of a single 1280x720 frame, a sixth of that frame's latency.  With
+// the counts in a (band x cluster) matrix the running position of every cluster is a column scan: one thread per cluster, the loads
+// of a column independent of each other (only the stored values form a chain), coalesced across clusters.  Only when no band of
+// the batch needed a chained sub-band (pool_counter == 0; otherwise the walk below does the work) and the matrix fits a fixed
+// budget (api.cu); the throughput configuration (256 frames, four-row bands) keeps the walk.
+__global__ void __launch_bounds__(128)
+cluster_band_prefix_dense_kernel(uint32_t *__restrict__ dense, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ nclusters,
+                                 const uint32_t *__restrict__ pool_counter, Caps caps, BandPlan bp)
+{
+    if (*pool_counter != 0) return;
+    const int b = blockIdx.y;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= min(nclusters[b], caps.clusters_per_frame)) return;
+    uint32_t run = clusters[(size_t)b * caps.clusters_per_frame + c].offset;
+    uint32_t *col = dense + (size_t)b * bp.nbands * caps.clusters_per_frame + c;
+    constexpr int U = 16;
+    for (int j0 = 0; j0 < bp.nbands; j0 += U) {
+        uint32_t v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) v[k] = j0 + k < bp.nbands ? col[(size_t)(j0 + k) * caps.clusters_per_frame] : 0u;
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (j0 + k < bp.nbands) { col[(size_t)(j0 + k) * caps.clusters_per_frame] = run; run += v[k]; }
     }
 }
 
@@ -493,10 +524,11 @@ cluster_band_resolve_kernel(const ClusterSlot *__restrict__ table, ClbArea *__re
 // cursors: clusters_per_frame words in shared memory when they fit, otherwise the caller passes a global array.
 __global__ void __launch_bounds__(CLB_CAP)
 cluster_band_prefix_kernel(ClbArea *__restrict__ areas, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ nclusters,
-                           uint32_t *__restrict__ global_cursors, Caps caps, BandPlan bp)
+                           uint32_t *__restrict__ global_cursors, Caps caps, BandPlan bp, const uint32_t *__restrict__ dense_done_unless)
 {
     extern __shared__ uint32_t s_cursor[];
     const int b = blockIdx.x, t = threadIdx.x;
+    if (dense_done_unless != nullptr && *dense_done_unless == 0) return;      // the dense form above did the work (no chained sub-band)
     uint32_t *cur = global_cursors ? global_cursors + (size_t)b * caps.clusters_per_frame : s_cursor;
     const uint32_t ncl = min(nclusters[b], caps.clusters_per_frame);
     for (uint32_t c = t; c < ncl; c += CLB_CAP) cur[c] = clusters[(size_t)b * caps.clusters_per_frame + c].offset;
@@ -539,7 +571,7 @@ cluster_band_prefix_kernel(ClbArea *__restrict__ areas, const ClusterRec *__rest
 // scatter: one warp per (sub-)band
 __global__ void __launch_bounds__(32)
 cluster_band_scatter_kernel(const uint32_t *__restrict__ stage, const ClbArea *__restrict__ areas, const uint32_t *__restrict__ pool_counter,
-                            uint32_t *__restrict__ scankey, Geom g, Caps caps, BandPlan bp)
+                            uint32_t *__restrict__ scankey, Geom g, Caps caps, BandPlan bp, const uint32_t *__restrict__ dense)
 {
     __shared__ uint32_t cur[CLB_CAP];
     const int lane = threadIdx.x;
@@ -554,10 +586,13 @@ cluster_band_scatter_kernel(const uint32_t *__restrict__ stage, const ClbArea *_
     for (int s = lane; s < CLB_CAP; s += 32) cur[s] = CLB_NONE;
     __syncwarp();
     bool any = false;
+    const bool dense_on = dense != nullptr && *pool_counter == 0;
     for (uint32_t i = lane; i < n_used; i += 32) {
         const ClbRec r = A->rec[i];
-        cur[r.slot] = r.cnt;
-        any |= r.cnt != CLB_NONE;
+        uint32_t first = r.cnt;                                 // the walk's result, or (dense form) cell (band, cluster) of the scanned matrix
+        if (dense_on) first = (uint32_t)r.key < caps.clusters_per_frame ? dense[(size_t)job * caps.clusters_per_frame + (uint32_t)r.key] : CLB_NONE;
+        cur[r.slot] = first;
+        any |= first != CLB_NONE;
     }
     if (!__any_sync(full, any)) return;                         // no selected cluster crosses this band
     __syncwarp();
