@@ -344,6 +344,8 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
         CB_SORT_ATTR(SortS8<3>) CB_SORT_ATTR(SortS16<3>) CB_SORT_ATTR(SortM<3>) CB_SORT_ATTR(SortL1<3>) CB_SORT_ATTR(SortL2<3>)
         // (function attributes are shared by every context of the device: always the same value, the most a context may ask for)
         ok = ok && cudaFuncSetAttribute(cluster_band_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(lfps_big_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LFB_SMEM) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(lfps_big_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, LFB_SMEM) == cudaSuccess;
 #undef CB_SORT_ATTR
         {   // 4-subsets of {0..9} in colex order (subsets of {0..k-1} first), packed m0<<12|m1<<8|m2<<4|m3
             uint16_t combos[210];
@@ -783,8 +785,24 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             CK(cudaEventRecord(ctx->ev_tier[i], ctx->tier_stream[i]));
             CK(cudaStreamWaitEvent(st, ctx->ev_tier[i], 0));
         }
+        // small batches: the largest clusters get a CTA each (lfps_big_kernel, a side stream) instead of a warp -- one frame's latency is
+        // its largest cluster's chain; large batches keep one warp per cluster (same work, more clusters in flight)
+        int n_big = 0x7fffffff;
+        if (B <= 8) n_big = 768;
+        if (const char *e = getenv("CB_LFPS_BIG")) n_big = atoi(e) > 0 ? std::max(600, atoi(e)) : 0x7fffffff;      // A/B hook (0 = off)
+        if (n_big != 0x7fffffff) {
+            CK(cudaEventRecord(ctx->ev_fork, st));
+            CK(cudaStreamWaitEvent(ctx->tier_stream[0], ctx->ev_fork, 0));
+            if (n_big > QT2) lfps_big_kernel<3><<<ctx->num_sms * 2, LFB_THREADS, LFB_SMEM, ctx->tier_stream[0]>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride,
+                                                                                                      d_misc + 8, d_misc + 28, ctx->d_errs, ctx->d_cp, g, caps, n_big);
+            else lfps_big_kernel<2><<<ctx->num_sms * 2, LFB_THREADS, LFB_SMEM, ctx->tier_stream[0]>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride,
+                                                                                                  d_misc + 8, d_misc + 28, ctx->d_errs, ctx->d_cp, g, caps, n_big);
+            CK(cudaEventRecord(ctx->ev_tier[0], ctx->tier_stream[0]));
+            launches++;
+        }
         lfps_kernel<<<ctx->num_sms * 8, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 26,
-                                                                  ctx->d_errs, ctx->d_cp, g, caps);
+                                                                  ctx->d_errs, ctx->d_cp, g, caps, n_big);
+        if (n_big != 0x7fffffff) CK(cudaStreamWaitEvent(st, ctx->ev_tier[0], 0));
         fit_quads_kernel<<<ctx->num_sms * 8, FQ_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 27,
                                                                        ctx->d_errs, ctx->d_cp, ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
         launches += 12;

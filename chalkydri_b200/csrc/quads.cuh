@@ -367,7 +367,7 @@ struct __align__(16) LfWarp {
 __global__ void __launch_bounds__(LF_WARPS * 32)
 lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const ClusterRec *__restrict__ clusters,
             const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork /* stride 2, 4 tiers */,
-            uint32_t *__restrict__ work_counter, double *__restrict__ errs_all, double *__restrict__ cp_all, Geom g, Caps caps)
+            uint32_t *__restrict__ work_counter, double *__restrict__ errs_all, double *__restrict__ cp_all, Geom g, Caps caps, int n_big)
 {
     __shared__ LfWarp sh[LF_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -382,7 +382,7 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
         if (!tier_item<0, 3>(wi, nwork, worklists, wl_stride, item)) return;
         const int b = item / caps.clusters_per_frame;
         const ClusterRec rec = clusters[item];
-        if (rec.cursor == 0xffffffffu || rec.count < 24) continue;
+        if (rec.cursor == 0xffffffffu || rec.count < 24 || (int)rec.count >= n_big) continue;      // (>= n_big: lfps_big_kernel)
         const int n = (int)rec.count;
         const int ksz = min(20, n / 12);
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;     // multiple of LF_CP
@@ -487,6 +487,141 @@ lfps_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_
             errs[i] = lf.err;
         }
         __syncwarp();
+    }
+}
+
+// ---- prefix moments + window errors, ONE CTA per LARGE cluster (small batches) -----------------------------------------------
+// With one warp per cluster the largest cluster of a frame is a serial chain: per 32 points the warp computes the terms, runs
+// the six-lane additions, then the window errors, one phase after the other -- 1 us per step, 168 us for the 5 000-point cluster
+// of a 1280x720 frame, a quarter of that frame's latency.  Only the additions are sequential.  Here a CTA streams the cluster in
+// chunks of LFB_C points through a four-chunk ring in shared memory as a three-stage pipeline, one __syncthreads per chunk:
+//   workers (7 warps)  A(c): terms of chunk c (gradient taps, square root) -> ring
+//   chain   (1 warp)   B(c - 1): the six prefix sums over chunk c - 1, in place, in point order (one DADD per point and moment)
+//   workers            C(c - 2): window errors for the points whose window ends in chunk c - 2 (they read back at most 41 entries:
+//                      chunks c - 2 and c - 3), checkpoints of that chunk, copy of the first 2 ksz entries
+// so the cluster costs about its chain: 10 cycles per point.  Every value is computed by the same expressions in the same order as
+// in lfps_kernel (same terms, same additions, same fit_line_m calls), so errs[] and the checkpoints are identical.  Used for the
+// clusters of at least n_big points when the batch is small (api.cu); lfps_kernel skips those.
+constexpr int LFB_THREADS = 256, LFB_C = 256, LFB_RING = 4 * LFB_C, LFB_PITCH = LFB_RING + 2;     // pitch: chain lanes 4 banks apart
+constexpr int LFB_SMEM = (6 * LFB_PITCH + 6 * LF_HPITCH) * (int)sizeof(double) + 16;
+template <int T_LO>
+__global__ void __launch_bounds__(LFB_THREADS)
+lfps_big_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const ClusterRec *__restrict__ clusters,
+                const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork /* stride 2, 4 tiers */,
+                uint32_t *__restrict__ work_counter, double *__restrict__ errs_all, double *__restrict__ cp_all, Geom g, Caps caps, int n_big)
+{
+    extern __shared__ __align__(16) unsigned char lfb_smem[];
+    double (*ring)[LFB_PITCH] = reinterpret_cast<double (*)[LFB_PITCH]>(lfb_smem);
+    double (*head)[LF_HPITCH] = reinterpret_cast<double (*)[LF_HPITCH]>(lfb_smem + 6 * LFB_PITCH * sizeof(double));
+    uint32_t *s_work = reinterpret_cast<uint32_t *>(lfb_smem + (6 * LFB_PITCH + 6 * LF_HPITCH) * sizeof(double));
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NWORK = LFB_THREADS - 32;                 // worker threads (warps 1..7)
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) *s_work = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t wi = *s_work;
+        uint32_t item;
+        if (!tier_item<T_LO, 3>(wi, nwork, worklists, wl_stride, item)) return;
+        const int b = item / caps.clusters_per_frame;
+        const ClusterRec rec = clusters[item];
+        if (rec.cursor == 0xffffffffu || (int)rec.count < n_big || rec.count < 24) continue;
+        const int n = (int)rec.count;
+        const int ksz = min(20, n / 12);
+        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;     // multiple of LF_CP
+        const uint32_t *XY = sorted_xy + pbase;
+        double *errs = errs_all + pbase;
+        double *cp = cp_all + (pbase / LF_CP) * 6;
+        const uint8_t *img = in + (size_t)b * g.frame_stride;
+        const int nchunks = (n + LFB_C - 1) / LFB_C;
+        auto ring_entry = [&](int idx, M6 &e) {
+            const int s = idx % LFB_RING;
+            e.Mx = ring[0][s]; e.My = ring[1][s]; e.Mxx = ring[2][s]; e.Mxy = ring[3][s]; e.Myy = ring[4][s]; e.W = ring[5][s];
+        };
+        double acc = 0;                                     // chain lanes: running sum of moment `lane`
+        for (int it = 0; it < nchunks + 2; it++) {
+            if (wid == 0) {
+                // ---- B(it - 1): the chain ----
+                const int c = it - 1;
+                if (c >= 0 && c < nchunks && lane < 6) {
+                    const int cnt = min(LFB_C, n - c * LFB_C);
+                    double *r = &ring[lane][(c * LFB_C) % LFB_RING];
+                    int k = 0;
+                    double2 *r2 = reinterpret_cast<double2 *>(r);
+                    for (; k + 8 <= cnt; k += 8) {              // 128-bit shared-memory accesses, the additions stay one dependent chain
+                        double2 v0 = r2[k / 2], v1 = r2[k / 2 + 1], v2 = r2[k / 2 + 2], v3 = r2[k / 2 + 3];
+                        acc += v0.x; v0.x = acc; acc += v0.y; v0.y = acc;
+                        acc += v1.x; v1.x = acc; acc += v1.y; v1.y = acc;
+                        acc += v2.x; v2.x = acc; acc += v2.y; v2.y = acc;
+                        acc += v3.x; v3.x = acc; acc += v3.y; v3.y = acc;
+                        r2[k / 2] = v0; r2[k / 2 + 1] = v1; r2[k / 2 + 2] = v2; r2[k / 2 + 3] = v3;
+                    }
+                    for (; k < cnt; k++) { acc += r[k]; r[k] = acc; }
+                }
+            } else {
+                const int wt = tid - 32;
+                // ---- A(it): terms of chunk it ----
+                if (it < nchunks) {
+                    const int cnt = min(LFB_C, n - it * LFB_C);
+                    for (int p = wt; p < cnt; p += NWORK) {
+                        const int j = it * LFB_C + p, s = j % LFB_RING;
+                        const uint32_t xy = XY[j];
+                        const int px = (int)(xy & 0xffff), py = (int)(xy >> 16);
+                        const double fx = px * .5 + 0.5, fy = py * .5 + 0.5;
+                        const int ix = (int)fx, iy = (int)fy;
+                        double W = 1;
+                        if (ix > 0 && ix + 1 < g.w && iy > 0 && iy + 1 < g.h) {
+                            const uint8_t *row = img + (size_t)(iy * g.f) * g.stride;
+                            const int gl = row[(ix - 1) * g.f], gr = row[(ix + 1) * g.f];
+                            const int gu = row[(ptrdiff_t)ix * g.f - (ptrdiff_t)g.f * g.stride], gd = row[(ptrdiff_t)ix * g.f + (ptrdiff_t)g.f * g.stride];
+                            const int grad_x = gr - gl, grad_y = gd - gu;
+                            W = sqrt((double)(grad_x * grad_x + grad_y * grad_y)) + 1;
+                        }
+                        ring[0][s] = W * fx; ring[1][s] = W * fy; ring[2][s] = W * fx * fx; ring[3][s] = W * fx * fy; ring[4][s] = W * fy * fy; ring[5][s] = W;
+                    }
+                }
+                // ---- C(it - 2): everything that reads the finished prefix of chunk it - 2 ----
+                const int c = it - 2;
+                if (c >= 0) {
+                    const int cnt = min(LFB_C, n - c * LFB_C);
+                    for (int q = wt; q < cnt; q += NWORK) {
+                        const int j = c * LFB_C + q, s = j % LFB_RING;
+                        if ((j & (LF_CP - 1)) == LF_CP - 1) {
+#pragma unroll
+                            for (int m = 0; m < 6; m++) cp[(size_t)(j / LF_CP) * 6 + m] = ring[m][s];
+                        }
+                        if (j < 2 * ksz) {
+#pragma unroll
+                            for (int m = 0; m < 6; m++) head[m][j] = ring[m][s];
+                        } else {
+                            // window centred on i = j - ksz: i0 = j - 2 ksz >= 0, i1 = j
+                            M6 a, p;
+                            ring_entry(j, a);
+                            p = a;
+                            const int i0 = j - 2 * ksz;
+                            if (i0 > 0) ring_entry(i0 - 1, p);
+                            LineFit lf;
+                            fit_line_m(a, p, p, i0 > 0 ? 1 : 0, 2 * ksz + 1, false, lf);
+                            errs[j - ksz] = lf.err;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // windows that wrap: i in [0, ksz) and [n - ksz, n)
+        for (int t = tid; t < 2 * ksz; t += LFB_THREADS) {
+            const int i = t < ksz ? t : n - 2 * ksz + t;
+            int i0 = i - ksz; if (i0 < 0) i0 += n;
+            int i1 = i + ksz; if (i1 >= n) i1 -= n;
+            M6 a, p, l;
+            a.Mx = head[0][i1]; a.My = head[1][i1]; a.Mxx = head[2][i1]; a.Mxy = head[3][i1]; a.Myy = head[4][i1]; a.W = head[5][i1];
+            ring_entry(i0 - 1, p);
+            ring_entry(n - 1, l);
+            LineFit lf;
+            fit_line_m(a, p, l, 2, n - i0 + i1 + 1, false, lf);
+            errs[i] = lf.err;
+        }
     }
 }
 
