@@ -803,8 +803,19 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         lfps_kernel<<<ctx->num_sms * 8, LF_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 26,
                                                                   ctx->d_errs, ctx->d_cp, g, caps, n_big);
         if (n_big != 0x7fffffff) CK(cudaStreamWaitEvent(st, ctx->ev_tier[0], 0));
+        if (n_big != 0x7fffffff) {      // the same split for the corner search: the large clusters' scans on eight warps each, side stream
+            CK(cudaEventRecord(ctx->ev_fork, st));
+            CK(cudaStreamWaitEvent(ctx->tier_stream[0], ctx->ev_fork, 0));
+            if (n_big > QT2) fit_quads_big_kernel<3><<<ctx->num_sms * 2, FQB_WARPS * 32, sizeof(FqBig), ctx->tier_stream[0]>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 29,
+                        ctx->d_errs, ctx->d_cp, ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm, n_big);
+            else fit_quads_big_kernel<2><<<ctx->num_sms * 2, FQB_WARPS * 32, sizeof(FqBig), ctx->tier_stream[0]>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 29,
+                        ctx->d_errs, ctx->d_cp, ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm, n_big);
+            CK(cudaEventRecord(ctx->ev_tier[0], ctx->tier_stream[0]));
+            launches++;
+        }
         fit_quads_kernel<<<ctx->num_sms * 8, FQ_WARPS * 32, 0, st>>>(d_frames, ctx->d_scankey, ctx->d_clusters, ctx->d_worklist, wl_stride, d_misc + 8, d_misc + 27,
-                                                                       ctx->d_errs, ctx->d_cp, ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm);
+                                                                       ctx->d_errs, ctx->d_cp, ctx->d_quads, d_nq, d_misc + 3, d_misc, g, caps, prm, n_big);
+        if (n_big != 0x7fffffff) CK(cudaStreamWaitEvent(st, ctx->ev_tier[0], 0));
         launches += 12;
         CK(cudaEventRecord(ctx->ev[5], st));
     } else {

@@ -125,18 +125,225 @@ struct FqWarp {
     int kept[10];
 };
 
+// Smoothed errors, local maxima and the running list of the best max_nmaxima + 1 maxima (one per lane: te / ti, descending error;
+// ties: lower index first) over the points [ja, jb) of a cluster of n points (ja a multiple of 32); nm counts the maxima seen.
+// One warp; et / ys are its tiles in shared memory.
+__device__ __forceinline__ void fq_scan(double *__restrict__ et, double *__restrict__ ys, const double *__restrict__ errs, int n, int ja, int jb,
+                                        const DetParams &prm, int lane, double &te, int &ti, int &nm)
+{
+    const uint32_t full = 0xffffffffu;
+    double t11 = __shfl_sync(full, te, 10);           // error of the 11th list entry (-inf while the list is short)
+    // tile loads run one step ahead of their use (the errs array comes from L2 / HBM)
+    auto load_err = [&](int idx) { if (idx < 0) idx += n; while (idx >= n) idx -= n; return errs[idx]; };
+    double pre0 = load_err(ja - 4 + lane), pre1 = lane < 8 ? load_err(ja - 4 + 32 + lane) : 0.0;
+    for (int j0 = ja; j0 < jb; j0 += 32) {
+        et[lane] = pre0;
+        if (lane < 8) et[32 + lane] = pre1;
+        if (j0 + 32 < jb) {
+            pre0 = load_err(j0 + 32 - 4 + lane);
+            if (lane < 8) pre1 = load_err(j0 + 32 - 4 + 32 + lane);
+        }
+        __syncwarp();
+        for (int u = lane; u < 34; u += 32) {
+            double acc = 0;
+#pragma unroll
+            for (int i = 0; i < 7; i++) acc += et[u + i] * prm.smooth_f[i];
+            ys[u] = acc;
+        }
+        __syncwarp();
+        bool is_max = false;
+        double e = 0;
+        if (j0 + lane < jb) {
+            e = ys[lane + 1];
+            is_max = e > ys[lane + 2] && e > ys[lane];
+        }
+        nm += __popc(__ballot_sync(full, is_max));
+        // only maxima above the current 11th best can enter the list (an equal error with a later index cannot)
+        uint32_t bal = __ballot_sync(full, is_max && e > t11);
+        while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const double ev = __shfl_sync(full, e, src);
+            const int pos = __popc(__ballot_sync(full, lane < 11 && te >= ev));
+            const double up_te = __shfl_up_sync(full, te, 1);
+            const int up_ti = __shfl_up_sync(full, ti, 1);
+            if (lane == pos) { te = ev; ti = j0 + src; }
+            else if (lane > pos) { te = up_te; ti = up_ti; }
+            t11 = __shfl_sync(full, te, 10);
+        }
+        __syncwarp();
+    }
+}
+
+// The rest of fit_quad() once the maxima list of a cluster is known (one warp): threshold on the list, the <= 21 prefix-moment
+// entries rebuilt from checkpoints, pair table, 4-corner search, corners, area / convexity tests, output.
+__device__ __forceinline__ void fq_finish(FqWarp &S, double te, int ti, int nm, int n, int b, const ClusterRec &rec, size_t pbase,
+                                          const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const double *__restrict__ cp_all,
+                                          QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
+                                          uint32_t *__restrict__ errflag, const Geom &g, const Caps &caps, const DetParams &prm, int lane)
+{
+    const int tid = lane;
+    const uint32_t full = 0xffffffffu;
+    const int reversed_border = 0;          // reversed clusters never get past the sort (tag36h11 has a normal border only)
+    if (nm < 4) return;
+    const int max_nmaxima = min(prm.max_nmaxima, 10);
+    bool keep;
+    if (nm > max_nmaxima) {
+        const double thresh = __shfl_sync(full, te, max_nmaxima);
+        keep = lane < max_nmaxima && te > thresh;
+    } else {
+        keep = lane < nm;
+    }
+    const uint32_t kb = __ballot_sync(full, keep);
+    const int nk = __popc(kb);
+    {
+        int rank = 0;
+        for (int q = 0; q < 11; q++) {
+            const int oi = __shfl_sync(full, ti, q);
+            if ((kb >> q) & 1) rank += oi < ti ? 1 : 0;
+        }
+        if (keep) S.kept[rank] = ti;
+    }
+    __syncwarp();
+    if (nk < 4) return;   // (upstream's loops would simply find nothing)
+
+    // ---- the prefix-moment entries the corner search reads: lfps[kept[m]], lfps[kept[m] - 1], lfps[n - 1] ----
+    if (tid <= 2 * nk) {
+        const int idx = tid == 2 * nk ? n - 1 : S.kept[tid >> 1] - (tid & 1);
+        if (idx >= 0) {
+            double acc[6];
+            replay_entry(in + (size_t)b * g.frame_stride, sorted_xy + pbase, cp_all + (pbase / LF_CP) * 6, idx, g, acc);
+            M6 &e = S.ent[tid];
+            e.Mx = acc[0]; e.My = acc[1]; e.Mxx = acc[2]; e.Mxy = acc[3]; e.Myy = acc[4]; e.W = acc[5];
+        }
+    }
+    __syncwarp();
+    // pair table: fit_line(lfps, n, kept[a], kept[c]) for a != c
+    for (int t = tid; t < nk * nk; t += 32) {
+        const int a = t / nk, c = t % nk;
+        if (a == c) continue;
+        const int i0 = S.kept[a], i1 = S.kept[c];
+        LineFit lf;
+        if (i0 < i1) fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], i0 > 0 ? 1 : 0, i1 - i0 + 1, true, lf);
+        else fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], 2, n - i0 + i1 + 1, true, lf);
+        S.p_err[a][c] = lf.err; S.p_mse[a][c] = lf.mse; S.p_nx[a][c] = lf.nx; S.p_ny[a][c] = lf.ny;
+        S.p_ex[a][c] = lf.Ex; S.p_ey[a][c] = lf.Ey;
+    }
+    __syncwarp();
+    // 4-corner search; (m0,m1,m2,m3) packed big-endian orders like upstream's loop nest, so the minimum over
+    // (err, packed) is upstream's "first minimum"
+    double best_err = __longlong_as_double(0x7ff0000000000000ll);
+    int best_combo = 1 << 30;
+    {
+        const double max_mse = (double)prm.max_line_fit_mse;
+        const int ncomb = nk * (nk - 1) * (nk - 2) * (nk - 3) / 24;
+        for (int ci = tid; ci < ncomb; ci += 32) {
+            const int pk = c_combos[ci];
+            const int m0 = pk >> 12, m1 = (pk >> 8) & 15, m2 = (pk >> 4) & 15, m3 = pk & 15;
+            if (S.p_mse[m0][m1] > max_mse) continue;
+            if (S.p_mse[m1][m2] > max_mse) continue;
+            const double dt = S.p_nx[m0][m1] * S.p_nx[m1][m2] + S.p_ny[m0][m1] * S.p_ny[m1][m2];
+            if (fabs(dt) > prm.cos_critical_rad) continue;
+            if (S.p_mse[m2][m3] > max_mse) continue;
+            if (S.p_mse[m3][m0] > max_mse) continue;
+            const double err = S.p_err[m0][m1] + S.p_err[m1][m2] + S.p_err[m2][m3] + S.p_err[m3][m0];
+            if (err < best_err || (err == best_err && pk < best_combo)) { best_err = err; best_combo = pk; }
+        }
+    }
+    {
+        double bmin = best_err;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(full, bmin, o); bmin = ob < bmin ? ob : bmin; }
+        int cand = (best_err == bmin && best_combo != (1 << 30)) ? best_combo : (1 << 30);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(full, cand, o));
+        best_err = bmin; best_combo = cand;
+    }
+    if (best_combo == (1 << 30)) return;
+    if (!(best_err / n < (double)prm.max_line_fit_mse)) return;
+
+    // ---- corners (four lanes), area and convexity tests (one lane) -----------------------------------------------
+    const int mi[4] = {(best_combo >> 12) & 15, (best_combo >> 8) & 15, (best_combo >> 4) & 15, best_combo & 15};
+    bool bad = false;
+    if (tid < 4) {
+        const int a = mi[tid], c = mi[(tid + 1) & 3];
+        S.lines[tid][0] = S.p_ex[a][c]; S.lines[tid][1] = S.p_ey[a][c]; S.lines[tid][2] = S.p_nx[a][c]; S.lines[tid][3] = S.p_ny[a][c];
+        bad = S.p_mse[a][c] > (double)prm.max_line_fit_mse;
+    }
+    if (__any_sync(full, bad)) return;
+    if (tid < 4) {
+        const int i = tid;
+        const double A00 = S.lines[i][3], A01 = -S.lines[(i + 1) & 3][3];
+        const double A10 = -S.lines[i][2], A11 = S.lines[(i + 1) & 3][2];
+        const double B0 = -S.lines[i][0] + S.lines[(i + 1) & 3][0];
+        const double B1 = -S.lines[i][1] + S.lines[(i + 1) & 3][1];
+        const double det = A00 * A11 - A10 * A01;
+        const double W00 = A11 / det, W01 = -A01 / det;
+        if (fabs(det) < 0.001) bad = true;
+        else {
+            const double L0 = W00 * B0 + W01 * B1;
+            S.qp[i][0] = (float)(S.lines[i][0] + L0 * A00);
+            S.qp[i][1] = (float)(S.lines[i][1] + L0 * A10);
+        }
+    }
+    if (__any_sync(full, bad)) return;
+    if (tid == 0) {
+        float qp[4][2];
+        for (int i = 0; i < 4; i++) { qp[i][0] = S.qp[i][0]; qp[i][1] = S.qp[i][1]; }
+        bool good = true;
+        if (good) {
+            double area = 0, length[3], p;
+            for (int i = 0; i < 3; i++) {
+                const int a = i, c = (i + 1) % 3;
+                const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
+                length[i] = sqrt(ddx * ddx + ddy * ddy);
+            }
+            p = (length[0] + length[1] + length[2]) / 2;
+            area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
+            const int idxs[4] = {2, 3, 0, 2};
+            for (int i = 0; i < 3; i++) {
+                const int a = idxs[i], c = idxs[i + 1];
+                const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
+                length[i] = sqrt(ddx * ddx + ddy * ddy);
+            }
+            p = (length[0] + length[1] + length[2]) / 2;
+            area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
+            if (area < 0.95 * prm.min_tag_width * prm.min_tag_width) good = false;
+        }
+        if (good) {
+            for (int i = 0; i < 4; i++) {
+                const int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
+                const double dx1 = (double)qp[i1][0] - (double)qp[i0][0], dy1 = (double)qp[i1][1] - (double)qp[i0][1];
+                const double dx2 = (double)qp[i2][0] - (double)qp[i1][0], dy2 = (double)qp[i2][1] - (double)qp[i1][1];
+                const double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
+                if ((cos_dtheta > prm.cos_critical_rad || cos_dtheta < -prm.cos_critical_rad) || dx1 * dy2 < dy1 * dx2) { good = false; break; }
+            }
+        }
+        if (good) {
+            const uint32_t qf = atomicAdd(&nquads[b], 1u);
+            if (qf >= caps.quads_per_frame) atomicOr(errflag, ERR_QUADS_FULL);
+            else {
+                const uint32_t qi = atomicAdd(nquads_total, 1u);   // < batch * quads_per_frame by construction
+                QuadRec q;
+                for (int i = 0; i < 4; i++) { q.p[i][0] = qp[i][0]; q.p[i][1] = qp[i][1]; }
+                q.reversed_border = reversed_border; q.npoints = n; q.key = rec.key; q.frame = b; q.pad = 0;
+                quads[qi] = q;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FQ_WARPS * 32)
 fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const ClusterRec *__restrict__ clusters,
                  const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork /* stride 2, 4 tiers */,
                  uint32_t *__restrict__ work_counter, const double *__restrict__ errs_all, const double *__restrict__ cp_all,
                  QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
-                 uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm)
+                 uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm, int n_big)
 {
     __shared__ FqWarp sh[FQ_WARPS];
-    const int lane = threadIdx.x & 31, tid = lane;
+    const int lane = threadIdx.x & 31;
     const uint32_t full = 0xffffffffu;
     FqWarp &S = sh[threadIdx.x >> 5];
-    const int reversed_border = 0;          // reversed clusters never get past sort #1 (tag36h11 has a normal border only)
     for (;;) {
         __syncwarp();
         uint32_t wi = 0;
@@ -146,202 +353,80 @@ fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ so
         if (!tier_item<0, 3>(wi, nwork, worklists, wl_stride, item)) return;
         const int b = item / caps.clusters_per_frame;
         const ClusterRec rec = clusters[item];
-        if (rec.cursor == 0xffffffffu || rec.count < 24) continue;
+        if (rec.cursor == 0xffffffffu || rec.count < 24 || (int)rec.count >= n_big) continue;      // (>= n_big: fit_quads_big_kernel)
         const int n = (int)rec.count;
         const int ksz = min(20, n / 12);
         if (ksz < 2) continue;
         const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
-        const double *errs = errs_all + pbase;
-
-        // ---- smoothed errors, local maxima, running top list (descending error; ties: lower index first) ----
-        double te = __longlong_as_double(0xfff0000000000000ll), t11 = te;     // t11: error of the 11th list entry (-inf while the list is short)
+        double te = __longlong_as_double(0xfff0000000000000ll);
         int ti = 1 << 30, nm = 0;
-        // tile loads run one step ahead of their use (the errs array comes from L2 / HBM)
-        auto load_err = [&](int idx) { if (idx < 0) idx += n; while (idx >= n) idx -= n; return errs[idx]; };
-        double pre0 = load_err(-4 + lane), pre1 = lane < 8 ? load_err(-4 + 32 + lane) : 0.0;
-        for (int j0 = 0; j0 < n; j0 += 32) {
-            S.et[lane] = pre0;
-            if (lane < 8) S.et[32 + lane] = pre1;
-            if (j0 + 32 < n) {
-                pre0 = load_err(j0 + 32 - 4 + lane);
-                if (lane < 8) pre1 = load_err(j0 + 32 - 4 + 32 + lane);
-            }
-            __syncwarp();
-            for (int u = lane; u < 34; u += 32) {
-                double acc = 0;
-#pragma unroll
-                for (int i = 0; i < 7; i++) acc += S.et[u + i] * prm.smooth_f[i];
-                S.ys[u] = acc;
-            }
-            __syncwarp();
-            bool is_max = false;
-            double e = 0;
-            if (j0 + lane < n) {
-                e = S.ys[lane + 1];
-                is_max = e > S.ys[lane + 2] && e > S.ys[lane];
-            }
-            nm += __popc(__ballot_sync(full, is_max));
-            // only maxima above the current 11th best can enter the list (an equal error with a later index cannot)
-            uint32_t bal = __ballot_sync(full, is_max && e > t11);
-            while (bal) {
-                const int src = __ffs(bal) - 1;
-                bal &= bal - 1;
-                const double ev = __shfl_sync(full, e, src);
+        fq_scan(S.et, S.ys, errs_all + pbase, n, 0, n, prm, lane, te, ti, nm);
+        fq_finish(S, te, ti, nm, n, b, rec, pbase, in, sorted_xy, cp_all, quads, nquads, nquads_total, errflag, g, caps, prm, lane);
+    }
+}
+
+// ONE CTA per LARGE cluster (small batches): the scan over the window errors is the part of fit_quads_kernel that grows with the
+// cluster (0.65 us per 32 points, 100 us for 5 000 points).  Eight warps scan an eighth each, every warp keeps its own list of the best
+// 11 maxima; warp 0 merges the lists by inserting the candidates in warp order -- within a warp's list equal errors are already in
+// index order and lower warps hold lower indices, so the merged list is the one a single scan builds -- and finishes the cluster.
+constexpr int FQB_WARPS = 8;
+struct FqBig {
+    FqWarp w0;
+    double et[FQB_WARPS][40], ys[FQB_WARPS][34];
+    double lte[FQB_WARPS][11];
+    int lti[FQB_WARPS][11], lnm[FQB_WARPS];
+    uint32_t work;
+};
+template <int T_LO>
+__global__ void __launch_bounds__(FQB_WARPS * 32)
+fit_quads_big_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const ClusterRec *__restrict__ clusters,
+                     const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork /* stride 2, 4 tiers */,
+                     uint32_t *__restrict__ work_counter, const double *__restrict__ errs_all, const double *__restrict__ cp_all,
+                     QuadRec *__restrict__ quads, uint32_t *__restrict__ nquads, uint32_t *__restrict__ nquads_total,
+                     uint32_t *__restrict__ errflag, Geom g, Caps caps, DetParams prm, int n_big)
+{
+    extern __shared__ __align__(16) unsigned char fqb_smem[];
+    FqBig &S = *reinterpret_cast<FqBig *>(fqb_smem);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t full = 0xffffffffu;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) S.work = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        uint32_t item;
+        if (!tier_item<T_LO, 3>(S.work, nwork, worklists, wl_stride, item)) return;
+        const int b = item / caps.clusters_per_frame;
+        const ClusterRec rec = clusters[item];
+        if (rec.cursor == 0xffffffffu || (int)rec.count < n_big || rec.count < 24) continue;
+        const int n = (int)rec.count;
+        const size_t pbase = (size_t)b * caps.points_per_frame + rec.offset;
+        const int seg = ((n + FQB_WARPS - 1) / FQB_WARPS + 31) / 32 * 32;
+        const int ja = min(wid * seg, n), jb = min(ja + seg, n);
+        double te = __longlong_as_double(0xfff0000000000000ll);
+        int ti = 1 << 30, nm = 0;
+        if (ja < jb) fq_scan(S.et[wid], S.ys[wid], errs_all + pbase, n, ja, jb, prm, lane, te, ti, nm);
+        if (lane < 11) { S.lte[wid][lane] = te; S.lti[wid][lane] = ti; }
+        if (lane == 0) S.lnm[wid] = nm;
+        __syncthreads();
+        if (wid != 0) continue;
+        // merge: warp 0's own list is the start; the others' entries are inserted in warp order, best first
+        for (int w = 1; w < FQB_WARPS; w++) {
+            nm += S.lnm[w];
+            for (int q = 0; q < 11; q++) {
+                const int ci = S.lti[w][q];
+                if (ci == (1 << 30)) break;                       // the rest of this list is empty
+                const double ev = S.lte[w][q];
+                const double t11 = __shfl_sync(full, te, 10);
+                if (!(ev > t11)) break;                           // (the list is descending: nothing further down can enter either)
                 const int pos = __popc(__ballot_sync(full, lane < 11 && te >= ev));
                 const double up_te = __shfl_up_sync(full, te, 1);
                 const int up_ti = __shfl_up_sync(full, ti, 1);
-                if (lane == pos) { te = ev; ti = j0 + src; }
+                if (lane == pos) { te = ev; ti = ci; }
                 else if (lane > pos) { te = up_te; ti = up_ti; }
-                t11 = __shfl_sync(full, te, 10);
-            }
-            __syncwarp();
-        }
-        if (nm < 4) continue;
-        const int max_nmaxima = min(prm.max_nmaxima, 10);
-        bool keep;
-        if (nm > max_nmaxima) {
-            const double thresh = __shfl_sync(full, te, max_nmaxima);
-            keep = lane < max_nmaxima && te > thresh;
-        } else {
-            keep = lane < nm;
-        }
-        const uint32_t kb = __ballot_sync(full, keep);
-        const int nk = __popc(kb);
-        {
-            int rank = 0;
-            for (int q = 0; q < 11; q++) {
-                const int oi = __shfl_sync(full, ti, q);
-                if ((kb >> q) & 1) rank += oi < ti ? 1 : 0;
-            }
-            if (keep) S.kept[rank] = ti;
-        }
-        __syncwarp();
-        if (nk < 4) continue;   // (upstream's loops would simply find nothing)
-
-        // ---- the prefix-moment entries the corner search reads: lfps[kept[m]], lfps[kept[m] - 1], lfps[n - 1] ----
-        if (tid <= 2 * nk) {
-            const int idx = tid == 2 * nk ? n - 1 : S.kept[tid >> 1] - (tid & 1);
-            if (idx >= 0) {
-                double acc[6];
-                replay_entry(in + (size_t)b * g.frame_stride, sorted_xy + pbase, cp_all + (pbase / LF_CP) * 6, idx, g, acc);
-                M6 &e = S.ent[tid];
-                e.Mx = acc[0]; e.My = acc[1]; e.Mxx = acc[2]; e.Mxy = acc[3]; e.Myy = acc[4]; e.W = acc[5];
             }
         }
-        __syncwarp();
-        // pair table: fit_line(lfps, n, kept[a], kept[c]) for a != c
-        for (int t = tid; t < nk * nk; t += 32) {
-            const int a = t / nk, c = t % nk;
-            if (a == c) continue;
-            const int i0 = S.kept[a], i1 = S.kept[c];
-            LineFit lf;
-            if (i0 < i1) fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], i0 > 0 ? 1 : 0, i1 - i0 + 1, true, lf);
-            else fit_line_m(S.ent[2 * c], S.ent[2 * a + 1], S.ent[2 * nk], 2, n - i0 + i1 + 1, true, lf);
-            S.p_err[a][c] = lf.err; S.p_mse[a][c] = lf.mse; S.p_nx[a][c] = lf.nx; S.p_ny[a][c] = lf.ny;
-            S.p_ex[a][c] = lf.Ex; S.p_ey[a][c] = lf.Ey;
-        }
-        __syncwarp();
-        // 4-corner search; (m0,m1,m2,m3) packed big-endian orders like upstream's loop nest, so the minimum over
-        // (err, packed) is upstream's "first minimum"
-        double best_err = __longlong_as_double(0x7ff0000000000000ll);
-        int best_combo = 1 << 30;
-        {
-            const double max_mse = (double)prm.max_line_fit_mse;
-            const int ncomb = nk * (nk - 1) * (nk - 2) * (nk - 3) / 24;
-            for (int ci = tid; ci < ncomb; ci += 32) {
-                const int pk = c_combos[ci];
-                const int m0 = pk >> 12, m1 = (pk >> 8) & 15, m2 = (pk >> 4) & 15, m3 = pk & 15;
-                if (S.p_mse[m0][m1] > max_mse) continue;
-                if (S.p_mse[m1][m2] > max_mse) continue;
-                const double dt = S.p_nx[m0][m1] * S.p_nx[m1][m2] + S.p_ny[m0][m1] * S.p_ny[m1][m2];
-                if (fabs(dt) > prm.cos_critical_rad) continue;
-                if (S.p_mse[m2][m3] > max_mse) continue;
-                if (S.p_mse[m3][m0] > max_mse) continue;
-                const double err = S.p_err[m0][m1] + S.p_err[m1][m2] + S.p_err[m2][m3] + S.p_err[m3][m0];
-                if (err < best_err || (err == best_err && pk < best_combo)) { best_err = err; best_combo = pk; }
-            }
-        }
-        {
-            double bmin = best_err;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { const double ob = __shfl_xor_sync(full, bmin, o); bmin = ob < bmin ? ob : bmin; }
-            int cand = (best_err == bmin && best_combo != (1 << 30)) ? best_combo : (1 << 30);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(full, cand, o));
-            best_err = bmin; best_combo = cand;
-        }
-        if (best_combo == (1 << 30)) continue;
-        if (!(best_err / n < (double)prm.max_line_fit_mse)) continue;
-
-        // ---- corners (four lanes), area and convexity tests (one lane) -----------------------------------------------
-        const int mi[4] = {(best_combo >> 12) & 15, (best_combo >> 8) & 15, (best_combo >> 4) & 15, best_combo & 15};
-        bool bad = false;
-        if (tid < 4) {
-            const int a = mi[tid], c = mi[(tid + 1) & 3];
-            S.lines[tid][0] = S.p_ex[a][c]; S.lines[tid][1] = S.p_ey[a][c]; S.lines[tid][2] = S.p_nx[a][c]; S.lines[tid][3] = S.p_ny[a][c];
-            bad = S.p_mse[a][c] > (double)prm.max_line_fit_mse;
-        }
-        if (__any_sync(full, bad)) continue;
-        if (tid < 4) {
-            const int i = tid;
-            const double A00 = S.lines[i][3], A01 = -S.lines[(i + 1) & 3][3];
-            const double A10 = -S.lines[i][2], A11 = S.lines[(i + 1) & 3][2];
-            const double B0 = -S.lines[i][0] + S.lines[(i + 1) & 3][0];
-            const double B1 = -S.lines[i][1] + S.lines[(i + 1) & 3][1];
-            const double det = A00 * A11 - A10 * A01;
-            const double W00 = A11 / det, W01 = -A01 / det;
-            if (fabs(det) < 0.001) bad = true;
-            else {
-                const double L0 = W00 * B0 + W01 * B1;
-                S.qp[i][0] = (float)(S.lines[i][0] + L0 * A00);
-                S.qp[i][1] = (float)(S.lines[i][1] + L0 * A10);
-            }
-        }
-        if (__any_sync(full, bad)) continue;
-        if (tid == 0) {
-            float qp[4][2];
-            for (int i = 0; i < 4; i++) { qp[i][0] = S.qp[i][0]; qp[i][1] = S.qp[i][1]; }
-            bool good = true;
-            if (good) {
-                double area = 0, length[3], p;
-                for (int i = 0; i < 3; i++) {
-                    const int a = i, c = (i + 1) % 3;
-                    const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
-                    length[i] = sqrt(ddx * ddx + ddy * ddy);
-                }
-                p = (length[0] + length[1] + length[2]) / 2;
-                area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
-                const int idxs[4] = {2, 3, 0, 2};
-                for (int i = 0; i < 3; i++) {
-                    const int a = idxs[i], c = idxs[i + 1];
-                    const double ddx = (double)qp[c][0] - (double)qp[a][0], ddy = (double)qp[c][1] - (double)qp[a][1];
-                    length[i] = sqrt(ddx * ddx + ddy * ddy);
-                }
-                p = (length[0] + length[1] + length[2]) / 2;
-                area += sqrt(p * (p - length[0]) * (p - length[1]) * (p - length[2]));
-                if (area < 0.95 * prm.min_tag_width * prm.min_tag_width) good = false;
-            }
-            if (good) {
-                for (int i = 0; i < 4; i++) {
-                    const int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
-                    const double dx1 = (double)qp[i1][0] - (double)qp[i0][0], dy1 = (double)qp[i1][1] - (double)qp[i0][1];
-                    const double dx2 = (double)qp[i2][0] - (double)qp[i1][0], dy2 = (double)qp[i2][1] - (double)qp[i1][1];
-                    const double cos_dtheta = (dx1 * dx2 + dy1 * dy2) / sqrt((dx1 * dx1 + dy1 * dy1) * (dx2 * dx2 + dy2 * dy2));
-                    if ((cos_dtheta > prm.cos_critical_rad || cos_dtheta < -prm.cos_critical_rad) || dx1 * dy2 < dy1 * dx2) { good = false; break; }
-                }
-            }
-            if (good) {
-                const uint32_t qf = atomicAdd(&nquads[b], 1u);
-                if (qf >= caps.quads_per_frame) atomicOr(errflag, ERR_QUADS_FULL);
-                else {
-                    const uint32_t qi = atomicAdd(nquads_total, 1u);   // < batch * quads_per_frame by construction
-                    QuadRec q;
-                    for (int i = 0; i < 4; i++) { q.p[i][0] = qp[i][0]; q.p[i][1] = qp[i][1]; }
-                    q.reversed_border = reversed_border; q.npoints = n; q.key = rec.key; q.frame = b; q.pad = 0;
-                    quads[qi] = q;
-                }
-            }
-        }
+        if (min(20, n / 12) < 2) continue;
+        fq_finish(S.w0, te, ti, nm, n, b, rec, pbase, in, sorted_xy, cp_all, quads, nquads, nquads_total, errflag, g, caps, prm, lane);
     }
 }
 
