@@ -235,6 +235,31 @@ def test_threshold_shape_timing_keeps_the_map(oracle, monkeypatch):
     det.close()
 
 
+def test_graph_replay_of_the_single_frame_pipeline(oracle):
+    """From its second call with one geometry on, a small batch runs as ONE captured CUDA graph (api.cu detect_device_chunk): every
+    replay, on different frame contents, gives the oracle's detections; changing a parameter drops the graphs and takes effect."""
+    frames, _ = synth.render_batch(1280, 720, 5, 4, seed=21, unique=5, edge_px=(60, 150))
+    det = make_detector(1280, 720, 1)
+    for k in (0, 1, 2, 3, 4, 1):
+        out, counts = det.detect_batch(frames[k][None])
+        assert_same_detections(out[0, :counts[0]], oracle.detect(frames[k]))
+    t = det.timing()
+    assert t["total_ms"] > 0 and t["kernel_launches"] >= 20            # the graph keeps the launch count it was captured with
+    # bits_corrected is a kernel parameter baked into the graph: a tag with two flipped bits decodes at 3, not at 1
+    frame, truth = synth.render_frame(1280, 720, 3, seed=5, edge_px=(80, 150), bit_errors=2)
+    for _ in range(3):
+        out, counts = det.detect_batch(frame[None])
+    ref3 = oracle.detect(frame)
+    assert_same_detections(out[0, :counts[0]], ref3)
+    assert det._L.cb_set_family_tag36h11(det.ctx, 1) == 0
+    for _ in range(3):
+        out, counts = det.detect_batch(frame[None])
+    ref1 = oracle.detect(frame, oracle.default_params(bits_corrected=1))
+    assert_same_detections(out[0, :counts[0]], ref1)
+    assert len(ref1) < len(ref3)
+    det.close()
+
+
 def test_c3_full_resolution_small_tags(oracle):
     frame, truth = synth.render_frame(4608, 2592, 40, seed=4, edge_px=(40, 300), small_tags=10)
     det = make_detector(4608, 2592, 1, 256)
