@@ -586,6 +586,7 @@ static ThrChoice threshold_plan(cb_ctx *ctx, const uint8_t *d_frames, const Geom
             cudaEventDestroy(e0); cudaEventDestroy(e1);
         }
     }
+    if (getenv("CB_THR_VERBOSE")) fprintf(stderr, "chalkydri_b200: threshold plan %dx%d x %d: CB_THR_CFG=%d CB_THR_YSEGS=%d\n", g.W, g.H, g.batch, best.variant, best.ysegs);
     ctx->thr_plans[key] = best;
     return best;
 }

@@ -11,10 +11,12 @@ timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-c2 --no-
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launch_list_bench_py.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-c2 --no-c4 --no-sqpnp --latency-iters 0 > gpurun_out/r02_ncu_bench.log 2>&1
 python tools/launch_table.py gpurun_out/r02_launch_list_bench_py.csv 24 > gpurun_out/r02_launch_list_bench_py.txt 2>&1; tail -28 gpurun_out/r02_launch_list_bench_py.txt
-# the threshold launch of the pipeline: count the launches (shape timing first), then capture the last one with --set full
-timeout 300 python tools/profile_run.py 256 2 c1 > gpurun_out/p.log 2>&1 || exit 1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:threshold_tm" --csv --log-file gpurun_out/r02_thr_launches.csv python tools/profile_run.py 256 2 c1 > gpurun_out/ncu.log 2>&1
-N=$(grep -c "threshold_tm" gpurun_out/r02_thr_launches.csv); echo "threshold launches: $N"
-timeout 600 ncu --set full --import-source on --clock-control none -k "regex:threshold_tm" --launch-skip $((N - 1)) -c 1 -o gpurun_out/r02_thr -f python tools/profile_run.py 256 2 c1 > gpurun_out/ncu.log 2>&1
+# the threshold launch of the pipeline.  The per-geometry shape timing must not run under the profiler (ncu serialises and replays
+# the timed launches, so it would pick a shape by profiler overhead): take the shape an unprofiled run chooses and pin it.
+CB_THR_VERBOSE=1 timeout 300 python tools/profile_run.py 256 2 c1 > gpurun_out/p.log 2> gpurun_out/r02_thr_plan.txt || exit 1
+grep "threshold plan" gpurun_out/r02_thr_plan.txt
+export $(grep -o "CB_THR_CFG=[0-9]*" gpurun_out/r02_thr_plan.txt | tail -1) $(grep -o "CB_THR_YSEGS=[0-9]*" gpurun_out/r02_thr_plan.txt | tail -1)
+echo "pinned: CB_THR_CFG=$CB_THR_CFG CB_THR_YSEGS=$CB_THR_YSEGS"
+timeout 600 ncu --set full --import-source on --clock-control none -k "regex:threshold_tm" -c 1 -o gpurun_out/r02_thr -f python tools/profile_run.py 256 2 c1 > gpurun_out/ncu.log 2>&1
 python tools/ncu_summary.py gpurun_out/r02_thr.ncu-rep threshold --traffic c1 256 "ncu --set full of the pipeline's threshold launch on 256 x 1280x720 (profiles/r02_ncu_threshold.txt): (dram read + write) / 256 frames" > gpurun_out/r02_ncu_threshold.txt 2>&1; cat gpurun_out/r02_ncu_threshold.txt
 cp profiles/threshold_traffic.json gpurun_out/r02_threshold_traffic.json
