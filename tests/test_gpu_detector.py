@@ -224,7 +224,9 @@ def test_every_threshold_kernel_shape_bit_exact(oracle, monkeypatch, cfg):
 
 
 def test_threshold_shape_timing_keeps_the_map(oracle, monkeypatch):
-    """Large batches time the kernel shapes once per geometry (threshold_plan): whatever shape wins, the map is the oracle's."""
+    """CB_THR_TUNE=1 times the kernel shapes once per geometry on large batches (threshold_plan): whatever shape wins, the map is the
+    oracle's."""
+    monkeypatch.setenv("CB_THR_TUNE", "1")
     monkeypatch.delenv("CB_THR_CFG", raising=False)
     monkeypatch.delenv("CB_THR_YSEGS", raising=False)
     frames, _ = synth.render_batch(1280, 720, 48, 4, seed=77, unique=3, edge_px=(60, 150))        # 44 MB: above the timing threshold

@@ -45,6 +45,15 @@ def run(rank, local, world, dist, reps=3, total=TOTAL):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the wait around the single-process pool phase must not touch the GPUs: an NCCL barrier parks a spinning kernel on every waiting
+    # rank's GPU, which the pool is using at that moment (measured: the pool's second GPU took 84 ms instead of 42)
+    cpu_group = dist.new_group(backend="gloo") if dist is not None else None
+
+    def cpu_barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(group=cpu_group)
+
     def rmax(x):
         if dist is None:
             return x
@@ -98,7 +107,7 @@ def run(rank, local, world, dist, reps=3, total=TOTAL):
     capi.free_pinned(h)
     del g_out, g_counts
     shared.close()
-    barrier()
+    cpu_barrier()
     if rank == 0:
         shared.unlink()
         # single process, one thread + context per GPU (cb_pool_detect_gray); the other ranks wait at the barrier below
@@ -129,7 +138,7 @@ def run(rank, local, world, dist, reps=3, total=TOTAL):
             capi.free_pinned(hp)
         except Exception as e:                           # noqa: BLE001
             res["single_process_pool"] = {"error": f"{type(e).__name__}: {e}"}
-    barrier()
+    cpu_barrier()
     return res
 
 
