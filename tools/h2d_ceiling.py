@@ -61,13 +61,9 @@ res = {"n_gpus": world, "cpus": os.cpu_count()}
 for label, pin in (("default_affinity", False), ("gpu_local_affinity", True)):
     note = ""
     if pin:
-        try:
-            import pynvml as nv
-            nv.nvmlInit()
-            nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByPciBusId(torch.cuda.get_device_properties(local).pci_bus_id.encode()))
-            note = f"{len(os.sched_getaffinity(0))} cpus"
-        except Exception as e:            # noqa: BLE001
-            note = f"not set: {type(e).__name__}: {e}"
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from bench import set_gpu_local_affinity             # the same binding bench.py's ranks use
+        note = set_gpu_local_affinity(local)
     res[label] = {"affinity": note, "c1_236MB": measure(256 * 1280 * 720), "c2_405MB": measure(256 * 1456 * 1088)}
 if rank == 0:
     print(json.dumps(res), flush=True)
