@@ -14,6 +14,7 @@ their own batch (weak scaling, no collective on the data path).
   also_c2      : the same arms on BASELINE.json configs[1] (256 x 1456x1088, 8 tags), with the per-stage times
   c4_stream    : BASELINE.json configs[3] (4096 x 1280x800 frames sharded over the N GPUs, lists gathered to one host array)
   sqpnp_1M     : BASELINE.json configs[4] (1 M pose problems), N = 1 only
+  cat_703x905  : the reference's own benchmark shape (crates/chalkydri-apriltags/bench.rs: Detector::new(703, 905) + process_frame), N = 1 only
   p50_frame_latency_ms : one 1280x720 frame through the reference-shaped call (host frame in, list out)
 
 Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -339,6 +340,7 @@ def main():
     ap.add_argument("--no-c2", action="store_true", help="skip the configs[1] measurement")
     ap.add_argument("--no-c4", action="store_true", help="skip the configs[3] stream")
     ap.add_argument("--no-sqpnp", action="store_true", help="skip the configs[4] measurement")
+    ap.add_argument("--no-cat", action="store_true", help="skip the CAT process_frame measurement (the reference's own benchmark shape)")
     ap.add_argument("--latency-iters", type=int, default=50)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -450,6 +452,14 @@ def main():
         except Exception as e:                            # noqa: BLE001
             sq = {"error": f"{type(e).__name__}: {e}"}
 
+    cat = None
+    if rank == 0 and world == 1 and not args.no_cat:
+        try:
+            from tools import bench_cat
+            cat = bench_cat.run(iters=30, cpu_iters=0 if args.no_cpu_baseline else 2)
+        except Exception as e:                            # noqa: BLE001
+            cat = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         peaks = {}
         try:
@@ -490,7 +500,7 @@ def main():
             "wall_ms_per_step_device_arm": m1["wall_dev"] / args.steps * 1e3,
             "p50_frame_latency_ms": p50,
             "detections_per_step": m1["ndet"], "expected_tags_per_step": m1["want"],
-            "also_c2": also_c2, "c4_stream": c4, "sqpnp_1M": sq,
+            "also_c2": also_c2, "c4_stream": c4, "sqpnp_1M": sq, "cat_703x905": cat,
         }
         if cpu:
             line["cpu_baseline"] = cpu
