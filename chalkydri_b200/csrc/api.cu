@@ -752,7 +752,11 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
                 static const bool dense_off = getenv("CB_BAND_PREFIX") && strcmp(getenv("CB_BAND_PREFIX"), "walk") == 0;      // A/B hook
                 if (!dense_off && cells * sizeof(uint32_t) <= ((size_t)48 << 20)) {
                     if (ctx->band_dense_cells < cells) {
-                        if (ctx->d_band_dense) { CK(cudaStreamSynchronize(st)); cudaFree(ctx->d_band_dense); ctx->d_band_dense = nullptr; ctx->band_dense_cells = 0; }
+                        if (ctx->d_band_dense) {
+                            CK(cudaStreamSynchronize(st));
+                            cudaFree(ctx->d_band_dense); ctx->d_band_dense = nullptr; ctx->band_dense_cells = 0;
+                            drop_graphs(ctx);       // graphs captured for other geometries hold the old address
+                        }
                         CK(cudaMalloc((void **)&ctx->d_band_dense, cells * sizeof(uint32_t)));
                         ctx->band_dense_cells = cells;
                     }
