@@ -766,7 +766,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             }
             cluster_band_resolve_kernel<<<(nall + CLB_WARPS - 1) / CLB_WARPS, CLB_WARPS * 32, 0, st>>>(ctx->d_table, ctx->d_areas, d_pool, g, caps, bp, d_dense);
             if (d_dense) {
-                cluster_band_prefix_dense_kernel<<<dim3((caps.clusters_per_frame + 127) / 128, B), 128, 0, st>>>(d_dense, ctx->d_clusters, d_ncl, d_pool, caps, bp);
+                cluster_band_prefix_dense_kernel<<<dim3((caps.clusters_per_frame + 31) / 32, B), 128, 0, st>>>(d_dense, ctx->d_clusters, d_ncl, d_pool, caps, bp);
                 launches++;
             }
             cluster_band_prefix_kernel<<<B, CLB_CAP, ctx->d_cursors ? 0 : caps.clusters_per_frame * sizeof(uint32_t), st>>>(ctx->d_areas, ctx->d_clusters, d_ncl,

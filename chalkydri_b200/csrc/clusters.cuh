@@ -499,24 +499,41 @@ cluster_band_resolve_kernel(const ClusterSlot *__restrict__ table, ClbArea *__re
 // of a column independent of each other (only the stored values form a chain), coalesced across clusters.  Only when no band of
 // the batch needed a chained sub-band (pool_counter == 0; otherwise the walk below does the work) and the matrix fits a fixed
 // budget (api.cu); the throughput configuration (256 frames, four-row bands) keeps the walk.
+// (128 threads = 32 clusters x 4 quarters of the band range: every thread sums its quarter, the quarters' sums give its start, then it
+// writes the running positions of its quarter -- twice the loads, a quarter of the chain.)
 __global__ void __launch_bounds__(128)
 cluster_band_prefix_dense_kernel(uint32_t *__restrict__ dense, const ClusterRec *__restrict__ clusters, const uint32_t *__restrict__ nclusters,
                                  const uint32_t *__restrict__ pool_counter, Caps caps, BandPlan bp)
 {
+    __shared__ uint32_t part[4][32];
     if (*pool_counter != 0) return;
-    const int b = blockIdx.y;
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= min(nclusters[b], caps.clusters_per_frame)) return;
-    uint32_t run = clusters[(size_t)b * caps.clusters_per_frame + c].offset;
+    const int b = blockIdx.y, lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const uint32_t c = blockIdx.x * 32 + lane;
+    const bool on = c < min(nclusters[b], caps.clusters_per_frame);
+    const int per = (bp.nbands + 3) / 4, j_lo = min(q * per, bp.nbands), j_hi = min(j_lo + per, bp.nbands);
     uint32_t *col = dense + (size_t)b * bp.nbands * caps.clusters_per_frame + c;
     constexpr int U = 16;
-    for (int j0 = 0; j0 < bp.nbands; j0 += U) {
+    uint32_t sum = 0;
+    if (on)
+        for (int j0 = j_lo; j0 < j_hi; j0 += U) {
+            uint32_t v[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) v[k] = j0 + k < j_hi ? col[(size_t)(j0 + k) * caps.clusters_per_frame] : 0u;
+#pragma unroll
+            for (int k = 0; k < U; k++) sum += v[k];
+        }
+    part[q][lane] = sum;
+    __syncthreads();
+    if (!on) return;
+    uint32_t run = clusters[(size_t)b * caps.clusters_per_frame + c].offset;
+    for (int k = 0; k < q; k++) run += part[k][lane];
+    for (int j0 = j_lo; j0 < j_hi; j0 += U) {
         uint32_t v[U];
 #pragma unroll
-        for (int k = 0; k < U; k++) v[k] = j0 + k < bp.nbands ? col[(size_t)(j0 + k) * caps.clusters_per_frame] : 0u;
+        for (int k = 0; k < U; k++) v[k] = j0 + k < j_hi ? col[(size_t)(j0 + k) * caps.clusters_per_frame] : 0u;
 #pragma unroll
         for (int k = 0; k < U; k++)
-            if (j0 + k < bp.nbands) { col[(size_t)(j0 + k) * caps.clusters_per_frame] = run; run += v[k]; }
+            if (j0 + k < j_hi) { col[(size_t)(j0 + k) * caps.clusters_per_frame] = run; run += v[k]; }
     }
 }
 
