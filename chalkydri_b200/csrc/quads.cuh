@@ -333,7 +333,9 @@ __device__ __forceinline__ void fq_finish(FqWarp &S, double te, int ti, int nm, 
     }
 }
 
-__global__ void __launch_bounds__(FQ_WARPS * 32)
+// (eight CTAs per SM: the register allocation is held to 64 -- 12 bytes of spills -- because the kernel is latency bound: 24 -> 32
+// warps per SM took 3 % off the quad stage; the decoder, with 450 bytes of spills at 64 registers, lost 3 % the same way)
+__global__ void __launch_bounds__(FQ_WARPS * 32, 8)
 fit_quads_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ sorted_xy, const ClusterRec *__restrict__ clusters,
                  const uint32_t *__restrict__ worklists, size_t wl_stride, const uint32_t *__restrict__ nwork /* stride 2, 4 tiers */,
                  uint32_t *__restrict__ work_counter, const double *__restrict__ errs_all, const double *__restrict__ cp_all,
