@@ -771,7 +771,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             }
             cluster_band_prefix_kernel<<<B, CLB_CAP, ctx->d_cursors ? 0 : caps.clusters_per_frame * sizeof(uint32_t), st>>>(ctx->d_areas, ctx->d_clusters, d_ncl,
                                                                                                                       ctx->d_cursors, caps, bp, d_dense ? d_pool : nullptr);
-            cluster_band_scatter_kernel<<<nall, 32, 0, st>>>(d_stage, ctx->d_areas, d_pool, ctx->d_scankey, g, caps, bp, d_dense);
+            cluster_band_scatter_kernel<<<(nall + CLB_SC_WARPS - 1) / CLB_SC_WARPS, CLB_SC_WARPS * 32, 0, st>>>(d_stage, ctx->d_areas, d_pool, ctx->d_scankey, g, caps, bp, d_dense);
             launches += 5;
         }
         if (g.h > 2 && g.w > 2 && ctx->cluster_mode == 1) {

@@ -585,15 +585,18 @@ cluster_band_prefix_kernel(ClbArea *__restrict__ areas, const ClusterRec *__rest
     }
 }
 
-// scatter: one warp per (sub-)band
-__global__ void __launch_bounds__(32)
+// scatter: one warp per (sub-)band, CLB_SC_WARPS independent warps per CTA (an SM holds at most 32 CTAs, so one-warp CTAs cap it at half
+// of its warps, and this pass waits on memory)
+constexpr int CLB_SC_WARPS = 4;
+__global__ void __launch_bounds__(CLB_SC_WARPS * 32)
 cluster_band_scatter_kernel(const uint32_t *__restrict__ stage, const ClbArea *__restrict__ areas, const uint32_t *__restrict__ pool_counter,
                             uint32_t *__restrict__ scankey, Geom g, Caps caps, BandPlan bp, const uint32_t *__restrict__ dense)
 {
-    __shared__ uint32_t cur[CLB_CAP];
-    const int lane = threadIdx.x;
+    __shared__ uint32_t cur_all[CLB_SC_WARPS][CLB_CAP];
+    uint32_t *cur = cur_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
     const uint32_t full = 0xffffffffu, lt = (1u << lane) - 1u;
-    const uint32_t a = blockIdx.x;
+    const uint32_t a = blockIdx.x * CLB_SC_WARPS + (threadIdx.x >> 5);
     const uint32_t nfirst = (uint32_t)g.batch * bp.nbands;
     if (a >= nfirst + min(*pool_counter, bp.pool_cap)) return;
     const ClbArea *A = areas + a;
