@@ -4,6 +4,7 @@
 set -x
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
+(timeout 300 python tests/fuzz_parity.py 120 11 | tail -3; timeout 300 python tests/fuzz_large.py 8 5 | tail -9) > gpurun_out/r02_fuzz_parity.log 2>&1; tail -1 gpurun_out/r02_fuzz_parity.log
 timeout 900 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo rc=$?
 timeout 600 python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_ref.err; echo rc=$?
 # launch list of bench.py itself (short form of the same command), only after it exited 0 without ncu
