@@ -38,7 +38,7 @@ static thread_local std::string g_create_error;
 struct ThrChoice { int variant, ysegs; };
 typedef std::tuple<int, int, int, int> ThrKey;      // W, H, stride, batch
 
-enum Stage { ST_THRESH = 1, ST_LABELS = 2, ST_QUADS = 3, ST_FULL = 4 };
+enum Stage { ST_THRESH = 1, ST_LABELS = 2, ST_QUADS = 3, ST_FULL = 4, ST_CLUSTERS = 10 /* stop after the cluster passes (tap) */ };
 
 struct cb_ctx {
     int device = 0;
@@ -786,6 +786,14 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             launches += 3;
         }
         CK(cudaEventRecord(ctx->ev[4], st));
+        if (stage == ST_CLUSTERS) {      // cb_clusters: the selected clusters with their points in scan order, before any sort touches them
+            CK(cudaEventRecord(ctx->ev[5], st));
+            CK(cudaEventRecord(ctx->ev[6], st));
+            CK(cudaGetLastError());
+            ctx->timing.kernel_launches = launches;
+            ctx->timing.threshold_launches = thr_launches;
+            return CB_OK;
+        }
         // ---- A5 quad fitting ----
         // sort #1 | sort #2 | prefix moments | fit, largest tier first inside each (long jobs).
         // misc: [8 + 2t] items of tier t; work counters: [16..20] sort #1, [21..25] sort #2, [26] moments, [27] fit
@@ -1493,6 +1501,43 @@ int cb_quads(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stri
         for (int b = 0; b < batch; b++) t += ctx->h_small[ctx->max_batch + b];
         *npoints_total = t;
     }
+    return CB_OK;
+}
+
+int cb_clusters(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, int16_t *pts,
+                int32_t *cluster_of, int64_t cap, int64_t *npoints, int32_t *nclusters)
+{
+    Geom g;
+    if (!pts || !cluster_of || !npoints || !nclusters || cap < 0) return CB_ERR_ARG;
+    int rc = tap_common(ctx, frames, width, height, stride, frame_stride, batch, ST_CLUSTERS, g);
+    if (rc) return rc;
+    rc = check_errflag(ctx);
+    if (rc) return rc;
+    const Caps &caps = ctx->caps;
+    int64_t k = 0;
+    int32_t cluster_base = 0;
+    for (int b = 0; b < batch; cluster_base += nclusters[b], b++) {
+        const uint32_t ncl = std::min(ctx->h_small[b], caps.clusters_per_frame);          // d_ncl[b]
+        nclusters[b] = (int32_t)ncl;
+        std::vector<ClusterRec> recs(ncl);
+        if (ncl) CK(cudaMemcpy(recs.data(), ctx->d_clusters + (size_t)b * caps.clusters_per_frame, ncl * sizeof(ClusterRec), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> keys;
+        for (uint32_t c = 0; c < ncl; c++) {
+            keys.resize(recs[c].count);
+            if (recs[c].count) CK(cudaMemcpy(keys.data(), ctx->d_scankey + (size_t)b * caps.points_per_frame + recs[c].offset, recs[c].count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            for (uint32_t i = 0; i < recs[c].count; i++, k++) {
+                if (k >= cap) continue;
+                // scan key (clusters.cuh): (pixel index << 3) | (probe << 1) | (v1 > v0); the point upstream stores for it (sort.cuh decode_point)
+                const uint32_t key = keys[i], pix = key >> 3;
+                const int d = (key >> 1) & 3, sgn = key & 1;
+                const int x = (int)(pix % (uint32_t)g.w), y = (int)(pix / (uint32_t)g.w);
+                const int dx = d == 2 ? -1 : (d == 1 ? 0 : 1), dy = d == 0 ? 0 : 1, dv = sgn ? 255 : -255;
+                pts[4 * k] = (int16_t)(2 * x + dx); pts[4 * k + 1] = (int16_t)(2 * y + dy); pts[4 * k + 2] = (int16_t)(dx * dv); pts[4 * k + 3] = (int16_t)(dy * dv);
+                cluster_of[k] = cluster_base + (int32_t)c;
+            }
+        }
+    }
+    *npoints = k;
     return CB_OK;
 }
 

@@ -236,6 +236,17 @@ class Detector:
         self._check(self._L.cb_decimated_size(self._ctx, W, H, C.byref(w), C.byref(h)))
         return w.value, h.value
 
+    def clusters(self, frames: np.ndarray, cap: int = 1 << 21):
+        """Stage tap of gradient_clusters(): (pts [n,4] int16 = x, y, gx, gy as upstream stores them, cluster_of [n], nclusters [B]);
+        the selected clusters only, points in upstream's append order."""
+        B, H, W = frames.shape
+        pts = np.zeros((cap, 4), np.int16); cl = np.zeros(cap, np.int32); ncl = np.zeros(B, np.int32)
+        n = C.c_int64()
+        self._check(self._L.cb_clusters(self._ctx, capi.ptr(frames), W, H, W, H * W, B, capi.ptr(pts), capi.ptr(cl), cap, C.byref(n), capi.ptr(ncl)))
+        if n.value > cap:
+            raise ChalkydriError(capi.CB_ERR_OVERFLOW, f"{n.value} points exceed the capacity {cap}")
+        return pts[:n.value], cl[:n.value], ncl
+
     def threshold(self, frames: np.ndarray) -> np.ndarray:
         B, H, W = frames.shape
         w, h = self.decimated_size(W, H)

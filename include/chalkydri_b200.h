@@ -129,6 +129,11 @@ int cb_threshold(cb_ctx *ctx, const uint8_t *frames, int width, int height, int 
 /* connected_components(): labels[batch][h][w] = smallest pixel index (y*w+x) of the component; sizes = its size */
 int cb_labels(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
               uint32_t *labels, uint32_t *sizes);
+/* gradient_clusters(): the clusters fit_quad() can accept (24 <= n <= 3(2w+2h) boundary points), every cluster's points in upstream's
+ * append order (scan order y, x, probe), before any sort.  pts[k] = (x, y, gx, gy) exactly as upstream stores a point (half-pixel
+ * coordinates 2x+dx, 2y+dy; gradient +-255 along the probe), cluster_of[k] = running cluster number over the batch (frame 0's clusters first; nclusters[b] per frame).  npoints = points the frames hold (may exceed cap: then only the first cap were written), nclusters[batch]. */
+int cb_clusters(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, int16_t *pts,
+                int32_t *cluster_of, int64_t cap, int64_t *npoints, int32_t *nclusters);
 /* fit_quads(): quads[batch][cap] corners in decimated coordinates (float[4][2]) + counts */
 int cb_quads(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
              float *quads, int cap, int32_t *counts, int64_t *npoints_total);

@@ -126,6 +126,8 @@ unsafe extern "C" {
                         out: *mut u8) -> c_int;
     pub fn cb_labels(ctx: *mut cb_ctx, frames: *const u8, width: c_int, height: c_int, stride: c_int, frame_stride: usize, batch: c_int,
                      labels: *mut u32, sizes: *mut u32) -> c_int;
+    pub fn cb_clusters(ctx: *mut cb_ctx, frames: *const u8, width: c_int, height: c_int, stride: c_int, frame_stride: usize, batch: c_int,
+                       pts: *mut i16, cluster_of: *mut i32, cap: i64, npoints: *mut i64, nclusters: *mut i32) -> c_int;
     pub fn cb_quads(ctx: *mut cb_ctx, frames: *const u8, width: c_int, height: c_int, stride: c_int, frame_stride: usize, batch: c_int,
                     quads: *mut f32, cap: c_int, counts: *mut i32, npoints_total: *mut i64) -> c_int;
     pub fn cb_get_timing(ctx: *const cb_ctx, t: *mut cb_timing) -> c_int;

@@ -170,6 +170,14 @@ impl Detector {
                                           quads.len() as c_int, &mut count, &mut npoints) })?;
         Ok((count as usize, npoints))
     }
+    /// Stage tap of gradient_clusters(): `pts[k] = [x, y, gx, gy]` as upstream stores a point, `cluster_of[k]`; returns (points, clusters).
+    pub fn clusters(&mut self, image: &Image, pts: &mut [[i16; 4]], cluster_of: &mut [i32]) -> Result<(i64, i32), Error> {
+        let (mut n, mut ncl) = (0i64, 0i32);
+        check(self.ctx, unsafe { cb_clusters(self.ctx, image.buf.as_ptr(), image.width, image.height, image.stride,
+                                             (image.stride as usize) * (image.height as usize), 1, pts.as_mut_ptr() as *mut i16,
+                                             cluster_of.as_mut_ptr(), pts.len().min(cluster_of.len()) as i64, &mut n, &mut ncl) })?;
+        Ok((n, ncl))
+    }
     pub fn decimated_size(&self, width: i32, height: i32) -> (i32, i32) {
         let (mut w, mut h) = (0, 0);
         unsafe { cb_decimated_size(self.ctx, width, height, &mut w, &mut h) };

@@ -262,6 +262,35 @@ def test_graph_replay_of_the_single_frame_pipeline(oracle):
     det.close()
 
 
+@pytest.mark.parametrize("W,H,tags,seed,edge", [(1280, 720, 4, 1, (60, 150)), (642, 486, 3, 4, (40, 100)), (1456, 1088, 8, 2, (40, 200))])
+def test_gradient_clusters_bit_exact(oracle, W, H, tags, seed, edge):
+    """Row A4 directly (cb_clusters): every cluster fit_quad() can accept holds exactly upstream's boundary points -- as a set against
+    the oracle's point dump, and in upstream's append order (scan order y, x, probe) inside the cluster -- and no such cluster is
+    missing.  Cluster ids are not compared (union-find representatives are an implementation detail); point sets are."""
+    frames, _ = synth.render_batch(W, H, 2, tags, seed=seed, edge_px=edge)
+    frames[1, : H // 2] = np.random.default_rng(seed).integers(0, 256, (H // 2, W), dtype=np.uint8)      # noise: thousands of small clusters
+    det = make_detector(W, H, 2)
+    pts, cl, ncl = det.clusters(frames)
+    w, h = (W + 1) // 2, (H + 1) // 2
+    lim = 3 * (2 * w + 2 * h)
+    base = 0
+    for b in range(2):
+        _, taps = oracle.detect(frames[b], taps=True, pts_cap=4_000_000)
+        ids, first, counts = np.unique(taps["pts_cluster"], return_index=True, return_counts=True)      # (the dump is grouped by cluster)
+        want = {frozenset(map(tuple, taps["pts"][f:f + c].tolist())) for f, c in zip(first, counts) if 24 <= c <= lim}
+        got = set()
+        for c in range(base, base + int(ncl[b])):
+            p = pts[cl == c]
+            got.add(frozenset(map(tuple, p.tolist())))
+            assert len(p) >= 24 and len(set(map(tuple, p.tolist()))) == len(p), "a point twice in one cluster"
+            rows = (p[:, 1].astype(np.int64) - (p[:, 3] != 0)) // 2                  # pixel row of the probing pixel
+            assert (np.diff(rows) >= 0).all(), "the points of a cluster are not in scan order"
+        base += int(ncl[b])
+        assert len(got) == ncl[b] == len(want) and got == want
+    assert base == cl.max() + 1
+    det.close()
+
+
 def test_c3_full_resolution_small_tags(oracle):
     frame, truth = synth.render_frame(4608, 2592, 40, seed=4, edge_px=(40, 300), small_tags=10)
     det = make_detector(4608, 2592, 1, 256)
