@@ -312,7 +312,7 @@ __device__ __forceinline__ int band_insert(unsigned long long *keys, unsigned lo
 // queue in shared memory.  Consumer, whenever 32 points are queued: ONE match.any on the keys, one table probe per distinct
 // key, one coalesced 128-byte store of staging words -- every lane busy, where probing the four directions one after the
 // other kept about a quarter of the lanes busy and cost four match rounds per step.
-__global__ void __launch_bounds__(32, 24)
+__global__ void __launch_bounds__(32, 32)
 cluster_band_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restrict__ labels, ClusterSlot *__restrict__ table,
                           uint32_t *__restrict__ errflag, uint32_t *__restrict__ stage, ClbArea *__restrict__ areas,
                           uint32_t *__restrict__ pool_counter, Geom g, Caps caps, BandPlan bp)
