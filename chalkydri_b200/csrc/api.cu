@@ -704,7 +704,10 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     if (stage >= ST_LABELS) {
         // ---- A3 connected components ----
         dim3 grid((g.w + CCL_TW - 1) / CCL_TW, (g.h + CCL_TH - 1) / CCL_TH, B);
-        ccl_local_kernel<0><<<grid, CCL_THREADS, 0, st>>>(ctx->d_thresh, ctx->d_labels, ctx->d_sizes, g);
+        // local roots go to a list (in the staging area of the cluster passes, free until they start) instead of a dense sizes plane
+        static const bool dense_sizes = getenv("CB_CCL") && strcmp(getenv("CB_CCL"), "dense") == 0;      // A/B hook: round 1's form
+        uint32_t *d_roots = dense_sizes ? nullptr : reinterpret_cast<uint32_t *>(ctx->d_ent);
+        ccl_local_kernel<0><<<grid, CCL_THREADS, 0, st>>>(ctx->d_thresh, ctx->d_labels, ctx->d_sizes, g, d_roots, d_misc + 7);
         launches++;
         const int nrows = (g.h - 1) / CCL_TH, ncols = (g.w - 1) / CCL_TW + 1;   // borders: rows k*TH (k>=1); columns k*TW and k*TW-1
         if (nrows > 0) {
@@ -718,7 +721,8 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
             launches++;
         }
         const uint32_t total = (uint32_t)B * g.npix;
-        ccl_flatten_roots_kernel<<<(total + 256 * ROOTS_PER - 1) / (256 * ROOTS_PER), 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, total);
+        if (d_roots) ccl_flatten_list_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, d_roots, d_misc + 7);
+        else ccl_flatten_roots_kernel<<<(total + 256 * ROOTS_PER - 1) / (256 * ROOTS_PER), 256, 0, st>>>(ctx->d_labels, ctx->d_sizes, total);
         dim3 gfin((g.w + 256 * MARK_PER - 1) / (256 * MARK_PER), g.h, B);
         ccl_finish_kernel<<<gfin, 256, 0, st>>>(ctx->d_thresh, ctx->d_labels, ctx->d_sizes, ctx->d_mark, g);
         launches += 2;

@@ -110,12 +110,17 @@ __device__ __forceinline__ void uf_union(uint32_t *L, uint32_t a, uint32_t b)
 // the row is compressed at once -- every pixel points at its current root before the next row starts, so the walks of
 // the union-find stay one or two hops long instead of growing with the height of the component.  The seven strip
 // borders are stitched afterwards, then every pixel is flattened and the run starts credit their run to the root.
+// root_list != nullptr (detector): instead of a dense sizes[] plane (local size at local roots, 0 elsewhere -- 4 bytes per pixel written
+// here and read back by the flatten pass just to find the few non-zeros) the tile appends its local roots to a batch-wide list
+// (one global atomic per CTA reserves the range) and writes sizes[] at the roots only; ccl_flatten_list_kernel walks the list.
 template <int MODE>
 __global__ void __launch_bounds__(CCL_THREADS)
-ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, Geom g)
+ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, Geom g,
+                 uint32_t *__restrict__ root_list = nullptr, uint32_t *__restrict__ nroots = nullptr)
 {
     __shared__ uint32_t L[CCL_TW * CCL_TH];
     __shared__ uint32_t Cnt[CCL_TW * CCL_TH];
+    __shared__ uint32_t s_wsum[CCL_THREADS / 32 + 1];
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * CCL_TW, y0 = blockIdx.y * CCL_TH;
     const uint8_t *t = thresh + (size_t)b * g.h * g.tp;
@@ -216,6 +221,7 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
         roots[k] = L[L[i]];
     }
     const uint32_t base = (uint32_t)b * g.npix;
+    uint32_t rootmask = 0;                                   // bit k: pixel k of this thread is a local root inside the image
 #pragma unroll
     for (int k = 0; k < PER; k++) {
         const int i = threadIdx.x + k * CCL_THREADS;
@@ -226,7 +232,46 @@ ccl_local_kernel(const uint8_t *__restrict__ thresh, uint32_t *__restrict__ labe
             const int rx = x0 + (int)(r % CCL_TW), ry = y0 + (int)(r / CCL_TW);
             const size_t gi = (size_t)base + (size_t)y * g.w + x;
             labels[gi] = base + (uint32_t)(ry * g.w + rx);
-            sizes[gi] = (r == (uint32_t)i) ? Cnt[i] : 0u;     // local component size at the local root, 0 elsewhere
+            if (root_list == nullptr) sizes[gi] = (r == (uint32_t)i) ? Cnt[i] : 0u;     // local component size at the local root, 0 elsewhere
+            else if (r == (uint32_t)i) { sizes[gi] = Cnt[i]; rootmask |= 1u << k; }
+        }
+    }
+    if (root_list != nullptr) {
+        // exclusive position of this thread's roots inside the CTA's range: warp scan, warp totals through shared memory, one atomic
+        const uint32_t mine = __popc(rootmask);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(full, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < CCL_THREADS / 32; w++) { const uint32_t v = s_wsum[w]; s_wsum[w] = tot; tot += v; }
+            s_wsum[CCL_THREADS / 32] = tot ? atomicAdd(nroots, tot) : 0u;
+        }
+        __syncthreads();
+        uint32_t pos = s_wsum[CCL_THREADS / 32] + s_wsum[wid] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < PER; k++)
+            if ((rootmask >> k) & 1u) {
+                const int i = threadIdx.x + k * CCL_THREADS;
+                root_list[pos++] = base + (uint32_t)((y0 + i / CCL_TW) * g.w + x0 + i % CCL_TW);
+            }
+    }
+}
+
+// pass 3a of the detector, list form: every listed local root walks to its final root, links straight to it and adds its local size
+__global__ void __launch_bounds__(256) ccl_flatten_list_kernel(uint32_t *__restrict__ labels, uint32_t *__restrict__ sizes, const uint32_t *__restrict__ root_list,
+                                                               const uint32_t *__restrict__ nroots)
+{
+    const uint32_t n = *nroots;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t i = root_list[k];
+        const uint32_t root = uf_find(labels, i);
+        if (root != i) {
+            const uint32_t c = sizes[i];
+            labels[i] = root;
+            atomicAdd(&sizes[root], c);
         }
     }
 }
