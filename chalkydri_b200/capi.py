@@ -42,7 +42,7 @@ class PoolTiming(C.Structure):
 # every symbol include/chalkydri_b200.h declares
 EXPORTS = ["cb_create", "cb_destroy", "cb_last_error", "cb_set_family_tag36h11", "cb_set_params", "cb_detect_gray",
            "cb_detect_gray_device", "cb_detect_gray_submit", "cb_detect_gray_collect", "cb_detect_gray_pending", "cb_detect_rgb", "cb_detect_yuyv", "cb_detect_yuv420", "cb_rgb_to_gray", "cb_yuyv_to_gray", "cb_decimated_size", "cb_threshold", "cb_labels",
-           "cb_quads", "cb_clusters", "cb_get_timing", "cb_sqpnp_set", "cb_sqpnp_batch", "cb_sqpnp_batch_device",
+           "cb_quads", "cb_clusters", "cb_get_timing", "cb_frame_flags", "cb_sqpnp_set", "cb_sqpnp_batch", "cb_sqpnp_batch_device",
            "cb_create_solver_camera_transform", "cb_unproject_opencv5", "cb_set_field", "cb_set_camera", "cb_detect_pose_gray", "cb_detect_pose_gray_submit", "cb_detect_pose_gray_collect", "cb_pack_vision_measurements", "cb_cat_calc_otsu", "cb_cat_thresh",
            "cb_cat_detect_corners", "cb_cat_check_edges", "cb_cat_process_frame", "cb_cat_detect_tags", "cb_cat_connected_components", "cb_host_alloc", "cb_host_free",
            "cb_device_alloc", "cb_device_free", "cb_memcpy_h2d", "cb_memcpy_d2h", "cb_device_count", "cb_version",
@@ -103,6 +103,7 @@ def lib():
         L.cb_cat_process_frame.argtypes = [vp, vp, i32, i32, vp, vp, i64, vp, vp, i64, vp]
         L.cb_cat_detect_tags.argtypes = [vp, vp, i32, i32, i32, vp, vp]
         L.cb_clusters.argtypes = [vp, vp, i32, i32, i32, sz, i32, vp, vp, i64, vp, vp]
+        L.cb_frame_flags.argtypes = [vp, vp, i32]
         L.cb_cat_connected_components.argtypes = [vp, vp, i32, i32, vp, vp]
         L.cb_host_alloc.restype = vp; L.cb_host_alloc.argtypes = [sz]
         L.cb_host_free.restype = None; L.cb_host_free.argtypes = [vp]

@@ -55,6 +55,7 @@ struct cb_ctx {
         cb_detection *h_dets = nullptr;
         int32_t *h_counts = nullptr;
         uint32_t *h_err = nullptr;               // error flag per chunk
+        uint32_t *h_ferr = nullptr;              // overflow word per frame
         cudaEvent_t start = nullptr, done = nullptr;
         int batch = 0, nchunks = 0, launches = 0, thr_launches = 0;
         // fused detect -> pose batches (cb_detect_pose_gray_submit): gyro staging in, poses out
@@ -132,6 +133,8 @@ struct cb_ctx {
 
     cudaEvent_t ev[10]{};
     cb_timing timing{};
+    std::vector<uint32_t> frame_flags;            // overflow bits per frame of the last completed detection call (cb_frame_flags)
+    uint32_t *h_frame_err = nullptr; size_t h_frame_err_cap = 0;      // pinned: the same for the chunks of a pipelined call
     std::map<ThrKey, ThrChoice> thr_plans;          // threshold kernel shape per frame geometry (threshold_plan)
     // small batches: the pipeline of one geometry captured as a CUDA graph on its second use (detect_device_chunk)
     struct GraphSlot { int seen = 0; bool failed = false; cudaGraphExec_t exec = nullptr; int launches = 0, thr_launches = 0; };
@@ -221,10 +224,12 @@ void cb_destroy(cb_ctx *ctx)
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->h_chunk_err) cudaFreeHost(ctx->h_chunk_err);
+    if (ctx->h_frame_err) cudaFreeHost(ctx->h_frame_err);
     for (auto &sl : ctx->ss) {
         if (sl.h_dets) cudaFreeHost(sl.h_dets);
         if (sl.h_counts) cudaFreeHost(sl.h_counts);
         if (sl.h_err) cudaFreeHost(sl.h_err);
+        if (sl.h_ferr) cudaFreeHost(sl.h_ferr);
         if (sl.start) cudaEventDestroy(sl.start);
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.h_gyro) cudaFreeHost(sl.h_gyro);
@@ -307,6 +312,7 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     c.points_per_frame = (uint32_t)((std::max<size_t>(65536, dpix + dpix / 2) + 7) / 8 * 8);   // noisy frames emit ~0.85 points / pixel
     c.quads_per_frame = (uint32_t)std::max<size_t>(2048, dpix / 32);   // pure-noise frames produce thousands of candidate quads
     c.dets_per_frame = (uint32_t)max_dets_per_frame;
+    if (const char *e = getenv("CB_TEST_QUADS_PER_FRAME")) c.quads_per_frame = (uint32_t)std::max(1, atoi(e));      // test hook: reach the overflow path
     ok = ok && alloc((void **)&ctx->d_in, ctx->in_bytes + 64);
     ok = ok && alloc((void **)&ctx->d_thresh, ctx->map_bytes) && alloc((void **)&ctx->d_mark, ctx->map_bytes);
     ok = ok && alloc((void **)&ctx->d_tmin, ctx->tile_bytes) && alloc((void **)&ctx->d_tmax, ctx->tile_bytes);
@@ -340,10 +346,10 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     ok = ok && alloc((void **)&ctx->d_raw, B * c.quads_per_frame * sizeof(RawDet));
     ok = ok && alloc((void **)&ctx->d_dets, B * c.dets_per_frame * sizeof(cb_detection));
     ok = ok && alloc((void **)&ctx->d_counts, B * sizeof(int32_t));
-    ok = ok && alloc((void **)&ctx->d_small, (4 * B + 48) * sizeof(uint32_t));
+    ok = ok && alloc((void **)&ctx->d_small, (5 * B + 48) * sizeof(uint32_t));
     ok = ok && cudaMallocHost((void **)&ctx->h_dets, B * c.dets_per_frame * sizeof(cb_detection)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&ctx->h_counts, B * sizeof(int32_t)) == cudaSuccess;
-    ok = ok && cudaMallocHost((void **)&ctx->h_small, (4 * B + 48) * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&ctx->h_small, (5 * B + 48) * sizeof(uint32_t)) == cudaSuccess;
     if (ok) {
         ok = ok && cudaMemcpyToSymbol(c_codes, kHostCodes, sizeof(kHostCodes)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
@@ -414,6 +420,17 @@ int cb_decimated_size(const cb_ctx *ctx, int width, int height, int *w, int *h)
     const int f = (int)ctx->prm.quad_decimate;
     *w = 1 + (width - 1) / f; *h = 1 + (height - 1) / f;
     return CB_OK;
+}
+
+int cb_frame_flags(const cb_ctx *ctx, uint32_t *flags, int n)
+{
+    if (!ctx || n < 0 || (n > 0 && !flags)) return CB_ERR_ARG;
+    int bad = 0;
+    for (int i = 0; i < n; i++) {
+        flags[i] = i < (int)ctx->frame_flags.size() ? ctx->frame_flags[i] : 0u;
+        bad += flags[i] != 0;
+    }
+    return bad;
 }
 
 int cb_get_timing(const cb_ctx *ctx, cb_timing *t)
@@ -632,8 +649,8 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     const size_t wl_stride = (size_t)ctx->max_batch * caps.clusters_per_frame;       // four tier work lists, back to back
     uint32_t *d_ncl = ctx->d_small, *d_npt = ctx->d_small + ctx->max_batch, *d_nq = ctx->d_small + 2 * ctx->max_batch,
              *d_nraw = ctx->d_small + 3 * ctx->max_batch, *d_misc = ctx->d_small + 4 * ctx->max_batch;
-    // misc: [0] errflag, [1] nwork, [2] work_counter, [3] nquads_total, [4] decode counter
-    CK(cudaMemsetAsync(ctx->d_small, 0, (4 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), st));
+    // misc: [0] errflag, [1] nwork, [2] work_counter, [3] nquads_total, [4] decode counter; behind misc: one overflow word per frame
+    CK(cudaMemsetAsync(ctx->d_small, 0, (5 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), st));
     CK(cudaEventRecord(ctx->ev[1], st));
     // ---- A1+A2 threshold ----
     const bool fast = g.f == 2 && (g.stride % 16 == 0) && (g.frame_stride % 16 == 0) && ((uintptr_t)d_frames % 16 == 0) && g.tw > 0 && g.th > 0;
@@ -873,7 +890,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
     if (stage >= ST_FULL) {
         // ---- A6-A9 refine, homography, decode, reconcile ----
         decode_quads_kernel<<<ctx->num_sms * 6, DEC_WARPS * 32, 0, st>>>(d_frames, ctx->d_quads, d_misc + 3, d_misc + 4, ctx->d_raw, d_nraw, g, caps, prm, ctx->dc);
-        reconcile_kernel<<<(B + REC_WARPS - 1) / REC_WARPS, REC_WARPS * 32, 0, st>>>(ctx->d_raw, d_nraw, ctx->d_dets, ctx->d_counts, caps, B);
+        reconcile_kernel<<<(B + REC_WARPS - 1) / REC_WARPS, REC_WARPS * 32, 0, st>>>(ctx->d_raw, d_nraw, ctx->d_dets, ctx->d_counts, caps, B, d_misc + 48);
         launches += 2;
         if (ctx->pose_active) {
             PoseBufs pb = pose_bufs(ctx);
@@ -911,18 +928,28 @@ static int finish_timing(cb_ctx *ctx, bool h2d, bool d2h)
     return CB_OK;
 }
 
-static int check_errflag(cb_ctx *ctx)
+// A frame that overflowed one of its fixed-size device tables (cluster hash, clusters, points, quads) reports an empty list and a flag
+// word (cb_frame_flags); the other frames of the batch are complete, so the call itself succeeds -- upstream has no such tables, and
+// one cluttered camera frame must not fail a batch.  The text stays available through cb_last_error.
+static void note_overflow(cb_ctx *ctx, uint32_t flag, int frames)
+{
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%d frame(s) overflowed a device table (flags 0x%x:%s%s%s%s) and report no detections; cb_frame_flags tells which", frames, flag,
+             (flag & ERR_HASH_FULL) ? " cluster-hash" : "", (flag & ERR_CLUSTERS_FULL) ? " clusters" : "", (flag & ERR_POINTS_FULL) ? " points" : "",
+             (flag & ERR_QUADS_FULL) ? " quads" : "");
+    ctx->err = buf;
+}
+// (simple path and stage taps: everything is in h_small)
+static int check_errflag(cb_ctx *ctx, int batch = 0)
 {
     const uint32_t flag = ctx->h_small[4 * (size_t)ctx->max_batch];
-    if (flag) {
-        return fail(ctx, CB_ERR_OVERFLOW, "device table overflow (flags 0x%x:%s%s%s%s); create the context with a larger frame size / batch capacity",
-                    flag, (flag & ERR_HASH_FULL) ? " cluster-hash" : "", (flag & ERR_CLUSTERS_FULL) ? " clusters" : "",
-                    (flag & ERR_POINTS_FULL) ? " points" : "", (flag & ERR_QUADS_FULL) ? " quads" : "");
-    }
+    ctx->frame_flags.assign((size_t)batch, 0u);
+    int bad = 0;
+    for (int b = 0; b < batch; b++) { ctx->frame_flags[b] = ctx->h_small[4 * (size_t)ctx->max_batch + 48 + b]; bad += ctx->frame_flags[b] != 0; }
+    if (flag) note_overflow(ctx, flag, bad);
     return CB_OK;
 }
 
-// full detector on device frames; copies detections back to the caller's arrays
 // The kernels of a chunk and the read-back of its lists, queued on ctx->stream
 static int queue_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g)
 {
@@ -931,7 +958,7 @@ static int queue_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g)
     const size_t B = g.batch;
     CK(cudaMemcpyAsync(ctx->h_dets, ctx->d_dets, B * ctx->caps.dets_per_frame * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (4 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (5 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     return CB_OK;
 }
 
@@ -987,7 +1014,7 @@ static int detect_device_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom 
     } else {
         finish_timing(ctx, timed_h2d, true);
     }
-    int rc = check_errflag(ctx);
+    int rc = check_errflag(ctx, (int)B);
     if (rc) return rc;
     memcpy(out_counts, ctx->h_counts, B * sizeof(int32_t));
     for (size_t b = 0; b < B; b++)
@@ -1024,6 +1051,7 @@ int cb_detect_gray_device(cb_ctx *ctx, const uint8_t *frames_dev, int width, int
     if (!ctx || !frames_dev || !out || !out_counts) return CB_ERR_ARG;
     CB_NOT_STREAMING(ctx);
     CK(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> all_flags;
     cb_timing acc{};
     for (int b0 = 0; b0 < batch; b0 += ctx->max_batch) {
         const int n = std::min(ctx->max_batch, batch - b0);
@@ -1032,10 +1060,12 @@ int cb_detect_gray_device(cb_ctx *ctx, const uint8_t *frames_dev, int width, int
         if (rc) return rc;
         rc = detect_device_chunk(ctx, frames_dev + (size_t)b0 * frame_stride, g, out + (size_t)b0 * ctx->caps.dets_per_frame, out_counts + b0, false);
         if (rc) return rc;
+        all_flags.insert(all_flags.end(), ctx->frame_flags.begin(), ctx->frame_flags.end());
         for (int i = 0; i < n; i++)
             for (int k = 0; k < out_counts[b0 + i]; k++) out[(size_t)(b0 + i) * ctx->caps.dets_per_frame + k].frame = b0 + i;
         accumulate_timing(acc, ctx->timing);
     }
+    ctx->frame_flags = all_flags;
     ctx->timing = acc;
     return CB_OK;
 }
@@ -1080,6 +1110,11 @@ static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, 
     if (nchunks > 4096) return fail(ctx, CB_ERR_ARG, "too many chunks");
     uint8_t *bufs[2] = {ctx->d_in, ctx->d_in + (size_t)half * dfs};
     cb_timing acc{};
+    if (ctx->h_frame_err_cap < (size_t)batch) {
+        if (ctx->h_frame_err) { cudaFreeHost(ctx->h_frame_err); ctx->h_frame_err = nullptr; ctx->h_frame_err_cap = 0; }
+        CK(cudaMallocHost((void **)&ctx->h_frame_err, (size_t)batch * sizeof(uint32_t)));
+        ctx->h_frame_err_cap = (size_t)batch;
+    }
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     CK(cudaEventRecord(ctx->ev_consumed[0], ctx->stream));   // make the first waits trivially satisfied
     CK(cudaEventRecord(ctx->ev_consumed[1], ctx->stream));
@@ -1112,13 +1147,18 @@ static int detect_gray_pipelined(cb_ctx *ctx, const uint8_t *frames, int width, 
         CK(cudaMemcpyAsync(ctx->h_dets + (size_t)off * D, ctx->d_dets, (size_t)n * D * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_counts + off, ctx->d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->h_chunk_err + c, ctx->d_small + 4 * (size_t)ctx->max_batch, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_frame_err + b0, ctx->d_small + 4 * (size_t)ctx->max_batch + 48, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         acc.kernel_launches += ctx->timing.kernel_launches;
         acc.threshold_launches += ctx->timing.threshold_launches;
     }
     CK(cudaEventRecord(ctx->ev[7], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int c = 0; c < nchunks; c++)
-        if (ctx->h_chunk_err[c]) { ctx->h_small[4 * (size_t)ctx->max_batch] = ctx->h_chunk_err[c]; return check_errflag(ctx); }
+    {
+        uint32_t flag = 0;
+        for (int c = 0; c < nchunks; c++) flag |= ctx->h_chunk_err[c];
+        ctx->frame_flags.assign(ctx->h_frame_err, ctx->h_frame_err + batch);
+        if (flag) { int bad = 0; for (int b = 0; b < batch; b++) bad += ctx->frame_flags[b] != 0; note_overflow(ctx, flag, bad); }
+    }
     for (int b = done_base; b < batch; b++) {
         out_counts[b] = ctx->h_counts[b - done_base];
         memcpy(out + (size_t)b * D, ctx->h_dets + (size_t)(b - done_base) * D, (size_t)out_counts[b] * sizeof(cb_detection));
@@ -1145,6 +1185,7 @@ int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, in
         return detect_gray_pipelined(ctx, frames, width, height, stride, frame_stride, batch, out, out_counts);
     }
     cb_timing acc{};
+    std::vector<uint32_t> all_flags;
     for (int b0 = 0; b0 < batch; b0 += ctx->max_batch) {
         const int n = std::min(ctx->max_batch, batch - b0);
         size_t dfs;
@@ -1159,8 +1200,10 @@ int cb_detect_gray(cb_ctx *ctx, const uint8_t *frames, int width, int height, in
         for (int i = 0; i < n; i++)
             for (int k = 0; k < out_counts[b0 + i]; k++) out[(size_t)(b0 + i) * ctx->caps.dets_per_frame + k].frame = b0 + i;
         accumulate_timing(acc, ctx->timing);
+        all_flags.insert(all_flags.end(), ctx->frame_flags.begin(), ctx->frame_flags.end());
     }
     ctx->timing = acc;
+    ctx->frame_flags = all_flags;
     return CB_OK;
 }
 
@@ -1191,6 +1234,7 @@ static int stream_submit(cb_ctx *ctx, const uint8_t *frames, int width, int heig
         CK(cudaMallocHost((void **)&sl.h_dets, (size_t)ctx->max_batch * D * sizeof(cb_detection)));
         CK(cudaMallocHost((void **)&sl.h_counts, (size_t)ctx->max_batch * sizeof(int32_t)));
         CK(cudaMallocHost((void **)&sl.h_err, 8 * sizeof(uint32_t)));
+        CK(cudaMallocHost((void **)&sl.h_ferr, (size_t)ctx->max_batch * sizeof(uint32_t)));
         CK(cudaEventCreate(&sl.start));
         CK(cudaEventCreate(&sl.done));
     }
@@ -1245,6 +1289,7 @@ static int stream_submit(cb_ctx *ctx, const uint8_t *frames, int width, int heig
         CK(cudaMemcpyAsync(sl.h_dets + (size_t)b0 * D, ctx->d_dets, (size_t)n * D * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(sl.h_counts + b0, ctx->d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(sl.h_err + c, ctx->d_small + 4 * (size_t)ctx->max_batch, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(sl.h_ferr + b0, ctx->d_small + 4 * (size_t)ctx->max_batch + 48, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         sl.launches += ctx->timing.kernel_launches;
         sl.thr_launches += ctx->timing.threshold_launches;
         sl.nchunks++;
@@ -1277,8 +1322,12 @@ static int stream_collect(cb_ctx *ctx, cb_detection *out, int32_t *out_counts, c
     ctx->ss_head ^= 1;            // the batch leaves the queue whatever its outcome
     ctx->ss_pending--;
     if (e != cudaSuccess) return fail(ctx, CB_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
-    for (int c = 0; c < sl.nchunks; c++)
-        if (sl.h_err[c]) { ctx->h_small[4 * (size_t)ctx->max_batch] = sl.h_err[c]; return check_errflag(ctx); }
+    {
+        uint32_t flag = 0;
+        for (int c = 0; c < sl.nchunks; c++) flag |= sl.h_err[c];
+        ctx->frame_flags.assign(sl.h_ferr, sl.h_ferr + sl.batch);
+        if (flag) { int bad = 0; for (int b = 0; b < sl.batch; b++) bad += ctx->frame_flags[b] != 0; note_overflow(ctx, flag, bad); }
+    }
     const size_t D = ctx->caps.dets_per_frame;
     for (int b = 0; b < sl.batch; b++) {
         out_counts[b] = sl.h_counts[b];
@@ -1449,11 +1498,11 @@ static int tap_common(cb_ctx *ctx, const uint8_t *frames, int width, int height,
     if (rc) return rc;
     rc = run_pipeline(ctx, ctx->d_in, g, stage);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (4 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (5 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev[7], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     finish_timing(ctx, true, true);
-    return check_errflag(ctx);
+    return check_errflag(ctx, batch);
 }
 
 int cb_threshold(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, uint8_t *out)
@@ -1514,8 +1563,6 @@ int cb_clusters(cb_ctx *ctx, const uint8_t *frames, int width, int height, int s
     Geom g;
     if (!pts || !cluster_of || !npoints || !nclusters || cap < 0) return CB_ERR_ARG;
     int rc = tap_common(ctx, frames, width, height, stride, frame_stride, batch, ST_CLUSTERS, g);
-    if (rc) return rc;
-    rc = check_errflag(ctx);
     if (rc) return rc;
     const Caps &caps = ctx->caps;
     int64_t k = 0;

@@ -172,7 +172,7 @@ cluster_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restric
             ent[d] = CL_ENT_OVERFLOW | (sign << 31);
             if (lane == leader) {
                 const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
-                if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
+                if (s == 0xffffffffu) flag_overflow(errflag, blockIdx.z, ERR_HASH_FULL);
                 else atomicAdd(&tab[s].count, npeers);
             }
         }
@@ -187,7 +187,7 @@ cluster_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__restric
         tile_cnt[tile * CL_CAP + e] = S.cnt[e];
         if (key == EMPTY_KEY) continue;
         const uint32_t s = slot_insert(tab, caps.slots_per_frame, key);
-        if (s == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
+        if (s == 0xffffffffu) flag_overflow(errflag, blockIdx.z, ERR_HASH_FULL);
         else atomicAdd(&tab[s].count, S.cnt[e]);
     }
 }
@@ -353,7 +353,7 @@ cluster_band_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__re
                 r.key = key; r.cnt = cnt; r.slot = (uint32_t)s;
                 A->rec[n_used + __popc(bu & lt)] = r;
                 const uint32_t gs = slot_insert(tab, caps.slots_per_frame, key);
-                if (gs == 0xffffffffu) atomicOr(errflag, ERR_HASH_FULL);
+                if (gs == 0xffffffffu) flag_overflow(errflag, b, ERR_HASH_FULL);
                 else atomicAdd(&tab[gs].count, cnt);
                 K[s] = EMPTY_KEY; Cn[s] = 0;
             }
@@ -364,7 +364,7 @@ cluster_band_count_kernel(const uint8_t *__restrict__ mark, const uint32_t *__re
             if (lane == 0) next = atomicAdd(pool_counter, 1u);
             next = __shfl_sync(full, next, 0);
             // no chained area left: the call fails with ERR_HASH_FULL; this area is simply reused so that the walk stays in bounds
-            if (next >= bp.pool_cap) { if (lane == 0) atomicOr(errflag, ERR_HASH_FULL); next = CLB_NONE; }
+            if (next >= bp.pool_cap) { if (lane == 0) flag_overflow(errflag, b, ERR_HASH_FULL); next = CLB_NONE; }
             else next += nfirst;
         }
         if (lane == 0) { A->n_used = n_used; A->st_start = sub_start; A->st_end = npts; A->next = next; A->band = job; }
@@ -674,8 +674,8 @@ cluster_select_kernel(ClusterSlot *__restrict__ table, ClusterRec *__restrict__ 
     const uint32_t ci = ci0 + __popc(m & lt), off = off0 + scan - padded;
     const int tier = cnt <= t0 ? 0 : (cnt <= t1 ? 1 : (cnt <= t2 ? 2 : 3));     // work list of the quad-fitting tier
     bool ok = sel;
-    if (ok && ci >= caps.clusters_per_frame) { atomicOr(errflag, ERR_CLUSTERS_FULL); ok = false; }
-    if (ok && off + cnt > caps.points_per_frame) { atomicOr(errflag, ERR_POINTS_FULL); ok = false; }
+    if (ok && ci >= caps.clusters_per_frame) { flag_overflow(errflag, b, ERR_CLUSTERS_FULL); ok = false; }
+    if (ok && off + cnt > caps.points_per_frame) { flag_overflow(errflag, b, ERR_POINTS_FULL); ok = false; }
     uint32_t pos = 0;
 #pragma unroll
     for (int t = 0; t < 4; t++) {

@@ -69,6 +69,14 @@ struct Caps {
 
 // error flag bits written by kernels
 enum : uint32_t { ERR_HASH_FULL = 1, ERR_CLUSTERS_FULL = 2, ERR_POINTS_FULL = 4, ERR_QUADS_FULL = 8 };
+// A fixed per-frame table overflowed in frame b: the batch-wide flag word and, 48 words behind it, the frame's own word (api.cu lays
+// the small counters out as [.. | misc 48 | frame flags B]).  Every table is per frame, so the other frames of the batch are complete;
+// the reconcile pass empties the list of a flagged frame.
+__device__ __forceinline__ void flag_overflow(uint32_t *errflag, int b, uint32_t bit)
+{
+    atomicOr(errflag, bit);
+    atomicOr(errflag + 48 + b, bit);
+}
 
 static constexpr int kNumCodes = 587;
 

@@ -524,7 +524,7 @@ __device__ __forceinline__ bool det_less(const cb_detection &a, const cb_detecti
 constexpr int REC_WARPS = 4, REC_MAX = 128;
 __global__ void __launch_bounds__(REC_WARPS * 32)
 reconcile_kernel(RawDet *__restrict__ raw, const uint32_t *__restrict__ nraw, cb_detection *__restrict__ out,
-                 int32_t *__restrict__ counts, Caps caps, int batch)
+                 int32_t *__restrict__ counts, Caps caps, int batch, const uint32_t *__restrict__ frame_err)
 {
     __shared__ uint16_t s_idx[REC_WARPS][REC_MAX];
     __shared__ int s_n[REC_WARPS];
@@ -533,6 +533,7 @@ reconcile_kernel(RawDet *__restrict__ raw, const uint32_t *__restrict__ nraw, cb
     if (b >= batch) return;
     RawDet *r = raw + (size_t)b * caps.quads_per_frame;
     int n = (int)min(nraw[b], caps.quads_per_frame);
+    if (frame_err[b]) n = 0;          // a table of this frame overflowed: its list would be incomplete, it reports nothing (and its flag)
     const bool indexed = n <= REC_MAX;
     uint16_t *ix = s_idx[wid];
     if (lane == 0) {

@@ -321,7 +321,7 @@ __device__ __forceinline__ void fq_finish(FqWarp &S, double te, int ti, int nm, 
         }
         if (good) {
             const uint32_t qf = atomicAdd(&nquads[b], 1u);
-            if (qf >= caps.quads_per_frame) atomicOr(errflag, ERR_QUADS_FULL);
+            if (qf >= caps.quads_per_frame) flag_overflow(errflag, b, ERR_QUADS_FULL);
             else {
                 const uint32_t qi = atomicAdd(nquads_total, 1u);   // < batch * quads_per_frame by construction
                 QuadRec q;

@@ -236,6 +236,14 @@ class Detector:
         self._check(self._L.cb_decimated_size(self._ctx, W, H, C.byref(w), C.byref(h)))
         return w.value, h.value
 
+    def frame_flags(self, n: int) -> np.ndarray:
+        """Overflow bits per frame of the last completed detection call (cb_frame_flags): a flagged frame reported an empty list."""
+        f = np.zeros(n, np.uint32)
+        rc = self._L.cb_frame_flags(self._ctx, capi.ptr(f), n)
+        if rc < 0:
+            self._check(rc)
+        return f
+
     def clusters(self, frames: np.ndarray, cap: int = 1 << 21):
         """Stage tap of gradient_clusters(): (pts [n,4] int16 = x, y, gx, gy as upstream stores them, cluster_of [n], nclusters [B]);
         the selected clusters only, points in upstream's append order."""

@@ -23,7 +23,7 @@ extern "C" {
 #define CB_ERR_ARG (-1)        /* bad argument (null pointer, size beyond the context's capacity, ...) */
 #define CB_ERR_CUDA (-2)       /* CUDA runtime error; text in cb_last_error */
 #define CB_ERR_UNSUPPORTED (-3)/* parameter value the kernels do not implement (quad_sigma != 0, decimate 1.5, ...) */
-#define CB_ERR_OVERFLOW (-4)   /* a per-frame device table overflowed (clusters / points / quads); raise capacities */
+#define CB_ERR_OVERFLOW (-4)   /* an output list does not fit the capacity the caller gave (CAT lists, stage taps) */
 #define CB_ERR_STATE (-5)      /* family not set etc. */
 
 typedef struct cb_ctx cb_ctx;
@@ -134,6 +134,13 @@ int cb_labels(cb_ctx *ctx, const uint8_t *frames, int width, int height, int str
  * coordinates 2x+dx, 2y+dy; gradient +-255 along the probe), cluster_of[k] = running cluster number over the batch (frame 0's clusters first; nclusters[b] per frame).  npoints = points the frames hold (may exceed cap: then only the first cap were written), nclusters[batch]. */
 int cb_clusters(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch, int16_t *pts,
                 int32_t *cluster_of, int64_t cap, int64_t *npoints, int32_t *nclusters);
+/* The detector's device tables (cluster hash, clusters, points, candidate quads) are sized per frame from the context's frame size.
+ * A frame that overflows one of them -- upstream has no such limit; think of a frame of pure noise -- reports an EMPTY detection list
+ * and a flag word; the other frames of the batch are complete and the call returns CB_OK (cb_last_error holds a note).  flags[i] for
+ * frame i of the last completed detection call (blocking call: at return; streaming form: at collect): bit 0 cluster hash, 1 clusters,
+ * 2 points, 3 quads.  Returns the number of flagged frames among the first n. */
+int cb_frame_flags(const cb_ctx *ctx, uint32_t *flags, int n);
+
 /* fit_quads(): quads[batch][cap] corners in decimated coordinates (float[4][2]) + counts */
 int cb_quads(cb_ctx *ctx, const uint8_t *frames, int width, int height, int stride, size_t frame_stride, int batch,
              float *quads, int cap, int32_t *counts, int64_t *npoints_total);

@@ -130,6 +130,7 @@ unsafe extern "C" {
                        pts: *mut i16, cluster_of: *mut i32, cap: i64, npoints: *mut i64, nclusters: *mut i32) -> c_int;
     pub fn cb_quads(ctx: *mut cb_ctx, frames: *const u8, width: c_int, height: c_int, stride: c_int, frame_stride: usize, batch: c_int,
                     quads: *mut f32, cap: c_int, counts: *mut i32, npoints_total: *mut i64) -> c_int;
+    pub fn cb_frame_flags(ctx: *const cb_ctx, flags: *mut u32, n: c_int) -> c_int;
     pub fn cb_get_timing(ctx: *const cb_ctx, t: *mut cb_timing) -> c_int;
     // ---- solver ----
     pub fn cb_sqpnp_set(ctx: *mut cb_ctx, max_iter: c_int, tolerance: f64) -> c_int;

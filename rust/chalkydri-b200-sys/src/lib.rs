@@ -118,6 +118,10 @@ impl Detector {
         if rc != CB_OK { panic!("chalkydri_b200: {}", last_error(self.ctx)); }
         self.out[..count as usize].iter().map(|d| Detection(*d)).collect()
     }
+    /// Overflow bits per frame of the last completed call (a flagged frame reported an empty list); returns how many are flagged.
+    pub fn frame_flags(&self, flags: &mut [u32]) -> usize {
+        unsafe { cb_frame_flags(self.ctx, flags.as_mut_ptr(), flags.len() as c_int).max(0) as usize }
+    }
     /// Batched form: `batch` frames `frame_stride` bytes apart; `out[b * max_dets + k]`, `counts[b]`.
     pub fn detect_batch(&mut self, frames: &[u8], width: i32, height: i32, stride: i32, frame_stride: usize, out: &mut [cb_detection],
                         counts: &mut [i32]) -> Result<(), Error> {

@@ -291,6 +291,40 @@ def test_gradient_clusters_bit_exact(oracle, W, H, tags, seed, edge):
     det.close()
 
 
+def test_overflowing_frame_is_isolated(oracle, monkeypatch):
+    """A frame that overflows a per-frame device table (here: the candidate-quad list, shrunk through a test hook) reports an empty
+    list and its flag; the other frames of the batch are complete and the call succeeds -- in the blocking call, the chunked blocking
+    call and the streaming form."""
+    monkeypatch.setenv("CB_TEST_QUADS_PER_FRAME", "600")
+    from chalkydri_b200 import capi
+    W, H, B = 1280, 720, 72                                   # 72 frames: the blocking call takes its pipelined (chunked) path
+    frames, _ = synth.render_batch(W, H, B, 4, seed=9, unique=4, edge_px=(60, 150))
+    noisy = (5, 40, 71)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in noisy:                                           # a field of 16-pixel dark squares: more than a thousand candidate quads
+        frames[b] = np.where(((xx + 3 * b) % 28 < 16) & ((yy + b) % 28 < 16), 30, 220).astype(np.uint8)
+    det = make_detector(W, H, B)
+    refs = {b: oracle.detect(frames[b]) for b in (0, 1, 6, 39, 70)}
+
+    def check(out, counts):
+        flags = det.frame_flags(B)
+        assert [b for b in range(B) if flags[b]] == list(noisy) and all(flags[b] & 8 for b in noisy)
+        assert all(counts[b] == 0 for b in noisy)
+        for b, ref in refs.items():
+            assert_same_detections(out[b, :counts[b]], ref)
+
+    check(*det.detect_batch(frames))                          # pipelined blocking call
+    o8, c8 = det.detect_batch(frames[:8])                     # simple path
+    f8 = det.frame_flags(8)
+    assert f8[5] & 8 and c8[5] == 0 and not f8[:5].any() and not f8[6:].any()
+    assert_same_detections(o8[0, :c8[0]], refs[0])
+    pin = capi.pinned_array(frames.shape, np.uint8); pin[:] = frames
+    det.submit(pin)
+    check(*det.collect())                                     # streaming form
+    capi.free_pinned(pin)
+    det.close()
+
+
 def test_c3_full_resolution_small_tags(oracle):
     frame, truth = synth.render_frame(4608, 2592, 40, seed=4, edge_px=(40, 300), small_tags=10)
     det = make_detector(4608, 2592, 1, 256)
