@@ -894,7 +894,7 @@ static int run_pipeline(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g, int
         launches += 2;
         if (ctx->pose_active) {
             PoseBufs pb = pose_bufs(ctx);
-            assemble_pose_problems_kernel<<<(B + 63) / 64, 64, 0, st>>>(ctx->d_dets, ctx->d_counts, (int)caps.dets_per_frame, ctx->d_field_ids, ctx->d_field_poses,
+            assemble_pose_problems_kernel<<<(B + ASM_WARPS - 1) / ASM_WARPS, ASM_WARPS * 32, 0, st>>>(ctx->d_dets, ctx->d_counts, (int)caps.dets_per_frame, ctx->d_field_ids, ctx->d_field_poses,
                                                                          ctx->n_field, ctx->d_cam9, pb.gyro, SQ_MAX_TAGS, pb.tags, pb.bearings, pb.n_tags,
                                                                          ctx->pose_frame_base, B);
             // a few hundred problems are one latency-bound wave of warps (~2 ms): solved on a side stream they disappear

@@ -956,6 +956,166 @@ sq_newton_kernel(SqScratch sc, long long nsys, SqParams prm)
 #undef SQK
 #undef SQB
 
+// ---- Newton refinement for a handful of problems (the reference's call shape: one frame -> one problem, lib.rs:293-379) ----------
+// With a thread per system one problem is six lanes of one warp running 15 iterations of a scalar 15x15 LU: 223 us, more than half of
+// the pose chain of a single frame.  Here a CTA of two warps takes one problem and every system gets SQS_G = 8 lanes (three systems
+// per warp).  The augmented system [K | b] (15 x 16) lives in shared memory; lane m of a group owns the columns m and m + 8 (the
+// right-hand side is column 15).  A pivot step is two phases separated by __syncwarp: (A) every lane of the group reads column I,
+// finds the pivot and forms the 14 - I multipliers itself (redundant, no broadcast); (B) it swaps and updates its own columns --
+// with uniform control flow: the lanes of a warp own different columns, so a branch on the column would serialise them; invalid
+// columns are computed on a clamped address and not stored.  The forward substitution is folded into the elimination (the
+// right-hand side is just another column: b[r] -= l[r][i] * b[i] happens with the same operands in the same order as in L y = b
+// afterwards), so L is never stored; the back substitution runs redundantly on every lane.  Each element sees the operations of
+// sq_newton_kernel in the same order: bit for bit the same rotations
+// (tests/test_gpu_sqpnp.py::test_small_batch_newton_is_bit_identical).
+constexpr int SQS_G = 8, SQS_PER_WARP = 3, SQS_PITCH = 248;           // pitch (doubles) between the systems of a warp: 16 banks apart
+template <int I>
+__device__ __forceinline__ void sqs_lu_step(double *__restrict__ M, int m, bool active, bool &singular)
+{
+    double cf[15];                                   // column I, rows I .. 14; then the multipliers of the rows below the pivot row
+    int piv = I;
+    // (finished groups and the idle lanes run along on their own system without storing anything: no branch, no divergence)
+#pragma unroll
+    for (int r = I; r < 15; r++) cf[r] = M[r * 16 + I];
+    // partial pivoting: first maximum of |K[r][I]|, r >= I, in row order
+    double best = fabs(cf[I]), diag = cf[I];
+#pragma unroll
+    for (int r = I + 1; r < 15; r++) {
+        const double v = fabs(cf[r]);
+        const bool gt = v > best;
+        best = gt ? v : best; piv = gt ? r : piv; diag = gt ? cf[r] : diag;
+    }
+    if (active && diag == 0) singular = true;
+    const bool go = active && diag != 0;
+    __syncwarp();
+    {
+        const double inv_diag = 1.0 / diag;
+        const double old_top = cf[I];
+#pragma unroll
+        for (int r = I + 1; r < 15; r++) cf[r] = (r == piv ? old_top : cf[r]) * inv_diag;      // rows after the swap
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (8 * j + 7 < I) continue;             // (compile time: these columns hold L, which nothing reads)
+            const int c = m + SQS_G * j;
+            const bool valid = go && c >= I;
+            const int cc = valid ? c : 15;
+            const double top_old = M[I * 16 + cc], top = M[piv * 16 + cc];      // the pivot row after the swap: `top`
+            double v[15];
+#pragma unroll
+            for (int r = I + 1; r < 15; r++) v[r] = M[r * 16 + cc];
+#pragma unroll
+            for (int r = I + 1; r < 15; r++) v[r] = (r == piv ? top_old : v[r]) - cf[r] * top;
+            if (valid) {
+                M[I * 16 + cc] = top;                // (column I: U[I][I] = diag)
+                if (c > I) {
+#pragma unroll
+                    for (int r = I + 1; r < 15; r++) M[r * 16 + cc] = v[r];
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(64)
+sq_newton_small_kernel(SqScratch sc, long long nprob, SqParams prm)
+{
+    __shared__ __align__(16) double s_sys[2 * SQS_PER_WARP * SQS_PITCH];
+    const long long prob = blockIdx.x;
+    if (prob >= nprob || !sc.valid[prob]) return;
+    const uint32_t full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, grp = min(lane / SQS_G, SQS_PER_WARP - 1), m = lane % SQS_G;
+    const long long sys = prob * 6 + wid * SQS_PER_WARP + grp;
+    double *M = s_sys + (wid * SQS_PER_WARP + grp) * SQS_PITCH;
+    const double *__restrict__ om = sc.omega + prob * 81;
+    bool done = lane >= SQS_PER_WARP * SQS_G;        // lanes 24 .. 31 only keep the barriers company
+    double r[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) r[k] = sc.r[sys * 9 + k];
+    for (int it = 0; it < prm.max_iter; it++) {
+        if (__all_sync(full, done)) break;
+        const bool active = !done;
+        if (active) {
+            // ---- the KKT system [Omega J^T; J 0] [delta; lambda] = [-Omega r; -h] (lib.rs:62-115): lane m fills row m of the Omega
+            //      block (lane 0 also row 8) and, for m < 6, constraint m ----
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = m + SQS_G * h;
+                if (row < 9) {
+                    double acc = 0;
+#pragma unroll
+                    for (int j = 0; j < 9; j++) { const double o = __ldg(om + j * 9 + row); M[row * 16 + j] = o; acc += o * r[j]; }
+                    M[row * 16 + 15] = -acc;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                if (k != m) continue;
+                const int ca = k < 3 ? k : (k == 5 ? 1 : 0), cb_ = k < 3 ? k : (k == 3 ? 1 : 2);
+                double jr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                double hval;
+                if (k < 3) {
+                    hval = (r[3 * ca] * r[3 * ca] + r[3 * ca + 1] * r[3 * ca + 1] + r[3 * ca + 2] * r[3 * ca + 2]) - 1.0;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) jr[3 * ca + q] = 2.0 * r[3 * ca + q];
+                } else {
+                    hval = r[3 * ca] * r[3 * cb_] + r[3 * ca + 1] * r[3 * cb_ + 1] + r[3 * ca + 2] * r[3 * cb_ + 2];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) { jr[3 * ca + q] = r[3 * cb_ + q]; jr[3 * cb_ + q] = r[3 * ca + q]; }
+                }
+#pragma unroll
+                for (int j = 0; j < 9; j++) { M[(9 + k) * 16 + j] = jr[j]; M[j * 16 + 9 + k] = jr[j]; }
+#pragma unroll
+                for (int j = 9; j < 15; j++) M[(9 + k) * 16 + j] = 0;
+                M[(9 + k) * 16 + 15] = -hval;
+            }
+        }
+        __syncwarp();
+        bool singular = false;
+        sqs_lu_step<0>(M, m, active, singular); sqs_lu_step<1>(M, m, active, singular); sqs_lu_step<2>(M, m, active, singular);
+        sqs_lu_step<3>(M, m, active, singular); sqs_lu_step<4>(M, m, active, singular); sqs_lu_step<5>(M, m, active, singular);
+        sqs_lu_step<6>(M, m, active, singular); sqs_lu_step<7>(M, m, active, singular); sqs_lu_step<8>(M, m, active, singular);
+        sqs_lu_step<9>(M, m, active, singular); sqs_lu_step<10>(M, m, active, singular); sqs_lu_step<11>(M, m, active, singular);
+        sqs_lu_step<12>(M, m, active, singular); sqs_lu_step<13>(M, m, active, singular); sqs_lu_step<14>(M, m, active, singular);
+        if (active) {
+            if (singular) done = true;
+            else {
+                // back substitution U x = y (y: the eliminated right-hand side), every lane of the group for itself
+                double b[15];
+#pragma unroll
+                for (int i = 0; i < 15; i++) b[i] = M[i * 16 + 15];
+#pragma unroll
+                for (int i = 14; i >= 0; i--) {
+                    b[i] = b[i] / M[i * 16 + i];
+#pragma unroll
+                    for (int rr = 0; rr < i; rr++) b[rr] -= M[rr * 16 + i] * b[i];
+                }
+                double nsq = 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) nsq += b[k] * b[k];
+#pragma unroll
+                for (int k = 0; k < 9; k++) r[k] += b[k];
+                if (nsq < prm.tol_sq) done = true;
+            }
+        }
+        __syncwarp();                                // the next iteration's fill overwrites what the slower lanes still read
+    }
+    if (lane < SQS_PER_WARP * SQS_G && m == 0) {
+        // energy = r . (Omega r)
+        double e = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            double acc = 0;
+#pragma unroll
+            for (int j = 0; j < 9; j++) acc += __ldg(om + j * 9 + i) * r[j];
+            e += r[i] * acc;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) sc.r[sys * 9 + k] = r[k];
+        sc.energy[sys] = e;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 sq_finish_kernel(const cb_iso3 *__restrict__ tags, const int32_t *__restrict__ n_tags, int max_tags, const cb_iso3 *__restrict__ robot_to_cam_p,
                  const double *__restrict__ gyro_arr, long long nprob, SqScratch sc, cb_pose *__restrict__ out, uint8_t *__restrict__ ok, SqParams prm)
@@ -1121,40 +1281,55 @@ __global__ void unproject_opencv5_kernel(const double *__restrict__ params, cons
     bearings[3 * i] = b[0]; bearings[3 * i + 1] = b[1]; bearings[3 * i + 2] = b[2];
 }
 
-// The body of AprilTags::process between detect() and solve_robot_pose() (crates/apriltags/src/lib.rs:303-327), one thread per
+// The body of AprilTags::process between detect() and solve_robot_pose() (crates/apriltags/src/lib.rs:303-327), one WARP per
 // frame: detections in list order; tags missing from the field layout are skipped (:306-308); a tag is used only if all four
 // corners un-project (:324-327).  Writes frame b's SQPnP problem (tags, 4 bearings per tag, tag count); no gyro reading (NaN) or
 // no usable tag leaves the count at 0, which the solver answers with "None".  At most max_tags tags are used.
-__global__ void assemble_pose_problems_kernel(const cb_detection *__restrict__ dets, const int32_t *__restrict__ counts, int dets_per_frame,
-                                              const int32_t *__restrict__ field_ids, const cb_iso3 *__restrict__ field_poses, int n_field,
-                                              const double *__restrict__ cam9, const double *__restrict__ gyro, int max_tags,
-                                              cb_iso3 *__restrict__ tags, double *__restrict__ bearings, int32_t *__restrict__ n_tags,
-                                              int frame_base, int n_frames)
+// Eight detections per step: lane 4 d + c un-projects corner c of detection d (the fixed-point iteration of one corner is a chain of
+// divisions, ~2 us; one thread per frame spent 37 us on a four-tag frame), a ballot tells which detections kept all four corners and
+// their rank among the used tags.
+constexpr int ASM_WARPS = 4;
+__global__ void __launch_bounds__(ASM_WARPS * 32)
+assemble_pose_problems_kernel(const cb_detection *__restrict__ dets, const int32_t *__restrict__ counts, int dets_per_frame,
+                              const int32_t *__restrict__ field_ids, const cb_iso3 *__restrict__ field_poses, int n_field,
+                              const double *__restrict__ cam9, const double *__restrict__ gyro, int max_tags,
+                              cb_iso3 *__restrict__ tags, double *__restrict__ bearings, int32_t *__restrict__ n_tags,
+                              int frame_base, int n_frames)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.x * ASM_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (f >= n_frames) return;
+    const uint32_t full = 0xffffffffu;
     const int b = frame_base + f;
     int used = 0;
     const double gy = gyro[b];
     if (gy == gy) {
         const cb_detection *d = dets + (size_t)f * dets_per_frame;
         const int n = counts[f];
-        for (int k = 0; k < n && used < max_tags; k++) {
+        const int c = lane & 3, first = lane & ~3;
+        for (int k0 = 0; k0 < n && used < max_tags; k0 += 8) {
+            const int k = k0 + (lane >> 2);
             int t = -1;
-            for (int q = 0; q < n_field; q++)
-                if (field_ids[q] == d[k].id) { t = q; break; }
-            if (t < 0) continue;
-            double br[4][3];
-            bool all = true;
-            for (int c = 0; c < 4; c++) all = unproject_opencv5(cam9, d[k].p[c][0], d[k].p[c][1], br[c]) && all;
-            if (!all) continue;
-            tags[(size_t)b * max_tags + used] = field_poses[t];
-            double *o = bearings + ((size_t)b * max_tags + used) * 12;
-            for (int c = 0; c < 4; c++) { o[3 * c] = br[c][0]; o[3 * c + 1] = br[c][1]; o[3 * c + 2] = br[c][2]; }
-            used++;
+            double br[3] = {0, 0, 0};
+            bool corner_ok = false;
+            if (k < n) {
+                const int id = d[k].id;
+                for (int q = 0; q < n_field; q++)
+                    if (field_ids[q] == id) { t = q; break; }
+                if (t >= 0) corner_ok = unproject_opencv5(cam9, d[k].p[c][0], d[k].p[c][1], br);
+            }
+            const uint32_t okb = __ballot_sync(full, corner_ok);
+            const bool tag_ok = ((okb >> first) & 0xfu) == 0xfu;
+            const uint32_t lead = __ballot_sync(full, tag_ok && c == 0);
+            const int slot = used + __popc(lead & ((1u << first) - 1u));
+            if (tag_ok && slot < max_tags) {
+                if (c == 0) tags[(size_t)b * max_tags + slot] = field_poses[t];
+                double *o = bearings + ((size_t)b * max_tags + slot) * 12 + 3 * c;
+                o[0] = br[0]; o[1] = br[1]; o[2] = br[2];
+            }
+            used = min(max_tags, used + __popc(lead));
         }
     }
-    n_tags[b] = used;
+    if (lane == 0) n_tags[b] = used;
 }
 
 }  // namespace cb

@@ -143,3 +143,25 @@ def test_every_visible_field_tag_enters_the_solve(oracle):
     with pytest.raises(ValueError):
         s.solve_robot_pose(np.zeros(MAX_TAGS + 1, ISO_DTYPE), np.zeros((4 * (MAX_TAGS + 1), 3)), r2c, 0.0, 600.0)
     s.close()
+
+
+def test_small_batch_newton_is_bit_identical():
+    """Calls of up to 512 problems refine with sq_newton_small_kernel (a warp per problem, five lanes per KKT system: the latency form for
+    the reference's one-frame call, lib.rs:293-379), larger calls with sq_newton_kernel (a thread per system).  Same operations on every
+    element in the same order: the poses must agree bit for bit -- single-tag (rank-deficient Omega, pivoting matters), two-tag and
+    noise-free problems, and a call that mixes valid problems with empty ones."""
+    from chalkydri_b200.solver import SqPnP
+    s = SqPnP.new()
+    for seed, frac, noise in [(7, 0.5, 0.25), (8, 0.0, 0.0), (9, 1.0, 1.0)]:
+        tags, bearings, n_tags, r2c, gyro, _ = make_problems(3000, seed, frac, noise)
+        n_tags = n_tags.copy()
+        n_tags[::37] = 0                                   # None problems in between
+        big, ok_big = s.solve_robot_pose_batch(tags, bearings, n_tags, r2c, gyro, 600.0)
+        assert ok_big.mean() > 0.9
+        for lo, hi in [(0, 512), (512, 513), (513, 900), (900, 1400), (1400, 1407), (2488, 3000)]:
+            small, ok_small = s.solve_robot_pose_batch(tags[lo:hi], bearings[lo:hi], n_tags[lo:hi], r2c, gyro[lo:hi], 600.0)
+            assert ok_small.tolist() == ok_big[lo:hi].tolist()
+            m = ok_small.astype(bool)
+            for key in ("rot", "pos", "std_devs"):
+                assert small[key][m].tobytes() == big[key][lo:hi][m].tobytes(), (seed, lo, hi, key)
+    s.close()
