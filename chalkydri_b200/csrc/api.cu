@@ -92,6 +92,11 @@ struct cb_ctx {
     double pose_sign_change_error = 0;   // ... and solves them on pose_stream, under the kernels of the next chunk
     cudaStream_t pose_stream = nullptr;
     cudaEvent_t ev_pose_ready = nullptr, ev_pose_done = nullptr;
+    // chunks of <= 4 frames (the reference's one-frame call): the solve is joined and its poses are read back inside the chunk, so the
+    // whole detect -> pose call is one capturable sequence (queue_chunk); larger chunks leave the solve running under the next chunk
+    bool pose_join = false;
+    cb_pose *h_pose_stage = nullptr; uint8_t *h_pose_ok_stage = nullptr; int32_t *h_pose_nt_stage = nullptr;      // pinned, 4 frames
+    cb_pose *pose_dst = nullptr; uint8_t *pose_ok_dst = nullptr; int32_t *pose_nt_dst = nullptr;                 // the caller's arrays
     int num_sms = 148;
 
     // device buffers (sized for max_batch frames of max_w x max_h at decimation >= 1)
@@ -138,7 +143,7 @@ struct cb_ctx {
     std::map<ThrKey, ThrChoice> thr_plans;          // threshold kernel shape per frame geometry (threshold_plan)
     // small batches: the pipeline of one geometry captured as a CUDA graph on its second use (detect_device_chunk)
     struct GraphSlot { int seen = 0; bool failed = false; cudaGraphExec_t exec = nullptr; int launches = 0, thr_launches = 0; };
-    std::map<std::tuple<int, int, int, int, const void *>, GraphSlot> graphs;      // W, H, stride, batch, device frames
+    std::map<std::tuple<int, int, int, int, const void *, int, double>, GraphSlot> graphs;      // W, H, stride, batch, device frames, 1 + first pose frame (0: no poses), sign_change_error
     bool graph_off = false;
 };
 
@@ -225,6 +230,9 @@ void cb_destroy(cb_ctx *ctx)
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->h_chunk_err) cudaFreeHost(ctx->h_chunk_err);
     if (ctx->h_frame_err) cudaFreeHost(ctx->h_frame_err);
+    if (ctx->h_pose_stage) cudaFreeHost(ctx->h_pose_stage);
+    if (ctx->h_pose_ok_stage) cudaFreeHost(ctx->h_pose_ok_stage);
+    if (ctx->h_pose_nt_stage) cudaFreeHost(ctx->h_pose_nt_stage);
     for (auto &sl : ctx->ss) {
         if (sl.h_dets) cudaFreeHost(sl.h_dets);
         if (sl.h_counts) cudaFreeHost(sl.h_counts);
@@ -959,6 +967,16 @@ static int queue_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g)
     CK(cudaMemcpyAsync(ctx->h_dets, ctx->d_dets, B * ctx->caps.dets_per_frame * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (5 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->pose_active && ctx->pose_join) {
+        // the chunk's solve (queued on pose_stream by run_pipeline) ran beside the read-back of the lists; join it and fetch the poses
+        PoseBufs pb = pose_bufs(ctx);
+        const size_t o = (size_t)ctx->pose_frame_base;
+        CK(cudaEventRecord(ctx->ev_pose_done, ctx->pose_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pose_done, 0));
+        CK(cudaMemcpyAsync(ctx->h_pose_stage, pb.poses + o, B * sizeof(cb_pose), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pose_ok_stage, pb.ok + o, B, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pose_nt_stage, pb.n_tags + o, B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     return CB_OK;
 }
 
@@ -971,9 +989,11 @@ static int detect_device_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom 
 {
     if (!ctx->family_set) return fail(ctx, CB_ERR_STATE, "no tag family set: call cb_set_family_tag36h11 first");
     static const bool graphs_env_off = getenv("CB_GRAPH") && atoi(getenv("CB_GRAPH")) == 0;       // A/B hook
-    const bool eligible = g.batch <= 4 && !ctx->pose_active && !ctx->external_map && !ctx->graph_off && !graphs_env_off;
+    const bool with_poses = ctx->pose_active && ctx->pose_join;
+    const bool eligible = g.batch <= 4 && (!ctx->pose_active || with_poses) && !ctx->external_map && !ctx->graph_off && !graphs_env_off;
     bool used_graph = false;
-    const auto gkey = std::make_tuple(g.W, g.H, g.stride, g.batch, (const void *)d_frames);
+    const auto gkey = std::make_tuple(g.W, g.H, g.stride, g.batch, (const void *)d_frames, with_poses ? 1 + ctx->pose_frame_base : 0,
+                                      with_poses ? ctx->pose_sign_change_error : 0.0);
     if (eligible && (ctx->graphs.size() < 32 || ctx->graphs.count(gkey))) {      // (a caller cycling through many device buffers: plain launches)
         cb_ctx::GraphSlot &slot = ctx->graphs[gkey];
         if (!slot.exec && !slot.failed && slot.seen >= 1) {
@@ -1019,6 +1039,12 @@ static int detect_device_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom 
     memcpy(out_counts, ctx->h_counts, B * sizeof(int32_t));
     for (size_t b = 0; b < B; b++)
         memcpy(out + b * ctx->caps.dets_per_frame, ctx->h_dets + b * ctx->caps.dets_per_frame, (size_t)ctx->h_counts[b] * sizeof(cb_detection));
+    if (with_poses) {
+        const size_t o = (size_t)ctx->pose_frame_base;
+        memcpy(ctx->pose_dst + o, ctx->h_pose_stage, B * sizeof(cb_pose));
+        memcpy(ctx->pose_ok_dst + o, ctx->h_pose_ok_stage, B);
+        if (ctx->pose_nt_dst) memcpy(ctx->pose_nt_dst + o, ctx->h_pose_nt_stage, B * sizeof(int32_t));
+    }
     return CB_OK;
 }
 
@@ -1254,6 +1280,7 @@ static int stream_submit(cb_ctx *ctx, const uint8_t *frames, int width, int heig
         if (ctx->pose_cap < 2 * ctx->max_batch) {
             // a pose batch in flight implies the buffer already has this size, so nothing is using the old one
             if (ctx->d_pose_buf) { CK(cudaStreamSynchronize(ctx->pose_stream)); cudaFree(ctx->d_pose_buf); ctx->d_pose_buf = nullptr; ctx->pose_cap = 0; }
+            drop_graphs(ctx);
             CK(cudaMalloc((void **)&ctx->d_pose_buf, pose_buf_bytes((size_t)2 * ctx->max_batch)));
             ctx->pose_cap = 2 * ctx->max_batch;
         }

@@ -179,3 +179,39 @@ def test_blocking_pose_call_with_a_pose_batch_in_flight_leaves_it_intact():
         for b in range(4):
             if want_raw[3][b]:
                 assert got_raw[2][b].tobytes() == want_raw[2][b].tobytes()
+
+
+def test_graph_replay_of_the_one_frame_pose_call():
+    """cb_detect_pose_gray on <= 4 frames joins its solve inside the chunk, so from the second call with a geometry on the whole detect ->
+    un-project -> SQPnP sequence is one captured CUDA graph.  Six one-frame calls on one task (plain, capture, four replays; frames,
+    gyro readings and a heartbeat frame changing under the graph) against a fresh task per frame (always the plain path): same
+    detections, same Some/None, poses bit for bit; then a parameter change drops the graph and the next call is right again."""
+    W, H = 1280, 720
+    frames, _ = synth.render_batch(W, H, 6, 1, seed=41, edge_px=(90, 200))
+    frames[2] = synth.render_batch(W, H, 1, 4, seed=42, edge_px=(70, 160))[0][0]
+    frames[4] = 128
+    gyros = [0.1, -0.4, 0.25, None, 0.0, 1.2]
+    t, _ = make_task(W, H, 1, Comm(0.0))
+    got = []
+    for i in range(6):
+        t.process_batch(1_000_000, [999_000], frames[i:i + 1], gyro=[gyros[i]])
+        got.append([a.copy() for a in t.last_batch])
+    for i in range(6):
+        f, _ = make_task(W, H, 1, Comm(0.0))
+        f.process_batch(1_000_000, [999_000], frames[i:i + 1], gyro=[gyros[i]])
+        out, counts, poses, ok, ntags = f.last_batch
+        assert counts.tolist() == got[i][1].tolist() and ok.tolist() == got[i][3].tolist() and ntags.tolist() == got[i][4].tolist(), i
+        assert out[0, :counts[0]].tobytes() == got[i][0][0, :counts[0]].tobytes(), i
+        if ok[0]:
+            assert poses.tobytes() == got[i][2].tobytes(), i
+    assert [int(g[3][0]) for g in got] == [1, 1, 0, 0, 0, 1]      # (frame 2: four randomly placed tags are no consistent scene -> None)
+    # a solver parameter is baked into the graph: changing it drops the graph and the answer follows the new value
+    from chalkydri_b200 import capi
+    L = capi.lib()
+    assert L.cb_sqpnp_set(t.detector.ctx, 0, 1e-8) == 0          # no Newton iteration at all
+    t.process_batch(1_000_000, [999_000], frames[0:1], gyro=[gyros[0]])
+    assert t.last_batch[3][0] == 0 or t.last_batch[2].tobytes() != got[0][2].tobytes()
+    assert L.cb_sqpnp_set(t.detector.ctx, 15, 1e-8) == 0           # the defaults again (lib.rs:203-204)
+    t.process_batch(1_000_000, [999_000], frames[0:1], gyro=[gyros[0]])
+    t.process_batch(1_000_000, [999_000], frames[0:1], gyro=[gyros[0]])
+    assert t.last_batch[2].tobytes() == got[0][2].tobytes()
