@@ -16,6 +16,8 @@ their own batch (weak scaling, no collective on the data path).
   sqpnp_1M     : BASELINE.json configs[4] (1 M pose problems), N = 1 only
   cat_703x905  : the reference's own benchmark shape (crates/chalkydri-apriltags/bench.rs: Detector::new(703, 905) + process_frame), N = 1 only
   p50_frame_latency_ms : one 1280x720 frame through the reference-shaped call (host frame in, list out)
+  p50_detect_pose_latency_ms : the same frame through AprilTags::process' shape (crates/apriltags/src/lib.rs:293-379): host frame in,
+                 detections + robot pose out (cb_detect_pose_gray: detect -> field lookup -> un-project -> SQPnP), N = 1 only
 
 Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
@@ -290,6 +292,48 @@ class Arms:
             self.capi.free_pinned(a)
 
 
+def detect_pose_latency(c1_frame: np.ndarray, iters=100):
+    """p50 wall time of one frame through the fused detect -> pose call (the reference's per-frame `process`): a frame with one tag
+    (a consistent scene for the field layout, so the answer is a pose) and the c1 workload's frame (four randomly placed tags: all
+    four enter the solve, whose answer is None -- same work, no pose)."""
+    from chalkydri_b200 import capi, synth
+    from chalkydri_b200.pipeline import AprilTags
+
+    class Comm:
+        def gyro_angle(self):
+            return 0.1
+
+        def publish(self, *a):
+            pass
+
+    H, W = c1_frame.shape
+    keys = ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3")
+    config = {"family": "tag36h11", "bits_corrected": 3, "cam_id": 7,
+              "robot_to_cam": json.dumps({"x": 0.2, "y": 0.1, "z": 0.5, "roll": 0.0, "pitch": -10.0, "yaw": 15.0}),
+              "calib": json.dumps({"OpenCVModel5": dict(zip(keys, synth.scaled_calib(W, H)))})}
+    task = AprilTags.new(config, Comm(), max_width=W, max_height=H, max_batch=1)
+    pin = capi.pinned_array((1, H, W), np.uint8)
+
+    def run(frame):
+        pin[0] = frame
+        lat = []
+        for i in range(iters + 10):
+            t0 = time.perf_counter()
+            task.process_batch(1_000_000, [999_000], pin)
+            if i >= 10:
+                lat.append((time.perf_counter() - t0) * 1e3)
+        return {"p50_ms": float(np.median(lat)), "detections": int(task.last_batch[1][0]), "tags_in_the_solve": int(task.last_batch[4][0]),
+                "pose": bool(task.last_batch[3][0])}
+
+    one_tag = synth.render_batch(W, H, 1, 1, seed=21, edge_px=(90, 200))[0][0]
+    res = run(one_tag)
+    res["frame"] = "1280x720, one tag36h11 tag"
+    res["c1_frame"] = run(c1_frame)
+    task.detector.close()
+    capi.free_pinned(pin)
+    return res
+
+
 def sqpnp_1m(n=1_000_000):
     """BASELINE.json configs[4]: 1 M pose problems through cb_sqpnp_batch (kernel events and the whole host call), the CPU
     restatement of chalkydri_sqpnp on a bounded sample beside it."""
@@ -452,6 +496,13 @@ def main():
         except Exception as e:                            # noqa: BLE001
             sq = {"error": f"{type(e).__name__}: {e}"}
 
+    pose_lat = None
+    if rank == 0 and world == 1 and not args.no_sqpnp:
+        try:
+            pose_lat = detect_pose_latency(make_frames("c1", 0, batch=1)[0][0])
+        except Exception as e:                            # noqa: BLE001
+            pose_lat = {"error": f"{type(e).__name__}: {e}"}
+
     cat = None
     if rank == 0 and world == 1 and not args.no_cat:
         try:
@@ -499,6 +550,7 @@ def main():
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_ms_per_step_device_arm": m1["wall_dev"] / args.steps * 1e3,
             "p50_frame_latency_ms": p50,
+            "p50_detect_pose_latency_ms": pose_lat,
             "detections_per_step": m1["ndet"], "expected_tags_per_step": m1["want"],
             "also_c2": also_c2, "c4_stream": c4, "sqpnp_1M": sq, "cat_703x905": cat,
         }
