@@ -135,6 +135,7 @@ struct cb_ctx {
     cb_detection *h_dets = nullptr;
     int32_t *h_counts = nullptr;
     uint32_t *h_small = nullptr;
+    size_t out_block_bytes = 0;                   // d_dets | d_counts | d_small (and h_*) are one allocation of this size
 
     cudaEvent_t ev[10]{};
     cb_timing timing{};
@@ -218,16 +219,14 @@ void cb_destroy(cb_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = {ctx->d_in, ctx->d_gray, ctx->d_thresh, ctx->d_mark, ctx->d_tmin, ctx->d_tmax, ctx->d_labels, ctx->d_sizes,
                     ctx->d_table, ctx->d_areas, ctx->d_cursors, ctx->d_cat, ctx->d_cat_tot, ctx->d_ent, ctx->d_tile_keys, ctx->d_tile_cnt, ctx->d_clusters, ctx->d_worklist, ctx->d_scankey, ctx->d_errs, ctx->d_cp, ctx->d_scratch,
-                    ctx->d_quads, ctx->d_raw, ctx->d_dets, ctx->d_counts, ctx->d_small};
+                    ctx->d_quads, ctx->d_raw, ctx->d_dets /* the read-back block: lists, counts, counters */};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->d_in2) cudaFree(ctx->d_in2);
     for (auto &kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (ctx->d_sq_scratch) cudaFree(ctx->d_sq_scratch);
     if (ctx->d_band_dense) cudaFree(ctx->d_band_dense);
     for (void *p : {(void *)ctx->d_field_ids, (void *)ctx->d_field_poses, (void *)ctx->d_cam9, (void *)ctx->d_pose_buf}) if (p) cudaFree(p);
-    if (ctx->h_dets) cudaFreeHost(ctx->h_dets);
-    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
-    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    if (ctx->h_dets) cudaFreeHost(ctx->h_dets);          // (h_counts, h_small live in the same block)
     if (ctx->h_chunk_err) cudaFreeHost(ctx->h_chunk_err);
     if (ctx->h_frame_err) cudaFreeHost(ctx->h_frame_err);
     if (ctx->h_pose_stage) cudaFreeHost(ctx->h_pose_stage);
@@ -352,12 +351,22 @@ cb_ctx *cb_create(int device, int max_width, int max_height, int max_batch, int 
     ok = ok && alloc((void **)&ctx->d_scratch, B * c.points_per_frame * 2 * sizeof(unsigned long long));
     ok = ok && alloc((void **)&ctx->d_quads, B * c.quads_per_frame * sizeof(QuadRec));
     ok = ok && alloc((void **)&ctx->d_raw, B * c.quads_per_frame * sizeof(RawDet));
-    ok = ok && alloc((void **)&ctx->d_dets, B * c.dets_per_frame * sizeof(cb_detection));
-    ok = ok && alloc((void **)&ctx->d_counts, B * sizeof(int32_t));
-    ok = ok && alloc((void **)&ctx->d_small, (5 * B + 48) * sizeof(uint32_t));
-    ok = ok && cudaMallocHost((void **)&ctx->h_dets, B * c.dets_per_frame * sizeof(cb_detection)) == cudaSuccess;
-    ok = ok && cudaMallocHost((void **)&ctx->h_counts, B * sizeof(int32_t)) == cudaSuccess;
-    ok = ok && cudaMallocHost((void **)&ctx->h_small, (5 * B + 48) * sizeof(uint32_t)) == cudaSuccess;
+    {
+        // what a call reads back -- detection lists, counts, counters and flags -- is ONE block on either side, so a small context
+        // (the one-frame call) fetches it with one copy instead of three (queue_chunk)
+        const size_t b_dets = (B * c.dets_per_frame * sizeof(cb_detection) + 255) / 256 * 256, b_counts = (B * sizeof(int32_t) + 255) / 256 * 256;
+        ctx->out_block_bytes = b_dets + b_counts + (5 * B + 48) * sizeof(uint32_t);
+        uint8_t *d_blk = nullptr, *h_blk = nullptr;
+        ok = ok && alloc((void **)&d_blk, ctx->out_block_bytes);
+        ok = ok && cudaMallocHost((void **)&h_blk, ctx->out_block_bytes) == cudaSuccess;
+        if (ok) {
+            ctx->d_dets = (cb_detection *)d_blk; ctx->d_counts = (int32_t *)(d_blk + b_dets); ctx->d_small = (uint32_t *)(d_blk + b_dets + b_counts);
+            ctx->h_dets = (cb_detection *)h_blk; ctx->h_counts = (int32_t *)(h_blk + b_dets); ctx->h_small = (uint32_t *)(h_blk + b_dets + b_counts);
+        } else {
+            if (d_blk) cudaFree(d_blk);
+            if (h_blk) cudaFreeHost(h_blk);
+        }
+    }
     if (ok) {
         ok = ok && cudaMemcpyToSymbol(c_codes, kHostCodes, sizeof(kHostCodes)) == cudaSuccess;
         ok = ok && cudaMemcpyToSymbol(c_bit_x, kHostBitX, sizeof(kHostBitX)) == cudaSuccess;
@@ -964,9 +973,14 @@ static int queue_chunk(cb_ctx *ctx, const uint8_t *d_frames, const Geom &g)
     int rc = run_pipeline(ctx, d_frames, g, ST_FULL);
     if (rc) return rc;
     const size_t B = g.batch;
-    CK(cudaMemcpyAsync(ctx->h_dets, ctx->d_dets, B * ctx->caps.dets_per_frame * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (5 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->out_block_bytes <= ((size_t)64 << 10)) {
+        // a small context: the whole read-back block in one copy (a copy costs ~6 us whatever its size up to here)
+        CK(cudaMemcpyAsync(ctx->h_dets, ctx->d_dets, ctx->out_block_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(ctx->h_dets, ctx->d_dets, B * ctx->caps.dets_per_frame * sizeof(cb_detection), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, B * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_small, ctx->d_small, (5 * (size_t)ctx->max_batch + 48) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (ctx->pose_active && ctx->pose_join) {
         // the chunk's solve (queued on pose_stream by run_pipeline) ran beside the read-back of the lists; join it and fetch the poses
         PoseBufs pb = pose_bufs(ctx);
