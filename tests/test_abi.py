@@ -250,3 +250,12 @@ def test_cpp_header_covers_the_abi():
     for s in ("cb_detect_gray", "cb_detect_gray_submit", "cb_detect_gray_collect", "cb_detect_pose_gray", "cb_sqpnp_batch",
               "cb_cat_process_frame", "cb_cat_connected_components", "cb_pool_detect_gray", "cb_pack_vision_measurements"):
         assert s in used
+
+
+def test_integration_guide_indexes_every_symbol():
+    """INTEGRATION.md section 5 names every symbol the header declares, each with the reference interface it stands for."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    index = doc[doc.index("## 5. Symbol index"):]
+    missing = [s for s in header_symbols() if ("`" + s + "`") not in index]
+    assert missing == [], missing
+    assert index.count("lib.rs:") >= 10                    # file:line citations, not prose
